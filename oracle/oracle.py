@@ -1,0 +1,180 @@
+"""ctypes wrapper over oracle/librlr_oracle.so (built by oracle/Makefile).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+Parity pin: tests/golden/ (generated from the unmodified reference by gen_golden.py).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "librlr_oracle.so")
+
+POLICY_ID = {"Shortest": 0, "Qroute": 1, "HybridQ": 2, "MaHybridQ": 3}
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(HERE, "rlr_oracle.c")
+    if force or not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "-s", "-B"])
+    return SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            build()
+        L = C.CDLL(SO)
+        p, i32, i64, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
+        L.orc_create.restype = p
+        L.orc_create.argtypes = [i32, p, p, i32]
+        L.orc_destroy.argtypes = [p]
+        L.orc_set_hparams.argtypes = [p, f64, f64, i32]
+        L.orc_set_stream.argtypes = [p, C.c_uint64, C.c_uint64]
+        L.orc_table_size.restype = i64
+        L.orc_table_size.argtypes = [p]
+        L.orc_table.restype = C.POINTER(C.c_double)
+        L.orc_table.argtypes = [p, i32]
+        L.orc_choice.restype = C.POINTER(C.c_uint8)
+        L.orc_choice.argtypes = [p]
+        L.orc_distance.restype = C.POINTER(C.c_double)
+        L.orc_distance.argtypes = [p]
+        L.orc_status.restype = i32
+        L.orc_status.argtypes = [p, p]
+        L.orc_counters.argtypes = [p, p]
+        L.orc_queue_len.restype = i64
+        L.orc_queue_len.argtypes = [p, i32]
+        L.orc_queue_get.argtypes = [p, i32, p]
+        L.orc_qtable_structure.argtypes = [p]
+        L.orc_reset.argtypes = [p]
+        L.orc_shortest_build.argtypes = [p]
+        L.orc_heap_perm.argtypes = [i32, p]
+        L.orc_philox4x32.argtypes = [p, p, p]
+        L.orc_run.restype = i64
+        L.orc_run.argtypes = [p, i64, i32, p, p, f64, f64, f64, f64, p, p, p, p, i64, p]
+        L.orc_run_many.restype = i64
+        L.orc_run_many.argtypes = [p, i32, i64, p, f64, f64, f64, i32, p, p]
+        L.orc_max_threads.restype = i32
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+COUNTER_NAMES = ("clock", "all_packets", "end_packets", "drop_packets", "active_packets",
+                 "hops", "route_time", "sends")
+
+
+class OracleEnv:
+    """One environment replica + its agent (reference `Network` + `Policy`)."""
+
+    def __init__(self, links, policy, discount=0.99, discount_trace=0.6, add_entropy=True,
+                 seed=0, replica=0):
+        L = lib()
+        self.N = len(links)
+        self.deg = np.array([len(links[x]) for x in range(self.N)], dtype=np.int32)
+        self.row_ptr = np.zeros(self.N + 1, dtype=np.int32)
+        self.row_ptr[1:] = np.cumsum(self.deg)
+        self.col = np.array([y for x in range(self.N) for y in links[x]], dtype=np.int32)
+        self.policy = policy
+        self.h = L.orc_create(self.N, _ptr(self.row_ptr), _ptr(self.col), POLICY_ID[policy])
+        L.orc_set_hparams(self.h, discount, discount_trace, int(add_entropy))
+        L.orc_set_stream(self.h, seed, replica)
+        self.tsize = L.orc_table_size(self.h)
+        self.toff = self.row_ptr.astype(np.int64) * self.N
+        self.Q = np.ctypeslib.as_array(L.orc_table(self.h, 0), shape=(self.tsize,))
+        self.Theta = np.ctypeslib.as_array(L.orc_table(self.h, 1), shape=(self.tsize,))
+        self.Trace = np.ctypeslib.as_array(L.orc_table(self.h, 2), shape=(self.tsize,))
+        self.choice = np.ctypeslib.as_array(L.orc_choice(self.h), shape=(self.tsize,))
+        self.distance = np.ctypeslib.as_array(L.orc_distance(self.h), shape=(self.N, self.N))
+        if policy == "Shortest":
+            L.orc_shortest_build(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.orc_destroy(self.h)
+            self.h = None
+
+    def set_qtable(self, normals, initP=0.0):
+        """normals: flat [tsize] N(initQ,1) draws in packed layout; applies qroute.py:16-20."""
+        self.Q[:] = normals
+        lib().orc_qtable_structure(self.h)
+        self.Theta[:] = initP
+        self.Trace[:] = 0.0
+
+    def reset(self):
+        lib().orc_reset(self.h)
+
+    def counters(self):
+        out = np.zeros(8, dtype=np.int64)
+        lib().orc_counters(self.h, _ptr(out))
+        return dict(zip(COUNTER_NAMES, (int(v) for v in out)))
+
+    def queue(self, x):
+        n = lib().orc_queue_len(self.h, x)
+        out = np.zeros((n, 5), dtype=np.int32)
+        if n:
+            lib().orc_queue_get(self.h, x, _ptr(out))
+        return out
+
+    def status(self):
+        clk = C.c_int64(0)
+        st = lib().orc_status(self.h, C.byref(clk))
+        return st, clk.value
+
+    def run(self, n_steps, lambd=None, inj=None, lr_q=0.1, lr_p=0.1, lr_e=0.1, sendlog=False):
+        """inj=(cnt, pairs) -> trace mode; else Philox mode at rate `lambd`."""
+        rt = np.zeros(n_steps, dtype=np.int64)
+        en = np.zeros(n_steps, dtype=np.int64)
+        hp = np.zeros(n_steps, dtype=np.int64)
+        log = np.zeros((n_steps * self.N, 4), dtype=np.int32) if sendlog else None
+        nlog = C.c_int64(0)
+        if inj is not None:
+            cnt = np.ascontiguousarray(inj[0], dtype=np.int32)
+            pairs = np.ascontiguousarray(inj[1], dtype=np.int32)
+            assert len(cnt) >= n_steps
+            mode, enlam = 0, 0.0
+        else:
+            cnt = pairs = None
+            mode, enlam = 1, float(np.exp(-np.float64(lambd) / np.float64(self.N)))
+        done = lib().orc_run(self.h, n_steps, mode, _ptr(cnt), _ptr(pairs), enlam, lr_q, lr_p,
+                             lr_e, _ptr(rt), _ptr(en), _ptr(hp), _ptr(log),
+                             0 if log is None else len(log), C.byref(nlog))
+        res = {"steps_done": int(done), "route_time": rt, "end_packets": en, "hops": hp}
+        if sendlog:
+            res["sendlog"] = log[:nlog.value].copy()
+        return res
+
+
+def run_many(envs, n_steps, lambd, lr_q=0.1, lr_p=0.1, lr_e=0.1, nthreads=0, metrics=False):
+    """Philox-mode batch over independent OracleEnv objects on `nthreads` host threads."""
+    n = len(envs)
+    hs = (C.c_void_p * n)(*[e.h for e in envs])
+    lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (n,))
+    enlam = np.exp(-lam / np.float64(envs[0].N))
+    rt = np.zeros((n, n_steps), dtype=np.int64) if metrics else None
+    en = np.zeros((n, n_steps), dtype=np.int64) if metrics else None
+    sends = lib().orc_run_many(hs, n, n_steps, _ptr(np.ascontiguousarray(enlam)), lr_q, lr_p,
+                               lr_e, nthreads, _ptr(rt), _ptr(en))
+    return (int(sends), rt, en) if metrics else int(sends)
+
+
+def heap_perm(k):
+    out = np.zeros(k, dtype=np.int32)
+    lib().orc_heap_perm(k, _ptr(out))
+    return out.tolist()
+
+
+def philox4x32(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32)
+    k = np.asarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    lib().orc_philox4x32(_ptr(c), _ptr(k), _ptr(out))
+    return out

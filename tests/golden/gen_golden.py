@@ -1,0 +1,97 @@
+"""Generates tests/golden/kat.json and tests/golden/np_tables.npz from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):  python tests/golden/gen_golden.py
+The reference has no tests or golden vectors of its own; these known answers are the
+pin for oracle/rlr_oracle.c (tests/test_oracle_golden.py) and, through it, for the CUDA path.
+
+Inputs are reproducible from the case description alone: NumPy's legacy RandomState stream is
+frozen, so `seed` regenerates the constructor's normals and (trace mode) the injections; Philox
+mode regenerates injections and policy samples from (philox_seed, replica).
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness as H  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def h(a, dt):
+    return hashlib.sha256(np.ascontiguousarray(a, dtype=dt).tobytes()).hexdigest()
+
+
+CASES = [
+    # trace mode: bit-for-bit the reference's own RNG stream
+    dict(net="6x6.net", policy="Qroute", T=10000, lambd=2.0, seed=1),          # BASELINE config 1
+    dict(net="6x6-modified.net", policy="Qroute", T=3000, lambd=2.0, seed=1),
+    dict(net="lata.net", policy="Qroute", T=2000, lambd=2.0, seed=1),
+    dict(net="6x6.net", policy="Qroute", T=2000, lambd=0.5, seed=1),
+    dict(net="6x6.net", policy="Qroute", T=2000, lambd=1.0, seed=5, lr={"q": 0.5}),
+    dict(net="6x6.net", policy="Qroute", T=1500, lambd=3.0, seed=2, agent_kwargs={"discount": 0.9, "initQ": -2}),
+    dict(net="6x6.net", policy="Shortest", T=10000, lambd=1.0, seed=1),
+    dict(net="6x6.net", policy="Shortest", T=10000, lambd=2.0, seed=1),
+    dict(net="6x6.net", policy="Shortest", T=10000, lambd=4.0, seed=1),
+    dict(net="6x6-modified.net", policy="Shortest", T=2000, lambd=2.5, seed=3),
+    dict(net="lata.net", policy="Shortest", T=1000, lambd=3.0, seed=1),
+    # Philox mode: reference driven by the Philox twin (oracle/philox_twin.py)
+    dict(net="6x6.net", policy="Qroute", T=2000, lambd=1.0, seed=1, rng="philox", philox_seed=7, replica=3),
+    dict(net="6x6.net", policy="Shortest", T=2000, lambd=4.0, seed=1, rng="philox", philox_seed=7, replica=3),
+    dict(net="lata.net", policy="Qroute", T=800, lambd=2.0, seed=4, rng="philox", philox_seed=0, replica=0),
+    # sampled policies; det_math: the reference's np.exp/np.log2 swapped for the deterministic pair
+    dict(net="6x6.net", policy="HybridQ", T=3000, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3, det_math=True),
+    dict(net="lata.net", policy="HybridQ", T=1000, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3, det_math=True),
+    dict(net="6x6.net", policy="HybridQ", T=1000, lambd=1.0, seed=9, rng="philox", philox_seed=11, replica=(1 << 33) + 5,
+         det_math=True, lr={"q": 0.2, "p": 0.05, "e": 0.3}, agent_kwargs={"add_entropy": False, "discount": 0.9}),
+    dict(net="6x6.net", policy="MaHybridQ", T=4000, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3,
+         det_math=True, lr={"q": 0.1, "p": 0.001}),
+    dict(net="6x6.net", policy="MaHybridQ", T=3000, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3, det_math=True),  # F7: NaN at 2526
+    dict(net="6x6-modified.net", policy="MaHybridQ", T=1500, lambd=1.0, seed=1, rng="philox", philox_seed=7, replica=3,
+         det_math=True, lr={"q": 0.1, "p": 0.001}),
+    # sampled policies with NumPy's own exp/log2: short horizon, tables compared with a tolerance
+    dict(net="6x6.net", policy="HybridQ", T=300, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3, keep_tables=True),
+    dict(net="6x6.net", policy="MaHybridQ", T=300, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3,
+         lr={"q": 0.1, "p": 0.001}, keep_tables=True),
+]
+
+
+def main():
+    out, arrays = [], {}
+    for i, c in enumerate(CASES):
+        kw = dict(c)
+        keep = kw.pop("keep_tables", False)
+        r = H.run(kw.pop("net"), kw.pop("policy"), kw.pop("T"), kw.pop("lambd"), **kw)
+        rec = dict(c)
+        rec["id"] = i
+        rec["expect"] = {
+            "counters": r["counters"], "ave_route_time": r["ave_route_time"],
+            "sendlog_sha256": r["sendlog_sha256"], "n_sends": r["n_sends"],
+            "inj_sha256": h(np.concatenate([r["inj_cnt"], r["inj_pairs"].reshape(-1)]), "<i4"),
+            "route_time_sha256": h(r["route_time"], "<i8"), "end_packets_sha256": h(r["end_packets"], "<i8"),
+            "hops_sha256": h(r["hops"], "<i8"),
+            "queues_sha256": h(np.concatenate([q.reshape(-1) for q in r["queues"]] + [np.array([len(q) for q in r["queues"]])]), "<i4"),
+            "error": r["error"],
+        }
+        for name in ("Q0", "Qtable", "Theta", "Trace"):
+            if name in r:
+                rec["expect"][name + "_sha256"] = h(r[name], "<f8")
+                rec["expect"][name + "_sum"] = float(r[name].sum())
+                if keep:
+                    arrays[f"case{i}_{name}"] = r[name]
+        if "distance" in r:
+            rec["expect"]["distance_sha256"] = h(r["distance"], "<f8")
+            rec["expect"]["choice_sha256"] = h(r["choice"], "u1")
+        out.append(rec)
+        print(i, c["net"], c["policy"], r["counters"], r["error"], flush=True)
+    with open(os.path.join(HERE, "kat.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    np.savez_compressed(os.path.join(HERE, "np_tables.npz"), **arrays)
+
+
+if __name__ == "__main__":
+    main()
