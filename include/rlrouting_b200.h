@@ -1,0 +1,158 @@
+/*
+ * rlrouting_b200.h — C ABI of the B200-native batched packet-routing simulator.
+ *
+ * The reference (xuxife/rlrouting) is pure Python and has NO FFI; its plugin boundary is the two
+ * Python interfaces `Network` (env.py:213-450) and `Policy` (base_policy.py:5-66).  This header
+ * is the boundary a maintainer binds UNDER those interfaces (ctypes stub in INTEGRATION.md): every
+ * entry point below names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative RLR_E_* code, and
+ *     rlr_last_error_string() describes the last failure on the calling thread;
+ *   - the caller (PyTorch in the shipped host layer) allocates and owns EVERY device buffer; the
+ *     library borrows the pointers in rlr_buffers_t for the lifetime of the handle and allocates
+ *     nothing on the device;
+ *   - kernels are launched on the stream passed in (a cudaStream_t cast to void*); nothing here
+ *     synchronises the device;
+ *   - one host thread per handle; no callbacks into the host language;
+ *   - asynchronous device conditions (queue ring overflow; NaN softmax probabilities, where the
+ *     reference raises ValueError out of np.random.choice, hybrid.py:20-23) are reported through
+ *     the sticky per-replica status words in rlr_buffers_t.status, never by dropping a packet.
+ */
+#ifndef RLROUTING_B200_H
+#define RLROUTING_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLR_ABI_VERSION 1
+
+enum { RLR_OK = 0, RLR_E_INVALID = -1, RLR_E_UNSUPPORTED = -2, RLR_E_CUDA = -3, RLR_E_STATE = -4 };
+
+/* Policy ids: Shortest (shortest.py:6-58), Qroute (qroute.py:6-53), HybridQ (hybrid.py:41-62),
+ * MaHybridQ (multi_agent.py:6-50). */
+enum { RLR_POLICY_SHORTEST = 0, RLR_POLICY_QROUTE = 1, RLR_POLICY_HYBRIDQ = 2, RLR_POLICY_MAHYBRIDQ = 3 };
+
+/* Injection: RLR_INJECT_TRACE replays host-generated draws of the reference's NumPy legacy stream
+ * (env.py:307-310); RLR_INJECT_PHILOX draws on the device (Philox4x32-10 keyed per replica, clock,
+ * node; Poisson splitting, SURVEY §8c law ii). */
+enum { RLR_INJECT_TRACE = 0, RLR_INJECT_PHILOX = 1 };
+
+/* Sticky per-replica status codes (status[2*r] = code, status[2*r+1] = clock of the first event). */
+enum { RLR_STATUS_OK = 0, RLR_STATUS_NAN_PROB = 1, RLR_STATUS_QUEUE_OVERFLOW = 2 };
+
+/* Per-replica counters, int64 each (Network attributes, env.py:267-276 / 321-331). */
+enum {
+    RLR_CTR_ALL_PACKETS = 0, RLR_CTR_END_PACKETS = 1, RLR_CTR_DROP_PACKETS = 2, RLR_CTR_HOPS = 3,
+    RLR_CTR_ROUTE_TIME = 4, RLR_CTR_SENDS = 5, RLR_CTR_RESERVED0 = 6, RLR_CTR_RESERVED1 = 7,
+    RLR_NUM_COUNTERS = 8
+};
+
+typedef struct rlr_handle rlr_handle_t;
+
+/* Graph in the order Network.read_network builds it (env.py:282-296); HOST pointers, copied. */
+typedef struct {
+    int32_t n_nodes;          /* N                                                          */
+    int32_t sum_deg;          /* sum of degrees                                             */
+    int32_t max_deg;
+    const int32_t *row_ptr;   /* [N+1]  links[x] = col[row_ptr[x] .. row_ptr[x+1])          */
+    const int32_t *col;       /* [sum_deg]                                                  */
+} rlr_topology_t;
+
+typedef struct {
+    int64_t replicas;         /* environments simulated by this handle (on one device)      */
+    int64_t replica_base;     /* global index of local replica 0: Philox stream id = base+r */
+    int32_t policy;           /* RLR_POLICY_*                                               */
+    int32_t queue_capacity;   /* ring slots per (replica, node); power of two               */
+    int32_t replicas_per_block; /* 0 = choose                                               */
+    int32_t threads_per_block;  /* 0 = choose; >= replicas_per_block * N, multiple of 32    */
+    int32_t tables_in_smem;   /* -1 = choose, 0 = tables stay in HBM, 1 = staged in smem    */
+    int32_t device;           /* CUDA device ordinal the buffers live on                    */
+} rlr_config_t;
+
+/* Raw DEVICE pointers borrowed from the caller.  R = replicas, N = n_nodes,
+ * TS = N * sum_deg (table[x][d][k] at N*row_ptr[x] + d*deg[x] + k, the reference's per-node
+ * (N, deg_x) arrays of qroute.py:13-15 packed back to back). */
+typedef struct {
+    double *q_table;          /* [R][TS]  Qroute.Qtable            (NULL for Shortest)       */
+    double *theta;            /* [R][TS]  PolicyGradient.Theta     (HybridQ, MaHybridQ)      */
+    double *trace;            /* [R][TS]  MaHybridQ.Trace                                     */
+    void *ring;               /* [R][N][cap] 16-byte packet records (Node.queue, env.py:100) */
+    uint32_t *q_head;         /* [R][N] monotonically increasing pop counter                 */
+    uint32_t *q_tail;         /* [R][N] monotonically increasing push counter                */
+    int64_t *counters;        /* [R][RLR_NUM_COUNTERS]                                       */
+    int32_t *status;          /* [R][2]                                                      */
+    uint8_t *next_hop;        /* [N][N] Shortest: action index chosen at x for dest d        */
+    double *distance;         /* [N][N] Shortest.distance (float64, inf = unreachable)       */
+    uint8_t *choice;          /* [TS]   Shortest.choice masks, packed like the tables        */
+    int32_t *topo_row_ptr;    /* [N+1]   device copy of the CSR (uploaded by the caller)     */
+    int32_t *topo_col;        /* [sum_deg]                                                   */
+    uint8_t *heap_pos;        /* [(N+1)*N] heap_pos[k*N + rank]: pop position among k ties   */
+} rlr_buffers_t;
+
+typedef struct {
+    int32_t inject_mode;      /* RLR_INJECT_*                                                */
+    int32_t add_entropy;      /* HybridQ(add_entropy=...)  hybrid.py:44                      */
+    /* trace mode (device pointers): injections of replica r at local step s are
+     * inj_pairs[inj_base[r] + inj_off[r*(n_steps+1) + s] .. + inj_off[r*(n_steps+1) + s+1])
+     * each packed as source | dest << 16 */
+    const int32_t *inj_off;
+    const int64_t *inj_base;
+    const uint32_t *inj_pairs;
+    /* Philox mode */
+    const double *enlam;      /* device [R]: exp(-lambda_r / N)                              */
+    uint64_t seed;
+    /* learning rates lr['q'], lr['p'], lr['e'] (qroute.py:46, hybrid.py:55, multi_agent.py:17) */
+    double lr_q, lr_p, lr_e;
+    double discount;          /* qroute.py:9 / hybrid.py:44                                  */
+    double discount_trace;    /* multi_agent.py:10                                           */
+    int32_t clock0;           /* Network.clock before the first step                         */
+    int32_t reserved;
+    /* outputs (device pointers, may be NULL) */
+    void *metrics;            /* [R][n_steps] 16-byte records {int64 route_time, uint32 end_packets,
+                                 uint32 hops}: cumulative counters after each step (env.py:409-413) */
+    uint32_t *sendlog;        /* [R][n_steps][N]: y | dest << 16 for a send by node x, else 0xFFFFFFFF */
+} rlr_run_params_t;
+
+/* ---- introspection ---- */
+int rlr_abi_version(void);
+const char *rlr_last_error_string(void);
+
+/* ---- lifecycle: replaces Network.__init__ (env.py:237-250) for R replicas ---- */
+int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t **out);
+int rlr_destroy(rlr_handle_t *h);
+int rlr_bind_buffers(rlr_handle_t *h, const rlr_buffers_t *bufs);
+
+/* Chosen launch geometry, for reporting: threads per block, replicas per block, dynamic shared
+ * memory bytes, and whether the tables are staged in shared memory. */
+int rlr_launch_info(const rlr_handle_t *h, int32_t *threads, int32_t *replicas_per_block,
+                    int32_t *smem_bytes, int32_t *tables_in_smem);
+
+/* ---- Network.reset (env.py:267-280) + Node.reset (env.py:99-101) + agent.clean()
+ *      (multi_agent.py:48-50): zero queues, counters and status; MaHybridQ traces are zeroed;
+ *      Q / Theta are kept. ---- */
+int rlr_reset(rlr_handle_t *h, void *stream);
+
+/* ---- Qroute.__init__ structure overrides (qroute.py:16-20) applied to q_table already holding
+ *      the N(initQ,1) draws; Theta = initP (hybrid.py:13-14); Trace = 0 (multi_agent.py:14-15) ---- */
+int rlr_init_tables(rlr_handle_t *h, double initP, void *stream);
+
+/* ---- Shortest.__init__ + _calc_distance (shortest.py:20-58, multiway=False): fills distance,
+ *      choice and next_hop ---- */
+int rlr_build_shortest_tables(rlr_handle_t *h, void *stream);
+
+/* ---- the hot path: n_steps iterations of Network.train's loop body (env.py:400-413) with
+ *      slot=1, freq=1: new_packet + inject, step (send phase + event drain), agent.learn ---- */
+int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *params, void *stream);
+
+/* ---- sums the per-replica counters into out[RLR_NUM_COUNTERS] (device pointer, int64) so a
+ *      load level's statistics can be all-reduced across GPUs ---- */
+int rlr_reduce_stats(rlr_handle_t *h, int64_t *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLROUTING_B200_H */

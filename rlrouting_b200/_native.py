@@ -1,0 +1,110 @@
+"""ctypes binding of the C ABI in include/rlrouting_b200.h (built from csrc/rlr_kernels.cu).
+
+There is NO CPU fallback: if the shared library is missing or does not load, importing the product
+raises.  `build()` compiles it in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "csrc", "rlr_kernels.cu")
+HDR = os.path.join(ROOT, "include", "rlrouting_b200.h")
+SO = os.path.join(HERE, "csrc", "librlrouting_b200.so")
+
+ABI_VERSION = 1
+NUM_COUNTERS = 8
+CTR = {"all_packets": 0, "end_packets": 1, "drop_packets": 2, "hops": 3, "route_time": 4, "sends": 5}
+POLICY_SHORTEST, POLICY_QROUTE, POLICY_HYBRIDQ, POLICY_MAHYBRIDQ = 0, 1, 2, 3
+INJECT_TRACE, INJECT_PHILOX = 0, 1
+STATUS_OK, STATUS_NAN_PROB, STATUS_QUEUE_OVERFLOW = 0, 1, 2
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-fmad=false", "-Xcompiler", "-fPIC", "-shared"]
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/rlr_kernels.cu -> csrc/librlrouting_b200.so for sm_100a."""
+    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+        return SO
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", SO, SRC]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    subprocess.check_call(cmd)
+    return SO
+
+
+class Topology(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("sum_deg", C.c_int32), ("max_deg", C.c_int32),
+                ("row_ptr", C.c_void_p), ("col", C.c_void_p)]
+
+
+class Config(C.Structure):
+    _fields_ = [("replicas", C.c_int64), ("replica_base", C.c_int64), ("policy", C.c_int32),
+                ("queue_capacity", C.c_int32), ("replicas_per_block", C.c_int32),
+                ("threads_per_block", C.c_int32), ("tables_in_smem", C.c_int32), ("device", C.c_int32)]
+
+
+class Buffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "q_table", "theta", "trace", "ring", "q_head", "q_tail", "counters", "status", "next_hop",
+        "distance", "choice", "topo_row_ptr", "topo_col", "heap_pos")]
+
+
+class RunParams(C.Structure):
+    _fields_ = [("inject_mode", C.c_int32), ("add_entropy", C.c_int32),
+                ("inj_off", C.c_void_p), ("inj_base", C.c_void_p), ("inj_pairs", C.c_void_p),
+                ("enlam", C.c_void_p), ("seed", C.c_uint64),
+                ("lr_q", C.c_double), ("lr_p", C.c_double), ("lr_e", C.c_double),
+                ("discount", C.c_double), ("discount_trace", C.c_double),
+                ("clock0", C.c_int32), ("reserved", C.c_int32),
+                ("metrics", C.c_void_p), ("sendlog", C.c_void_p)]
+
+
+EXPORTS = ("rlr_abi_version", "rlr_last_error_string", "rlr_create", "rlr_destroy", "rlr_bind_buffers",
+           "rlr_launch_info", "rlr_reset", "rlr_init_tables", "rlr_build_shortest_tables",
+           "rlr_run_steps", "rlr_reduce_stats")
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO):
+        raise ImportError(
+            f"{SO} is missing: the CUDA extension is not built (run `python -c 'import __graft_entry__ as g; "
+            "g.build()'`). rlrouting_b200 has no CPU fallback.")
+    L = C.CDLL(SO)
+    for name in EXPORTS:
+        if not hasattr(L, name):
+            raise ImportError(f"{SO} does not export {name}")
+    p = C.c_void_p
+    L.rlr_abi_version.restype = C.c_int
+    L.rlr_last_error_string.restype = C.c_char_p
+    L.rlr_create.argtypes = [C.POINTER(Topology), C.POINTER(Config), C.POINTER(p)]
+    L.rlr_destroy.argtypes = [p]
+    L.rlr_bind_buffers.argtypes = [p, C.POINTER(Buffers)]
+    L.rlr_launch_info.argtypes = [p] + [C.POINTER(C.c_int32)] * 4
+    L.rlr_reset.argtypes = [p, p]
+    L.rlr_init_tables.argtypes = [p, C.c_double, p]
+    L.rlr_build_shortest_tables.argtypes = [p, p]
+    L.rlr_run_steps.argtypes = [p, C.c_int64, C.POINTER(RunParams), p]
+    L.rlr_reduce_stats.argtypes = [p, p, p]
+    if L.rlr_abi_version() != ABI_VERSION:
+        raise ImportError(f"ABI mismatch: library {L.rlr_abi_version()} != binding {ABI_VERSION}")
+    _lib = L
+    return L
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeError(f"rlrouting_b200 native error {rc}: {lib().rlr_last_error_string().decode()}")

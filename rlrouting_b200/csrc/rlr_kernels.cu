@@ -1,0 +1,982 @@
+// rlr_kernels.cu — sm_100a kernels + C ABI (include/rlrouting_b200.h) of the batched packet-routing
+// simulator.  Written from scratch for B200; the reference (xuxife/rlrouting) is pure Python.
+//
+// Execution model
+//   * one thread per (replica, node); a CTA owns G whole replicas and runs ALL n_steps of a launch,
+//     so the send -> arrive -> learn ordering of Network.step (env.py:333-365) is two CTA barriers;
+//   * per-node queue cursors and the record at the head of the queue live in registers for the
+//     whole launch (the head record is prefetched one step ahead of its use);
+//   * the per-replica tables (Q / Theta / Trace, fp64) are staged into shared memory when they fit
+//     (6x6: 28.8 KB per table) so the per-hop row reads never leave the SM; otherwise (lata, fp64)
+//     they stay in HBM and the same code reads them through L1/L2;
+//   * arrivals are GATHERED by the receiving node from its neighbours' send slots and appended in
+//     the heap-tie order of the reference, so no atomics touch the queues and the
+//     result is deterministic.
+//
+// All fp64 arithmetic on tables uses the explicitly rounded intrinsics (__dmul_rn/__dadd_rn/...),
+// never FMA, because the reference evaluates every NumPy scalar operation separately.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rlrouting_b200.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define RLR_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(RLR_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+constexpr int kMaxThreads = 512;
+constexpr int kSmemLimit = 227 * 1024;
+
+// ------------------------------------------------------------------------------------------------
+// Device parameter block of the step kernel
+// ------------------------------------------------------------------------------------------------
+struct StepParams {
+    int N, sdeg, G, R;
+    int cap, K, clock0, ntab;
+    long long tsize;
+    const int *row_ptr;
+    const int *col;
+    const unsigned char *heap_pos;
+    const unsigned char *next_hop;
+    double *Q, *Theta, *Trace;
+    uint4 *ring;
+    unsigned *qhead, *qtail;
+    long long *counters;
+    int *status;
+    int inject_mode, add_entropy;
+    const int *inj_off;
+    const long long *inj_base;
+    const unsigned *inj_pairs;
+    const double *enlam;
+    unsigned long long seed;
+    long long replica_base;
+    double lr_q, lr_p, lr_e, discount, discount_trace;
+    uint4 *metrics;
+    unsigned *sendlog;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11).  Stream law shared with oracle/rlr_oracle.c:
+//   counter = (clock, node | purpose<<16 | block<<24, replica_lo, replica_hi), key = seed.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+struct PhiloxStream {
+    uint4 w;
+    unsigned c0, c1, c2, c3;
+    uint2 key;
+    int have, block;
+    __device__ __forceinline__ PhiloxStream(unsigned long long seed, unsigned long long replica, int clock,
+                                            int node, int purpose)
+        : c0((unsigned)clock), c1((unsigned)node | ((unsigned)purpose << 16)), c2((unsigned)replica),
+          c3((unsigned)(replica >> 32)), key(make_uint2((unsigned)seed, (unsigned)(seed >> 32))), have(0), block(0)
+    {
+    }
+    __device__ __forceinline__ unsigned next()
+    {
+        if (have == 0) {
+            w = philox4x32_10(make_uint4(c0, c1 | ((unsigned)block << 24), c2, c3), key);
+            have = 4;
+            ++block;
+        }
+        const unsigned r = w.x;
+        w.x = w.y; w.y = w.z; w.z = w.w;
+        --have;
+        return r;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Deterministic exp / log2: the algorithm documented in DESIGN.md §5 and restated independently in
+// oracle/rlr_oracle.c — IEEE +,-,*,/ and rint only, so CPU and GPU agree bit for bit.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pow2i(int k) { return __longlong_as_double((long long)(k + 1023) << 52); }
+
+__device__ __forceinline__ double hstep(double p, double r, double c) { return __dadd_rn(__dmul_rn(p, r), c); }
+
+__device__ double det_exp(double x)
+{
+    if (x != x) return x;
+    if (x > 709.782712893384) return CUDART_INF;
+    if (x < -745.2) return 0.0;
+    const double kf = rint(__dmul_rn(x, 1.4426950408889634));
+    double r = __dsub_rn(x, __dmul_rn(kf, 0.6931471803691238));
+    r = __dsub_rn(r, __dmul_rn(kf, 1.9082149292705877e-10));
+    double p = 1.0 / 6227020800.0;
+    p = hstep(p, r, 1.0 / 479001600.0);
+    p = hstep(p, r, 1.0 / 39916800.0);
+    p = hstep(p, r, 1.0 / 3628800.0);
+    p = hstep(p, r, 1.0 / 362880.0);
+    p = hstep(p, r, 1.0 / 40320.0);
+    p = hstep(p, r, 1.0 / 5040.0);
+    p = hstep(p, r, 1.0 / 720.0);
+    p = hstep(p, r, 1.0 / 120.0);
+    p = hstep(p, r, 1.0 / 24.0);
+    p = hstep(p, r, 1.0 / 6.0);
+    p = hstep(p, r, 0.5);
+    p = hstep(p, r, 1.0);
+    p = hstep(p, r, 1.0);
+    const int k = (int)kf, k1 = k / 2, k2 = k - k1;
+    return __dmul_rn(__dmul_rn(p, pow2i(k1)), pow2i(k2));
+}
+
+__device__ double det_log2(double x)
+{
+    if (x != x || x < 0.0) return CUDART_NAN;
+    if (x == 0.0) return -CUDART_INF;
+    if (x == CUDART_INF) return x;
+    int e = 0;
+    if (x < 2.2250738585072014e-308) { x = __dmul_rn(x, 18014398509481984.0); e = -54; }
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    e += (int)(b >> 52) - 1023;
+    double m = __longlong_as_double((long long)((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
+    if (m > 1.4142135623730951) { m = __dmul_rn(m, 0.5); e += 1; }
+    const double s = __ddiv_rn(__dsub_rn(m, 1.0), __dadd_rn(m, 1.0)), z = __dmul_rn(s, s);
+    double q = 1.0 / 25.0;
+    q = hstep(q, z, 1.0 / 23.0);
+    q = hstep(q, z, 1.0 / 21.0);
+    q = hstep(q, z, 1.0 / 19.0);
+    q = hstep(q, z, 1.0 / 17.0);
+    q = hstep(q, z, 1.0 / 15.0);
+    q = hstep(q, z, 1.0 / 13.0);
+    q = hstep(q, z, 1.0 / 11.0);
+    q = hstep(q, z, 1.0 / 9.0);
+    q = hstep(q, z, 1.0 / 7.0);
+    q = hstep(q, z, 1.0 / 5.0);
+    q = hstep(q, z, 1.0 / 3.0);
+    q = hstep(q, z, 1.0);
+    const double lnm = __dmul_rn(__dmul_rn(2.0, s), q);
+    return __dadd_rn((double)e, __dmul_rn(lnm, 1.4426950408889634));
+}
+
+// ndarray.sum() order for a short row (NumPy pairwise sum, n < 128): sequential below 8 elements,
+// else 8 running accumulators combined as ((0+1)+(2+3))+((4+5)+(6+7)) plus a sequential tail.
+template <int MAXD>
+__device__ __forceinline__ double np_sum_row(const double (&a)[MAXD], int n)
+{
+    if (MAXD < 8 || n < 8) {
+        double r = 0.0;
+#pragma unroll
+        for (int j = 0; j < MAXD; ++j)
+            if (j < n) r = __dadd_rn(r, a[j]);
+        return r;
+    }
+    double acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = a[j < MAXD ? j : 0];
+    const int nb = n - (n % 8);
+#pragma unroll
+    for (int j = 8; j < MAXD; ++j)
+        if (j < nb) acc[j & 7] = __dadd_rn(acc[j & 7], a[j]);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(acc[0], acc[1]), __dadd_rn(acc[2], acc[3])),
+                           __dadd_rn(__dadd_rn(acc[4], acc[5]), __dadd_rn(acc[6], acc[7])));
+#pragma unroll
+    for (int j = 8; j < MAXD; ++j)
+        if (j >= nb && j < n) res = __dadd_rn(res, a[j]);
+    return res;
+}
+
+// Same order over the senders of one replica, values indexed by node (non-senders skipped):
+// MaHybridQ.learn's max_Q_y.sum() / max_Q_x_d.sum() (multi_agent.py:28-29).
+__device__ double np_sum_compacted(const double *v, const short *target, int N, int n)
+{
+    if (n < 8) {
+        double r = 0.0;
+        for (int x = 0; x < N; ++x)
+            if (target[x] >= 0) r = __dadd_rn(r, v[x]);
+        return r;
+    }
+    double acc[8];
+    const int nb = n - (n % 8);
+    int idx = 0;
+    double res = 0.0;
+    for (int x = 0; x < N; ++x) {
+        if (target[x] < 0) continue;
+        const double a = v[x];
+        if (idx < 8) {
+            acc[idx] = a;
+        } else if (idx < nb) {
+            acc[idx & 7] = __dadd_rn(acc[idx & 7], a);
+        } else {
+            if (idx == nb)
+                res = __dadd_rn(__dadd_rn(__dadd_rn(acc[0], acc[1]), __dadd_rn(acc[2], acc[3])),
+                                __dadd_rn(__dadd_rn(acc[4], acc[5]), __dadd_rn(acc[6], acc[7])));
+            res = __dadd_rn(res, a);
+        }
+        ++idx;
+    }
+    if (n == nb)
+        res = __dadd_rn(__dadd_rn(__dadd_rn(acc[0], acc[1]), __dadd_rn(acc[2], acc[3])),
+                        __dadd_rn(__dadd_rn(acc[4], acc[5]), __dadd_rn(acc[6], acc[7])));
+    return res;
+}
+
+// Number of set bits in [lo, hi) of the CTA-wide "node sent this step" bit array (one word per warp).
+__device__ __forceinline__ int count_bits(const unsigned *wmask, int lo, int hi)
+{
+    if (hi <= lo) return 0;
+    const int w0 = lo >> 5, w1 = (hi - 1) >> 5;
+    int c = 0;
+    for (int w = w0; w <= w1; ++w) {
+        unsigned m = wmask[w];
+        if (w == w0) m &= 0xFFFFFFFFu << (lo & 31);
+        if (w == w1) m &= 0xFFFFFFFFu >> (31 - ((hi - 1) & 31));
+        c += __popc(m);
+    }
+    return c;
+}
+
+__device__ __forceinline__ void set_status(int *status, long long r, int code, int clock)
+{
+    if (atomicCAS(&status[2 * r], 0, code) == 0) status[2 * r + 1] = clock;
+}
+
+__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// Shared-memory carve-up, identical on host (sizing) and device (pointers).
+struct SmemLayout {
+    size_t tables, rec, target, wmask, rowptr, col, nexthop, ull, u32, f64, total;
+    __host__ __device__ SmemLayout(int N, int sdeg, int G, int threads, int policy, bool smem_tables, long long tsize, int ntab)
+    {
+        const int GN = G * N;
+        size_t o = 0;
+        tables = o; o += smem_tables ? align16((size_t)G * ntab * tsize * 8) : 0;
+        rec = o; o += align16((size_t)GN * 16);
+        f64 = o; o += (policy == RLR_POLICY_MAHYBRIDQ) ? align16((size_t)(3 * GN + 4 * G) * 8) : 0;
+        ull = o; o += align16((size_t)G * 3 * 8);            // route_time, sends, injected
+        u32 = o; o += align16((size_t)G * 4 * 4);            // end, hops, dead, k
+        wmask = o; o += align16((size_t)(threads / 32 + 1) * 4);
+        rowptr = o; o += align16((size_t)(N + 1) * 4);
+        col = o; o += align16((size_t)sdeg * 2);
+        target = o; o += align16((size_t)GN * 2);
+        nexthop = o; o += (policy == RLR_POLICY_SHORTEST) ? align16((size_t)N * N) : 0;
+        total = o;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// The step kernel: n_steps iterations of Network.train's loop body (env.py:400-413, slot=freq=1).
+// ------------------------------------------------------------------------------------------------
+template <int POLICY, int MAXD, bool SMEM_TABLES>
+__global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_constant__ StepParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int N = p.N, G = p.G, GN = G * N;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const SmemLayout L(N, p.sdeg, G, blockDim.x, POLICY, SMEM_TABLES, p.tsize, p.ntab);
+    double *s_tables = reinterpret_cast<double *>(smem + L.tables);
+    uint4 *s_rec = reinterpret_cast<uint4 *>(smem + L.rec);
+    double *s_f64 = reinterpret_cast<double *>(smem + L.f64);
+    unsigned long long *s_ull = reinterpret_cast<unsigned long long *>(smem + L.ull);
+    unsigned *s_u32 = reinterpret_cast<unsigned *>(smem + L.u32);
+    unsigned *s_wmask = reinterpret_cast<unsigned *>(smem + L.wmask);
+    int *s_rowptr = reinterpret_cast<int *>(smem + L.rowptr);
+    unsigned short *s_col = reinterpret_cast<unsigned short *>(smem + L.col);
+    short *s_target = reinterpret_cast<short *>(smem + L.target);
+    unsigned char *s_nexthop = smem + L.nexthop;
+    // per-replica accumulators of this launch
+    unsigned long long *s_rt = s_ull, *s_sends = s_ull + G, *s_inj = s_ull + 2 * G;
+    unsigned *s_end = s_u32, *s_hops = s_u32 + G, *s_dead = s_u32 + 2 * G;
+    // MaHybridQ scratch: r, max_Q_y, max_Q_x_d per node; three sums + spare per replica
+    double *s_r = s_f64, *s_qy = s_f64 + GN, *s_qx = s_f64 + 2 * GN, *s_sum = s_f64 + 3 * GN;
+
+    const long long rblock = (long long)blockIdx.x * G;            // first replica of this CTA
+    const int g = t / N, x = t - g * N;
+    const long long r = rblock + g;
+    const bool is_node = (t < GN) && (r < p.R);
+    const int gbase = g * N;
+    const long long tstride = (long long)p.ntab * p.tsize;         // smem doubles per replica
+
+    // ---- stage topology (+ tables) into shared memory ----
+    for (int i = t; i <= N; i += blockDim.x) s_rowptr[i] = p.row_ptr[i];
+    for (int i = t; i < p.sdeg; i += blockDim.x) s_col[i] = (unsigned short)p.col[i];
+    if (POLICY == RLR_POLICY_SHORTEST)
+        for (int i = t; i < N * N; i += blockDim.x) s_nexthop[i] = p.next_hop[i];
+    for (int i = t; i < G; i += blockDim.x) {
+        s_rt[i] = 0; s_sends[i] = 0; s_inj[i] = 0; s_end[i] = 0; s_hops[i] = 0;
+        s_dead[i] = (rblock + i < p.R) ? (unsigned)(p.status[2 * (rblock + i)] != 0) : 1u;
+    }
+    if (SMEM_TABLES) {
+        const long long per = p.tsize / 2;                          // double2 per table
+        for (int gg = 0; gg < G; ++gg) {
+            if (rblock + gg >= p.R) break;
+            for (int tb = 0; tb < p.ntab; ++tb) {
+                const double *src = (tb == 0 ? p.Q : tb == 1 ? p.Theta : p.Trace) + (rblock + gg) * p.tsize;
+                double2 *dst = reinterpret_cast<double2 *>(s_tables + gg * tstride + tb * p.tsize);
+                const double2 *s2 = reinterpret_cast<const double2 *>(src);
+                for (long long i = t; i < per; i += blockDim.x) dst[i] = s2[i];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- per-thread state ----
+    double *Qr = nullptr, *Thr = nullptr, *Trr = nullptr;          // this replica's tables
+    if (POLICY != RLR_POLICY_SHORTEST && t < GN && r < p.R) {
+        if (SMEM_TABLES) {
+            Qr = s_tables + g * tstride;
+            Thr = Qr + p.tsize;
+            Trr = Qr + 2 * p.tsize;
+        } else {
+            Qr = p.Q + r * p.tsize;
+            Thr = p.Theta ? p.Theta + r * p.tsize : nullptr;
+            Trr = p.Trace ? p.Trace + r * p.tsize : nullptr;
+        }
+    }
+    const unsigned capmask = (unsigned)p.cap - 1u;
+    unsigned head = 0, tail = 0;
+    uint4 next_rec = make_uint4(0, 0, 0, 0);
+    uint4 *myring = nullptr;
+    int rp = 0, deg = 0;
+    long long toffx = 0;
+    double enlam = 0.0;
+    unsigned my_sends = 0, my_inj = 0;
+    long long base_rt = 0, base_end = 0, base_hops = 0;
+    if (is_node) {
+        head = p.qhead[r * N + x];
+        tail = p.qtail[r * N + x];
+        myring = p.ring + ((size_t)r * N + x) * (size_t)p.cap;
+        if (head != tail) next_rec = myring[head & capmask];
+        rp = s_rowptr[x];
+        deg = s_rowptr[x + 1] - rp;
+        toffx = (long long)N * rp;
+        if (p.inject_mode == RLR_INJECT_PHILOX) enlam = p.enlam[r];
+        if (x == 0) {
+            base_rt = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_ROUTE_TIME];
+            base_end = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_END_PACKETS];
+            base_hops = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_HOPS];
+        }
+    }
+    const unsigned long long stream_id = (unsigned long long)(p.replica_base + r);
+
+    auto append = [&](uint4 rec, int clock) {
+        if (tail - head >= (unsigned)p.cap) {           // never drop silently: sticky status
+            set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
+            return;
+        }
+        myring[tail & capmask] = rec;
+        if (head == tail) next_rec = rec;
+        ++tail;
+    };
+
+    for (int s = 0; s < p.K; ++s) {
+        const int clock = p.clock0 + s;
+        const bool live = is_node && !s_dead[g];
+        bool sending = false;
+        int d = 0, k = 0;
+        double oldq = 0.0, max_qy = 0.0, max_qxd = 0.0, rwd = 0.0;
+        double sm[MAXD];
+        if (live) {
+            // ---- A. new_packet + inject (env.py:298-319) ----
+            if (p.inject_mode == RLR_INJECT_PHILOX) {
+                PhiloxStream ps(p.seed, stream_id, clock, x, 0);
+                int n = 0;
+                double prod = 1.0;
+                for (;;) {
+                    const double u = __dmul_rn(__dadd_rn((double)ps.next(), 0.5), 1.0 / 4294967296.0);
+                    prod = __dmul_rn(prod, u);
+                    if (prod > enlam) ++n; else break;
+                }
+                for (int i = 0; i < n; ++i) {
+                    unsigned dd = __umulhi(ps.next(), (unsigned)(N - 1));
+                    if (dd >= (unsigned)x) ++dd;
+                    append(make_uint4(dd | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock), clock);
+                }
+                my_inj += n;
+            } else {
+                const int *off = p.inj_off + r * (long long)(p.K + 1) + s;
+                const int o0 = off[0], o1 = off[1];
+                const unsigned *pairs = p.inj_pairs + p.inj_base[r];
+                for (int i = o0; i < o1; ++i) {
+                    const unsigned pr = pairs[i];
+                    if ((int)(pr & 0xFFFFu) == x) {
+                        append(make_uint4((pr >> 16) | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock), clock);
+                        ++my_inj;
+                    }
+                }
+            }
+            // ---- B. Node._send_default (env.py:162-191): pop the head, choose, get_info ----
+            if (head != tail) {
+                sending = true;
+                uint4 rec = next_rec;
+                ++head;
+                d = (int)(rec.x & 0xFFFFu);
+                if (POLICY == RLR_POLICY_SHORTEST) {
+                    k = s_nexthop[x * N + d];                                   // shortest.py:38-41
+                } else if (POLICY == RLR_POLICY_QROUTE) {
+                    const double *row = Qr + toffx + (long long)d * deg;        // qroute.py:22-27
+                    double best = row[0];
+#pragma unroll
+                    for (int j = 1; j < MAXD; ++j)
+                        if (j < deg) { const double v = row[j]; if (v > best) { best = v; k = j; } }
+                    max_qxd = best;
+                    oldq = best;
+                } else {
+                    // PolicyGradient.choose (hybrid.py:16-23): softmax(theta) sampled by inverse CDF
+                    const double *th = Thr + toffx + (long long)d * deg;
+                    double e[MAXD];
+#pragma unroll
+                    for (int j = 0; j < MAXD; ++j) e[j] = (j < deg) ? det_exp(th[j]) : 0.0;
+                    const double ssum = np_sum_row<MAXD>(e, deg);
+                    bool bad = false;
+                    double c = 0.0, cdf[MAXD];
+#pragma unroll
+                    for (int j = 0; j < MAXD; ++j) {
+                        sm[j] = (j < deg) ? __ddiv_rn(e[j], ssum) : 0.0;
+                        if (j < deg) { bad |= (sm[j] != sm[j]); c = __dadd_rn(c, sm[j]); }
+                        cdf[j] = c;
+                    }
+                    if (bad) {
+                        set_status(p.status, r, RLR_STATUS_NAN_PROB, clock);
+                        s_dead[g] = 1u;        // takes effect next step; this step's state is void
+                    }
+                    PhiloxStream ps(p.seed, stream_id, clock, x, 1);
+                    const unsigned a = ps.next() >> 5, b = ps.next() >> 6;
+                    const double u = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+#pragma unroll
+                    for (int j = 0; j < MAXD - 1; ++j)
+                        if (j < deg - 1 && k == j && __ddiv_rn(cdf[j], c) <= u) k = j + 1;
+                    const double *row = Qr + toffx + (long long)d * deg;        // hybrid.py:49-53
+                    double best = row[0];
+                    oldq = row[0];
+#pragma unroll
+                    for (int j = 1; j < MAXD; ++j)
+                        if (j < deg) { const double v = row[j]; if (v > best) best = v; if (j == k) oldq = v; }
+                    max_qxd = best;
+                }
+                const int y = s_col[rp + k];
+                rec.y += 1u;                                                    // p.hops += 1, env.py:141
+                rwd = (double)(-(clock - (int)rec.w) - 1);                      // r = -q_y - t_y, qroute.py:37
+                if (POLICY != RLR_POLICY_SHORTEST) {                            // max_Q_y, qroute.py:29-30
+                    const int rpy = s_rowptr[y], degy = s_rowptr[y + 1] - rpy;
+                    const double *ry = Qr + (long long)N * rpy + (long long)d * degy;
+                    double m = ry[0];
+                    for (int j = 1; j < degy; ++j) { const double v = ry[j]; if (v > m) m = v; }
+                    max_qy = m;
+                }
+                s_rec[t] = rec;
+                s_target[t] = (short)y;
+                if (POLICY == RLR_POLICY_MAHYBRIDQ) { s_r[t] = rwd; s_qy[t] = max_qy; s_qx[t] = max_qxd; }
+                if (head != tail) next_rec = myring[head & capmask];           // prefetch next head
+                ++my_sends;
+                if (p.sendlog) p.sendlog[(r * p.K + s) * N + x] = (unsigned)y | ((unsigned)d << 16);
+            } else {
+                s_target[t] = -1;
+                if (p.sendlog) p.sendlog[(r * p.K + s) * N + x] = 0xFFFFFFFFu;
+            }
+        } else if (t < GN) {
+            s_target[t] = -1;
+            if (is_node && p.sendlog) p.sendlog[(r * p.K + s) * N + x] = 0xFFFFFFFFu;
+        }
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, sending);
+        if (lane == 0) s_wmask[warp] = bal;
+        __syncthreads();                                                        // ---- barrier 1 ----
+
+        int ksend = -1;
+        if (live) {
+            // ---- C. event drain (env.py:349-364): gather arrivals from neighbours in heap-tie order ----
+            unsigned am = 0;
+#pragma unroll
+            for (int j = 0; j < MAXD; ++j)
+                if (j < deg && s_target[gbase + s_col[rp + j]] == (short)x) am |= 1u << j;
+            if (am) {
+                unsigned posv[MAXD];
+#pragma unroll
+                for (int j = 0; j < MAXD; ++j) posv[j] = 0;
+                if (am & (am - 1u)) {
+                    ksend = count_bits(s_wmask, gbase, gbase + N);
+#pragma unroll
+                    for (int j = 0; j < MAXD; ++j)
+                        if ((am >> j) & 1u) {
+                            const int z = s_col[rp + j];
+                            posv[j] = p.heap_pos[ksend * N + count_bits(s_wmask, gbase, gbase + z)];
+                        }
+                }
+                while (am) {
+                    int bj = 0;
+                    unsigned bp = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int j = 0; j < MAXD; ++j)
+                        if (((am >> j) & 1u) && posv[j] < bp) { bp = posv[j]; bj = j; }
+                    am &= ~(1u << bj);
+                    uint4 rec = s_rec[gbase + s_col[rp + bj]];
+                    if ((int)(rec.x & 0xFFFFu) == x) {                          // Network.end_packet, env.py:321-331
+                        atomicAdd(&s_end[g], 1u);
+                        atomicAdd(&s_rt[g], (unsigned long long)(clock + 1 - (int)rec.z));
+                        atomicAdd(&s_hops[g], rec.y);
+                    } else {                                                    // Node.receive, env.py:127-130
+                        rec.w = (unsigned)(clock + 1);
+                        append(rec, clock);
+                    }
+                }
+            }
+        }
+        // ---- D. agent.learn ----
+        if (POLICY == RLR_POLICY_QROUTE) {
+            if (sending) {                                                      // qroute.py:40-44
+                const double tq = __dmul_rn(p.discount, max_qy);
+                const double u1 = __dadd_rn(rwd, tq);
+                const double u2 = __dsub_rn(u1, oldq);
+                Qr[toffx + (long long)d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, u2));
+            }
+        } else if (POLICY == RLR_POLICY_HYBRIDQ) {
+            if (sending) {                                                      // hybrid.py:55-62
+                double rr = rwd;
+                if (p.add_entropy) {                                            // hybrid.py:38-39
+                    double tmp[MAXD];
+#pragma unroll
+                    for (int j = 0; j < MAXD; ++j) tmp[j] = (j < deg) ? __dmul_rn(sm[j], det_log2(sm[j])) : 0.0;
+                    rr = __dsub_rn(rr, __dmul_rn(p.lr_e, np_sum_row<MAXD>(tmp, deg)));
+                }
+                const double tq = __dmul_rn(p.discount, max_qy);
+                const double u1 = __dadd_rn(rr, tq);
+                Qr[toffx + (long long)d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, __dsub_rn(u1, oldq)));
+                const double adv = __dsub_rn(u1, max_qxd);                      // hybrid.py:32-36
+                double *th = Thr + toffx + (long long)d * deg;
+#pragma unroll
+                for (int j = 0; j < MAXD; ++j)
+                    if (j < deg) {
+                        double gj = -sm[j];
+                        if (j == k) gj = __dadd_rn(gj, 1.0);
+                        th[j] = __dadd_rn(th[j], __dmul_rn(__dmul_rn(p.lr_p, gj), adv));
+                    }
+            }
+        } else if (POLICY == RLR_POLICY_MAHYBRIDQ) {
+            // MaHybridQ.learn (multi_agent.py:17-43)
+            if (t < GN && x < 3 && live) {                                      // three sums per replica
+                const int n = count_bits(s_wmask, gbase, gbase + N);
+                const double *v = (x == 0) ? s_r : (x == 1) ? s_qy : s_qx;
+                s_sum[g * 4 + x] = np_sum_compacted(v + gbase, s_target + gbase, N, n);
+            }
+            if (N < 3 && t < GN && x == 0 && live) {
+                const int n = count_bits(s_wmask, gbase, gbase + N);
+                for (int q = 1; q < 3; ++q)
+                    s_sum[g * 4 + q] = np_sum_compacted((q == 1 ? s_qy : s_qx) + gbase, s_target + gbase, N, n);
+            }
+            // dense pass 1: Trace *= discount_trace                                (multi_agent.py:32-33)
+            for (int gg = 0; gg < G; ++gg) {
+                if (rblock + gg >= p.R || s_dead[gg]) continue;
+                double *tr = SMEM_TABLES ? s_tables + gg * tstride + 2 * p.tsize : p.Trace + (rblock + gg) * p.tsize;
+                for (long long i = t; i < p.tsize; i += blockDim.x) tr[i] = __dmul_rn(tr[i], p.discount_trace);
+            }
+            __syncthreads();
+            if (sending) {                                                      // multi_agent.py:35-40
+                double *trow = Trr + toffx + (long long)d * deg;
+#pragma unroll
+                for (int j = 0; j < MAXD; ++j)
+                    if (j < deg) {
+                        double gj = -sm[j];
+                        if (j == k) gj = __dadd_rn(gj, 1.0);
+                        trow[j] = __dadd_rn(trow[j], gj);
+                    }
+                const double u1 = __dadd_rn(rwd, __dmul_rn(p.discount, max_qy));
+                Qr[toffx + (long long)d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, __dsub_rn(u1, oldq)));
+            }
+            __syncthreads();
+            // dense pass 2: Theta += (lr_p * delta) * Trace                        (multi_agent.py:28-30,42-43)
+            for (int gg = 0; gg < G; ++gg) {
+                if (rblock + gg >= p.R || s_dead[gg]) continue;
+                const double d1 = __dadd_rn(s_sum[gg * 4 + 0], 0.0);            // + reward_shape (always 0)
+                const double d3 = __dadd_rn(d1, __dmul_rn(p.discount, s_sum[gg * 4 + 1]));
+                const double ld = __dmul_rn(p.lr_p, __dsub_rn(d3, s_sum[gg * 4 + 2]));
+                double *th = SMEM_TABLES ? s_tables + gg * tstride + p.tsize : p.Theta + (rblock + gg) * p.tsize;
+                const double *tr = SMEM_TABLES ? s_tables + gg * tstride + 2 * p.tsize : p.Trace + (rblock + gg) * p.tsize;
+                for (long long i = t; i < p.tsize; i += blockDim.x) th[i] = __dadd_rn(th[i], __dmul_rn(ld, tr[i]));
+            }
+        }
+        __syncthreads();                                                        // ---- barrier 2 ----
+        if (is_node && x == 0 && p.metrics) {                                   // env.py:409-413
+            const long long rt = base_rt + (long long)s_rt[g];
+            const unsigned en = (unsigned)(base_end + s_end[g]), hp = (unsigned)(base_hops + s_hops[g]);
+            p.metrics[r * p.K + s] = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hp);
+        }
+    }
+
+    // ---- write back ----
+    if (is_node) {
+        p.qhead[r * N + x] = head;
+        p.qtail[r * N + x] = tail;
+        if (my_sends) atomicAdd(&s_sends[g], (unsigned long long)my_sends);
+        if (my_inj) atomicAdd(&s_inj[g], (unsigned long long)my_inj);
+    }
+    __syncthreads();
+    if (is_node && x == 0) {
+        long long *c = p.counters + r * RLR_NUM_COUNTERS;
+        c[RLR_CTR_ALL_PACKETS] += (long long)s_inj[g];
+        c[RLR_CTR_END_PACKETS] += (long long)s_end[g];
+        c[RLR_CTR_HOPS] += (long long)s_hops[g];
+        c[RLR_CTR_ROUTE_TIME] += (long long)s_rt[g];
+        c[RLR_CTR_SENDS] += (long long)s_sends[g];
+    }
+    if (SMEM_TABLES) {
+        const long long per = p.tsize / 2;
+        for (int gg = 0; gg < G; ++gg) {
+            if (rblock + gg >= p.R) break;
+            for (int tb = 0; tb < p.ntab; ++tb) {
+                double *dstp = (tb == 0 ? p.Q : tb == 1 ? p.Theta : p.Trace) + (rblock + gg) * p.tsize;
+                const double2 *src = reinterpret_cast<const double2 *>(s_tables + gg * tstride + tb * p.tsize);
+                double2 *d2 = reinterpret_cast<double2 *>(dstp);
+                for (long long i = t; i < per; i += blockDim.x) d2[i] = src[i];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Qroute.__init__ structure overrides (qroute.py:16-20), Theta = initP, Trace = 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void rlr_init_tables_kernel(double *Q, double *Theta, double *Trace, const int *row_ptr, const int *col,
+                                       int N, int sdeg, long long R, double initP)
+{
+    const long long tsize = (long long)N * sdeg;
+    const long long total = R * sdeg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / sdeg;
+        const int e = (int)(i - r * sdeg);
+        int x = 0;
+        while (row_ptr[x + 1] <= e) ++x;          // small N: linear search
+        const int rp = row_ptr[x], deg = row_ptr[x + 1] - rp, j = e - rp, y = col[e];
+        double *tab = Q + r * tsize + (long long)N * rp;
+        for (int k = 0; k < deg; ++k) tab[(long long)y * deg + k] = (j == k) ? -1.0 : -0.0;   // -eye
+        if (j == 0)
+            for (int k = 0; k < deg; ++k) tab[(long long)x * deg + k] = 0.0;                  // table[x] = 0
+    }
+    const long long tot2 = R * tsize;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tot2; i += (long long)gridDim.x * blockDim.x) {
+        if (Theta) Theta[i] = initP;
+        if (Trace) Trace[i] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shortest.__init__ + _calc_distance (shortest.py:20-58), multiway=False.  Columns z of the
+// distance matrix are mutually independent (distance[.,z] reads only distance[.,z]), so one thread
+// replays the reference's sequential Gauss-Seidel (x, y in links[x]) sweeps for its destination z.
+// ------------------------------------------------------------------------------------------------
+__global__ void rlr_apsp_kernel(double *distance, unsigned char *choice, unsigned char *next_hop, const int *row_ptr,
+                                const int *col, int N)
+{
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= N) return;
+    for (int x = 0; x < N; ++x) distance[x * N + z] = CUDART_INF;                  // shortest.py:24
+    for (int x = 0; x < N; ++x) {                                                   // shortest.py:28-34
+        const int rp = row_ptr[x], deg = row_ptr[x + 1] - rp;
+        unsigned char *c = choice + (long long)N * rp + (long long)z * deg;
+        for (int j = 0; j < deg; ++j) c[j] = 0;
+        if (x == z) distance[x * N + z] = 0.0;
+        for (int j = 0; j < deg; ++j)
+            if (col[rp + j] == z) { distance[x * N + z] = 1.0; c[j] = 1; }
+    }
+    bool changing = true;                                                           // shortest.py:43-58
+    while (changing) {
+        changing = false;
+        for (int x = 0; x < N; ++x) {
+            const int rp = row_ptr[x], deg = row_ptr[x + 1] - rp;
+            unsigned char *c = choice + (long long)N * rp + (long long)z * deg;
+            for (int j = 0; j < deg; ++j) {
+                const double nd = distance[col[rp + j] * N + z] + 1.0;
+                if (distance[x * N + z] > nd) {
+                    distance[x * N + z] = nd;
+                    for (int q = 0; q < deg; ++q) c[q] = 0;
+                    c[j] = 1;
+                    changing = true;
+                }
+            }
+        }
+    }
+    for (int x = 0; x < N; ++x) {                                                   // choose(): first True
+        const int rp = row_ptr[x], deg = row_ptr[x + 1] - rp;
+        const unsigned char *c = choice + (long long)N * rp + (long long)z * deg;
+        int k = 0;
+        while (k < deg - 1 && !c[k]) ++k;
+        next_hop[x * N + z] = (unsigned char)k;
+    }
+}
+
+__global__ void rlr_reduce_stats_kernel(const long long *counters, long long R, long long *out)
+{
+    __shared__ long long acc[RLR_NUM_COUNTERS];
+    if (threadIdx.x < RLR_NUM_COUNTERS) acc[threadIdx.x] = 0;
+    __syncthreads();
+    long long loc[RLR_NUM_COUNTERS];
+#pragma unroll
+    for (int c = 0; c < RLR_NUM_COUNTERS; ++c) loc[c] = 0;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x)
+#pragma unroll
+        for (int c = 0; c < RLR_NUM_COUNTERS; ++c) loc[c] += counters[r * RLR_NUM_COUNTERS + c];
+#pragma unroll
+    for (int c = 0; c < RLR_NUM_COUNTERS; ++c) {
+        long long v = loc[c];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd((unsigned long long *)&acc[c], (unsigned long long)v);
+    }
+    __syncthreads();
+    if (threadIdx.x < RLR_NUM_COUNTERS && acc[threadIdx.x])
+        atomicAdd((unsigned long long *)&out[threadIdx.x], (unsigned long long)acc[threadIdx.x]);
+}
+
+using StepKernel = void (*)(const StepParams);
+
+template <int POLICY, int MAXD>
+StepKernel pick_smem(bool smem_tables)
+{
+    return smem_tables ? (StepKernel)rlr_step_kernel<POLICY, MAXD, true> : (StepKernel)rlr_step_kernel<POLICY, MAXD, false>;
+}
+
+template <int POLICY>
+StepKernel pick_deg(int max_deg, bool smem_tables)
+{
+    if (max_deg <= 4) return pick_smem<POLICY, 4>(smem_tables);
+    if (max_deg <= 8) return pick_smem<POLICY, 8>(smem_tables);
+    return pick_smem<POLICY, 16>(smem_tables);
+}
+
+StepKernel pick_kernel(int policy, int max_deg, bool smem_tables)
+{
+    switch (policy) {
+    case RLR_POLICY_SHORTEST: return pick_deg<RLR_POLICY_SHORTEST>(max_deg, false);
+    case RLR_POLICY_QROUTE: return pick_deg<RLR_POLICY_QROUTE>(max_deg, smem_tables);
+    case RLR_POLICY_HYBRIDQ: return pick_deg<RLR_POLICY_HYBRIDQ>(max_deg, smem_tables);
+    default: return pick_deg<RLR_POLICY_MAHYBRIDQ>(max_deg, smem_tables);
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Host side of the C ABI
+// ------------------------------------------------------------------------------------------------
+struct rlr_handle {
+    int N, sdeg, max_deg, policy, ntab;
+    long long R, replica_base, tsize;
+    int cap, G, threads, smem_bytes, device;
+    bool smem_tables, bound;
+    std::vector<int> row_ptr, col;
+    rlr_buffers_t bufs;
+    StepKernel kernel;
+};
+
+extern "C" {
+
+int rlr_abi_version(void) { return RLR_ABI_VERSION; }
+
+const char *rlr_last_error_string(void) { return g_last_error.c_str(); }
+
+int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t **out)
+{
+    if (!topo || !cfg || !out) return fail(RLR_E_INVALID, "rlr_create: null argument");
+    const int N = topo->n_nodes;
+    if (N < 2 || N > 256) return fail(RLR_E_UNSUPPORTED, "rlr_create: n_nodes must be in [2, 256]");
+    if (topo->max_deg < 1 || topo->max_deg > 16) return fail(RLR_E_UNSUPPORTED, "rlr_create: max_deg must be in [1, 16]");
+    if (!topo->row_ptr || !topo->col || topo->row_ptr[0] != 0 || topo->row_ptr[N] != topo->sum_deg)
+        return fail(RLR_E_INVALID, "rlr_create: malformed CSR");
+    if (topo->sum_deg % 2) return fail(RLR_E_INVALID, "rlr_create: sum_deg must be even (undirected graph)");
+    for (int x = 0; x < N; ++x) {
+        const int dg = topo->row_ptr[x + 1] - topo->row_ptr[x];
+        if (dg < 1 || dg > topo->max_deg) return fail(RLR_E_INVALID, "rlr_create: node degree outside [1, max_deg]");
+    }
+    if (cfg->replicas < 1) return fail(RLR_E_INVALID, "rlr_create: replicas must be >= 1");
+    if (cfg->policy < RLR_POLICY_SHORTEST || cfg->policy > RLR_POLICY_MAHYBRIDQ)
+        return fail(RLR_E_UNSUPPORTED, "rlr_create: unknown policy id");
+    const int cap = cfg->queue_capacity;
+    if (cap < 2 || (cap & (cap - 1))) return fail(RLR_E_INVALID, "rlr_create: queue_capacity must be a power of two >= 2");
+
+    RLR_CUDA(cudaSetDevice(cfg->device));
+    rlr_handle *h = new rlr_handle();
+    h->N = N; h->sdeg = topo->sum_deg; h->max_deg = topo->max_deg; h->policy = cfg->policy;
+    h->ntab = cfg->policy;                       // Shortest 0, Qroute 1 (Q), HybridQ 2 (+Theta), MaHybridQ 3 (+Trace)
+    h->R = cfg->replicas; h->replica_base = cfg->replica_base;
+    h->tsize = (long long)N * topo->sum_deg;
+    h->cap = cap; h->bound = false; h->device = cfg->device;
+    h->row_ptr.assign(topo->row_ptr, topo->row_ptr + N + 1);
+    h->col.assign(topo->col, topo->col + topo->sum_deg);
+    memset(&h->bufs, 0, sizeof(h->bufs));
+
+    // launch geometry
+    const size_t table_bytes = (size_t)h->ntab * h->tsize * 8;
+    int G = cfg->replicas_per_block;
+    int smem_tables = cfg->tables_in_smem;
+    if (h->policy == RLR_POLICY_SHORTEST) smem_tables = 0;
+    auto smem_for = [&](int g, int thr, bool st) {
+        return SmemLayout(N, h->sdeg, g, thr, h->policy, st, h->tsize, h->ntab).total;
+    };
+    if (smem_tables < 0) smem_tables = (table_bytes > 0 && smem_for(1, 256, true) <= (size_t)kSmemLimit) ? 1 : 0;
+    if (G <= 0) G = smem_tables ? 1 : (N >= 96 ? 1 : (128 / N > 0 ? 128 / N : 1));
+    if ((long long)G > h->R) G = (int)h->R;
+    int threads = cfg->threads_per_block;
+    if (threads <= 0) {
+        threads = ((G * N + 31) / 32) * 32;
+        if (h->policy == RLR_POLICY_MAHYBRIDQ && threads < 256) threads = 256;
+    }
+    if (threads % 32 || threads < G * N || threads > kMaxThreads) {
+        delete h;
+        return fail(RLR_E_INVALID, "rlr_create: threads_per_block must be a multiple of 32 in [G*N, 512]");
+    }
+    const size_t smem = smem_for(G, threads, smem_tables != 0);
+    if (smem > (size_t)kSmemLimit) {
+        delete h;
+        return fail(RLR_E_UNSUPPORTED, "rlr_create: shared-memory footprint exceeds 227 KB (lower replicas_per_block or set tables_in_smem=0)");
+    }
+    h->G = G; h->threads = threads; h->smem_bytes = (int)smem; h->smem_tables = smem_tables != 0;
+    h->kernel = pick_kernel(h->policy, h->max_deg, h->smem_tables);
+    cudaError_t e = cudaFuncSetAttribute((const void *)h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(RLR_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    }
+    *out = h;
+    return RLR_OK;
+}
+
+int rlr_destroy(rlr_handle_t *h)
+{
+    delete h;
+    return RLR_OK;
+}
+
+int rlr_bind_buffers(rlr_handle_t *h, const rlr_buffers_t *b)
+{
+    if (!h || !b) return fail(RLR_E_INVALID, "rlr_bind_buffers: null argument");
+    if (!b->ring || !b->q_head || !b->q_tail || !b->counters || !b->status || !b->topo_row_ptr || !b->topo_col || !b->heap_pos)
+        return fail(RLR_E_INVALID, "rlr_bind_buffers: ring, q_head, q_tail, counters, status, topo_* and heap_pos are required");
+    if (h->policy == RLR_POLICY_SHORTEST && (!b->next_hop || !b->distance || !b->choice))
+        return fail(RLR_E_INVALID, "rlr_bind_buffers: Shortest needs next_hop, distance and choice");
+    if (h->policy >= RLR_POLICY_QROUTE && !b->q_table) return fail(RLR_E_INVALID, "rlr_bind_buffers: q_table required");
+    if (h->policy >= RLR_POLICY_HYBRIDQ && !b->theta) return fail(RLR_E_INVALID, "rlr_bind_buffers: theta required");
+    if (h->policy >= RLR_POLICY_MAHYBRIDQ && !b->trace) return fail(RLR_E_INVALID, "rlr_bind_buffers: trace required");
+    if (((uintptr_t)b->ring & 15) || ((uintptr_t)b->q_table & 15) || ((uintptr_t)b->theta & 15) || ((uintptr_t)b->trace & 15))
+        return fail(RLR_E_INVALID, "rlr_bind_buffers: ring and tables must be 16-byte aligned");
+    h->bufs = *b;
+    h->bound = true;
+    return RLR_OK;
+}
+
+int rlr_launch_info(const rlr_handle_t *h, int32_t *threads, int32_t *replicas_per_block, int32_t *smem_bytes,
+                    int32_t *tables_in_smem)
+{
+    if (!h) return fail(RLR_E_INVALID, "rlr_launch_info: null handle");
+    if (threads) *threads = h->threads;
+    if (replicas_per_block) *replicas_per_block = h->G;
+    if (smem_bytes) *smem_bytes = h->smem_bytes;
+    if (tables_in_smem) *tables_in_smem = h->smem_tables ? 1 : 0;
+    return RLR_OK;
+}
+
+int rlr_reset(rlr_handle_t *h, void *stream)
+{
+    if (!h || !h->bound) return fail(RLR_E_STATE, "rlr_reset: buffers not bound");
+    RLR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t RN = (size_t)h->R * h->N;
+    RLR_CUDA(cudaMemsetAsync(h->bufs.q_head, 0, RN * 4, st));
+    RLR_CUDA(cudaMemsetAsync(h->bufs.q_tail, 0, RN * 4, st));
+    RLR_CUDA(cudaMemsetAsync(h->bufs.counters, 0, (size_t)h->R * RLR_NUM_COUNTERS * 8, st));
+    RLR_CUDA(cudaMemsetAsync(h->bufs.status, 0, (size_t)h->R * 2 * 4, st));
+    if (h->policy == RLR_POLICY_MAHYBRIDQ) RLR_CUDA(cudaMemsetAsync(h->bufs.trace, 0, (size_t)h->R * h->tsize * 8, st));
+    return RLR_OK;
+}
+
+int rlr_init_tables(rlr_handle_t *h, double initP, void *stream)
+{
+    if (!h || !h->bound) return fail(RLR_E_STATE, "rlr_init_tables: buffers not bound");
+    if (h->policy == RLR_POLICY_SHORTEST) return RLR_OK;
+    RLR_CUDA(cudaSetDevice(h->device));
+    const long long total = h->R * h->tsize;
+    int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    rlr_init_tables_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->bufs.q_table, h->bufs.theta, h->bufs.trace,
+                                                                      h->bufs.topo_row_ptr, h->bufs.topo_col, h->N, h->sdeg,
+                                                                      h->R, initP);
+    RLR_CUDA(cudaGetLastError());
+    return RLR_OK;
+}
+
+int rlr_build_shortest_tables(rlr_handle_t *h, void *stream)
+{
+    if (!h || !h->bound) return fail(RLR_E_STATE, "rlr_build_shortest_tables: buffers not bound");
+    if (!h->bufs.next_hop || !h->bufs.distance || !h->bufs.choice)
+        return fail(RLR_E_INVALID, "rlr_build_shortest_tables: next_hop, distance and choice are required");
+    RLR_CUDA(cudaSetDevice(h->device));
+    rlr_apsp_kernel<<<(h->N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(h->bufs.distance, h->bufs.choice, h->bufs.next_hop,
+                                                                        h->bufs.topo_row_ptr, h->bufs.topo_col, h->N);
+    RLR_CUDA(cudaGetLastError());
+    return RLR_OK;
+}
+
+int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, void *stream)
+{
+    if (!h || !h->bound) return fail(RLR_E_STATE, "rlr_run_steps: buffers not bound");
+    if (!rp) return fail(RLR_E_INVALID, "rlr_run_steps: null params");
+    if (n_steps < 0 || n_steps > (1 << 30)) return fail(RLR_E_INVALID, "rlr_run_steps: n_steps out of range");
+    if (n_steps == 0) return RLR_OK;
+    if (rp->inject_mode == RLR_INJECT_TRACE) {
+        if (!rp->inj_off || !rp->inj_base || !rp->inj_pairs) return fail(RLR_E_INVALID, "rlr_run_steps: trace mode needs inj_off, inj_base, inj_pairs");
+    } else if (rp->inject_mode == RLR_INJECT_PHILOX) {
+        if (!rp->enlam) return fail(RLR_E_INVALID, "rlr_run_steps: Philox mode needs enlam");
+    } else {
+        return fail(RLR_E_INVALID, "rlr_run_steps: unknown inject_mode");
+    }
+    if ((long long)rp->clock0 + n_steps > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: clock overflows int32");
+    RLR_CUDA(cudaSetDevice(h->device));
+    StepParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = h->N; p.sdeg = h->sdeg; p.G = h->G; p.R = (int)h->R;
+    p.cap = h->cap; p.K = (int)n_steps; p.clock0 = rp->clock0; p.ntab = h->ntab;
+    p.tsize = h->tsize;
+    p.row_ptr = h->bufs.topo_row_ptr; p.col = h->bufs.topo_col; p.heap_pos = h->bufs.heap_pos; p.next_hop = h->bufs.next_hop;
+    p.Q = h->bufs.q_table; p.Theta = h->bufs.theta; p.Trace = h->bufs.trace;
+    p.ring = (uint4 *)h->bufs.ring; p.qhead = h->bufs.q_head; p.qtail = h->bufs.q_tail;
+    p.counters = (long long *)h->bufs.counters; p.status = h->bufs.status;
+    p.inject_mode = rp->inject_mode; p.add_entropy = rp->add_entropy;
+    p.inj_off = rp->inj_off; p.inj_base = (const long long *)rp->inj_base; p.inj_pairs = rp->inj_pairs;
+    p.enlam = rp->enlam; p.seed = rp->seed; p.replica_base = h->replica_base;
+    p.lr_q = rp->lr_q; p.lr_p = rp->lr_p; p.lr_e = rp->lr_e; p.discount = rp->discount; p.discount_trace = rp->discount_trace;
+    p.metrics = (uint4 *)rp->metrics; p.sendlog = rp->sendlog;
+    const long long blocks = (h->R + h->G - 1) / h->G;
+    if (blocks > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: too many blocks");
+    h->kernel<<<(unsigned)blocks, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p);
+    RLR_CUDA(cudaGetLastError());
+    return RLR_OK;
+}
+
+int rlr_reduce_stats(rlr_handle_t *h, int64_t *out, void *stream)
+{
+    if (!h || !h->bound || !out) return fail(RLR_E_STATE, "rlr_reduce_stats: buffers not bound or null output");
+    RLR_CUDA(cudaSetDevice(h->device));
+    RLR_CUDA(cudaMemsetAsync(out, 0, RLR_NUM_COUNTERS * 8, (cudaStream_t)stream));
+    const int blocks = (int)((h->R + 255) / 256 < 148 * 4 ? (h->R + 255) / 256 : 148 * 4);
+    rlr_reduce_stats_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const long long *)h->bufs.counters, h->R, (long long *)out);
+    RLR_CUDA(cudaGetLastError());
+    return RLR_OK;
+}
+
+}  // extern "C"

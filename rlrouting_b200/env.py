@@ -1,0 +1,472 @@
+"""`Network`: the reference's simulator API (env.py:213-450) over R replicas on one B200.
+
+With no new keywords a `Network(file)` is ONE environment driven by NumPy's global legacy RNG, so
+`np.random.seed(1); nw = Network("6x6.net"); nw.agent = Qroute(nw); nw.train(10000, 2.0)` returns
+the reference's numbers bit for bit.  The additive keywords (`replicas`, `rng`, `seed`, ...) batch R
+independent environments; every counter property then returns an array of length R.
+
+Unsupported reference options raise NotImplementedError when they are requested, never mid-run,
+and there is no CPU fallback: `bandwidth != 1`, `transtime != 1`, `is_drop`,
+`slot != 1`, `freq != 1`, mode 'dual'/'bp', and agents that are not one of the built-in policies.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _native as nat
+from . import nets, trace
+from .base_policy import Policy
+from .topology import Topology
+
+
+class Packet:
+    """Read-back view of a queued packet (reference env.py:9-27)."""
+    __slots__ = ("source", "dest", "birth", "hops", "trans_time", "start_queue")
+
+    def __init__(self, source, dest, birth, hops=0, start_queue=0):
+        self.source, self.dest, self.birth, self.hops = source, dest, birth, hops
+        self.trans_time, self.start_queue = 1, start_queue
+
+    def __repr__(self):
+        return f"Packet<{self.source}->{self.dest}>"
+
+
+class Reward:
+    """What `Network.step` returns per send (reference env.py:52-70)."""
+
+    def __init__(self, source, packet, action, agent_info=None):
+        self.source, self.dest, self.action = source, packet.dest, action
+        self.packet, self.agent_info = packet, agent_info or {}
+
+    def __repr__(self):
+        return f"Reward<{self.source}->{self.dest} by {self.action}>"
+
+
+class Node:
+    """Read-only view of one node of replica 0 (reference env.py:73-210)."""
+
+    def __init__(self, ID, network):
+        self.ID, self.network = ID, network
+
+    @property
+    def links(self):
+        return self.network.links[self.ID]
+
+    @property
+    def queue(self):
+        return [Packet(int(s), int(d), int(b), int(h), int(q)) for d, s, h, b, q in self.network.queue_array(self.ID)]
+
+    @property
+    def sent(self):
+        return dict.fromkeys(self.links, 0)      # every event lands inside its step (env.py:349-353)
+
+    def __repr__(self):
+        return f"Node<{self.ID}, queue: {self.queue}, sent: {self.sent}>"
+
+
+def _floor_pow2(v):
+    return 1 << (int(v).bit_length() - 1)
+
+
+class Network:
+    def __init__(self, file, bandwidth=1, transtime=1, is_drop=False, *, replicas=1, device=None,
+                 rng="trace", seed=None, replica_base=0, queue_capacity=None,
+                 replicas_per_block=0, threads_per_block=0, tables_in_smem=-1):
+        if bandwidth != 1 or transtime != 1:
+            raise NotImplementedError("bandwidth != 1 / transtime != 1 need in-flight events that outlive a step "
+                                      "(SURVEY §8 row f2); not implemented on the device and there is no CPU fallback")
+        if is_drop:
+            raise NotImplementedError("is_drop=True (SURVEY §8 row f2) is not implemented on the device")
+        if rng not in ("trace", "philox"):
+            raise ValueError("rng must be 'trace' or 'philox'")
+        if replicas < 1:
+            raise ValueError("replicas must be >= 1")
+        self.bandwidth, self.transtime, self.is_drop = bandwidth, transtime, is_drop
+        self.replicas, self.rng, self.replica_base = int(replicas), rng, int(replica_base)
+        self.read_network(file)
+        self.nodes = OrderedDict((i, Node(i, self)) for i in self.links.keys())
+        self.sample, self._sample_idx = [], 0
+        # RNG streams.  trace: replica r replays the reference's legacy stream seeded `seed + r`; a
+        # single un-seeded replica uses NumPy's GLOBAL stream like the reference itself (train.py:15).
+        if rng == "trace":
+            if seed is None and self.replicas == 1:
+                self._rs = [np.random.mtrand._rand]
+            else:
+                base = 1 if seed is None else int(seed)
+                self._rs = [np.random.RandomState(base + self.replica_base + r) for r in range(self.replicas)]
+        self.seed = 0 if seed is None else int(seed)
+
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("rlrouting_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        nat.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        topo, R, N = self.topology, self.replicas, self.topology.N
+        if queue_capacity is None:
+            queue_capacity = min(max(_floor_pow2(max((1 << 30) // (R * N), 1)), 64), 32768)
+        if queue_capacity & (queue_capacity - 1):
+            raise ValueError("queue_capacity must be a power of two")
+        self.queue_capacity = int(queue_capacity)
+        self._launch_cfg = (int(replicas_per_block), int(threads_per_block), int(tables_in_smem))
+        dev = self.device
+        self._ring = torch.empty((R, N, self.queue_capacity, 4), dtype=torch.int32, device=dev)
+        self._q_head = torch.zeros((R, N), dtype=torch.int32, device=dev)
+        self._q_tail = torch.zeros((R, N), dtype=torch.int32, device=dev)
+        self._counters = torch.zeros((R, nat.NUM_COUNTERS), dtype=torch.int64, device=dev)
+        self._status = torch.zeros((R, 2), dtype=torch.int32, device=dev)
+        self._row_ptr = torch.from_numpy(topo.row_ptr).to(dev)
+        self._col = torch.from_numpy(topo.col).to(dev)
+        self._heap_pos = torch.from_numpy(np.ascontiguousarray(topo.heap_pos, dtype=np.uint8)).to(dev)
+        self._stats = torch.zeros(nat.NUM_COUNTERS, dtype=torch.int64, device=dev)
+        self._handles = []
+        self.launch_count = 0          # rlr_run_steps launches issued (bench.py reports it as gpu_launches)
+        self.last_h2d_bytes = self.last_d2h_bytes = 0
+        self._resident = {}
+        self.clock = 0
+        self._agent = Policy(self)
+        self.last_sendlog = None
+
+    # ------------------------------------------------------------------ topology (env.py:282-296)
+    def read_network(self, file):
+        self.topology = Topology.from_text(nets.resolve(file))
+        self.links = OrderedDict((k, list(v)) for k, v in self.topology.links.items())
+        self.proj = self.topology.proj
+
+    # ------------------------------------------------------------------ native handle plumbing
+    def _stream_ptr(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _make_handle(self, agent):
+        """One native handle per (network, agent): environment buffers from here, tables from the agent."""
+        topo = self.topology
+        t = nat.Topology(topo.N, topo.sum_deg, topo.max_deg, topo.row_ptr.ctypes.data, topo.col.ctypes.data)
+        rpb, tpb, tis = self._launch_cfg
+        cfg = nat.Config(self.replicas, self.replica_base, agent._kernel_policy, self.queue_capacity, rpb, tpb, tis,
+                         self.device.index or 0)
+        h = C.c_void_p()
+        nat.check(nat.lib().rlr_create(C.byref(t), C.byref(cfg), C.byref(h)))
+        d = agent._dev
+        ptr = lambda name: d[name].data_ptr() if name in d else None  # noqa: E731
+        b = nat.Buffers(ptr("Qtable"), ptr("Theta"), ptr("Trace"), self._ring.data_ptr(), self._q_head.data_ptr(),
+                        self._q_tail.data_ptr(), self._counters.data_ptr(), self._status.data_ptr(), ptr("next_hop"),
+                        ptr("distance"), ptr("choice"), self._row_ptr.data_ptr(), self._col.data_ptr(),
+                        self._heap_pos.data_ptr())
+        nat.check(nat.lib().rlr_bind_buffers(h, C.byref(b)))
+        self._handles.append(h)
+        return h
+
+    def launch_info(self):
+        h = getattr(self._agent, "_handle", None)
+        if h is None:
+            return None
+        v = [C.c_int32() for _ in range(4)]
+        nat.check(nat.lib().rlr_launch_info(h, *[C.byref(x) for x in v]))
+        return {"threads_per_block": v[0].value, "replicas_per_block": v[1].value, "smem_bytes": v[2].value,
+                "tables_in_smem": bool(v[3].value)}
+
+    def __del__(self):
+        try:
+            for h in self._handles:
+                nat.lib().rlr_destroy(h)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ agent binding (env.py:252-265)
+    @property
+    def agent(self):
+        return self._agent
+
+    @property
+    def mode(self):
+        return self._agent.mode
+
+    @agent.setter
+    def agent(self, new_agent):
+        if type(new_agent) is Policy:
+            self._agent = new_agent
+            return
+        if getattr(new_agent, "_kernel_policy", None) is None or getattr(new_agent, "_handle", None) is None:
+            raise NotImplementedError(f"{type(new_agent).__name__} is not one of the device policies (Shortest, Qroute, "
+                                      "HybridQ, MaHybridQ); custom Python policies would need a CPU path, which this "
+                                      "package does not have")
+        if new_agent.mode is not None:
+            raise NotImplementedError(f"mode {new_agent.mode!r} is not implemented on the device (SURVEY §8 rows f1/f2)")
+        if new_agent._network is not self:
+            raise ValueError("the agent was constructed for a different Network")
+        self._agent = new_agent
+
+    def bind(self, agent):
+        """Legacy spelling used by the reference's train.py:39."""
+        self.agent = agent
+
+    # ------------------------------------------------------------------ reset (env.py:267-280)
+    def reset(self):
+        self.clock = 0
+        h = getattr(self._agent, "_handle", None)
+        if h is not None:
+            nat.check(nat.lib().rlr_reset(h, self._stream_ptr()))
+        else:
+            for t in (self._q_head, self._q_tail, self._counters, self._status):
+                t.zero_()
+        self._agent.clean()
+
+    def clean(self):
+        """Legacy spelling used by the reference's train.py:51."""
+        self.reset()
+
+    # ------------------------------------------------------------------ pieces of the loop the kernel fuses
+    def new_packet(self, lambd):
+        raise NotImplementedError("new_packet/inject/step are fused into the device step kernel; drive the "
+                                  "simulation with Network.train (no CPU fallback)")
+
+    inject = step = sample_route_time = new_packet
+
+    # ------------------------------------------------------------------ the hot path (env.py:367-414)
+    def train(self, duration, lambd, slot=1, freq=1, lr={}, droprate=False, hop=False, *, lrq=None, lrp=None,
+              per_step=None, sendlog=False, steps_per_launch=None):
+        """Runs int(duration/slot) steps of inject -> step -> learn on the device.
+
+        Returns the reference's dict (`route_time` = cumulative mean delivery time after each step,
+        optional `droprate`, `hop`), each a vector of length steps for one replica or [R, steps] for
+        R replicas.  `lambd` may be a scalar or a length-R vector (one load per replica).
+        The legacy call `train(T, lambd=l, lrq=.., lrp=..)` (reference train.py:52) returns the tuple
+        (route_time, drop_rate) instead.
+        """
+        import torch
+        if slot != 1 or freq != 1:
+            raise NotImplementedError("slot != 1 / freq != 1 (SURVEY §8 row f2) are not implemented on the device")
+        agent = self._agent
+        h = getattr(agent, "_handle", None)
+        if h is None:
+            raise NotImplementedError("bind one of the device policies first (nw.agent = Qroute(nw) ...)")
+        legacy = lrq is not None or lrp is not None
+        lrd = dict(getattr(agent, "_lr_default", {}))
+        lrd.update(lr or {})
+        if lrq is not None:
+            lrd["q"] = lrq
+        if lrp is not None:
+            lrd["p"] = lrp
+        T, R, N, dev = int(duration / slot), self.replicas, self.topology.N, self.device
+        lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (R,)) * slot
+        if per_step is None:
+            per_step = R * T <= (1 << 26)
+        result = {"route_time": np.zeros((R, T) if per_step else (R, 1))}
+        if droprate:
+            result["droprate"] = np.zeros_like(result["route_time"])
+        if hop:
+            result["hop"] = np.zeros_like(result["route_time"])
+        if T == 0:
+            return self._finish(result, legacy, R)
+
+        rp = nat.RunParams()
+        rp.add_entropy = int(bool(getattr(agent, "add_entropy", True)))
+        rp.lr_q, rp.lr_p, rp.lr_e = float(lrd.get("q", 0.1)), float(lrd.get("p", 0.1)), float(lrd.get("e", 0.1))
+        rp.discount = float(getattr(agent, "discount", 0.99))
+        rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
+        rp.seed = self.seed
+        keep = []
+        h2d = 0
+        if self.rng == "trace":
+            rp.inject_mode = nat.INJECT_TRACE
+            offs = np.zeros((R, T + 1), dtype=np.int64)
+            pairs = []
+            for r in range(R):
+                cnt, pr = trace.draw_injections(self._rs[r], N, T, lam[r])
+                offs[r, 1:] = np.cumsum(cnt)
+                pairs.append((pr[:, 0].astype(np.uint32) | (pr[:, 1].astype(np.uint32) << 16)))
+            base = np.zeros(R, dtype=np.int64)
+            base[1:] = np.cumsum([len(p) for p in pairs])[:-1]
+            flat = np.concatenate(pairs) if pairs else np.zeros(0, dtype=np.uint32)
+            if flat.size == 0:
+                flat = np.zeros(1, dtype=np.uint32)
+            if int(offs.max()) >= 2 ** 31:
+                raise OverflowError("too many injections per replica for int32 offsets")
+            d_pairs = torch.from_numpy(flat.view(np.int32)).to(dev)
+            d_base = torch.from_numpy(base).to(dev)
+            rp.inj_base, rp.inj_pairs = d_base.data_ptr(), d_pairs.data_ptr()
+            keep += [d_pairs, d_base]
+            h2d += flat.nbytes + base.nbytes + R * (T + 1) * 4
+        else:
+            rp.inject_mode = nat.INJECT_PHILOX
+            enlam = torch.from_numpy(np.exp(-lam / np.float64(N))).to(dev)
+            rp.enlam = enlam.data_ptr()
+            keep.append(enlam)
+            h2d += R * 8
+
+        if steps_per_launch is None:
+            steps_per_launch = T if not per_step else max(1, min(T, (1 << 25) // R))
+        log_chunks, met_chunks = [], []
+        s0 = 0
+        stream = self._stream_ptr()
+        while s0 < T:
+            K = min(steps_per_launch, T - s0)
+            if self.rng == "trace":
+                d_off = torch.from_numpy(np.ascontiguousarray(offs[:, s0:s0 + K + 1]).astype(np.int32)).to(dev)
+                rp.inj_off = d_off.data_ptr()
+                keep.append(d_off)
+            rp.clock0 = self.clock + s0
+            met = torch.empty((R, K, 2), dtype=torch.int64, device=dev) if per_step else None
+            rp.metrics = met.data_ptr() if met is not None else None
+            log = torch.empty((R, K, N), dtype=torch.int32, device=dev) if sendlog else None
+            rp.sendlog = log.data_ptr() if log is not None else None
+            nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), stream))
+            self.launch_count += 1
+            if per_step:
+                met_chunks.append(met)
+            if log is not None:
+                log_chunks.append(log)
+            s0 += K
+        self.clock += T
+        status = self._status.cpu().numpy()                     # device -> host: synchronises the stream
+        self._raise_on_status(status)
+        self.last_h2d_bytes = h2d
+        self.last_d2h_bytes = status.nbytes + (R * T * 16 if per_step else R * nat.NUM_COUNTERS * 8) + \
+            (R * T * N * 4 if sendlog else 0)
+        if per_step:
+            m = torch.cat(met_chunks, dim=1).cpu().numpy()      # [R, T, 2] int64
+            rt = m[:, :, 0]
+            end = (m[:, :, 1] & 0xFFFFFFFF).astype(np.int64)
+            hops = ((m[:, :, 1] >> 32) & 0xFFFFFFFF).astype(np.int64)
+        else:
+            c = self._counters.cpu().numpy()
+            rt, end, hops = c[:, 4:5], c[:, 1:2], c[:, 3:4]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            result["route_time"] = np.where(end > 0, rt / np.maximum(end, 1), 0.0)     # env.py:444-446
+            if hop:
+                result["hop"] = np.where(end > 0, hops / np.maximum(end, 1), 0.0)      # env.py:440-442
+        if droprate:
+            result["droprate"] = np.zeros_like(result["route_time"])                    # is_drop is off: env.py:448-450
+        if sendlog:
+            self.last_sendlog = torch.cat(log_chunks, dim=1).cpu().numpy().view(np.uint32)
+        return self._finish(result, legacy, R)
+
+    def run_device(self, n_steps, lambd, lr={}):
+        """Device-resident variant of `train` for Philox mode: one rlr_run_steps launch, inputs (the
+        exp(-lambda/N) vector) and outputs (the [R, n_steps] per-step records) stay in HBM, nothing is
+        copied and the stream is not synchronised.  The records are left in `self.metrics_device`."""
+        import torch
+        if self.rng != "philox":
+            raise NotImplementedError("run_device needs rng='philox' (trace mode uploads host-generated injections)")
+        agent = self._agent
+        h = getattr(agent, "_handle", None)
+        if h is None:
+            raise NotImplementedError("bind one of the device policies first")
+        R, N, K = self.replicas, self.topology.N, int(n_steps)
+        lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (R,))
+        key = ("enlam", lam.tobytes() if lam.strides[0] else float(lam[0]))
+        if self._resident.get("enlam_key") != key:
+            self._resident["enlam"] = torch.from_numpy(np.exp(-lam / np.float64(N))).to(self.device)
+            self._resident["enlam_key"] = key
+        if self._resident.get("metrics_shape") != (R, K):
+            self._resident["metrics"] = torch.empty((R, K, 2), dtype=torch.int64, device=self.device)
+            self._resident["metrics_shape"] = (R, K)
+        lrd = dict(getattr(agent, "_lr_default", {}))
+        lrd.update(lr or {})
+        rp = nat.RunParams()
+        rp.inject_mode = nat.INJECT_PHILOX
+        rp.add_entropy = int(bool(getattr(agent, "add_entropy", True)))
+        rp.lr_q, rp.lr_p, rp.lr_e = float(lrd.get("q", 0.1)), float(lrd.get("p", 0.1)), float(lrd.get("e", 0.1))
+        rp.discount = float(getattr(agent, "discount", 0.99))
+        rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
+        rp.seed = self.seed
+        rp.enlam = self._resident["enlam"].data_ptr()
+        rp.clock0 = self.clock
+        rp.metrics = self._resident["metrics"].data_ptr()
+        nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), self._stream_ptr()))
+        self.launch_count += 1
+        self.clock += K
+
+    @property
+    def metrics_device(self):
+        return self._resident.get("metrics")
+
+    def check_status(self):
+        """Reads the sticky per-replica status words (one device->host copy) and raises the reference's
+        exception type: ValueError for NaN probabilities (hybrid.py:20-23), OverflowError for a full ring."""
+        self._raise_on_status(self._status.cpu().numpy())
+
+    @staticmethod
+    def _finish(result, legacy, R):
+        if R == 1:
+            result = {k: v[0] for k, v in result.items()}
+        if legacy:
+            return result["route_time"], result.get("droprate", np.zeros_like(result["route_time"]))
+        return result
+
+    def _raise_on_status(self, status):
+        bad = np.nonzero(status[:, 0])[0]
+        if bad.size == 0:
+            return
+        r = int(bad[0])
+        code, clk = int(status[r, 0]), int(status[r, 1])
+        if code == nat.STATUS_NAN_PROB:
+            raise ValueError(f"probabilities contain NaN (replica {r}, clock {clk}; {bad.size} replica(s) affected)")
+        raise OverflowError(f"queue ring overflow (replica {r}, clock {clk}; {bad.size} replica(s) affected): the "
+                            f"reference's queues are unbounded; re-run with queue_capacity > {self.queue_capacity}")
+
+    def sendlog_rows(self, r=0):
+        """Rows (clock_after_step, x, y, dest) of replica r from the last train(..., sendlog=True)."""
+        log = self.last_sendlog[r]
+        K, N = log.shape
+        s, x = np.nonzero(log != 0xFFFFFFFF)
+        v = log[s, x]
+        clock0 = self.clock - K
+        return np.stack([clock0 + s + 1, x, v & 0xFFFF, v >> 16], axis=1).astype(np.int32)
+
+    # ------------------------------------------------------------------ counters (env.py:271-276, 440-450)
+    def _ctr(self, name):
+        v = self._counters[:, nat.CTR[name]].cpu().numpy()
+        return int(v[0]) if self.replicas == 1 else v
+
+    all_packets = property(lambda self: self._ctr("all_packets"))
+    end_packets = property(lambda self: self._ctr("end_packets"))
+    drop_packets = property(lambda self: self._ctr("drop_packets"))
+    hops = property(lambda self: self._ctr("hops"))
+    route_time = property(lambda self: self._ctr("route_time"))
+    sends = property(lambda self: self._ctr("sends"))
+
+    @property
+    def active_packets(self):
+        return self.all_packets - self.end_packets - self.drop_packets
+
+    @staticmethod
+    def _ratio(a, b):
+        if np.ndim(b) == 0:
+            return a / b if b > 0 else 0
+        return np.where(b > 0, a / np.maximum(b, 1), 0.0)
+
+    ave_hops = property(lambda self: self._ratio(self.hops, self.end_packets))
+    ave_route_time = property(lambda self: self._ratio(self.route_time, self.end_packets))
+    drop_rate = property(lambda self: self._ratio(self.drop_packets, self.all_packets))
+
+    def counters(self):
+        """Dict of per-replica int64 arrays, one device->host copy."""
+        c = self._counters.cpu().numpy()
+        out = {k: c[:, i].copy() for k, i in nat.CTR.items()}
+        out["active_packets"] = out["all_packets"] - out["end_packets"] - out["drop_packets"]
+        out["clock"] = np.full(self.replicas, self.clock, dtype=np.int64)
+        return out
+
+    def stats_device(self):
+        """Sum of the per-replica counters as a device int64[8] tensor (rlr_reduce_stats), ready for an
+        NCCL all-reduce across ranks (rlrouting_b200.dist)."""
+        h = getattr(self._agent, "_handle", None)
+        if h is None:
+            raise NotImplementedError("bind a device policy first")
+        nat.check(nat.lib().rlr_reduce_stats(h, self._stats.data_ptr(), self._stream_ptr()))
+        return self._stats
+
+    def queue_array(self, x, r=0):
+        """Queue of node x of replica r, head first: rows (dest, source, hops, birth, start_queue)."""
+        head = int(self._q_head[r, x].item()) & 0xFFFFFFFF
+        tail = int(self._q_tail[r, x].item()) & 0xFFFFFFFF
+        n = (tail - head) & 0xFFFFFFFF
+        idx = (head + np.arange(n, dtype=np.int64)) & (self.queue_capacity - 1)
+        rec = self._ring[r, x].cpu().numpy()[idx].view(np.uint32).reshape(n, 4)
+        out = np.empty((n, 5), dtype=np.int32)
+        out[:, 0] = rec[:, 0] & 0xFFFF
+        out[:, 1] = rec[:, 0] >> 16
+        out[:, 2:] = rec[:, 1:].view(np.int32)
+        return out

@@ -1,0 +1,62 @@
+"""Q-routing (reference qroute.py:6-53).  The table lives on the device as [R, N*sum_deg] float64."""
+import numpy as np
+
+from . import _native as nat
+from . import trace
+from .base_policy import Policy
+
+
+def _draw_initial_q(network, initQ, times):
+    """One N(initQ,1) table per replica, consuming each replica's RNG exactly as the reference's
+    constructor does (qroute.py:13-15; twice for HybridQ/MaHybridQ)."""
+    topo = network.topology
+    out = np.empty((network.replicas, topo.tsize), dtype=np.float64)
+    if network.rng == "trace":
+        for r in range(network.replicas):
+            out[r] = topo.pack(trace.draw_qtable_normals(network._rs[r], topo, initQ, times))
+    else:
+        for r in range(network.replicas):
+            g = np.random.Generator(np.random.Philox(key=[network.seed, network.replica_base + r]))
+            out[r] = initQ + g.standard_normal(topo.tsize)
+    return out
+
+
+class Qroute(Policy):
+    attrs = Policy.attrs | set(['Qtable', 'discount', 'threshold'])
+    _kernel_policy = nat.POLICY_QROUTE
+    _table_names = ('Qtable',)
+    _lr_default = {'q': 0.1}                                                       # qroute.py:46
+    _q_draws = 1
+
+    def __init__(self, network, initQ=0, discount=0.99, threshold=0.1):
+        Policy.__init__(self, network)
+        self.discount = discount
+        self.threshold = threshold
+        self._alloc_tables(network, initQ, 0.0)
+
+    def _alloc_tables(self, network, initQ, initP):
+        import torch
+        q0 = _draw_initial_q(network, initQ, self._q_draws)
+        self._dev = {"Qtable": torch.from_numpy(q0).to(network.device)}
+        for name in self._table_names[1:]:
+            self._dev[name] = torch.empty_like(self._dev["Qtable"])
+        self._handle = network._make_handle(self)
+        # qroute.py:16-20 structure overrides; Theta = initP (hybrid.py:13-14); Trace = 0 (multi_agent.py:14-15)
+        nat.check(nat.lib().rlr_init_tables(self._handle, float(initP), network._stream_ptr()))
+
+    def set_initial_q(self, normals, initP=0.0):
+        """Replace the constructor's draws: `normals` is [tsize] or [R, tsize] (packed layout); the
+        structure overrides of qroute.py:16-20 are re-applied, Theta is reset to initP and Trace to 0."""
+        import torch
+        net = self._network
+        a = np.broadcast_to(np.asarray(normals, dtype=np.float64), (net.replicas, net.topology.tsize))
+        self._dev["Qtable"].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        nat.check(nat.lib().rlr_init_tables(self._handle, float(initP), net._stream_ptr()))
+
+    Qtable = property(lambda self: self._get_table("Qtable"), lambda self, v: self._set_table("Qtable", v))
+
+    def choose(self, source, dest, idx=False):
+        scores = self.Qtable[source][..., dest, :]
+        if idx:
+            return np.argmax(scores, axis=-1), scores.max(axis=-1)
+        return self.links[source][np.argmax(scores, axis=-1)]
