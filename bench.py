@@ -218,7 +218,7 @@ def run_b200(a):
     nw = make()
     info = nw.launch_info()
     for _ in range(a.warmup):
-        nw.train(sim, a.load, lr=LR, per_step=False)
+        nw.run_device(sim, a.load, lr=LR)           # same call as the timed loop (allocates its buffers once)
     barrier()
     c0 = nw.stats_device().clone()
     launches0 = nw.launch_count
@@ -227,11 +227,15 @@ def run_b200(a):
     barrier()
     tw0 = time.perf_counter()
     ev0.record()
+    marks = []
     for _ in range(a.steps):
         nw.run_device(sim, a.load, lr=LR)           # one rlr_run_steps launch, per-step metrics written on the device
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
     ev1.record()
     barrier()
     tw1 = time.perf_counter()
+    step_ms = [round(a_.elapsed_time(b_), 3) for a_, b_ in zip([ev0] + marks[:-1], marks)]
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     rdist.allreduce_max_(ms)
     clocks = sampler.stop(tw0, tw1) if sampler else None
@@ -292,7 +296,7 @@ def run_b200(a):
                      "algorithmic_bytes_per_hop": per_hop,
                      "note": "algorithmic bytes per SURVEY 8(d); tables are staged in shared memory, so DRAM traffic is "
                              "far below the algorithmic figure (profiles/)"},
-        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "step_ms": step_ms,
     }
     if not a.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_sample(a, a.cpu_seconds)

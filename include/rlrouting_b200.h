@@ -104,6 +104,7 @@ typedef struct {
     const uint32_t *inj_pairs;
     /* Philox mode */
     const double *enlam;      /* device [R]: exp(-lambda_r / N)                              */
+    const uint64_t *inj_thr;  /* device [R]: smallest w in [0, 2^32] with (w + 0.5) * 2^-32 > enlam[r] */
     uint64_t seed;
     /* learning rates lr['q'], lr['p'], lr['e'] (qroute.py:46, hybrid.py:55, multi_agent.py:17) */
     double lr_q, lr_p, lr_e;
@@ -120,6 +121,9 @@ typedef struct {
 /* ---- introspection ---- */
 int rlr_abi_version(void);
 const char *rlr_last_error_string(void);
+/* sizeof(rlr_topology_t), sizeof(rlr_config_t), sizeof(rlr_buffers_t), sizeof(rlr_run_params_t): lets a
+ * foreign-language binding verify its struct layout against the library it loaded. */
+int rlr_struct_sizes(int32_t out[4]);
 
 /* ---- lifecycle: replaces Network.__init__ (env.py:237-250) for R replicas ---- */
 int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t **out);

@@ -57,14 +57,14 @@ class Buffers(C.Structure):
 class RunParams(C.Structure):
     _fields_ = [("inject_mode", C.c_int32), ("add_entropy", C.c_int32),
                 ("inj_off", C.c_void_p), ("inj_base", C.c_void_p), ("inj_pairs", C.c_void_p),
-                ("enlam", C.c_void_p), ("seed", C.c_uint64),
+                ("enlam", C.c_void_p), ("inj_thr", C.c_void_p), ("seed", C.c_uint64),
                 ("lr_q", C.c_double), ("lr_p", C.c_double), ("lr_e", C.c_double),
                 ("discount", C.c_double), ("discount_trace", C.c_double),
                 ("clock0", C.c_int32), ("reserved", C.c_int32),
                 ("metrics", C.c_void_p), ("sendlog", C.c_void_p)]
 
 
-EXPORTS = ("rlr_abi_version", "rlr_last_error_string", "rlr_create", "rlr_destroy", "rlr_bind_buffers",
+EXPORTS = ("rlr_abi_version", "rlr_last_error_string", "rlr_struct_sizes", "rlr_create", "rlr_destroy", "rlr_bind_buffers",
            "rlr_launch_info", "rlr_reset", "rlr_init_tables", "rlr_build_shortest_tables",
            "rlr_run_steps", "rlr_reduce_stats")
 
@@ -97,6 +97,11 @@ def lib():
     L.rlr_reduce_stats.argtypes = [p, p, p]
     if L.rlr_abi_version() != ABI_VERSION:
         raise ImportError(f"ABI mismatch: library {L.rlr_abi_version()} != binding {ABI_VERSION}")
+    sizes = (C.c_int32 * 4)()
+    L.rlr_struct_sizes(sizes)
+    mine = [C.sizeof(Topology), C.sizeof(Config), C.sizeof(Buffers), C.sizeof(RunParams)]
+    if list(sizes) != mine:
+        raise ImportError(f"struct layout mismatch: library {list(sizes)} != binding {mine}")
     _lib = L
     return L
 

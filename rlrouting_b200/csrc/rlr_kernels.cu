@@ -67,6 +67,7 @@ struct StepParams {
     const long long *inj_base;
     const unsigned *inj_pairs;
     const double *enlam;
+    const unsigned long long *inj_thr;
     unsigned long long seed;
     long long replica_base;
     double lr_q, lr_p, lr_e, discount, discount_trace;
@@ -208,12 +209,12 @@ __device__ __forceinline__ double np_sum_row(const double (&a)[MAXD], int n)
 
 // Same order over the senders of one replica, values indexed by node (non-senders skipped):
 // MaHybridQ.learn's max_Q_y.sum() / max_Q_x_d.sum() (multi_agent.py:28-29).
-__device__ double np_sum_compacted(const double *v, const short *target, int N, int n)
+__device__ double np_sum_compacted(const double *v, const unsigned short *tp, int N, int n)
 {
     if (n < 8) {
         double r = 0.0;
         for (int x = 0; x < N; ++x)
-            if (target[x] >= 0) r = __dadd_rn(r, v[x]);
+            if (tp[x] != 0xFFFFu) r = __dadd_rn(r, v[x]);
         return r;
     }
     double acc[8];
@@ -221,7 +222,7 @@ __device__ double np_sum_compacted(const double *v, const short *target, int N, 
     int idx = 0;
     double res = 0.0;
     for (int x = 0; x < N; ++x) {
-        if (target[x] < 0) continue;
+        if (tp[x] == 0xFFFFu) continue;
         const double a = v[x];
         if (idx < 8) {
             acc[idx] = a;
@@ -241,21 +242,6 @@ __device__ double np_sum_compacted(const double *v, const short *target, int N, 
     return res;
 }
 
-// Number of set bits in [lo, hi) of the CTA-wide "node sent this step" bit array (one word per warp).
-__device__ __forceinline__ int count_bits(const unsigned *wmask, int lo, int hi)
-{
-    if (hi <= lo) return 0;
-    const int w0 = lo >> 5, w1 = (hi - 1) >> 5;
-    int c = 0;
-    for (int w = w0; w <= w1; ++w) {
-        unsigned m = wmask[w];
-        if (w == w0) m &= 0xFFFFFFFFu << (lo & 31);
-        if (w == w1) m &= 0xFFFFFFFFu >> (31 - ((hi - 1) & 31));
-        c += __popc(m);
-    }
-    return c;
-}
-
 __device__ __forceinline__ void set_status(int *status, long long r, int code, int clock)
 {
     if (atomicCAS(&status[2 * r], 0, code) == 0) status[2 * r + 1] = clock;
@@ -265,7 +251,7 @@ __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t
 
 // Shared-memory carve-up, identical on host (sizing) and device (pointers).
 struct SmemLayout {
-    size_t tables, rec, target, wmask, rowptr, col, nexthop, ull, u32, f64, total;
+    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, total;
     __host__ __device__ SmemLayout(int N, int sdeg, int G, int threads, int policy, bool smem_tables, long long tsize, int ntab)
     {
         const int GN = G * N;
@@ -274,21 +260,27 @@ struct SmemLayout {
         rec = o; o += align16((size_t)GN * 16);
         f64 = o; o += (policy == RLR_POLICY_MAHYBRIDQ) ? align16((size_t)(3 * GN + 4 * G) * 8) : 0;
         ull = o; o += align16((size_t)G * 3 * 8);            // route_time, sends, injected
-        u32 = o; o += align16((size_t)G * 4 * 4);            // end, hops, dead, k
+        u32 = o; o += align16((size_t)G * 4 * 4);            // end, hops, dead
         wmask = o; o += align16((size_t)(threads / 32 + 1) * 4);
         rowptr = o; o += align16((size_t)(N + 1) * 4);
         col = o; o += align16((size_t)sdeg * 2);
-        target = o; o += align16((size_t)GN * 2);
+        tp = o; o += align16((size_t)GN * 2);
+        heappos = o; o += align16((size_t)(N + 1) * N);
         nexthop = o; o += (policy == RLR_POLICY_SHORTEST) ? align16((size_t)N * N) : 0;
         total = o;
     }
 };
 
+constexpr unsigned kNoKey = 0xFFFFFFFFu;   // "no arrival" sort key (real keys are heap position << 16 | send slot)
+constexpr unsigned kNoSend = 0xFFFFu;      // s_tp entry of a node that did not send this step
+
 // ------------------------------------------------------------------------------------------------
 // The step kernel: n_steps iterations of Network.train's loop body (env.py:400-413, slot=freq=1).
+//   MAXD  >= max degree (row loops are fully unrolled and predicated)
+//   MAXW  >= 32-bit words a replica's N consecutive thread slots can span (3 for N <= 64, else 9)
 // ------------------------------------------------------------------------------------------------
-template <int POLICY, int MAXD, bool SMEM_TABLES>
-__global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_constant__ StepParams p)
+template <int POLICY, int MAXD, int MAXW, bool SMEM_TABLES>
+__global__ void __launch_bounds__(kMaxThreads, 1) rlr_step_kernel(const __grid_constant__ StepParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int N = p.N, G = p.G, GN = G * N;
@@ -302,7 +294,8 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
     unsigned *s_wmask = reinterpret_cast<unsigned *>(smem + L.wmask);
     int *s_rowptr = reinterpret_cast<int *>(smem + L.rowptr);
     unsigned short *s_col = reinterpret_cast<unsigned short *>(smem + L.col);
-    short *s_target = reinterpret_cast<short *>(smem + L.target);
+    unsigned short *s_tp = reinterpret_cast<unsigned short *>(smem + L.tp);   // target | warp-local rank << 8
+    unsigned char *s_heappos = smem + L.heappos;
     unsigned char *s_nexthop = smem + L.nexthop;
     // per-replica accumulators of this launch
     unsigned long long *s_rt = s_ull, *s_sends = s_ull + G, *s_inj = s_ull + 2 * G;
@@ -320,6 +313,7 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
     // ---- stage topology (+ tables) into shared memory ----
     for (int i = t; i <= N; i += blockDim.x) s_rowptr[i] = p.row_ptr[i];
     for (int i = t; i < p.sdeg; i += blockDim.x) s_col[i] = (unsigned short)p.col[i];
+    for (int i = t; i < (N + 1) * N; i += blockDim.x) s_heappos[i] = p.heap_pos[i];
     if (POLICY == RLR_POLICY_SHORTEST)
         for (int i = t; i < N * N; i += blockDim.x) s_nexthop[i] = p.next_hop[i];
     for (int i = t; i < G; i += blockDim.x) {
@@ -340,7 +334,7 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
     }
     __syncthreads();
 
-    // ---- per-thread state ----
+    // ---- per-thread state, constant over the launch ----
     double *Qr = nullptr, *Thr = nullptr, *Trr = nullptr;          // this replica's tables
     if (POLICY != RLR_POLICY_SHORTEST && t < GN && r < p.R) {
         if (SMEM_TABLES) {
@@ -355,21 +349,26 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
     }
     const unsigned capmask = (unsigned)p.cap - 1u;
     unsigned head = 0, tail = 0;
-    uint4 next_rec = make_uint4(0, 0, 0, 0);
+    uint4 pref = make_uint4(0, 0, 0, 0), fresh = pref;            // head record: prefetched from the ring / just appended
+    bool use_fresh = false;
     uint4 *myring = nullptr;
     int rp = 0, deg = 0;
-    long long toffx = 0;
     double enlam = 0.0;
     unsigned my_sends = 0, my_inj = 0;
     long long base_rt = 0, base_end = 0, base_hops = 0;
+    double *Qx = nullptr, *Thx = nullptr, *Trx = nullptr;          // table[x] of this node
     if (is_node) {
         head = p.qhead[r * N + x];
         tail = p.qtail[r * N + x];
         myring = p.ring + ((size_t)r * N + x) * (size_t)p.cap;
-        if (head != tail) next_rec = myring[head & capmask];
+        if (head != tail) pref = myring[head & capmask];
         rp = s_rowptr[x];
         deg = s_rowptr[x + 1] - rp;
-        toffx = (long long)N * rp;
+        if (POLICY != RLR_POLICY_SHORTEST) {
+            Qx = Qr + (long long)N * rp;
+            Thx = Thr ? Thr + (long long)N * rp : nullptr;
+            Trx = Trr ? Trr + (long long)N * rp : nullptr;
+        }
         if (p.inject_mode == RLR_INJECT_PHILOX) enlam = p.enlam[r];
         if (x == 0) {
             base_rt = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_ROUTE_TIME];
@@ -378,41 +377,63 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
         }
     }
     const unsigned long long stream_id = (unsigned long long)(p.replica_base + r);
+    // the replica's N thread slots as a window of the CTA-wide "sent this step" bit array (one word per warp)
+    const int wlo = gbase >> 5, nw = ((gbase + N - 1) >> 5) - wlo + 1;
+    const unsigned mfirst = 0xFFFFFFFFu << (gbase & 31), mlast = 0xFFFFFFFFu >> (31 - ((gbase + N - 1) & 31));
+    const unsigned prank_mask = ((1u << lane) - 1u) & ((gbase > (warp << 5)) ? (0xFFFFFFFFu << (gbase - (warp << 5))) : 0xFFFFFFFFu);
+    // neighbour send slots (own slot for j >= deg: a node never sends to itself, so it never matches) and the
+    // window word each one falls in
+    unsigned nb_slot[MAXD], nb_word[MAXD];
+#pragma unroll
+    for (int j = 0; j < MAXD; ++j) {
+        const int z = (is_node && j < deg) ? s_col[rp + j] : x;
+        nb_slot[j] = (unsigned)(gbase + z);
+        nb_word[j] = (unsigned)(((gbase + z) >> 5) - wlo);
+    }
+    unsigned long long inj_thr = ~0ull;
+    if (is_node && p.inject_mode == RLR_INJECT_PHILOX) inj_thr = p.inj_thr[r];
+    bool dead = is_node ? (s_dead[g] != 0u) : true;                 // only sampled policies can die mid-launch
+    unsigned *sendlog = (p.sendlog && is_node) ? p.sendlog + r * (long long)p.K * N + x : nullptr;
 
-    auto append = [&](uint4 rec, int clock) {
-        if (tail - head >= (unsigned)p.cap) {           // never drop silently: sticky status
-            set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
-            return;
-        }
+    // Ring append.  Overflow is detected once per step (tail - head > cap) and reported through the sticky
+    // status word; the masked index keeps a wrapped write inside this node's own ring.
+    auto append = [&](const uint4 &rec) {
         myring[tail & capmask] = rec;
-        if (head == tail) next_rec = rec;
+        if (head == tail) { fresh = rec; use_fresh = true; }
         ++tail;
     };
 
     for (int s = 0; s < p.K; ++s) {
         const int clock = p.clock0 + s;
-        const bool live = is_node && !s_dead[g];
+        if (POLICY >= RLR_POLICY_HYBRIDQ && is_node) dead = (s_dead[g] != 0u);
+        const bool live = !dead;
         bool sending = false;
-        int d = 0, k = 0;
+        int d = 0, k = 0, y = 0;
         double oldq = 0.0, max_qy = 0.0, max_qxd = 0.0, rwd = 0.0;
         double sm[MAXD];
         if (live) {
             // ---- A. new_packet + inject (env.py:298-319) ----
             if (p.inject_mode == RLR_INJECT_PHILOX) {
+                // Poisson(lambda/N) by the multiplication method.  The first uniform u0 = (w0 + 0.5) * 2^-32 gives
+                // n >= 1 iff u0 > exp(-lambda/N) iff w0 >= inj_thr (threshold computed exactly on the host), so the
+                // common n == 0 case is one integer compare; the rest continues in fp64 exactly like the oracle.
                 PhiloxStream ps(p.seed, stream_id, clock, x, 0);
-                int n = 0;
-                double prod = 1.0;
-                for (;;) {
-                    const double u = __dmul_rn(__dadd_rn((double)ps.next(), 0.5), 1.0 / 4294967296.0);
-                    prod = __dmul_rn(prod, u);
-                    if (prod > enlam) ++n; else break;
+                const unsigned w0 = ps.next();
+                if ((unsigned long long)w0 >= inj_thr) {
+                    int n = 1;
+                    double prod = __dmul_rn(__dadd_rn((double)w0, 0.5), 1.0 / 4294967296.0);
+                    for (;;) {
+                        const double u = __dmul_rn(__dadd_rn((double)ps.next(), 0.5), 1.0 / 4294967296.0);
+                        prod = __dmul_rn(prod, u);
+                        if (prod > enlam) ++n; else break;
+                    }
+                    for (int i = 0; i < n; ++i) {
+                        unsigned dd = __umulhi(ps.next(), (unsigned)(N - 1));
+                        if (dd >= (unsigned)x) ++dd;
+                        append(make_uint4(dd | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock));
+                    }
+                    my_inj += n;
                 }
-                for (int i = 0; i < n; ++i) {
-                    unsigned dd = __umulhi(ps.next(), (unsigned)(N - 1));
-                    if (dd >= (unsigned)x) ++dd;
-                    append(make_uint4(dd | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock), clock);
-                }
-                my_inj += n;
             } else {
                 const int *off = p.inj_off + r * (long long)(p.K + 1) + s;
                 const int o0 = off[0], o1 = off[1];
@@ -420,7 +441,7 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
                 for (int i = o0; i < o1; ++i) {
                     const unsigned pr = pairs[i];
                     if ((int)(pr & 0xFFFFu) == x) {
-                        append(make_uint4((pr >> 16) | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock), clock);
+                        append(make_uint4((pr >> 16) | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock));
                         ++my_inj;
                     }
                 }
@@ -428,13 +449,15 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
             // ---- B. Node._send_default (env.py:162-191): pop the head, choose, get_info ----
             if (head != tail) {
                 sending = true;
-                uint4 rec = next_rec;
+                uint4 rec = use_fresh ? fresh : pref;
+                use_fresh = false;
                 ++head;
+                if (head != tail) pref = myring[head & capmask];               // prefetch the next head
                 d = (int)(rec.x & 0xFFFFu);
                 if (POLICY == RLR_POLICY_SHORTEST) {
                     k = s_nexthop[x * N + d];                                   // shortest.py:38-41
                 } else if (POLICY == RLR_POLICY_QROUTE) {
-                    const double *row = Qr + toffx + (long long)d * deg;        // qroute.py:22-27
+                    const double *row = Qx + d * deg;                           // qroute.py:22-27
                     double best = row[0];
 #pragma unroll
                     for (int j = 1; j < MAXD; ++j)
@@ -443,7 +466,7 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
                     oldq = best;
                 } else {
                     // PolicyGradient.choose (hybrid.py:16-23): softmax(theta) sampled by inverse CDF
-                    const double *th = Thr + toffx + (long long)d * deg;
+                    const double *th = Thx + d * deg;
                     double e[MAXD];
 #pragma unroll
                     for (int j = 0; j < MAXD; ++j) e[j] = (j < deg) ? det_exp(th[j]) : 0.0;
@@ -466,7 +489,7 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
 #pragma unroll
                     for (int j = 0; j < MAXD - 1; ++j)
                         if (j < deg - 1 && k == j && __ddiv_rn(cdf[j], c) <= u) k = j + 1;
-                    const double *row = Qr + toffx + (long long)d * deg;        // hybrid.py:49-53
+                    const double *row = Qx + d * deg;                           // hybrid.py:49-53
                     double best = row[0];
                     oldq = row[0];
 #pragma unroll
@@ -474,72 +497,88 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
                         if (j < deg) { const double v = row[j]; if (v > best) best = v; if (j == k) oldq = v; }
                     max_qxd = best;
                 }
-                const int y = s_col[rp + k];
+                y = s_col[rp + k];
                 rec.y += 1u;                                                    // p.hops += 1, env.py:141
                 rwd = (double)(-(clock - (int)rec.w) - 1);                      // r = -q_y - t_y, qroute.py:37
                 if (POLICY != RLR_POLICY_SHORTEST) {                            // max_Q_y, qroute.py:29-30
                     const int rpy = s_rowptr[y], degy = s_rowptr[y + 1] - rpy;
-                    const double *ry = Qr + (long long)N * rpy + (long long)d * degy;
+                    const double *ry = Qr + N * rpy + d * degy;
                     double m = ry[0];
-                    for (int j = 1; j < degy; ++j) { const double v = ry[j]; if (v > m) m = v; }
+#pragma unroll
+                    for (int j = 1; j < MAXD; ++j)
+                        if (j < degy) { const double v = ry[j]; if (v > m) m = v; }
                     max_qy = m;
                 }
                 s_rec[t] = rec;
-                s_target[t] = (short)y;
                 if (POLICY == RLR_POLICY_MAHYBRIDQ) { s_r[t] = rwd; s_qy[t] = max_qy; s_qx[t] = max_qxd; }
-                if (head != tail) next_rec = myring[head & capmask];           // prefetch next head
                 ++my_sends;
-                if (p.sendlog) p.sendlog[(r * p.K + s) * N + x] = (unsigned)y | ((unsigned)d << 16);
-            } else {
-                s_target[t] = -1;
-                if (p.sendlog) p.sendlog[(r * p.K + s) * N + x] = 0xFFFFFFFFu;
             }
-        } else if (t < GN) {
-            s_target[t] = -1;
-            if (is_node && p.sendlog) p.sendlog[(r * p.K + s) * N + x] = 0xFFFFFFFFu;
         }
+        if (sendlog) sendlog[(long long)s * N] = sending ? ((unsigned)y | ((unsigned)d << 16)) : 0xFFFFFFFFu;
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, sending);
         if (lane == 0) s_wmask[warp] = bal;
+        if (t < GN) s_tp[t] = sending ? (unsigned short)(y | (__popc(bal & prank_mask) << 8)) : (unsigned short)kNoSend;
         __syncthreads();                                                        // ---- barrier 1 ----
 
-        int ksend = -1;
         if (live) {
             // ---- C. event drain (env.py:349-364): gather arrivals from neighbours in heap-tie order ----
-            unsigned am = 0;
+            unsigned cum[MAXW + 1];         // senders of this replica in the window words before word i
+            cum[0] = 0;
 #pragma unroll
-            for (int j = 0; j < MAXD; ++j)
-                if (j < deg && s_target[gbase + s_col[rp + j]] == (short)x) am |= 1u << j;
-            if (am) {
-                unsigned posv[MAXD];
+            for (int i = 0; i < MAXW; ++i) {
+                unsigned m = (i < nw) ? s_wmask[wlo + i] : 0u;
+                if (i == 0) m &= mfirst;
+                if (i == nw - 1) m &= mlast;
+                cum[i + 1] = cum[i] + __popc(m);
+            }
+            const unsigned char *hp = s_heappos + cum[MAXW] * N;               // row k = number of senders
+            unsigned cumpack = 0;                                               // cum[0..3] as bytes (N <= 255)
+            if (MAXW <= 3) cumpack = cum[0] | (cum[1] << 8) | (cum[2] << 16);
+            // sort key per neighbour slot: heap pop position << 16 | send slot, or kNoKey
+            unsigned key[MAXD];
 #pragma unroll
-                for (int j = 0; j < MAXD; ++j) posv[j] = 0;
-                if (am & (am - 1u)) {
-                    ksend = count_bits(s_wmask, gbase, gbase + N);
+            for (int j = 0; j < MAXD; ++j) {
+                const unsigned tp = s_tp[nb_slot[j]];
+                const bool match = (tp & 0xFFu) == (unsigned)x;                 // kNoSend's low byte is 255 > any node id
+                unsigned base = 0;
+                if (MAXW <= 3) {
+                    base = __byte_perm(cumpack, 0u, nb_word[j]) & 0xFFu;
+                } else {
 #pragma unroll
-                    for (int j = 0; j < MAXD; ++j)
-                        if ((am >> j) & 1u) {
-                            const int z = s_col[rp + j];
-                            posv[j] = p.heap_pos[ksend * N + count_bits(s_wmask, gbase, gbase + z)];
-                        }
+                    for (int i = 1; i < MAXW; ++i)
+                        if (nb_word[j] == (unsigned)i) base = cum[i];
                 }
-                while (am) {
-                    int bj = 0;
-                    unsigned bp = 0xFFFFFFFFu;
+                const unsigned pos = hp[match ? (tp >> 8) + base : 0u];
+                key[j] = match ? ((pos << 16) | nb_slot[j]) : kNoKey;
+            }
+            if (MAXD == 4) {                                                    // 5-comparator sorting network
+#define RLR_CE(a, b) { const unsigned lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; }
+                RLR_CE(0, 1) RLR_CE(2, 3) RLR_CE(0, 2) RLR_CE(1, 3) RLR_CE(1, 2)
+#undef RLR_CE
+            }
+            for (;;) {
+                unsigned best = key[0];
+                if (MAXD == 4) {
+                    key[0] = key[1]; key[1] = key[2]; key[2] = key[3]; key[3] = kNoKey;
+                } else {
+#pragma unroll
+                    for (int j = 1; j < MAXD; ++j) best = min(best, key[j]);
 #pragma unroll
                     for (int j = 0; j < MAXD; ++j)
-                        if (((am >> j) & 1u) && posv[j] < bp) { bp = posv[j]; bj = j; }
-                    am &= ~(1u << bj);
-                    uint4 rec = s_rec[gbase + s_col[rp + bj]];
-                    if ((int)(rec.x & 0xFFFFu) == x) {                          // Network.end_packet, env.py:321-331
-                        atomicAdd(&s_end[g], 1u);
-                        atomicAdd(&s_rt[g], (unsigned long long)(clock + 1 - (int)rec.z));
-                        atomicAdd(&s_hops[g], rec.y);
-                    } else {                                                    // Node.receive, env.py:127-130
-                        rec.w = (unsigned)(clock + 1);
-                        append(rec, clock);
-                    }
+                        if (key[j] == best) key[j] = kNoKey;
+                }
+                if (best == kNoKey) break;
+                uint4 rec = s_rec[best & 0xFFFFu];
+                if ((int)(rec.x & 0xFFFFu) == x) {                              // Network.end_packet, env.py:321-331
+                    atomicAdd(&s_end[g], 1u);
+                    atomicAdd(&s_rt[g], (unsigned long long)(clock + 1 - (int)rec.z));
+                    atomicAdd(&s_hops[g], rec.y);
+                } else {                                                        // Node.receive, env.py:127-130
+                    rec.w = (unsigned)(clock + 1);
+                    append(rec);
                 }
             }
+            if (tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
         }
         // ---- D. agent.learn ----
         if (POLICY == RLR_POLICY_QROUTE) {
@@ -547,7 +586,7 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
                 const double tq = __dmul_rn(p.discount, max_qy);
                 const double u1 = __dadd_rn(rwd, tq);
                 const double u2 = __dsub_rn(u1, oldq);
-                Qr[toffx + (long long)d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, u2));
+                Qx[d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, u2));
             }
         } else if (POLICY == RLR_POLICY_HYBRIDQ) {
             if (sending) {                                                      // hybrid.py:55-62
@@ -560,9 +599,9 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
                 }
                 const double tq = __dmul_rn(p.discount, max_qy);
                 const double u1 = __dadd_rn(rr, tq);
-                Qr[toffx + (long long)d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, __dsub_rn(u1, oldq)));
+                Qx[d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, __dsub_rn(u1, oldq)));
                 const double adv = __dsub_rn(u1, max_qxd);                      // hybrid.py:32-36
-                double *th = Thr + toffx + (long long)d * deg;
+                double *th = Thx + d * deg;
 #pragma unroll
                 for (int j = 0; j < MAXD; ++j)
                     if (j < deg) {
@@ -573,15 +612,20 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
             }
         } else if (POLICY == RLR_POLICY_MAHYBRIDQ) {
             // MaHybridQ.learn (multi_agent.py:17-43)
-            if (t < GN && x < 3 && live) {                                      // three sums per replica
-                const int n = count_bits(s_wmask, gbase, gbase + N);
-                const double *v = (x == 0) ? s_r : (x == 1) ? s_qy : s_qx;
-                s_sum[g * 4 + x] = np_sum_compacted(v + gbase, s_target + gbase, N, n);
-            }
-            if (N < 3 && t < GN && x == 0 && live) {
-                const int n = count_bits(s_wmask, gbase, gbase + N);
-                for (int q = 1; q < 3; ++q)
-                    s_sum[g * 4 + q] = np_sum_compacted((q == 1 ? s_qy : s_qx) + gbase, s_target + gbase, N, n);
+            if (live && x < 3) {                                                // three sums per replica
+                unsigned n = 0;
+#pragma unroll
+                for (int i = 0; i < MAXW; ++i) {
+                    unsigned m = (i < nw) ? s_wmask[wlo + i] : 0u;
+                    if (i == 0) m &= mfirst;
+                    if (i == nw - 1) m &= mlast;
+                    n += __popc(m);
+                }
+                for (int q = x; q < 3; q += (N < 3 ? 1 : 3)) {
+                    const double *v = (q == 0) ? s_r : (q == 1) ? s_qy : s_qx;
+                    s_sum[g * 4 + q] = np_sum_compacted(v + gbase, s_tp + gbase, N, (int)n);
+                    if (N >= 3) break;
+                }
             }
             // dense pass 1: Trace *= discount_trace                                (multi_agent.py:32-33)
             for (int gg = 0; gg < G; ++gg) {
@@ -591,7 +635,7 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
             }
             __syncthreads();
             if (sending) {                                                      // multi_agent.py:35-40
-                double *trow = Trr + toffx + (long long)d * deg;
+                double *trow = Trx + d * deg;
 #pragma unroll
                 for (int j = 0; j < MAXD; ++j)
                     if (j < deg) {
@@ -600,7 +644,7 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
                         trow[j] = __dadd_rn(trow[j], gj);
                     }
                 const double u1 = __dadd_rn(rwd, __dmul_rn(p.discount, max_qy));
-                Qr[toffx + (long long)d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, __dsub_rn(u1, oldq)));
+                Qx[d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, __dsub_rn(u1, oldq)));
             }
             __syncthreads();
             // dense pass 2: Theta += (lr_p * delta) * Trace                        (multi_agent.py:28-30,42-43)
@@ -617,8 +661,8 @@ __global__ void __launch_bounds__(kMaxThreads) rlr_step_kernel(const __grid_cons
         __syncthreads();                                                        // ---- barrier 2 ----
         if (is_node && x == 0 && p.metrics) {                                   // env.py:409-413
             const long long rt = base_rt + (long long)s_rt[g];
-            const unsigned en = (unsigned)(base_end + s_end[g]), hp = (unsigned)(base_hops + s_hops[g]);
-            p.metrics[r * p.K + s] = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hp);
+            const unsigned en = (unsigned)(base_end + s_end[g]), hps = (unsigned)(base_hops + s_hops[g]);
+            p.metrics[r * p.K + s] = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hps);
         }
     }
 
@@ -747,27 +791,32 @@ __global__ void rlr_reduce_stats_kernel(const long long *counters, long long R, 
 
 using StepKernel = void (*)(const StepParams);
 
-template <int POLICY, int MAXD>
+template <int POLICY, int MAXD, int MAXW>
 StepKernel pick_smem(bool smem_tables)
 {
-    return smem_tables ? (StepKernel)rlr_step_kernel<POLICY, MAXD, true> : (StepKernel)rlr_step_kernel<POLICY, MAXD, false>;
+    if (POLICY == RLR_POLICY_SHORTEST) return (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false>;
+    return smem_tables ? (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, true> : (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false>;
 }
 
 template <int POLICY>
-StepKernel pick_deg(int max_deg, bool smem_tables)
+StepKernel pick_deg(int n_nodes, int max_deg, bool smem_tables)
 {
-    if (max_deg <= 4) return pick_smem<POLICY, 4>(smem_tables);
-    if (max_deg <= 8) return pick_smem<POLICY, 8>(smem_tables);
-    return pick_smem<POLICY, 16>(smem_tables);
+    if (n_nodes <= 64) {
+        if (max_deg <= 4) return pick_smem<POLICY, 4, 3>(smem_tables);
+        if (max_deg <= 8) return pick_smem<POLICY, 8, 3>(smem_tables);
+        return pick_smem<POLICY, 16, 3>(smem_tables);
+    }
+    if (max_deg <= 8) return pick_smem<POLICY, 8, 9>(smem_tables);
+    return pick_smem<POLICY, 16, 9>(smem_tables);
 }
 
-StepKernel pick_kernel(int policy, int max_deg, bool smem_tables)
+StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables)
 {
     switch (policy) {
-    case RLR_POLICY_SHORTEST: return pick_deg<RLR_POLICY_SHORTEST>(max_deg, false);
-    case RLR_POLICY_QROUTE: return pick_deg<RLR_POLICY_QROUTE>(max_deg, smem_tables);
-    case RLR_POLICY_HYBRIDQ: return pick_deg<RLR_POLICY_HYBRIDQ>(max_deg, smem_tables);
-    default: return pick_deg<RLR_POLICY_MAHYBRIDQ>(max_deg, smem_tables);
+    case RLR_POLICY_SHORTEST: return pick_deg<RLR_POLICY_SHORTEST>(n_nodes, max_deg, false);
+    case RLR_POLICY_QROUTE: return pick_deg<RLR_POLICY_QROUTE>(n_nodes, max_deg, smem_tables);
+    case RLR_POLICY_HYBRIDQ: return pick_deg<RLR_POLICY_HYBRIDQ>(n_nodes, max_deg, smem_tables);
+    default: return pick_deg<RLR_POLICY_MAHYBRIDQ>(n_nodes, max_deg, smem_tables);
     }
 }
 
@@ -792,11 +841,21 @@ int rlr_abi_version(void) { return RLR_ABI_VERSION; }
 
 const char *rlr_last_error_string(void) { return g_last_error.c_str(); }
 
+int rlr_struct_sizes(int32_t out[4])
+{
+    if (!out) return fail(RLR_E_INVALID, "rlr_struct_sizes: null output");
+    out[0] = (int32_t)sizeof(rlr_topology_t);
+    out[1] = (int32_t)sizeof(rlr_config_t);
+    out[2] = (int32_t)sizeof(rlr_buffers_t);
+    out[3] = (int32_t)sizeof(rlr_run_params_t);
+    return RLR_OK;
+}
+
 int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t **out)
 {
     if (!topo || !cfg || !out) return fail(RLR_E_INVALID, "rlr_create: null argument");
     const int N = topo->n_nodes;
-    if (N < 2 || N > 256) return fail(RLR_E_UNSUPPORTED, "rlr_create: n_nodes must be in [2, 256]");
+    if (N < 2 || N > 255) return fail(RLR_E_UNSUPPORTED, "rlr_create: n_nodes must be in [2, 255]");
     if (topo->max_deg < 1 || topo->max_deg > 16) return fail(RLR_E_UNSUPPORTED, "rlr_create: max_deg must be in [1, 16]");
     if (!topo->row_ptr || !topo->col || topo->row_ptr[0] != 0 || topo->row_ptr[N] != topo->sum_deg)
         return fail(RLR_E_INVALID, "rlr_create: malformed CSR");
@@ -848,7 +907,7 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
         return fail(RLR_E_UNSUPPORTED, "rlr_create: shared-memory footprint exceeds 227 KB (lower replicas_per_block or set tables_in_smem=0)");
     }
     h->G = G; h->threads = threads; h->smem_bytes = (int)smem; h->smem_tables = smem_tables != 0;
-    h->kernel = pick_kernel(h->policy, h->max_deg, h->smem_tables);
+    h->kernel = pick_kernel(h->policy, h->N, h->max_deg, h->smem_tables);
     cudaError_t e = cudaFuncSetAttribute((const void *)h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         delete h;
@@ -941,7 +1000,7 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     if (rp->inject_mode == RLR_INJECT_TRACE) {
         if (!rp->inj_off || !rp->inj_base || !rp->inj_pairs) return fail(RLR_E_INVALID, "rlr_run_steps: trace mode needs inj_off, inj_base, inj_pairs");
     } else if (rp->inject_mode == RLR_INJECT_PHILOX) {
-        if (!rp->enlam) return fail(RLR_E_INVALID, "rlr_run_steps: Philox mode needs enlam");
+        if (!rp->enlam || !rp->inj_thr) return fail(RLR_E_INVALID, "rlr_run_steps: Philox mode needs enlam and inj_thr");
     } else {
         return fail(RLR_E_INVALID, "rlr_run_steps: unknown inject_mode");
     }
@@ -958,7 +1017,7 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     p.counters = (long long *)h->bufs.counters; p.status = h->bufs.status;
     p.inject_mode = rp->inject_mode; p.add_entropy = rp->add_entropy;
     p.inj_off = rp->inj_off; p.inj_base = (const long long *)rp->inj_base; p.inj_pairs = rp->inj_pairs;
-    p.enlam = rp->enlam; p.seed = rp->seed; p.replica_base = h->replica_base;
+    p.enlam = rp->enlam; p.inj_thr = (const unsigned long long *)rp->inj_thr; p.seed = rp->seed; p.replica_base = h->replica_base;
     p.lr_q = rp->lr_q; p.lr_p = rp->lr_p; p.lr_e = rp->lr_e; p.discount = rp->discount; p.discount_trace = rp->discount_trace;
     p.metrics = (uint4 *)rp->metrics; p.sendlog = rp->sendlog;
     const long long blocks = (h->R + h->G - 1) / h->G;

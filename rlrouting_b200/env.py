@@ -65,6 +65,14 @@ class Node:
         return f"Node<{self.ID}, queue: {self.queue}, sent: {self.sent}>"
 
 
+def injection_threshold(enlam):
+    """Smallest integer w in [0, 2^32] with (w + 0.5) * 2^-32 > enlam, exactly (all float64 steps below are
+    exact: scaling by 2^33, subtracting 1 and halving a value below 2^33 lose no bits).  The device tests
+    `w0 >= threshold` instead of evaluating the first Poisson uniform in fp64."""
+    e = np.asarray(enlam, dtype=np.float64) * 8589934592.0
+    return (np.floor((e - 1.0) / 2.0) + 1.0).clip(0.0, 4294967296.0).astype(np.uint64)
+
+
 def _floor_pow2(v):
     return 1 << (int(v).bit_length() - 1)
 
@@ -290,10 +298,12 @@ class Network:
             h2d += flat.nbytes + base.nbytes + R * (T + 1) * 4
         else:
             rp.inject_mode = nat.INJECT_PHILOX
-            enlam = torch.from_numpy(np.exp(-lam / np.float64(N))).to(dev)
-            rp.enlam = enlam.data_ptr()
-            keep.append(enlam)
-            h2d += R * 8
+            en_host = np.exp(-lam / np.float64(N))
+            enlam = torch.from_numpy(en_host).to(dev)
+            thr = torch.from_numpy(injection_threshold(en_host).view(np.int64)).to(dev)
+            rp.enlam, rp.inj_thr = enlam.data_ptr(), thr.data_ptr()
+            keep += [enlam, thr]
+            h2d += R * 16
 
         if steps_per_launch is None:
             steps_per_launch = T if not per_step else max(1, min(T, (1 << 25) // R))
@@ -357,7 +367,9 @@ class Network:
         lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (R,))
         key = ("enlam", lam.tobytes() if lam.strides[0] else float(lam[0]))
         if self._resident.get("enlam_key") != key:
-            self._resident["enlam"] = torch.from_numpy(np.exp(-lam / np.float64(N))).to(self.device)
+            en_host = np.exp(-lam / np.float64(N))
+            self._resident["enlam"] = torch.from_numpy(en_host).to(self.device)
+            self._resident["inj_thr"] = torch.from_numpy(injection_threshold(en_host).view(np.int64)).to(self.device)
             self._resident["enlam_key"] = key
         if self._resident.get("metrics_shape") != (R, K):
             self._resident["metrics"] = torch.empty((R, K, 2), dtype=torch.int64, device=self.device)
@@ -372,6 +384,7 @@ class Network:
         rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
         rp.seed = self.seed
         rp.enlam = self._resident["enlam"].data_ptr()
+        rp.inj_thr = self._resident["inj_thr"].data_ptr()
         rp.clock0 = self.clock
         rp.metrics = self._resident["metrics"].data_ptr()
         nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), self._stream_ptr()))

@@ -60,7 +60,7 @@ def heap_pop_order(k):
 
 
 class Topology:
-    MAX_NODES = 256     # node ids and heap positions are stored in 8/16-bit fields on the device
+    MAX_NODES = 255     # node ids and heap positions are stored in 8/16-bit fields on the device
     MAX_DEGREE = 16
 
     def __init__(self, links):

@@ -1,0 +1,112 @@
+"""CPU tests of the host-side logic: topology layout, heap-tie table, injection threshold, API
+validation, the C-ABI library's exports, replica sharding."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from rlrouting_b200 import _native as nat
+from rlrouting_b200 import dist, nets
+from rlrouting_b200.env import injection_threshold
+from rlrouting_b200.topology import Topology, heap_pop_order, parse_net
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "rlrouting_b200.h")).read()
+    declared = set(re.findall(r"\b(rlr_[a-z_]+)\s*\(", hdr))
+    assert declared == set(nat.EXPORTS)
+    lib = nat.lib()                                  # raises if the .so is missing or a symbol is absent
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.rlr_abi_version() == nat.ABI_VERSION
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    t = nat.Topology(1, 0, 0, None, None)
+    cfg = nat.Config(1, 0, 1, 64, 0, 0, -1, 0)
+    h = C.c_void_p()
+    assert lib.rlr_create(C.byref(t), C.byref(cfg), C.byref(h)) < 0
+    assert b"n_nodes" in lib.rlr_last_error_string()
+    assert lib.rlr_run_steps(None, 1, None, None) < 0
+
+
+def test_struct_sizes_match_header_layout():
+    sizes = (C.c_int32 * 4)()
+    assert nat.lib().rlr_struct_sizes(sizes) == 0
+    assert list(sizes) == [C.sizeof(nat.Topology), C.sizeof(nat.Config), C.sizeof(nat.Buffers), C.sizeof(nat.RunParams)]
+    assert C.sizeof(nat.Buffers) == 14 * 8
+
+
+def test_builtin_topologies_layout():
+    sizes = {"6x6.net": (36, 100, 4), "6x6-modified.net": (36, 100, 5), "lata.net": (116, 336, 9)}
+    for name, (n, sdeg, maxdeg) in sizes.items():
+        t = Topology.from_text(nets.net_text(name))
+        assert (t.N, t.sum_deg, t.max_deg, t.tsize) == (n, sdeg, maxdeg, n * sdeg)
+        assert t.row_ptr[-1] == sdeg and len(t.col) == sdeg
+        for x in range(n):
+            for j, y in enumerate(t.links[x]):
+                assert t.col[t.row_ptr[x] + j] == y
+                assert t.links[y][t.rev[t.row_ptr[x] + j]] == x          # undirected: the reverse slot exists
+        tabs = {x: np.arange(n * t.deg[x], dtype=np.float64).reshape(n, t.deg[x]) + 1000 * x for x in range(n)}
+        back = t.unpack(t.pack(tabs))
+        assert all(np.array_equal(back[x], tabs[x]) for x in range(n))
+
+
+@pytest.mark.reference
+def test_builtin_topologies_equal_reference_files():
+    for name in nets.TOPOLOGIES:
+        ref, _ = parse_net(open(os.path.join("/root/reference", name)).read())
+        assert ref == Topology.from_text(nets.net_text(name)).links
+
+
+def test_heap_position_table_is_inverse_of_pop_order():
+    t = Topology.from_text(nets.net_text("6x6.net"))
+    for k in range(1, t.N + 1):
+        order = heap_pop_order(k)
+        assert sorted(order) == list(range(k))
+        for j, rank in enumerate(order):
+            assert t.heap_pos[k, rank] == j
+
+
+def test_injection_threshold_is_exact():
+    rng = np.random.default_rng(0)
+    lam = np.concatenate([rng.uniform(0, 8, 2000), [0.0, 1e-12, 0.25, 2.0, 4.0, 50.0, 2000.0]])
+    for n_nodes in (2, 36, 116):
+        en = np.exp(-lam / n_nodes)
+        thr = injection_threshold(en)
+        for e, t in zip(en, thr):
+            t = int(t)
+            u = lambda w: (np.float64(w) + 0.5) * (1.0 / 4294967296.0)          # noqa: E731  (the oracle's expression)
+            if t <= 0xFFFFFFFF:
+                assert u(t) > e
+            if t > 0:
+                assert not (u(t - 1) > e)
+    assert int(injection_threshold(1.0)) == 1 << 32                              # lambda = 0: never inject
+
+
+def test_unsupported_options_fail_before_touching_the_device():
+    import rlrouting_b200 as rb
+    for kw in (dict(bandwidth=2), dict(transtime=2), dict(is_drop=True)):
+        with pytest.raises(NotImplementedError):
+            rb.Network("6x6.net", **kw)
+    with pytest.raises(ValueError):
+        rb.Network("6x6.net", rng="mt")
+    with pytest.raises(FileNotFoundError):
+        rb.Network("no-such-file.net")
+    with pytest.raises(NotImplementedError):
+        Topology({0: [], 1: []})                                                 # isolated nodes
+    with pytest.raises(NotImplementedError):
+        Topology({0: [0, 1], 1: [0]})                                            # self-loop
+
+
+def test_sharding_covers_every_replica_once():
+    for total in (1, 7, 64, 65536, 65537):
+        for world in (1, 2, 3, 8):
+            blocks = [dist.shard(total, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and sum(c for _, c in blocks) == total
+            for (b0, c0), (b1, _) in zip(blocks, blocks[1:]):
+                assert b0 + c0 == b1
+    base, lam, idx = dist.shard_loads([1.0, 2.0, 3.0, 4.0], 6, 1, 4)
+    assert base == 6 and list(lam) == [2.0] * 6 and list(idx) == [1] * 6
