@@ -113,8 +113,12 @@ typedef struct {
     int32_t clock0;           /* Network.clock before the first step                         */
     int32_t reserved;
     /* outputs (device pointers, may be NULL) */
-    void *metrics;            /* [R][n_steps] 16-byte records {int64 route_time, uint32 end_packets,
-                                 uint32 hops}: cumulative counters after each step (env.py:409-413) */
+    void *metrics;            /* [n_steps][R] 16-byte records {int64 route_time, uint32 end_packets, uint32 hops}:
+                                 cumulative counters after each step (env.py:409-413); step-major so a chunk
+                                 of steps is one contiguous block.  Required by route_time_out / hop_out. */
+    double *route_time_out;   /* [n_steps][R] Network.ave_route_time after each step (env.py:409, 444-446); step-major
+                                 so a chunk of steps is one contiguous block for the device->host copy */
+    double *hop_out;          /* [n_steps][R] Network.ave_hops after each step (env.py:412-413, 440-442) */
     uint32_t *sendlog;        /* [R][n_steps][N]: y | dest << 16 for a send by node x, else 0xFFFFFFFF */
 } rlr_run_params_t;
 

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "rlr_kernels.cu")
 HDR = os.path.join(ROOT, "include", "rlrouting_b200.h")
-SO = os.path.join(HERE, "csrc", "librlrouting_b200.so")
+SO = os.environ.get("RLR_LIB") or os.path.join(HERE, "csrc", "librlrouting_b200.so")   # RLR_LIB: experiment builds
 
 ABI_VERSION = 1
 NUM_COUNTERS = 8
@@ -61,7 +61,8 @@ class RunParams(C.Structure):
                 ("lr_q", C.c_double), ("lr_p", C.c_double), ("lr_e", C.c_double),
                 ("discount", C.c_double), ("discount_trace", C.c_double),
                 ("clock0", C.c_int32), ("reserved", C.c_int32),
-                ("metrics", C.c_void_p), ("sendlog", C.c_void_p)]
+                ("metrics", C.c_void_p), ("route_time_out", C.c_void_p), ("hop_out", C.c_void_p),
+                ("sendlog", C.c_void_p)]
 
 
 EXPORTS = ("rlr_abi_version", "rlr_last_error_string", "rlr_struct_sizes", "rlr_create", "rlr_destroy", "rlr_bind_buffers",

@@ -44,6 +44,9 @@ int fail(int code, const std::string &msg)
     } while (0)
 
 constexpr int kMaxThreads = 512;
+#ifndef RLR_MIN_BLOCKS
+#define RLR_MIN_BLOCKS 1
+#endif
 constexpr int kSmemLimit = 227 * 1024;
 
 // ------------------------------------------------------------------------------------------------
@@ -280,7 +283,7 @@ constexpr unsigned kNoSend = 0xFFFFu;      // s_tp entry of a node that did not 
 //   MAXW  >= 32-bit words a replica's N consecutive thread slots can span (3 for N <= 64, else 9)
 // ------------------------------------------------------------------------------------------------
 template <int POLICY, int MAXD, int MAXW, bool SMEM_TABLES>
-__global__ void __launch_bounds__(kMaxThreads, 1) rlr_step_kernel(const __grid_constant__ StepParams p)
+__global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(const __grid_constant__ StepParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int N = p.N, G = p.G, GN = G * N;
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) rlr_step_kernel(const __grid_c
             Trx = Trr ? Trr + (long long)N * rp : nullptr;
         }
         if (p.inject_mode == RLR_INJECT_PHILOX) enlam = p.enlam[r];
-        if (x == 0) {
+        if (x == N - 1) {                      // the last node's thread keeps the per-step metric record
             base_rt = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_ROUTE_TIME];
             base_end = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_END_PACKETS];
             base_hops = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_HOPS];
@@ -659,10 +662,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) rlr_step_kernel(const __grid_c
             }
         }
         __syncthreads();                                                        // ---- barrier 2 ----
-        if (is_node && x == 0 && p.metrics) {                                   // env.py:409-413
+        if (is_node && x == N - 1 && p.metrics) {                               // env.py:409-413 (cumulative counters)
             const long long rt = base_rt + (long long)s_rt[g];
             const unsigned en = (unsigned)(base_end + s_end[g]), hps = (unsigned)(base_hops + s_hops[g]);
-            p.metrics[r * p.K + s] = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hps);
+            p.metrics[(long long)s * p.R + r] = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hps);
         }
     }
 
@@ -787,6 +790,19 @@ __global__ void rlr_reduce_stats_kernel(const long long *counters, long long R, 
     __syncthreads();
     if (threadIdx.x < RLR_NUM_COUNTERS && acc[threadIdx.x])
         atomicAdd((unsigned long long *)&out[threadIdx.x], (unsigned long long)acc[threadIdx.x]);
+}
+
+// ave_route_time / ave_hops after each step (env.py:440-446): route_time / end_packets if end_packets > 0 else 0.
+// IEEE division of two exactly converted integers is Python's correctly rounded int / int.
+__global__ void rlr_ratio_kernel(const uint4 *metrics, long long n, double *route_time_out, double *hop_out)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 m = metrics[i];
+        const long long rt = (long long)(((unsigned long long)m.y << 32) | m.x);
+        const double en = (double)m.z;
+        if (route_time_out) route_time_out[i] = m.z ? __ddiv_rn((double)rt, en) : 0.0;
+        if (hop_out) hop_out[i] = m.z ? __ddiv_rn((double)m.w, en) : 0.0;
+    }
 }
 
 using StepKernel = void (*)(const StepParams);
@@ -1004,6 +1020,8 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     } else {
         return fail(RLR_E_INVALID, "rlr_run_steps: unknown inject_mode");
     }
+    if ((rp->route_time_out || rp->hop_out) && !rp->metrics)
+        return fail(RLR_E_INVALID, "rlr_run_steps: route_time_out / hop_out need the metrics record buffer");
     if ((long long)rp->clock0 + n_steps > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: clock overflows int32");
     RLR_CUDA(cudaSetDevice(h->device));
     StepParams p;
@@ -1024,6 +1042,12 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     if (blocks > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: too many blocks");
     h->kernel<<<(unsigned)blocks, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p);
     RLR_CUDA(cudaGetLastError());
+    if (rp->route_time_out || rp->hop_out) {
+        const long long n = n_steps * h->R;
+        const int rb = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+        rlr_ratio_kernel<<<rb, 256, 0, (cudaStream_t)stream>>>((const uint4 *)rp->metrics, n, rp->route_time_out, rp->hop_out);
+        RLR_CUDA(cudaGetLastError());
+    }
     return RLR_OK;
 }
 

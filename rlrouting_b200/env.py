@@ -15,7 +15,7 @@ from collections import OrderedDict
 import numpy as np
 
 from . import _native as nat
-from . import nets, trace
+from . import nets, pinned, trace
 from .base_policy import Policy
 from .topology import Topology
 
@@ -165,6 +165,12 @@ class Network:
         self._handles.append(h)
         return h
 
+    def _copy_stream(self):
+        import torch
+        if getattr(self, "_copier", None) is None:
+            self._copier = torch.cuda.Stream(device=self.device)
+        return self._copier
+
     def launch_info(self):
         h = getattr(self._agent, "_handle", None)
         if h is None:
@@ -242,7 +248,9 @@ class Network:
         The legacy call `train(T, lambd=l, lrq=.., lrp=..)` (reference train.py:52) returns the tuple
         (route_time, drop_rate) instead.
         """
+        import time
         import torch
+        _t = [time.perf_counter()]
         if slot != 1 or freq != 1:
             raise NotImplementedError("slot != 1 / freq != 1 (SURVEY §8 row f2) are not implemented on the device")
         agent = self._agent
@@ -260,12 +268,13 @@ class Network:
         lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (R,)) * slot
         if per_step is None:
             per_step = R * T <= (1 << 26)
-        result = {"route_time": np.zeros((R, T) if per_step else (R, 1))}
-        if droprate:
-            result["droprate"] = np.zeros_like(result["route_time"])
-        if hop:
-            result["hop"] = np.zeros_like(result["route_time"])
+        result = {}
         if T == 0:
+            result["route_time"] = np.zeros((R, 0))
+            if droprate:
+                result["droprate"] = np.zeros((R, 0))
+            if hop:
+                result["hop"] = np.zeros((R, 0))
             return self._finish(result, legacy, R)
 
         rp = nat.RunParams()
@@ -305,9 +314,17 @@ class Network:
             keep += [enlam, thr]
             h2d += R * 16
 
+        # Launch in chunks and stream each chunk's per-step vectors to pinned host memory on a side stream
+        # while the next chunk computes, so the device->host copy of [R, T] doubles hides behind the kernel.
         if steps_per_launch is None:
-            steps_per_launch = T if not per_step else max(1, min(T, (1 << 25) // R))
-        log_chunks, met_chunks = [], []
+            steps_per_launch = T if not per_step else max(1, min(max(-(-T // 4), 32), (1 << 25) // R))
+        _t.append(time.perf_counter())
+        compute = torch.cuda.current_stream(dev)
+        copier = self._copy_stream()
+        # results land in pooled page-locked buffers handed out zero-copy (rlrouting_b200.pinned)
+        host_rt, out_rt = pinned.POOL.take((T, R)) if per_step else (None, None)       # step-major
+        host_hop, out_hop = pinned.POOL.take((T, R)) if (per_step and hop) else (None, None)
+        log_chunks = []
         s0 = 0
         stream = self._stream_ptr()
         while s0 < T:
@@ -317,37 +334,53 @@ class Network:
                 rp.inj_off = d_off.data_ptr()
                 keep.append(d_off)
             rp.clock0 = self.clock + s0
-            met = torch.empty((R, K, 2), dtype=torch.int64, device=dev) if per_step else None
-            rp.metrics = met.data_ptr() if met is not None else None
+            d_rec = torch.empty((K, R, 2), dtype=torch.int64, device=dev) if per_step else None
+            rp.metrics = d_rec.data_ptr() if d_rec is not None else None
+            d_rt = torch.empty((K, R), dtype=torch.float64, device=dev) if per_step else None
+            d_hop = torch.empty((K, R), dtype=torch.float64, device=dev) if host_hop is not None else None
+            rp.route_time_out = d_rt.data_ptr() if d_rt is not None else None
+            rp.hop_out = d_hop.data_ptr() if d_hop is not None else None
             log = torch.empty((R, K, N), dtype=torch.int32, device=dev) if sendlog else None
             rp.sendlog = log.data_ptr() if log is not None else None
             nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), stream))
             self.launch_count += 1
             if per_step:
-                met_chunks.append(met)
+                done = torch.cuda.Event()
+                done.record(compute)
+                copier.wait_event(done)
+                with torch.cuda.stream(copier):
+                    host_rt[s0:s0 + K].copy_(d_rt, non_blocking=True)          # contiguous rows on both sides
+                    d_rt.record_stream(copier)
+                    if d_hop is not None:
+                        host_hop[s0:s0 + K].copy_(d_hop, non_blocking=True)
+                        d_hop.record_stream(copier)
             if log is not None:
                 log_chunks.append(log)
             s0 += K
         self.clock += T
-        status = self._status.cpu().numpy()                     # device -> host: synchronises the stream
+        _t.append(time.perf_counter())
+        status = self._status.cpu().numpy()                     # device -> host: synchronises the compute stream
+        _t.append(time.perf_counter())
+        copier.synchronize()
+        _t.append(time.perf_counter())
+        self.last_timing = {"setup_ms": 1e3 * (_t[1] - _t[0]), "issue_ms": 1e3 * (_t[2] - _t[1]),
+                            "wait_compute_ms": 1e3 * (_t[3] - _t[2]), "wait_copy_ms": 1e3 * (_t[4] - _t[3])}
         self._raise_on_status(status)
         self.last_h2d_bytes = h2d
-        self.last_d2h_bytes = status.nbytes + (R * T * 16 if per_step else R * nat.NUM_COUNTERS * 8) + \
-            (R * T * N * 4 if sendlog else 0)
+        self.last_d2h_bytes = status.nbytes + (R * T * 8 * (2 if host_hop is not None else 1) if per_step
+                                               else R * nat.NUM_COUNTERS * 8) + (R * T * N * 4 if sendlog else 0)
         if per_step:
-            m = torch.cat(met_chunks, dim=1).cpu().numpy()      # [R, T, 2] int64
-            rt = m[:, :, 0]
-            end = (m[:, :, 1] & 0xFFFFFFFF).astype(np.int64)
-            hops = ((m[:, :, 1] >> 32) & 0xFFFFFFFF).astype(np.int64)
+            result["route_time"] = out_rt.T                                    # [R, T] view; env.py:409, 444-446
+            if hop:
+                result["hop"] = out_hop.T                                      # env.py:412-413, 440-442
         else:
             c = self._counters.cpu().numpy()
             rt, end, hops = c[:, 4:5], c[:, 1:2], c[:, 3:4]
-        with np.errstate(divide="ignore", invalid="ignore"):
-            result["route_time"] = np.where(end > 0, rt / np.maximum(end, 1), 0.0)     # env.py:444-446
+            result["route_time"] = np.where(end > 0, rt / np.maximum(end, 1), 0.0)
             if hop:
-                result["hop"] = np.where(end > 0, hops / np.maximum(end, 1), 0.0)      # env.py:440-442
-        if droprate:
-            result["droprate"] = np.zeros_like(result["route_time"])                    # is_drop is off: env.py:448-450
+                result["hop"] = np.where(end > 0, hops / np.maximum(end, 1), 0.0)
+        if droprate:                                                                    # is_drop is off: env.py:448-450
+            result["droprate"] = np.broadcast_to(np.zeros((R, 1)), result["route_time"].shape)
         if sendlog:
             self.last_sendlog = torch.cat(log_chunks, dim=1).cpu().numpy().view(np.uint32)
         return self._finish(result, legacy, R)
@@ -372,7 +405,7 @@ class Network:
             self._resident["inj_thr"] = torch.from_numpy(injection_threshold(en_host).view(np.int64)).to(self.device)
             self._resident["enlam_key"] = key
         if self._resident.get("metrics_shape") != (R, K):
-            self._resident["metrics"] = torch.empty((R, K, 2), dtype=torch.int64, device=self.device)
+            self._resident["metrics"] = torch.empty((K, R, 2), dtype=torch.int64, device=self.device)
             self._resident["metrics_shape"] = (R, K)
         lrd = dict(getattr(agent, "_lr_default", {}))
         lrd.update(lr or {})
