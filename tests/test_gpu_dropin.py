@@ -1,0 +1,92 @@
+"""The reference's own script flow (train.py:8-57) against the drop-in modules in rlrouting_b200/compat,
+checked against the reference's known answers (tests/golden/kat.json)."""
+import os
+import pickle
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import load_cases
+
+pytestmark = pytest.mark.gpu
+COMPAT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rlrouting_b200", "compat")
+
+
+@pytest.fixture()
+def compat_path():
+    sys.path.insert(0, COMPAT)
+    saved = {m: sys.modules.pop(m, None) for m in ("env", "config", "qroute", "shortest", "hybrid", "multi_agent", "base_policy")}
+    yield
+    sys.path.remove(COMPAT)
+    for m, v in saved.items():
+        sys.modules.pop(m, None)
+        if v is not None:
+            sys.modules[m] = v
+
+
+def test_reference_script_flow_config1(compat_path, tmp_path):
+    """BASELINE config 1 through the reference's module names, its global-seed convention and the legacy calls
+    train.py makes (bind, clean, train(..., lrq=, lrp=) -> tuple, store)."""
+    ns = {}
+    exec("from env import *\nfrom config import *\nfrom shortest import Shortest\nfrom qroute import Qroute\n"
+         "from hybrid import HybridQ\nfrom multi_agent import MaHybridQ\n", ns)
+    np.random.seed(1)                                   # train.py:15
+    nw = ns["Network"]("6x6.net")                       # train.py:21
+    agent = ns["Qroute"](nw)
+    nw.bind(agent)                                      # train.py:39
+    nw.clean()                                          # train.py:51
+    route_time, drop_rate = nw.train(10000, lambd=2.0, lrq=0.1, lrp=0.001)     # train.py:52
+    exp = load_cases()[0]["expect"]
+    assert route_time.shape == (10000,) and drop_rate.shape == (10000,)
+    assert route_time[-1] == exp["ave_route_time"] == 2081.741862022773
+    assert (nw.all_packets, nw.end_packets, nw.route_time, nw.hops, nw.active_packets) == (19934, 14930, 31080406, 243694, 5004)
+    assert nw.ave_route_time == exp["ave_route_time"] and nw.drop_rate == 0
+    assert float(sum(v.sum() for v in agent.Qtable.values())) == pytest.approx(-3395208.639115376, rel=1e-12)
+    import pandas as pd
+    assert pd.DataFrame({2.0: route_time}).shape == (10000, 1)                  # train.py:56
+    # checkpoint interchange (base_policy.py:57-66): same pickle keys and array shapes as the reference
+    path = tmp_path / "q.pkl"
+    agent.store(str(path))
+    blob = pickle.load(open(path, "rb"))
+    assert set(blob) == {"links", "Qtable", "discount", "threshold"}
+    assert all(blob["Qtable"][x].shape == (36, len(nw.links[x])) for x in range(36))
+    fresh = ns["Qroute"](nw)
+    fresh.load(str(path))
+    assert all(np.array_equal(fresh.Qtable[x], agent.Qtable[x]) for x in range(36))
+    assert agent.choose(0, 35) in nw.links[0]
+    # nodes / queues are readable like the reference's objects
+    assert sum(len(nw.nodes[x].queue) for x in range(36)) == nw.active_packets
+
+
+def test_load_sweep_with_clean_between_levels(compat_path):
+    """train.py:43-52: one agent, loads swept with nw.clean() in between (tables carry over, env resets)."""
+    from env import Network
+    from shortest import Shortest
+    np.random.seed(1)
+    nw = Network("6x6.net")
+    nw.agent = Shortest(nw)
+    finals = {}
+    for l in (1.0, 2.0):
+        nw.clean()
+        rt, _ = nw.train(10000, lambd=l, lrq=0.1, lrp=0.001)
+        finals[l] = rt[-1]
+    # load 1.0 from a fresh seed is golden case 6 (5.4241584158415845); load 2.0 continues the same stream
+    assert finals[1.0] == load_cases()[6]["expect"]["ave_route_time"]
+    assert 5.0 < finals[2.0] < 30.0
+
+
+def test_unsupported_policies_and_calls_raise(compat_path):
+    from base_policy import Policy
+    from env import Network
+    nw = Network("6x6.net")
+
+    class Mine(Policy):
+        def choose(self, source, dest):
+            return self.links[source][0]
+    with pytest.raises(NotImplementedError):
+        nw.agent = Mine(nw)
+    with pytest.raises(NotImplementedError):
+        nw.train(10, 1.0)                       # no device policy bound
+    with pytest.raises(NotImplementedError):
+        nw.step(1)
