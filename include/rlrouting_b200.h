@@ -42,7 +42,7 @@ enum { RLR_POLICY_SHORTEST = 0, RLR_POLICY_QROUTE = 1, RLR_POLICY_HYBRIDQ = 2, R
 enum { RLR_INJECT_TRACE = 0, RLR_INJECT_PHILOX = 1 };
 
 /* Sticky per-replica status codes (status[2*r] = code, status[2*r+1] = clock of the first event). */
-enum { RLR_STATUS_OK = 0, RLR_STATUS_NAN_PROB = 1, RLR_STATUS_QUEUE_OVERFLOW = 2 };
+enum { RLR_STATUS_OK = 0, RLR_STATUS_NAN_PROB = 1, RLR_STATUS_QUEUE_OVERFLOW = 2, RLR_STATUS_INJECT_OVERFLOW = 3 };
 
 /* Per-replica counters, int64 each (Network attributes, env.py:267-276 / 321-331). */
 enum {
@@ -96,12 +96,14 @@ typedef struct {
 typedef struct {
     int32_t inject_mode;      /* RLR_INJECT_*                                                */
     int32_t add_entropy;      /* HybridQ(add_entropy=...)  hybrid.py:44                      */
-    /* trace mode (device pointers): injections of replica r at local step s are
-     * inj_pairs[inj_base[r] + inj_off[r*(n_steps+1) + s] .. + inj_off[r*(n_steps+1) + s+1])
-     * each packed as source | dest << 16 */
-    const int32_t *inj_off;
-    const int64_t *inj_base;
-    const uint32_t *inj_pairs;
+    /* Injection schedule, device [R][N][inj_cap] uint32: for each (replica, node) the ascending list of its
+     * injections over this call, one entry (local_step << 8 | dest) per packet, terminated by 0xFFFFFFFF.
+     * RLR_INJECT_TRACE: filled by the caller from the host replay of env.py:307-310.
+     * RLR_INJECT_PHILOX: scratch filled by the library (rlr_inject_schedule_kernel) from enlam / inj_thr / seed;
+     *   a node with more than inj_cap - 1 injections sets RLR_STATUS_INJECT_OVERFLOW. */
+    uint32_t *inj_events;
+    int32_t inj_cap;
+    int32_t reserved0;
     /* Philox mode */
     const double *enlam;      /* device [R]: exp(-lambda_r / N)                              */
     const uint64_t *inj_thr;  /* device [R]: smallest w in [0, 2^32] with (w + 0.5) * 2^-32 > enlam[r] */

@@ -19,7 +19,7 @@ NUM_COUNTERS = 8
 CTR = {"all_packets": 0, "end_packets": 1, "drop_packets": 2, "hops": 3, "route_time": 4, "sends": 5}
 POLICY_SHORTEST, POLICY_QROUTE, POLICY_HYBRIDQ, POLICY_MAHYBRIDQ = 0, 1, 2, 3
 INJECT_TRACE, INJECT_PHILOX = 0, 1
-STATUS_OK, STATUS_NAN_PROB, STATUS_QUEUE_OVERFLOW = 0, 1, 2
+STATUS_OK, STATUS_NAN_PROB, STATUS_QUEUE_OVERFLOW, STATUS_INJECT_OVERFLOW = 0, 1, 2, 3
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false", "-Xcompiler", "-fPIC", "-shared"]
@@ -56,7 +56,7 @@ class Buffers(C.Structure):
 
 class RunParams(C.Structure):
     _fields_ = [("inject_mode", C.c_int32), ("add_entropy", C.c_int32),
-                ("inj_off", C.c_void_p), ("inj_base", C.c_void_p), ("inj_pairs", C.c_void_p),
+                ("inj_events", C.c_void_p), ("inj_cap", C.c_int32), ("reserved0", C.c_int32),
                 ("enlam", C.c_void_p), ("inj_thr", C.c_void_p), ("seed", C.c_uint64),
                 ("lr_q", C.c_double), ("lr_p", C.c_double), ("lr_e", C.c_double),
                 ("discount", C.c_double), ("discount_trace", C.c_double),

@@ -65,12 +65,8 @@ struct StepParams {
     unsigned *qhead, *qtail;
     long long *counters;
     int *status;
-    int inject_mode, add_entropy;
-    const int *inj_off;
-    const long long *inj_base;
-    const unsigned *inj_pairs;
-    const double *enlam;
-    const unsigned long long *inj_thr;
+    int inj_cap, add_entropy;
+    const unsigned *inj_events;
     unsigned long long seed;
     long long replica_base;
     double lr_q, lr_p, lr_e, discount, discount_trace;
@@ -356,7 +352,6 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     bool use_fresh = false;
     uint4 *myring = nullptr;
     int rp = 0, deg = 0;
-    double enlam = 0.0;
     unsigned my_sends = 0, my_inj = 0;
     long long base_rt = 0, base_end = 0, base_hops = 0;
     double *Qx = nullptr, *Thx = nullptr, *Trx = nullptr;          // table[x] of this node
@@ -372,7 +367,6 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             Thx = Thr ? Thr + (long long)N * rp : nullptr;
             Trx = Trr ? Trr + (long long)N * rp : nullptr;
         }
-        if (p.inject_mode == RLR_INJECT_PHILOX) enlam = p.enlam[r];
         if (x == N - 1) {                      // the last node's thread keeps the per-step metric record
             base_rt = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_ROUTE_TIME];
             base_end = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_END_PACKETS];
@@ -393,8 +387,9 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         nb_slot[j] = (unsigned)(gbase + z);
         nb_word[j] = (unsigned)(((gbase + z) >> 5) - wlo);
     }
-    unsigned long long inj_thr = ~0ull;
-    if (is_node && p.inject_mode == RLR_INJECT_PHILOX) inj_thr = p.inj_thr[r];
+    // injection schedule of this node: events (local step << 8 | dest), ascending, 0xFFFFFFFF-terminated
+    const unsigned *evp = p.inj_events + ((size_t)(is_node ? r : 0) * N + (is_node ? x : 0)) * (size_t)p.inj_cap;
+    unsigned ev = is_node ? evp[0] : 0xFFFFFFFFu;
     bool dead = is_node ? (s_dead[g] != 0u) : true;                 // only sampled policies can die mid-launch
     unsigned *sendlog = (p.sendlog && is_node) ? p.sendlog + r * (long long)p.K * N + x : nullptr;
 
@@ -415,39 +410,11 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         double oldq = 0.0, max_qy = 0.0, max_qxd = 0.0, rwd = 0.0;
         double sm[MAXD];
         if (live) {
-            // ---- A. new_packet + inject (env.py:298-319) ----
-            if (p.inject_mode == RLR_INJECT_PHILOX) {
-                // Poisson(lambda/N) by the multiplication method.  The first uniform u0 = (w0 + 0.5) * 2^-32 gives
-                // n >= 1 iff u0 > exp(-lambda/N) iff w0 >= inj_thr (threshold computed exactly on the host), so the
-                // common n == 0 case is one integer compare; the rest continues in fp64 exactly like the oracle.
-                PhiloxStream ps(p.seed, stream_id, clock, x, 0);
-                const unsigned w0 = ps.next();
-                if ((unsigned long long)w0 >= inj_thr) {
-                    int n = 1;
-                    double prod = __dmul_rn(__dadd_rn((double)w0, 0.5), 1.0 / 4294967296.0);
-                    for (;;) {
-                        const double u = __dmul_rn(__dadd_rn((double)ps.next(), 0.5), 1.0 / 4294967296.0);
-                        prod = __dmul_rn(prod, u);
-                        if (prod > enlam) ++n; else break;
-                    }
-                    for (int i = 0; i < n; ++i) {
-                        unsigned dd = __umulhi(ps.next(), (unsigned)(N - 1));
-                        if (dd >= (unsigned)x) ++dd;
-                        append(make_uint4(dd | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock));
-                    }
-                    my_inj += n;
-                }
-            } else {
-                const int *off = p.inj_off + r * (long long)(p.K + 1) + s;
-                const int o0 = off[0], o1 = off[1];
-                const unsigned *pairs = p.inj_pairs + p.inj_base[r];
-                for (int i = o0; i < o1; ++i) {
-                    const unsigned pr = pairs[i];
-                    if ((int)(pr & 0xFFFFu) == x) {
-                        append(make_uint4((pr >> 16) | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock));
-                        ++my_inj;
-                    }
-                }
+            // ---- A. new_packet + inject (env.py:298-319): consume this step's events of the schedule ----
+            while ((ev >> 8) == (unsigned)s) {
+                append(make_uint4((ev & 0xFFu) | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock));
+                ++my_inj;
+                ev = *++evp;
             }
             // ---- B. Node._send_default (env.py:162-191): pop the head, choose, get_info ----
             if (head != tail) {
@@ -792,6 +759,48 @@ __global__ void rlr_reduce_stats_kernel(const long long *counters, long long R, 
         atomicAdd((unsigned long long *)&out[threadIdx.x], (unsigned long long)acc[threadIdx.x]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Injection schedule (Philox mode): Network.new_packet (env.py:298-312) for K steps, one thread per
+// (replica, node).  Poisson splitting: node x draws n ~ Poisson(lambda/N) by NumPy's multiplication method
+// (count uniforms until their product <= exp(-lambda/N)); the first uniform u0 = (w0 + 0.5) * 2^-32 gives
+// n >= 1 iff w0 >= thr (threshold computed exactly on the host), so the common n == 0 case is one integer
+// compare; each packet's destination is uniform over the other N-1 nodes.  Same word stream as the oracle.
+// Output: per (replica, node) an ascending list of events (local step << 8 | dest), 0xFFFFFFFF-terminated.
+// ------------------------------------------------------------------------------------------------
+__global__ void rlr_inject_schedule_kernel(unsigned *events, int cap, long long R, int N, int K, int clock0,
+                                           const double *enlam, const unsigned long long *thr, unsigned long long seed,
+                                           long long replica_base, int *status)
+{
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= R * N) return;
+    const long long r = idx / N;
+    const int x = (int)(idx - r * N);
+    const double en = enlam[r];
+    const unsigned long long th = thr[r];
+    unsigned *ev = events + idx * cap;
+    int n_ev = 0;
+    bool overflow = false;
+    for (int s = 0; s < K; ++s) {
+        PhiloxStream ps(seed, (unsigned long long)(replica_base + r), clock0 + s, x, 0);
+        const unsigned w0 = ps.next();
+        if ((unsigned long long)w0 < th) continue;
+        int n = 1;
+        double prod = __dmul_rn(__dadd_rn((double)w0, 0.5), 1.0 / 4294967296.0);
+        for (;;) {
+            const double u = __dmul_rn(__dadd_rn((double)ps.next(), 0.5), 1.0 / 4294967296.0);
+            prod = __dmul_rn(prod, u);
+            if (prod > en) ++n; else break;
+        }
+        for (int i = 0; i < n; ++i) {
+            unsigned dd = __umulhi(ps.next(), (unsigned)(N - 1));
+            if (dd >= (unsigned)x) ++dd;
+            if (n_ev < cap - 1) ev[n_ev++] = ((unsigned)s << 8) | dd; else overflow = true;
+        }
+    }
+    ev[n_ev] = 0xFFFFFFFFu;
+    if (overflow) set_status(status, r, RLR_STATUS_INJECT_OVERFLOW, clock0);
+}
+
 // ave_route_time / ave_hops after each step (env.py:440-446): route_time / end_packets if end_packets > 0 else 0.
 // IEEE division of two exactly converted integers is Python's correctly rounded int / int.
 __global__ void rlr_ratio_kernel(const uint4 *metrics, long long n, double *route_time_out, double *hop_out)
@@ -1013,13 +1022,13 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     if (!rp) return fail(RLR_E_INVALID, "rlr_run_steps: null params");
     if (n_steps < 0 || n_steps > (1 << 30)) return fail(RLR_E_INVALID, "rlr_run_steps: n_steps out of range");
     if (n_steps == 0) return RLR_OK;
-    if (rp->inject_mode == RLR_INJECT_TRACE) {
-        if (!rp->inj_off || !rp->inj_base || !rp->inj_pairs) return fail(RLR_E_INVALID, "rlr_run_steps: trace mode needs inj_off, inj_base, inj_pairs");
-    } else if (rp->inject_mode == RLR_INJECT_PHILOX) {
+    if (!rp->inj_events || rp->inj_cap < 2) return fail(RLR_E_INVALID, "rlr_run_steps: inj_events / inj_cap are required");
+    if (rp->inject_mode == RLR_INJECT_PHILOX) {
         if (!rp->enlam || !rp->inj_thr) return fail(RLR_E_INVALID, "rlr_run_steps: Philox mode needs enlam and inj_thr");
-    } else {
+    } else if (rp->inject_mode != RLR_INJECT_TRACE) {
         return fail(RLR_E_INVALID, "rlr_run_steps: unknown inject_mode");
     }
+    if (n_steps >= (1 << 24) - 1) return fail(RLR_E_INVALID, "rlr_run_steps: at most 2^24 - 2 steps per call");
     if ((rp->route_time_out || rp->hop_out) && !rp->metrics)
         return fail(RLR_E_INVALID, "rlr_run_steps: route_time_out / hop_out need the metrics record buffer");
     if ((long long)rp->clock0 + n_steps > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: clock overflows int32");
@@ -1033,11 +1042,17 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     p.Q = h->bufs.q_table; p.Theta = h->bufs.theta; p.Trace = h->bufs.trace;
     p.ring = (uint4 *)h->bufs.ring; p.qhead = h->bufs.q_head; p.qtail = h->bufs.q_tail;
     p.counters = (long long *)h->bufs.counters; p.status = h->bufs.status;
-    p.inject_mode = rp->inject_mode; p.add_entropy = rp->add_entropy;
-    p.inj_off = rp->inj_off; p.inj_base = (const long long *)rp->inj_base; p.inj_pairs = rp->inj_pairs;
-    p.enlam = rp->enlam; p.inj_thr = (const unsigned long long *)rp->inj_thr; p.seed = rp->seed; p.replica_base = h->replica_base;
+    p.inj_cap = rp->inj_cap; p.add_entropy = rp->add_entropy;
+    p.inj_events = rp->inj_events; p.seed = rp->seed; p.replica_base = h->replica_base;
     p.lr_q = rp->lr_q; p.lr_p = rp->lr_p; p.lr_e = rp->lr_e; p.discount = rp->discount; p.discount_trace = rp->discount_trace;
     p.metrics = (uint4 *)rp->metrics; p.sendlog = rp->sendlog;
+    if (rp->inject_mode == RLR_INJECT_PHILOX) {
+        const long long nthr = h->R * h->N;
+        rlr_inject_schedule_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+            rp->inj_events, rp->inj_cap, h->R, h->N, (int)n_steps, rp->clock0, rp->enlam,
+            (const unsigned long long *)rp->inj_thr, rp->seed, h->replica_base, h->bufs.status);
+        RLR_CUDA(cudaGetLastError());
+    }
     const long long blocks = (h->R + h->G - 1) / h->G;
     if (blocks > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: too many blocks");
     h->kernel<<<(unsigned)blocks, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p);

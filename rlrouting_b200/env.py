@@ -73,6 +73,23 @@ def injection_threshold(enlam):
     return (np.floor((e - 1.0) / 2.0) + 1.0).clip(0.0, 4294967296.0).astype(np.uint64)
 
 
+def schedule_capacity(lam_max, n_nodes, n_steps):
+    """Entries per (replica, node) of a Philox-mode injection schedule: the Poisson(lambda/N * steps) count of
+    one node, its mean plus 12 standard deviations plus slack (overflow probability < 1e-30), + terminator."""
+    m = float(lam_max) / n_nodes * n_steps
+    return int(m + 12.0 * np.sqrt(m) + 24) + 1
+
+
+def trace_schedule(cnt, pairs, n_nodes, s0, s1):
+    """Per-node event lists of steps [s0, s1) of one replica's trace: (events[int], node_of_event[int]) with
+    events = (local_step << 8 | dest) in (node, step, draw order)."""
+    steps = np.repeat(np.arange(len(cnt), dtype=np.int64), cnt)
+    sel = (steps >= s0) & (steps < s1)
+    src, dst, st = pairs[sel, 0].astype(np.int64), pairs[sel, 1].astype(np.int64), steps[sel] - s0
+    order = np.argsort(src, kind="stable")                       # stable: keeps (step, draw) order inside a node
+    return ((st[order] << 8) | dst[order]).astype(np.uint32), src[order]
+
+
 def _floor_pow2(v):
     return 1 << (int(v).bit_length() - 1)
 
@@ -164,6 +181,14 @@ class Network:
         nat.check(nat.lib().rlr_bind_buffers(h, C.byref(b)))
         self._handles.append(h)
         return h
+
+    def _scratch(self, tag, shape, dtype):
+        """Device scratch buffers reused across calls (PyTorch-owned, lent to the C layer)."""
+        import torch
+        buf = self._resident.get(tag)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+            buf = self._resident[tag] = torch.empty(shape, dtype=dtype, device=self.device)
+        return buf
 
     def _copy_stream(self):
         import torch
@@ -285,26 +310,10 @@ class Network:
         rp.seed = self.seed
         keep = []
         h2d = 0
+        traces = None
         if self.rng == "trace":
             rp.inject_mode = nat.INJECT_TRACE
-            offs = np.zeros((R, T + 1), dtype=np.int64)
-            pairs = []
-            for r in range(R):
-                cnt, pr = trace.draw_injections(self._rs[r], N, T, lam[r])
-                offs[r, 1:] = np.cumsum(cnt)
-                pairs.append((pr[:, 0].astype(np.uint32) | (pr[:, 1].astype(np.uint32) << 16)))
-            base = np.zeros(R, dtype=np.int64)
-            base[1:] = np.cumsum([len(p) for p in pairs])[:-1]
-            flat = np.concatenate(pairs) if pairs else np.zeros(0, dtype=np.uint32)
-            if flat.size == 0:
-                flat = np.zeros(1, dtype=np.uint32)
-            if int(offs.max()) >= 2 ** 31:
-                raise OverflowError("too many injections per replica for int32 offsets")
-            d_pairs = torch.from_numpy(flat.view(np.int32)).to(dev)
-            d_base = torch.from_numpy(base).to(dev)
-            rp.inj_base, rp.inj_pairs = d_base.data_ptr(), d_pairs.data_ptr()
-            keep += [d_pairs, d_base]
-            h2d += flat.nbytes + base.nbytes + R * (T + 1) * 4
+            traces = [trace.draw_injections(self._rs[r], N, T, lam[r]) for r in range(R)]
         else:
             rp.inject_mode = nat.INJECT_PHILOX
             en_host = np.exp(-lam / np.float64(N))
@@ -329,10 +338,21 @@ class Network:
         stream = self._stream_ptr()
         while s0 < T:
             K = min(steps_per_launch, T - s0)
-            if self.rng == "trace":
-                d_off = torch.from_numpy(np.ascontiguousarray(offs[:, s0:s0 + K + 1]).astype(np.int32)).to(dev)
-                rp.inj_off = d_off.data_ptr()
-                keep.append(d_off)
+            if traces is not None:                      # host replay of env.py:307-310 -> per-node event lists
+                evs = [trace_schedule(c, pr, N, s0, s0 + K) for c, pr in traces]
+                per_node = [np.bincount(node, minlength=N) for _, node in evs]
+                cap = int(max(pn.max() for pn in per_node)) + 1
+                sched = np.full((R, N, cap), 0xFFFFFFFF, dtype=np.uint32)
+                for r, ((e, node), pn) in enumerate(zip(evs, per_node)):
+                    start = np.concatenate([[0], np.cumsum(pn)[:-1]])
+                    sched[r, node, np.arange(len(e)) - start[node]] = e
+                d_sched = torch.from_numpy(sched.view(np.int32)).to(dev)
+                h2d += sched.nbytes
+            else:                                       # scratch for the device's Philox schedule kernel
+                cap = schedule_capacity(lam.max(), N, K)
+                d_sched = self._scratch("sched", (R, N, cap), torch.int32)
+            rp.inj_events, rp.inj_cap = d_sched.data_ptr(), cap
+            keep.append(d_sched)
             rp.clock0 = self.clock + s0
             d_rec = torch.empty((K, R, 2), dtype=torch.int64, device=dev) if per_step else None
             rp.metrics = d_rec.data_ptr() if d_rec is not None else None
@@ -418,6 +438,8 @@ class Network:
         rp.seed = self.seed
         rp.enlam = self._resident["enlam"].data_ptr()
         rp.inj_thr = self._resident["inj_thr"].data_ptr()
+        cap = schedule_capacity(lam.max(), N, K)
+        rp.inj_events, rp.inj_cap = self._scratch("sched", (R, N, cap), torch.int32).data_ptr(), cap
         rp.clock0 = self.clock
         rp.metrics = self._resident["metrics"].data_ptr()
         nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), self._stream_ptr()))
@@ -449,6 +471,9 @@ class Network:
         code, clk = int(status[r, 0]), int(status[r, 1])
         if code == nat.STATUS_NAN_PROB:
             raise ValueError(f"probabilities contain NaN (replica {r}, clock {clk}; {bad.size} replica(s) affected)")
+        if code == nat.STATUS_INJECT_OVERFLOW:
+            raise OverflowError(f"injection schedule overflow (replica {r}, clock {clk}): more packets at one node "
+                                "than the schedule buffer holds")
         raise OverflowError(f"queue ring overflow (replica {r}, clock {clk}; {bad.size} replica(s) affected): the "
                             f"reference's queues are unbounded; re-run with queue_capacity > {self.queue_capacity}")
 

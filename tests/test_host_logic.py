@@ -110,3 +110,17 @@ def test_sharding_covers_every_replica_once():
                 assert b0 + c0 == b1
     base, lam, idx = dist.shard_loads([1.0, 2.0, 3.0, 4.0], 6, 1, 4)
     assert base == 6 and list(lam) == [2.0] * 6 and list(idx) == [1] * 6
+
+
+def test_trace_schedule_orders_events_per_node():
+    from rlrouting_b200.env import schedule_capacity, trace_schedule
+    from rlrouting_b200 import trace
+    rs = np.random.RandomState(3)
+    cnt, pairs = trace.draw_injections(rs, 36, 400, 3.0)
+    ev, node = trace_schedule(cnt, pairs, 36, 100, 300)
+    steps = np.repeat(np.arange(400), cnt)
+    for x in range(36):
+        want = [((s - 100) << 8) | d for s, (src, d) in zip(steps, pairs) if src == x and 100 <= s < 300]
+        assert list(ev[node == x]) == want                       # (step, draw) order inside the node
+    assert len(ev) == int(((steps >= 100) & (steps < 300)).sum())
+    assert schedule_capacity(4.0, 36, 500) > 4.0 / 36 * 500 + 40
