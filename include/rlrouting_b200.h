@@ -154,6 +154,11 @@ int rlr_init_tables(rlr_handle_t *h, double initP, void *stream);
  *      choice and next_hop ---- */
 int rlr_build_shortest_tables(rlr_handle_t *h, void *stream);
 
+/* ---- Network.new_packet (env.py:298-312) for n_steps steps ahead of time, Philox mode: fills params->inj_events
+ *      from enlam / inj_thr / seed / clock0.  rlr_run_steps does this itself for RLR_INJECT_PHILOX; calling it
+ *      separately (on another stream, then running with RLR_INJECT_TRACE) overlaps it with the previous chunk. ---- */
+int rlr_build_inject_schedule(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *params, void *stream);
+
 /* ---- the hot path: n_steps iterations of Network.train's loop body (env.py:400-413) with
  *      slot=1, freq=1: new_packet + inject, step (send phase + event drain), agent.learn ---- */
 int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *params, void *stream);

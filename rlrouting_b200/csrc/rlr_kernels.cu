@@ -1016,6 +1016,21 @@ int rlr_build_shortest_tables(rlr_handle_t *h, void *stream)
     return RLR_OK;
 }
 
+int rlr_build_inject_schedule(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, void *stream)
+{
+    if (!h || !h->bound) return fail(RLR_E_STATE, "rlr_build_inject_schedule: buffers not bound");
+    if (!rp || !rp->inj_events || rp->inj_cap < 2 || !rp->enlam || !rp->inj_thr)
+        return fail(RLR_E_INVALID, "rlr_build_inject_schedule: inj_events, inj_cap, enlam and inj_thr are required");
+    if (n_steps < 1 || n_steps >= (1 << 24) - 1) return fail(RLR_E_INVALID, "rlr_build_inject_schedule: n_steps out of range");
+    RLR_CUDA(cudaSetDevice(h->device));
+    const long long nthr = h->R * h->N;
+    rlr_inject_schedule_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        rp->inj_events, rp->inj_cap, h->R, h->N, (int)n_steps, rp->clock0, rp->enlam,
+        (const unsigned long long *)rp->inj_thr, rp->seed, h->replica_base, h->bufs.status);
+    RLR_CUDA(cudaGetLastError());
+    return RLR_OK;
+}
+
 int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, void *stream)
 {
     if (!h || !h->bound) return fail(RLR_E_STATE, "rlr_run_steps: buffers not bound");
@@ -1047,11 +1062,8 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     p.lr_q = rp->lr_q; p.lr_p = rp->lr_p; p.lr_e = rp->lr_e; p.discount = rp->discount; p.discount_trace = rp->discount_trace;
     p.metrics = (uint4 *)rp->metrics; p.sendlog = rp->sendlog;
     if (rp->inject_mode == RLR_INJECT_PHILOX) {
-        const long long nthr = h->R * h->N;
-        rlr_inject_schedule_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-            rp->inj_events, rp->inj_cap, h->R, h->N, (int)n_steps, rp->clock0, rp->enlam,
-            (const unsigned long long *)rp->inj_thr, rp->seed, h->replica_base, h->bufs.status);
-        RLR_CUDA(cudaGetLastError());
+        const int rc = rlr_build_inject_schedule(h, n_steps, rp, stream);
+        if (rc != RLR_OK) return rc;
     }
     const long long blocks = (h->R + h->G - 1) / h->G;
     if (blocks > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: too many blocks");

@@ -190,6 +190,70 @@ class Network:
             buf = self._resident[tag] = torch.empty(shape, dtype=dtype, device=self.device)
         return buf
 
+    # ---- Philox injection schedules, built one chunk ahead on a side stream (double-buffered) ----
+    def _schedule(self, h, rp, clock0, K, lam_key, lam_max, next_key=None):
+        """Points rp at the injection schedule of steps [clock0, clock0+K) (Network.new_packet ahead of time).
+        If the previous call prefetched it on the side stream the compute stream only waits for that event,
+        otherwise it is built in-stream.  Call _schedule_done after the step kernel has been enqueued."""
+        import torch
+        st = self.__dict__.get("_sched")
+        if st is None:
+            st = self._sched = {"bufs": [None, None], "ready": [None, None], "used": [None, None],
+                                "stream": torch.cuda.Stream(device=self.device)}
+        cap = schedule_capacity(lam_max, self.topology.N, K)
+        shape = (self.replicas, self.topology.N, cap)
+        key = (clock0, K, lam_key, cap)
+        compute = torch.cuda.current_stream(self.device)
+        slot = next((i for i in (0, 1) if st["ready"][i] is not None and st["ready"][i][0] == key), None)
+        if slot is not None:
+            compute.wait_event(st["ready"][slot][1])                 # prefetched by the previous call
+        else:
+            slot = 0
+            if st["ready"][slot] is not None:                        # a stale prefetch may still be writing this slot
+                compute.wait_event(st["ready"][slot][1])
+            self._sched_buf(st, slot, shape)
+            rp.inj_events, rp.inj_cap, rp.clock0 = st["bufs"][slot].data_ptr(), cap, clock0
+            nat.check(nat.lib().rlr_build_inject_schedule(h, K, C.byref(rp), self._stream_ptr()))
+        st["ready"][slot] = None
+        rp.inj_events, rp.inj_cap, rp.clock0 = st["bufs"][slot].data_ptr(), cap, clock0
+        rp.inject_mode = nat.INJECT_TRACE                            # "events provided"
+        self._sched_cur = (slot, next_key, lam_key, lam_max)
+
+    def _sched_buf(self, st, slot, shape):
+        import torch
+        b = st["bufs"][slot]
+        if b is None or tuple(b.shape) != tuple(shape):
+            if b is not None:
+                torch.cuda.synchronize(self.device)                  # shape change: nothing may still use the old buffer
+            st["bufs"][slot] = torch.empty(shape, dtype=torch.int32, device=self.device)
+        return st["bufs"][slot]
+
+    def _schedule_done(self, h, rp):
+        """The step kernel reading the current slot is enqueued: remember that, then prefetch the next chunk's
+        schedule into the other slot on the side stream so it overlaps with the step kernel."""
+        import torch
+        st = self._sched
+        slot, next_key, lam_key, lam_max = self._sched_cur
+        used = torch.cuda.Event()
+        used.record(torch.cuda.current_stream(self.device))
+        st["used"][slot] = used
+        if next_key is None:
+            return
+        clock0, K = next_key
+        other = 1 - slot
+        cap = schedule_capacity(lam_max, self.topology.N, K)
+        self._sched_buf(st, other, (self.replicas, self.topology.N, cap))
+        side = st["stream"]
+        if st["used"][other] is not None:
+            side.wait_event(st["used"][other])                       # the step kernel that last read that slot
+        rp2 = nat.RunParams()
+        C.memmove(C.byref(rp2), C.byref(rp), C.sizeof(nat.RunParams))
+        rp2.inj_events, rp2.inj_cap, rp2.clock0 = st["bufs"][other].data_ptr(), cap, clock0
+        nat.check(nat.lib().rlr_build_inject_schedule(h, K, C.byref(rp2), C.c_void_p(side.cuda_stream)))
+        done = torch.cuda.Event()
+        done.record(side)
+        st["ready"][other] = ((clock0, K, lam_key, cap), done)
+
     def _copy_stream(self):
         import torch
         if getattr(self, "_copier", None) is None:
@@ -316,6 +380,7 @@ class Network:
             traces = [trace.draw_injections(self._rs[r], N, T, lam[r]) for r in range(R)]
         else:
             rp.inject_mode = nat.INJECT_PHILOX
+            lam_key = lam.tobytes() if lam.strides[0] else float(lam[0])
             en_host = np.exp(-lam / np.float64(N))
             enlam = torch.from_numpy(en_host).to(dev)
             thr = torch.from_numpy(injection_threshold(en_host).view(np.int64)).to(dev)
@@ -348,12 +413,12 @@ class Network:
                     sched[r, node, np.arange(len(e)) - start[node]] = e
                 d_sched = torch.from_numpy(sched.view(np.int32)).to(dev)
                 h2d += sched.nbytes
-            else:                                       # scratch for the device's Philox schedule kernel
-                cap = schedule_capacity(lam.max(), N, K)
-                d_sched = self._scratch("sched", (R, N, cap), torch.int32)
-            rp.inj_events, rp.inj_cap = d_sched.data_ptr(), cap
-            keep.append(d_sched)
-            rp.clock0 = self.clock + s0
+                rp.inj_events, rp.inj_cap = d_sched.data_ptr(), cap
+                keep.append(d_sched)
+                rp.clock0 = self.clock + s0
+            else:                                       # device Philox schedule, prefetched one chunk ahead
+                nxt = (self.clock + s0 + K, min(steps_per_launch, T - s0 - K)) if s0 + K < T else None
+                self._schedule(h, rp, self.clock + s0, K, lam_key, lam.max(), nxt)
             d_rec = torch.empty((K, R, 2), dtype=torch.int64, device=dev) if per_step else None
             rp.metrics = d_rec.data_ptr() if d_rec is not None else None
             d_rt = torch.empty((K, R), dtype=torch.float64, device=dev) if per_step else None
@@ -364,6 +429,8 @@ class Network:
             rp.sendlog = log.data_ptr() if log is not None else None
             nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), stream))
             self.launch_count += 1
+            if traces is None:
+                self._schedule_done(h, rp)
             if per_step:
                 done = torch.cuda.Event()
                 done.record(compute)
@@ -438,12 +505,11 @@ class Network:
         rp.seed = self.seed
         rp.enlam = self._resident["enlam"].data_ptr()
         rp.inj_thr = self._resident["inj_thr"].data_ptr()
-        cap = schedule_capacity(lam.max(), N, K)
-        rp.inj_events, rp.inj_cap = self._scratch("sched", (R, N, cap), torch.int32).data_ptr(), cap
-        rp.clock0 = self.clock
         rp.metrics = self._resident["metrics"].data_ptr()
+        self._schedule(h, rp, self.clock, K, key[1], lam.max(), (self.clock + K, K))    # next call's schedule is prefetched
         nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), self._stream_ptr()))
         self.launch_count += 1
+        self._schedule_done(h, rp)
         self.clock += K
 
     @property
