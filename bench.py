@@ -281,6 +281,14 @@ def run_b200(a):
     if rank != 0:
         return
     peak, peak_src = measured_peak()
+    traffic = None
+    try:                                            # DRAM bytes per launch from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(f"{a.net}|{a.policy}|{R}|{sim}|{'smem' if info['tables_in_smem'] else 'hbm'}")
+        if t:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
     abytes, per_hop = algorithmic_bytes(a, nw.topology, hops, inj, world * R * sim * a.steps)
     per_launch = abytes / max(launches * world, 1)
     achieved = per_launch / (ms_total / a.steps * 1e-3) / 1e9        # GB/s per GPU (one launch per GPU per step)
@@ -295,7 +303,7 @@ def run_b200(a):
                    "hops_in_timed_region": hops, "mean_delivery_time": final["ave_route_time"],
                    "parallelism": f"replica-parallel x{world}, no data-path collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "rlr_step_kernel",
+                     "traffic": traffic, "algorithmic_bytes_per_launch": per_launch, "peak_source": peak_src, "kernel": "rlr_step_kernel",
                      "algorithmic_bytes_per_hop": per_hop,
                      "note": "algorithmic bytes per SURVEY 8(d); tables are staged in shared memory, so DRAM traffic is "
                              "far below the algorithmic figure (profiles/)"},
