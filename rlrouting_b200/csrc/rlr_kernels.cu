@@ -389,7 +389,9 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     }
     // injection schedule of this node: events (local step << 8 | dest), ascending, 0xFFFFFFFF-terminated
     const unsigned *evp = p.inj_events + ((size_t)(is_node ? r : 0) * N + (is_node ? x : 0)) * (size_t)p.inj_cap;
-    unsigned ev = is_node ? evp[0] : 0xFFFFFFFFu;
+    unsigned ev = is_node ? evp[0] : 0xFFFFFFFFu;                   // current event and the one after it: the list is
+    unsigned ev_next = (is_node && ev != 0xFFFFFFFFu) ? evp[1] : 0xFFFFFFFFu;    // read two entries ahead of its use
+    evp += 1;
     bool dead = is_node ? (s_dead[g] != 0u) : true;                 // only sampled policies can die mid-launch
     unsigned *sendlog = (p.sendlog && is_node) ? p.sendlog + r * (long long)p.K * N + x : nullptr;
 
@@ -414,7 +416,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             while ((ev >> 8) == (unsigned)s) {
                 append(make_uint4((ev & 0xFFu) | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock));
                 ++my_inj;
-                ev = *++evp;
+                ev = ev_next;
+                if (ev != 0xFFFFFFFFu) ev_next = *++evp;
             }
             // ---- B. Node._send_default (env.py:162-191): pop the head, choose, get_info ----
             if (head != tail) {
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 if (i == nw - 1) m &= mlast;
                 cum[i + 1] = cum[i] + __popc(m);
             }
-            const unsigned char *hp = s_heappos + cum[MAXW] * N;               // row k = number of senders
+            const unsigned hp_row = cum[MAXW] * (unsigned)N;                    // heap_pos row k = number of senders
             unsigned cumpack = 0;                                               // cum[0..3] as bytes (N <= 255)
             if (MAXW <= 3) cumpack = cum[0] | (cum[1] << 8) | (cum[2] << 16);
             // sort key per neighbour slot: heap pop position << 16 | send slot, or kNoKey
@@ -518,7 +521,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                     for (int i = 1; i < MAXW; ++i)
                         if (nb_word[j] == (unsigned)i) base = cum[i];
                 }
-                const unsigned pos = hp[match ? (tp >> 8) + base : 0u];
+                const unsigned pos = s_heappos[hp_row + (match ? (tp >> 8) + base : 0u)];
                 key[j] = match ? ((pos << 16) | nb_slot[j]) : kNoKey;
             }
             if (MAXD == 4) {                                                    // 5-comparator sorting network
