@@ -13,6 +13,7 @@ Workload (BASELINE.json metric: "65,536 6x6 Q-routing replicas" on 8 GPUs, weak 
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -37,13 +38,31 @@ def parse():
     ap.add_argument("--net", default="6x6.net")
     ap.add_argument("--policy", default="Qroute", choices=["Shortest", "Qroute", "HybridQ", "MaHybridQ"])
     ap.add_argument("--load", type=float, default=2.0)
-    ap.add_argument("--queue-capacity", type=int, default=2048)
+    ap.add_argument("--queue-capacity", type=int, default=0, help="ring slots per (replica, node); 0 = from the run length")
     ap.add_argument("--replicas-per-block", type=int, default=0)
     ap.add_argument("--threads-per-block", type=int, default=0)
     ap.add_argument("--tables-in-smem", type=int, default=-1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
+
+
+def plan_capacity(a):
+    """The reference's queues are unbounded and grow ~linearly under congestion (Qroute 6x6 load 2.0
+    reaches 1,040 per node in 10k steps).  Size the rings for the whole run (both measurement passes restart from
+    clock 0) and, if that would not fit, shorten the simulator steps per bench step rather than overflow."""
+    if a.queue_capacity:
+        return
+    budget = 40e9                                                   # bytes of ring storage per GPU
+    n_nodes = {"6x6.net": 36, "6x6-modified.net": 36, "lata.net": 116}.get(a.net, 64)
+    max_cap = 1 << int(math.log2(budget / (a.replicas_per_gpu * n_nodes * 16)))
+    total = (a.steps + a.warmup) * a.sim_steps
+    need = 512 + 0.2 * total * max(a.load / 2.0, 1.0)
+    cap = 1 << max(int(math.ceil(math.log2(need))), 10)
+    if cap > max_cap:
+        cap = max_cap
+        a.sim_steps = max(1, int((cap - 512) / (0.2 * max(a.load / 2.0, 1.0)) / (a.steps + a.warmup)))
+    a.queue_capacity = cap
 
 
 def workload_name(a):
@@ -318,6 +337,7 @@ def run_b200(a):
 
 def main():
     a = parse()
+    plan_capacity(a)
     if a.impl == "reference":
         run_reference(a)
         return

@@ -241,6 +241,58 @@ __device__ double np_sum_compacted(const double *v, const unsigned short *tp, in
     return res;
 }
 
+// The same sum computed by one whole warp (MaHybridQ.learn's three reductions run on helper warps while the node
+// warps process arrivals).  v is indexed by thread slot; the replica's senders are the set bits of its window of the
+// CTA-wide "sent" bit array (words wm[wlo .. wlo+nw), first/last word masked).  n < 128 (NumPy's single pairwise block).
+template <int MAXW>
+__device__ double np_sum_warp(const double *v, const unsigned *wm, int wlo, int nw, unsigned mfirst, unsigned mlast, int lane)
+{
+    unsigned m[MAXW], cum[MAXW + 1];
+    cum[0] = 0;
+#pragma unroll
+    for (int i = 0; i < MAXW; ++i) {
+        m[i] = (i < nw) ? wm[wlo + i] : 0u;
+        if (i == 0) m[i] &= mfirst;
+        if (i == nw - 1) m[i] &= mlast;
+        cum[i + 1] = cum[i] + __popc(m[i]);
+    }
+    const int n = (int)cum[MAXW];
+    double a[4];                                    // element e = lane + 32 q of the compacted sender list
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int e = lane + 32 * q;
+        a[q] = 0.0;
+        if (e < n) {
+#pragma unroll
+            for (int i = 0; i < MAXW; ++i)
+                if ((unsigned)e >= cum[i] && (unsigned)e < cum[i + 1])
+                    a[q] = v[(wlo + i) * 32 + __fns(m[i], 0, e - (int)cum[i] + 1)];
+        }
+    }
+    const unsigned full = 0xFFFFFFFFu;
+    double res = 0.0;
+    if (n < 8) {
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, __shfl_sync(full, a[0], i));
+        return res;
+    }
+    const int nb = n - (n % 8);
+    double acc = a[0];                              // lanes 0..7 hold the eight running accumulators
+    for (int mm = 1; 8 * mm < nb; ++mm) {
+        const int q = mm >> 2, src = (lane + 8 * (mm & 3)) & 31;
+        const double val = __shfl_sync(full, q == 0 ? a[0] : q == 1 ? a[1] : q == 2 ? a[2] : a[3], src);
+        if (lane < 8 && lane + 8 * mm < nb) acc = __dadd_rn(acc, val);
+    }
+    const double t1 = __dadd_rn(acc, __shfl_down_sync(full, acc, 1));          // (r0+r1) at lane 0, (r2+r3) at lane 2, ...
+    const double t2 = __dadd_rn(t1, __shfl_down_sync(full, t1, 2));            // ((r0+r1)+(r2+r3)) at lane 0, ... at lane 4
+    res = __dadd_rn(t2, __shfl_down_sync(full, t2, 4));
+    res = __shfl_sync(full, res, 0);
+    for (int i = nb; i < n; ++i) {
+        const int q = i >> 5;
+        res = __dadd_rn(res, __shfl_sync(full, q == 0 ? a[0] : q == 1 ? a[1] : q == 2 ? a[2] : a[3], i & 31));
+    }
+    return res;
+}
+
 __device__ __forceinline__ void set_status(int *status, long long r, int code, int clock)
 {
     if (atomicCAS(&status[2 * r], 0, code) == 0) status[2 * r + 1] = clock;
@@ -487,6 +539,23 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 ++my_sends;
             }
         }
+        if (POLICY == RLR_POLICY_MAHYBRIDQ && t >= GN) {
+            // MaHybridQ.learn, multi_agent.py:32-33: Trace *= discount_trace.  Nothing reads Trace during the send
+            // phase, so the helper threads (t >= G*N) do this dense pass while the node threads send.
+            const int h = t - GN, nh = blockDim.x - GN;
+            for (int gg = 0; gg < G; ++gg) {
+                if (rblock + gg >= p.R || s_dead[gg]) continue;
+                double2 *tr = reinterpret_cast<double2 *>(SMEM_TABLES ? s_tables + gg * tstride + 2 * p.tsize
+                                                                      : p.Trace + (rblock + gg) * p.tsize);
+                const int n2 = (int)(p.tsize >> 1);
+                for (int i = h; i < n2; i += nh) {
+                    double2 v = tr[i];
+                    v.x = __dmul_rn(v.x, p.discount_trace);
+                    v.y = __dmul_rn(v.y, p.discount_trace);
+                    tr[i] = v;
+                }
+            }
+        }
         if (sendlog) sendlog[(long long)s * N] = sending ? ((unsigned)y | ((unsigned)d << 16)) : 0xFFFFFFFFu;
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, sending);
         if (lane == 0) s_wmask[warp] = bal;
@@ -584,29 +653,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                     }
             }
         } else if (POLICY == RLR_POLICY_MAHYBRIDQ) {
-            // MaHybridQ.learn (multi_agent.py:17-43)
-            if (live && x < 3) {                                                // three sums per replica
-                unsigned n = 0;
-#pragma unroll
-                for (int i = 0; i < MAXW; ++i) {
-                    unsigned m = (i < nw) ? s_wmask[wlo + i] : 0u;
-                    if (i == 0) m &= mfirst;
-                    if (i == nw - 1) m &= mlast;
-                    n += __popc(m);
-                }
-                for (int q = x; q < 3; q += (N < 3 ? 1 : 3)) {
-                    const double *v = (q == 0) ? s_r : (q == 1) ? s_qy : s_qx;
-                    s_sum[g * 4 + q] = np_sum_compacted(v + gbase, s_tp + gbase, N, (int)n);
-                    if (N >= 3) break;
-                }
-            }
-            // dense pass 1: Trace *= discount_trace                                (multi_agent.py:32-33)
-            for (int gg = 0; gg < G; ++gg) {
-                if (rblock + gg >= p.R || s_dead[gg]) continue;
-                double *tr = SMEM_TABLES ? s_tables + gg * tstride + 2 * p.tsize : p.Trace + (rblock + gg) * p.tsize;
-                for (long long i = t; i < p.tsize; i += blockDim.x) tr[i] = __dmul_rn(tr[i], p.discount_trace);
-            }
-            __syncthreads();
+            // MaHybridQ.learn (multi_agent.py:17-43).  Trace was decayed by the helper threads before barrier 1.
             if (sending) {                                                      // multi_agent.py:35-40
                 double *trow = Trx + d * deg;
 #pragma unroll
@@ -619,16 +666,39 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 const double u1 = __dadd_rn(rwd, __dmul_rn(p.discount, max_qy));
                 Qx[d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, __dsub_rn(u1, oldq)));
             }
+            {   // r.sum(), max_Q_y.sum(), max_Q_x_d.sum() (multi_agent.py:28-29), one helper warp per (replica, sum)
+                const int hw0 = (GN + 31) >> 5, nhw = (int)(blockDim.x >> 5) - hw0;
+                if (warp >= hw0) {
+                    for (int pair = warp - hw0; pair < 3 * G; pair += nhw) {
+                        const int gg = pair / 3, q = pair - 3 * gg;
+                        if (rblock + gg >= p.R || s_dead[gg]) continue;
+                        const int gb = gg * N, wl = gb >> 5, nwg = ((gb + N - 1) >> 5) - wl + 1;
+                        const double *v = (q == 0) ? s_r : (q == 1) ? s_qy : s_qx;
+                        const double sum = np_sum_warp<MAXW>(v, s_wmask, wl, nwg, 0xFFFFFFFFu << (gb & 31),
+                                                             0xFFFFFFFFu >> (31 - ((gb + N - 1) & 31)), lane);
+                        if (lane == 0) s_sum[gg * 4 + q] = sum;
+                    }
+                }
+            }
             __syncthreads();
-            // dense pass 2: Theta += (lr_p * delta) * Trace                        (multi_agent.py:28-30,42-43)
+            // dense pass: Theta += (lr_p * delta) * Trace                          (multi_agent.py:28-30,42-43)
             for (int gg = 0; gg < G; ++gg) {
                 if (rblock + gg >= p.R || s_dead[gg]) continue;
                 const double d1 = __dadd_rn(s_sum[gg * 4 + 0], 0.0);            // + reward_shape (always 0)
                 const double d3 = __dadd_rn(d1, __dmul_rn(p.discount, s_sum[gg * 4 + 1]));
                 const double ld = __dmul_rn(p.lr_p, __dsub_rn(d3, s_sum[gg * 4 + 2]));
-                double *th = SMEM_TABLES ? s_tables + gg * tstride + p.tsize : p.Theta + (rblock + gg) * p.tsize;
-                const double *tr = SMEM_TABLES ? s_tables + gg * tstride + 2 * p.tsize : p.Trace + (rblock + gg) * p.tsize;
-                for (long long i = t; i < p.tsize; i += blockDim.x) th[i] = __dadd_rn(th[i], __dmul_rn(ld, tr[i]));
+                double2 *th = reinterpret_cast<double2 *>(SMEM_TABLES ? s_tables + gg * tstride + p.tsize
+                                                                      : p.Theta + (rblock + gg) * p.tsize);
+                const double2 *tr = reinterpret_cast<const double2 *>(SMEM_TABLES ? s_tables + gg * tstride + 2 * p.tsize
+                                                                                  : p.Trace + (rblock + gg) * p.tsize);
+                const int n2 = (int)(p.tsize >> 1);
+                for (int i = t; i < n2; i += blockDim.x) {
+                    double2 a2 = th[i];
+                    const double2 b2 = tr[i];
+                    a2.x = __dadd_rn(a2.x, __dmul_rn(ld, b2.x));
+                    a2.y = __dadd_rn(a2.y, __dmul_rn(ld, b2.y));
+                    th[i] = a2;
+                }
             }
         }
         __syncthreads();                                                        // ---- barrier 2 ----
@@ -923,7 +993,15 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     int threads = cfg->threads_per_block;
     if (threads <= 0) {
         threads = ((G * N + 31) / 32) * 32;
-        if (h->policy == RLR_POLICY_MAHYBRIDQ && threads < 256) threads = 256;
+        if (h->policy == RLR_POLICY_MAHYBRIDQ) {           // + helper warps for the dense passes and the reductions
+            threads = ((G * N + 31) / 32) * 32 + 128;
+            if (threads < 256) threads = 256;
+            if (threads > kMaxThreads) threads = kMaxThreads;
+        }
+    }
+    if (h->policy == RLR_POLICY_MAHYBRIDQ && (N > 127 || threads < ((G * N + 31) / 32) * 32 + 96)) {
+        delete h;
+        return fail(RLR_E_UNSUPPORTED, "rlr_create: MaHybridQ needs n_nodes <= 127 and threads_per_block >= roundup32(G*N) + 96");
     }
     if (threads % 32 || threads < G * N || threads > kMaxThreads) {
         delete h;

@@ -135,7 +135,7 @@ BATCH = [
     ("6x6-modified.net", "HybridQ", 9, 300, 1.5, dict(replicas_per_block=3)),
     ("lata.net", "HybridQ", 3, 200, 2.0, {}),
     ("6x6.net", "MaHybridQ", 10, 300, 2.0, {}),
-    ("6x6.net", "MaHybridQ", 10, 300, 2.0, dict(replicas_per_block=2, threads_per_block=128)),
+    ("6x6.net", "MaHybridQ", 10, 300, 2.0, dict(replicas_per_block=2, threads_per_block=192)),
     ("6x6-modified.net", "MaHybridQ", 5, 200, 1.0, dict(tables_in_smem=0)),
     ("lata.net", "MaHybridQ", 2, 100, 2.0, {}),
 ]
