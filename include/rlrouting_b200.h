@@ -154,6 +154,14 @@ int rlr_init_tables(rlr_handle_t *h, double initP, void *stream);
  *      choice and next_hop ---- */
 int rlr_build_shortest_tables(rlr_handle_t *h, void *stream);
 
+/* ---- host helper (no device work): replays NumPy's legacy RandomState stream for n_steps calls of
+ *      Network.new_packet(lam) (env.py:298-312; np.random.poisson + np.random.randint) on the MT19937 state
+ *      exported by RandomState.get_state() (mt_key[624], *mt_pos; both updated).  cnt_out[n_steps] receives the
+ *      packet count of each step, pairs_out the packets as source | dest << 16.  Trace mode uses it instead of
+ *      calling NumPy once per draw. ---- */
+int rlr_trace_replay(uint32_t *mt_key, int32_t *mt_pos, int32_t n_nodes, int64_t n_steps, double lam,
+                     int32_t *cnt_out, uint32_t *pairs_out, int64_t pairs_cap, int64_t *n_pairs_out);
+
 /* ---- Network.new_packet (env.py:298-312) for n_steps steps ahead of time, Philox mode: fills params->inj_events
  *      from enlam / inj_thr / seed / clock0.  rlr_run_steps does this itself for RLR_INJECT_PHILOX; calling it
  *      separately (on another stream, then running with RLR_INJECT_TRACE) overlaps it with the previous chunk. ---- */

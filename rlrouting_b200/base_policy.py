@@ -87,7 +87,7 @@ class Policy:
         R = dev.shape[0]
         first = np.asarray(tables[0])
         if first.ndim == 2:
-            flat = np.broadcast_to(topo.pack(tables)[None, :], (R, topo.tsize))
+            flat = np.repeat(topo.pack(tables)[None, :], R, axis=0)
         else:
             flat = np.concatenate([np.asarray(tables[x], dtype=np.float64).reshape(R, -1) for x in range(topo.N)], axis=1)
         dev.copy_(torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float64)))

@@ -920,6 +920,94 @@ StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables)
 
 }  // namespace
 
+
+// ------------------------------------------------------------------------------------------------
+// Host-side replay of NumPy's legacy RandomState stream for Network.new_packet (env.py:298-312), so that trace
+// mode scales to tens of thousands of replicas.  Restates, for the calls the reference makes:
+//   np.random.poisson(lam), lam < 10  -> legacy random_poisson_mult: count doubles until their product <= exp(-lam)
+//   np.random.randint(0, N[, size=2]) -> masked rejection on 32-bit outputs (mask = smallest 2^b - 1 >= N - 1)
+//   doubles                           -> (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53
+// on the MT19937 state exported by RandomState.get_state().  Checked against NumPy in tests/test_host_logic.py.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Mt19937 {
+    uint32_t *key;
+    int pos;
+    void refill()
+    {
+        const uint32_t UPPER = 0x80000000u, LOWER = 0x7FFFFFFFu, MATRIX = 0x9908B0DFu;
+        int i;
+        for (i = 0; i < 624 - 397; ++i) {
+            const uint32_t y = (key[i] & UPPER) | (key[i + 1] & LOWER);
+            key[i] = key[i + 397] ^ (y >> 1) ^ ((y & 1u) ? MATRIX : 0u);
+        }
+        for (; i < 623; ++i) {
+            const uint32_t y = (key[i] & UPPER) | (key[i + 1] & LOWER);
+            key[i] = key[i + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? MATRIX : 0u);
+        }
+        const uint32_t y = (key[623] & UPPER) | (key[0] & LOWER);
+        key[623] = key[396] ^ (y >> 1) ^ ((y & 1u) ? MATRIX : 0u);
+        pos = 0;
+    }
+    uint32_t next()
+    {
+        if (pos == 624) refill();
+        uint32_t y = key[pos++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9D2C5680u;
+        y ^= (y << 15) & 0xEFC60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+    double next_double()
+    {
+        const int32_t a = (int32_t)(next() >> 5), b = (int32_t)(next() >> 6);
+        return (a * 67108864.0 + b) / 9007199254740992.0;
+    }
+    uint32_t bounded(uint32_t rng, uint32_t mask)
+    {
+        uint32_t v;
+        do { v = next() & mask; } while (v > rng);
+        return v;
+    }
+};
+}  // namespace
+
+extern "C" int rlr_trace_replay(uint32_t *mt_key, int32_t *mt_pos, int32_t n_nodes, int64_t n_steps, double lam,
+                                int32_t *cnt_out, uint32_t *pairs_out, int64_t pairs_cap, int64_t *n_pairs_out)
+{
+    if (!mt_key || !mt_pos || !cnt_out || !pairs_out || !n_pairs_out) return fail(RLR_E_INVALID, "rlr_trace_replay: null argument");
+    if (n_nodes < 2 || n_nodes > 65535) return fail(RLR_E_INVALID, "rlr_trace_replay: n_nodes out of range");
+    if (!(lam >= 0.0) || lam >= 10.0) return fail(RLR_E_UNSUPPORTED, "rlr_trace_replay: needs 0 <= lambda < 10 (NumPy switches to PTRS at 10)");
+    Mt19937 mt{mt_key, *mt_pos};
+    const uint32_t rng = (uint32_t)n_nodes - 1u;
+    uint32_t mask = rng;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    const double enlam = exp(-lam);
+    int64_t np = 0;
+    for (int64_t s = 0; s < n_steps; ++s) {
+        int32_t n = 0;
+        if (lam != 0.0) {                             // legacy_random_poisson: lam == 0 returns 0 without drawing
+            double prod = 1.0;
+            for (;;) {
+                prod *= mt.next_double();
+                if (prod > enlam) ++n; else break;
+            }
+        }
+        cnt_out[s] = n;
+        for (int32_t i = 0; i < n; ++i) {
+            const uint32_t src = mt.bounded(rng, mask);
+            uint32_t dst = mt.bounded(rng, mask);
+            while (dst == src) dst = mt.bounded(rng, mask);
+            if (np >= pairs_cap) return fail(RLR_E_INVALID, "rlr_trace_replay: pairs buffer too small");
+            pairs_out[np++] = src | (dst << 16);
+        }
+    }
+    *mt_pos = mt.pos;
+    *n_pairs_out = np;
+    return RLR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side of the C ABI
 // ------------------------------------------------------------------------------------------------

@@ -377,7 +377,7 @@ class Network:
         traces = None
         if self.rng == "trace":
             rp.inject_mode = nat.INJECT_TRACE
-            traces = [trace.draw_injections(self._rs[r], N, T, lam[r]) for r in range(R)]
+            traces = trace.draw_injections_many(self._rs, N, T, lam)
         else:
             rp.inject_mode = nat.INJECT_PHILOX
             lam_key = lam.tobytes() if lam.strides[0] else float(lam[0])

@@ -49,8 +49,8 @@ class Qroute(Policy):
         structure overrides of qroute.py:16-20 are re-applied, Theta is reset to initP and Trace to 0."""
         import torch
         net = self._network
-        a = np.broadcast_to(np.asarray(normals, dtype=np.float64), (net.replicas, net.topology.tsize))
-        self._dev["Qtable"].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        a = np.array(np.broadcast_to(np.asarray(normals, dtype=np.float64), (net.replicas, net.topology.tsize)))
+        self._dev["Qtable"].copy_(torch.from_numpy(a))
         nat.check(nat.lib().rlr_init_tables(self._handle, float(initP), net._stream_ptr()))
 
     Qtable = property(lambda self: self._get_table("Qtable"), lambda self, v: self._set_table("Qtable", v))

@@ -124,3 +124,21 @@ def test_trace_schedule_orders_events_per_node():
         assert list(ev[node == x]) == want                       # (step, draw) order inside the node
     assert len(ev) == int(((steps >= 100) & (steps < 300)).sum())
     assert schedule_capacity(4.0, 36, 500) > 4.0 / 36 * 500 + 40
+
+
+def test_native_trace_replay_equals_numpy_legacy_stream():
+    """rlr_trace_replay (C) must consume NumPy's legacy RandomState stream exactly as env.py:307-310 does."""
+    from rlrouting_b200 import trace
+    for seed in range(12):
+        for lam, n_nodes, steps in ((2.0, 36, 400), (0.0, 36, 30), (0.3, 116, 500), (9.5, 36, 150), (4.0, 2, 200), (1.0, 255, 200)):
+            a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+            for rs in (a, b):
+                rs.normal(0, 1, (36, 4))
+                rs.normal()                                   # leaves a cached gaussian in the state
+            x = trace.draw_injections(a, n_nodes, steps, lam, native=True)
+            y = trace.draw_injections(b, n_nodes, steps, lam, native=False)
+            assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1])
+            assert a.randint(0, 1 << 30) == b.randint(0, 1 << 30) and a.normal() == b.normal()   # stream continues identically
+    rs = np.random.RandomState(0)
+    cnt, pairs = trace.draw_injections(rs, 36, 100, 12.0)     # lambda >= 10: NumPy's PTRS branch, falls back to NumPy
+    assert cnt.sum() == len(pairs) and np.all(pairs[:, 0] != pairs[:, 1])
