@@ -113,7 +113,11 @@ typedef struct {
     double discount;          /* qroute.py:9 / hybrid.py:44                                  */
     double discount_trace;    /* multi_agent.py:10                                           */
     int32_t clock0;           /* Network.clock before the first step                         */
-    int32_t reserved;
+    int32_t phase;            /* 0 or 3: fused inject+step+learn (Network.train); 1: Network.step only (env.py:333-365,
+                                 rewards saved, nothing learned); 2: agent.learn of the rewards saved by phase 1.
+                                 Phases 1 and 2 need n_steps == 1 and `rewards`. */
+    void *rewards;            /* device [R][N] 48-byte Reward records (env.py:52-70): packet record (16 B);
+                                 {sending | k << 1 | y << 9 | dest << 17, q_y, 0, 0}; {max_Q_y, max_Q_x_d} */
     /* outputs (device pointers, may be NULL) */
     void *metrics;            /* [n_steps][R] 16-byte records {int64 route_time, uint32 end_packets, uint32 hops}:
                                  cumulative counters after each step (env.py:409-413); step-major so a chunk

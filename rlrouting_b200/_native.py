@@ -60,7 +60,7 @@ class RunParams(C.Structure):
                 ("enlam", C.c_void_p), ("inj_thr", C.c_void_p), ("seed", C.c_uint64),
                 ("lr_q", C.c_double), ("lr_p", C.c_double), ("lr_e", C.c_double),
                 ("discount", C.c_double), ("discount_trace", C.c_double),
-                ("clock0", C.c_int32), ("reserved", C.c_int32),
+                ("clock0", C.c_int32), ("phase", C.c_int32), ("rewards", C.c_void_p),
                 ("metrics", C.c_void_p), ("route_time_out", C.c_void_p), ("hop_out", C.c_void_p),
                 ("sendlog", C.c_void_p)]
 

@@ -66,6 +66,8 @@ struct StepParams {
     long long *counters;
     int *status;
     int inj_cap, add_entropy;
+    int phase;                    // bit 0: inject + send + arrive (Network.step); bit 1: agent.learn
+    uint4 *rewards;               // [R][N][3] saved Reward records (phase 1 writes, phase 2 reads)
     const unsigned *inj_events;
     unsigned long long seed;
     long long replica_base;
@@ -322,6 +324,18 @@ struct SmemLayout {
     }
 };
 
+// PolicyGradient._softmax (hybrid.py:16-18): exp(theta) / exp(theta).sum(), no max-subtraction; NumPy sum order.
+template <int MAXD>
+__device__ __forceinline__ void softmax_row(const double *th, int deg, double (&sm)[MAXD])
+{
+    double e[MAXD];
+#pragma unroll
+    for (int j = 0; j < MAXD; ++j) e[j] = (j < deg) ? det_exp(th[j]) : 0.0;
+    const double ssum = np_sum_row<MAXD>(e, deg);
+#pragma unroll
+    for (int j = 0; j < MAXD; ++j) sm[j] = (j < deg) ? __ddiv_rn(e[j], ssum) : 0.0;
+}
+
 constexpr unsigned kNoKey = 0xFFFFFFFFu;   // "no arrival" sort key (real keys are heap position << 16 | send slot)
 constexpr unsigned kNoSend = 0xFFFFu;      // s_tp entry of a node that did not send this step
 
@@ -330,7 +344,7 @@ constexpr unsigned kNoSend = 0xFFFFu;      // s_tp entry of a node that did not 
 //   MAXD  >= max degree (row loops are fully unrolled and predicated)
 //   MAXW  >= 32-bit words a replica's N consecutive thread slots can span (3 for N <= 64, else 9)
 // ------------------------------------------------------------------------------------------------
-template <int POLICY, int MAXD, int MAXW, bool SMEM_TABLES>
+template <int POLICY, int MAXD, int MAXW, bool SMEM_TABLES, bool SPLIT>
 __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(const __grid_constant__ StepParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -455,6 +469,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         ++tail;
     };
 
+    // SPLIT = false is the fused Network.train path (both phases, no flag tests in the loop)
+    const bool do_env = !SPLIT || (p.phase & 1) != 0, do_learn = !SPLIT || (p.phase & 2) != 0;
     for (int s = 0; s < p.K; ++s) {
         const int clock = p.clock0 + s;
         if (POLICY >= RLR_POLICY_HYBRIDQ && is_node) dead = (s_dead[g] != 0u);
@@ -463,7 +479,22 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         int d = 0, k = 0, y = 0;
         double oldq = 0.0, max_qy = 0.0, max_qxd = 0.0, rwd = 0.0;
         double sm[MAXD];
-        if (live) {
+        if (live && !do_env) {
+            // learn-only call (agent.learn after Network.step): restore this node's Reward of that step
+            const uint4 *rw = p.rewards + ((size_t)r * N + x) * 3;
+            const uint4 meta = rw[1];
+            sending = (meta.x & 1u) != 0u;
+            if (sending) {
+                k = (int)((meta.x >> 1) & 0xFFu); y = (int)((meta.x >> 9) & 0xFFu); d = (int)(meta.x >> 17);
+                rwd = (double)(-(int)meta.y - 1);
+                const double2 mq = *reinterpret_cast<const double2 *>(rw + 2);
+                max_qy = mq.x; max_qxd = mq.y;
+                if (POLICY != RLR_POLICY_SHORTEST) oldq = Qx[d * deg + k];
+                if (POLICY >= RLR_POLICY_HYBRIDQ) softmax_row<MAXD>(Thx + d * deg, deg, sm);
+                if (POLICY == RLR_POLICY_MAHYBRIDQ) { s_r[t] = rwd; s_qy[t] = max_qy; s_qx[t] = max_qxd; }
+            }
+        }
+        if (live && do_env) {
             // ---- A. new_packet + inject (env.py:298-319): consume this step's events of the schedule ----
             while ((ev >> 8) == (unsigned)s) {
                 append(make_uint4((ev & 0xFFu) | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock));
@@ -491,16 +522,11 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                     oldq = best;
                 } else {
                     // PolicyGradient.choose (hybrid.py:16-23): softmax(theta) sampled by inverse CDF
-                    const double *th = Thx + d * deg;
-                    double e[MAXD];
-#pragma unroll
-                    for (int j = 0; j < MAXD; ++j) e[j] = (j < deg) ? det_exp(th[j]) : 0.0;
-                    const double ssum = np_sum_row<MAXD>(e, deg);
+                    softmax_row<MAXD>(Thx + d * deg, deg, sm);
                     bool bad = false;
                     double c = 0.0, cdf[MAXD];
 #pragma unroll
                     for (int j = 0; j < MAXD; ++j) {
-                        sm[j] = (j < deg) ? __ddiv_rn(e[j], ssum) : 0.0;
                         if (j < deg) { bad |= (sm[j] != sm[j]); c = __dadd_rn(c, sm[j]); }
                         cdf[j] = c;
                     }
@@ -537,9 +563,18 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 s_rec[t] = rec;
                 if (POLICY == RLR_POLICY_MAHYBRIDQ) { s_r[t] = rwd; s_qy[t] = max_qy; s_qx[t] = max_qxd; }
                 ++my_sends;
+                if (!do_learn && p.rewards) {                                   // Network.step(): hand the Reward to the host
+                    uint4 *rw = p.rewards + ((size_t)r * N + x) * 3;
+                    rw[0] = rec;
+                    rw[1] = make_uint4(1u | ((unsigned)k << 1) | ((unsigned)y << 9) | ((unsigned)d << 17),
+                                       (unsigned)(clock - (int)rec.w), 0u, 0u);
+                    *reinterpret_cast<double2 *>(rw + 2) = make_double2(max_qy, max_qxd);
+                }
+            } else if (!do_learn && p.rewards) {
+                p.rewards[((size_t)r * N + x) * 3 + 1] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
-        if (POLICY == RLR_POLICY_MAHYBRIDQ && t >= GN) {
+        if (POLICY == RLR_POLICY_MAHYBRIDQ && t >= GN && do_learn) {
             // MaHybridQ.learn, multi_agent.py:32-33: Trace *= discount_trace.  Nothing reads Trace during the send
             // phase, so the helper threads (t >= G*N) do this dense pass while the node threads send.
             const int h = t - GN, nh = blockDim.x - GN;
@@ -562,7 +597,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         if (t < GN) s_tp[t] = sending ? (unsigned short)(y | (__popc(bal & prank_mask) << 8)) : (unsigned short)kNoSend;
         __syncthreads();                                                        // ---- barrier 1 ----
 
-        if (live) {
+        if (live && do_env) {
             // ---- C. event drain (env.py:349-364): gather arrivals from neighbours in heap-tie order ----
             unsigned cum[MAXW + 1];         // senders of this replica in the window words before word i
             cum[0] = 0;
@@ -623,7 +658,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             if (tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
         }
         // ---- D. agent.learn ----
-        if (POLICY == RLR_POLICY_QROUTE) {
+        if (!do_learn) {
+        } else if (POLICY == RLR_POLICY_QROUTE) {
             if (sending) {                                                      // qroute.py:40-44
                 const double tq = __dmul_rn(p.discount, max_qy);
                 const double u1 = __dadd_rn(rwd, tq);
@@ -889,32 +925,34 @@ __global__ void rlr_ratio_kernel(const uint4 *metrics, long long n, double *rout
 
 using StepKernel = void (*)(const StepParams);
 
-template <int POLICY, int MAXD, int MAXW>
+template <int POLICY, int MAXD, int MAXW, bool SPLIT>
 StepKernel pick_smem(bool smem_tables)
 {
-    if (POLICY == RLR_POLICY_SHORTEST) return (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false>;
-    return smem_tables ? (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, true> : (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false>;
+    if (POLICY == RLR_POLICY_SHORTEST) return (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT>;
+    return smem_tables ? (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, true, SPLIT>
+                       : (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT>;
 }
 
-template <int POLICY>
+template <int POLICY, bool SPLIT>
 StepKernel pick_deg(int n_nodes, int max_deg, bool smem_tables)
 {
     if (n_nodes <= 64) {
-        if (max_deg <= 4) return pick_smem<POLICY, 4, 3>(smem_tables);
-        if (max_deg <= 8) return pick_smem<POLICY, 8, 3>(smem_tables);
-        return pick_smem<POLICY, 16, 3>(smem_tables);
+        if (max_deg <= 4) return pick_smem<POLICY, 4, 3, SPLIT>(smem_tables);
+        if (max_deg <= 8) return pick_smem<POLICY, 8, 3, SPLIT>(smem_tables);
+        return pick_smem<POLICY, 16, 3, SPLIT>(smem_tables);
     }
-    if (max_deg <= 8) return pick_smem<POLICY, 8, 9>(smem_tables);
-    return pick_smem<POLICY, 16, 9>(smem_tables);
+    if (max_deg <= 8) return pick_smem<POLICY, 8, 9, SPLIT>(smem_tables);
+    return pick_smem<POLICY, 16, 9, SPLIT>(smem_tables);
 }
 
+template <bool SPLIT>
 StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables)
 {
     switch (policy) {
-    case RLR_POLICY_SHORTEST: return pick_deg<RLR_POLICY_SHORTEST>(n_nodes, max_deg, false);
-    case RLR_POLICY_QROUTE: return pick_deg<RLR_POLICY_QROUTE>(n_nodes, max_deg, smem_tables);
-    case RLR_POLICY_HYBRIDQ: return pick_deg<RLR_POLICY_HYBRIDQ>(n_nodes, max_deg, smem_tables);
-    default: return pick_deg<RLR_POLICY_MAHYBRIDQ>(n_nodes, max_deg, smem_tables);
+    case RLR_POLICY_SHORTEST: return pick_deg<RLR_POLICY_SHORTEST, SPLIT>(n_nodes, max_deg, false);
+    case RLR_POLICY_QROUTE: return pick_deg<RLR_POLICY_QROUTE, SPLIT>(n_nodes, max_deg, smem_tables);
+    case RLR_POLICY_HYBRIDQ: return pick_deg<RLR_POLICY_HYBRIDQ, SPLIT>(n_nodes, max_deg, smem_tables);
+    default: return pick_deg<RLR_POLICY_MAHYBRIDQ, SPLIT>(n_nodes, max_deg, smem_tables);
     }
 }
 
@@ -1018,7 +1056,7 @@ struct rlr_handle {
     bool smem_tables, bound;
     std::vector<int> row_ptr, col;
     rlr_buffers_t bufs;
-    StepKernel kernel;
+    StepKernel kernel, kernel_split;     // fused Network.train path / Network.step + agent.learn phases
 };
 
 extern "C" {
@@ -1101,8 +1139,11 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
         return fail(RLR_E_UNSUPPORTED, "rlr_create: shared-memory footprint exceeds 227 KB (lower replicas_per_block or set tables_in_smem=0)");
     }
     h->G = G; h->threads = threads; h->smem_bytes = (int)smem; h->smem_tables = smem_tables != 0;
-    h->kernel = pick_kernel(h->policy, h->N, h->max_deg, h->smem_tables);
+    h->kernel = pick_kernel<false>(h->policy, h->N, h->max_deg, h->smem_tables);
+    h->kernel_split = pick_kernel<true>(h->policy, h->N, h->max_deg, h->smem_tables);
     cudaError_t e = cudaFuncSetAttribute((const void *)h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute((const void *)h->kernel_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         delete h;
         return fail(RLR_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
@@ -1213,6 +1254,9 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
         return fail(RLR_E_INVALID, "rlr_run_steps: unknown inject_mode");
     }
     if (n_steps >= (1 << 24) - 1) return fail(RLR_E_INVALID, "rlr_run_steps: at most 2^24 - 2 steps per call");
+    if (rp->phase < 0 || rp->phase > 3) return fail(RLR_E_INVALID, "rlr_run_steps: phase must be 0 (= 3), 1, 2 or 3");
+    if ((rp->phase == 1 || rp->phase == 2) && (n_steps != 1 || !rp->rewards))
+        return fail(RLR_E_INVALID, "rlr_run_steps: the split phases (Network.step / agent.learn) run one step and need the rewards buffer");
     if ((rp->route_time_out || rp->hop_out) && !rp->metrics)
         return fail(RLR_E_INVALID, "rlr_run_steps: route_time_out / hop_out need the metrics record buffer");
     if ((long long)rp->clock0 + n_steps > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: clock overflows int32");
@@ -1227,6 +1271,7 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     p.ring = (uint4 *)h->bufs.ring; p.qhead = h->bufs.q_head; p.qtail = h->bufs.q_tail;
     p.counters = (long long *)h->bufs.counters; p.status = h->bufs.status;
     p.inj_cap = rp->inj_cap; p.add_entropy = rp->add_entropy;
+    p.phase = rp->phase == 0 ? 3 : rp->phase; p.rewards = (uint4 *)rp->rewards;
     p.inj_events = rp->inj_events; p.seed = rp->seed; p.replica_base = h->replica_base;
     p.lr_q = rp->lr_q; p.lr_p = rp->lr_p; p.lr_e = rp->lr_e; p.discount = rp->discount; p.discount_trace = rp->discount_trace;
     p.metrics = (uint4 *)rp->metrics; p.sendlog = rp->sendlog;
@@ -1236,7 +1281,7 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     }
     const long long blocks = (h->R + h->G - 1) / h->G;
     if (blocks > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: too many blocks");
-    h->kernel<<<(unsigned)blocks, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p);
+    (p.phase == 3 ? h->kernel : h->kernel_split)<<<(unsigned)blocks, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p);
     RLR_CUDA(cudaGetLastError());
     if (rp->route_time_out || rp->hop_out) {
         const long long n = n_steps * h->R;

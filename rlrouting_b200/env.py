@@ -307,6 +307,8 @@ class Network:
     # ------------------------------------------------------------------ reset (env.py:267-280)
     def reset(self):
         self.clock = 0
+        self._pending = [[] for _ in range(self.replicas)]
+        self._last_rewards = None
         h = getattr(self._agent, "_handle", None)
         if h is not None:
             nat.check(nat.lib().rlr_reset(h, self._stream_ptr()))
@@ -319,12 +321,148 @@ class Network:
         """Legacy spelling used by the reference's train.py:51."""
         self.reset()
 
-    # ------------------------------------------------------------------ pieces of the loop the kernel fuses
+    # ------------------------------------------------------------------ the loop's pieces, one call at a time
+    # Network.train fuses these on the device; they are also available separately with the reference's
+    # semantics (one kernel launch per call, so this path is for inspection and custom loops, not for speed).
     def new_packet(self, lambd):
-        raise NotImplementedError("new_packet/inject/step are fused into the device step kernel; drive the "
-                                  "simulation with Network.train (no CPU fallback)")
+        """env.py:298-312.  One replica: a list of Packet; R replicas: a list of R lists."""
+        import torch
+        R, N = self.replicas, self.topology.N
+        lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (R,))
+        out = []
+        if self.rng == "trace":
+            for r in range(R):
+                cnt, pairs = trace.draw_injections(self._rs[r], N, 1, lam[r])
+                out.append([Packet(int(sv), int(dv), self.clock) for sv, dv in pairs])
+        else:
+            h = self._handle_or_raise()
+            cap = schedule_capacity(lam.max(), N, 1) + 8
+            rp = nat.RunParams()
+            en_host = np.exp(-lam / np.float64(N))
+            enlam = torch.from_numpy(en_host).to(self.device)
+            thr = torch.from_numpy(injection_threshold(en_host).view(np.int64)).to(self.device)
+            buf = torch.empty((R, N, cap), dtype=torch.int32, device=self.device)
+            rp.enlam, rp.inj_thr, rp.seed, rp.clock0 = enlam.data_ptr(), thr.data_ptr(), self.seed, self.clock
+            rp.inj_events, rp.inj_cap = buf.data_ptr(), cap
+            nat.check(nat.lib().rlr_build_inject_schedule(h, 1, C.byref(rp), self._stream_ptr()))
+            ev = buf.cpu().numpy().view(np.uint32)
+            self._raise_on_status(self._status.cpu().numpy())
+            for r in range(R):
+                pk = []
+                for x in range(N):
+                    for e in ev[r, x]:
+                        if e == 0xFFFFFFFF:
+                            break
+                        pk.append(Packet(x, int(e & 0xFF), self.clock))
+                out.append(pk)
+        return out[0] if R == 1 else out
 
-    inject = step = sample_route_time = new_packet
+    def inject(self, packets):
+        """env.py:314-319.  The packets join their source queues at the next `step` (same clock, so identical state)."""
+        per = [packets] if self.replicas == 1 else packets
+        if len(per) != self.replicas:
+            raise ValueError("inject expects one packet list per replica")
+        pend = self.__dict__.setdefault("_pending", [[] for _ in range(self.replicas)])
+        for r, pk in enumerate(per):
+            for q in pk:
+                if q.source == q.dest:
+                    raise NotImplementedError("a packet whose source is its destination ends at injection in the "
+                                              "reference (env.py:124-126); not supported on the device")
+                pend[r].append((int(q.source), int(q.dest)))
+
+    def _handle_or_raise(self):
+        h = getattr(self._agent, "_handle", None)
+        if h is None:
+            raise NotImplementedError("bind one of the device policies first (nw.agent = Qroute(nw) ...)")
+        return h
+
+    def _run_params(self, agent, lr):
+        lrd = dict(getattr(agent, "_lr_default", {}))
+        lrd.update(lr or {})
+        rp = nat.RunParams()
+        rp.add_entropy = int(bool(getattr(agent, "add_entropy", True)))
+        rp.lr_q, rp.lr_p, rp.lr_e = float(lrd.get("q", 0.1)), float(lrd.get("p", 0.1)), float(lrd.get("e", 0.1))
+        rp.discount = float(getattr(agent, "discount", 0.99))
+        rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
+        rp.seed = self.seed
+        return rp
+
+    def step(self, duration=1):
+        """env.py:333-365: one send phase + event drain, nothing learned.  Returns the List[Reward] (one replica)
+        or a list of R lists, to be passed to `agent.learn`."""
+        import torch
+        if duration != 1:
+            raise NotImplementedError("step(duration != 1) (SURVEY §8 row f2) is not implemented on the device")
+        h = self._handle_or_raise()
+        R, N = self.replicas, self.topology.N
+        pend = self.__dict__.get("_pending") or [[] for _ in range(R)]
+        per_node = np.zeros((R, N), dtype=np.int64)
+        for r in range(R):
+            for sv, _ in pend[r]:
+                per_node[r, sv] += 1
+        cap = int(per_node.max()) + 2
+        sched = np.full((R, N, cap), 0xFFFFFFFF, dtype=np.uint32)
+        fill = np.zeros((R, N), dtype=np.int64)
+        for r in range(R):
+            for sv, dv in pend[r]:
+                sched[r, sv, fill[r, sv]] = dv              # local step 0
+                fill[r, sv] += 1
+        d_sched = torch.from_numpy(sched.view(np.int32)).to(self.device)
+        rew = self._scratch("rewards", (R, N, 12), torch.int32)
+        rp = self._run_params(self._agent, {})
+        rp.inject_mode, rp.inj_events, rp.inj_cap = nat.INJECT_TRACE, d_sched.data_ptr(), cap
+        rp.clock0, rp.phase, rp.rewards = self.clock, 1, rew.data_ptr()
+        nat.check(nat.lib().rlr_run_steps(h, 1, C.byref(rp), self._stream_ptr()))
+        self.launch_count += 1
+        self.clock += 1
+        self._pending = [[] for _ in range(R)]
+        raw = rew.cpu().numpy()
+        self._raise_on_status(self._status.cpu().numpy())
+        out = []
+        for r in range(R):
+            lst = []
+            for x in range(N):
+                rec = raw[r, x]
+                meta = int(rec[4]) & 0xFFFFFFFF
+                if not meta & 1:
+                    continue
+                y, dest = (meta >> 9) & 0xFF, meta >> 17
+                w0 = int(rec[0]) & 0xFFFFFFFF
+                pkt = Packet(w0 >> 16, w0 & 0xFFFF, int(rec[2]), int(rec[1]), int(rec[3]))
+                mq = rec[8:12].view(np.float64)
+                info = {"q_y": int(rec[5]), "t_y": 1}
+                if self._agent._kernel_policy != nat.POLICY_SHORTEST:
+                    info["max_Q_y"] = float(mq[0])
+                if self._agent._kernel_policy >= nat.POLICY_HYBRIDQ:
+                    info["max_Q_x_d"] = float(mq[1])
+                lst.append(Reward(x, pkt, int(y), info))
+            out.append(lst)
+        result = out[0] if R == 1 else out
+        self._last_rewards = (result, self.clock)
+        return result
+
+    def _learn(self, agent, rewards, lr):
+        """agent.learn(rewards, lr) for a device policy: learns from the rewards of the latest `step`."""
+        import torch
+        last = self.__dict__.get("_last_rewards")
+        if last is None or last[0] is not rewards or last[1] != self.clock or agent is not self._agent:
+            raise NotImplementedError("a device policy can only learn from the list returned by the latest Network.step() "
+                                      "of the network it is bound to (the rewards themselves stay on the device)")
+        h = self._handle_or_raise()
+        R, N = self.replicas, self.topology.N
+        empty = self._resident.get("empty_sched")
+        if empty is None:
+            empty = self._resident["empty_sched"] = torch.full((R, N, 2), -1, dtype=torch.int32, device=self.device)
+        rp = self._run_params(agent, lr)
+        rp.inject_mode, rp.inj_events, rp.inj_cap = nat.INJECT_TRACE, empty.data_ptr(), 2
+        rp.clock0, rp.phase, rp.rewards = self.clock - 1, 2, self._scratch("rewards", (R, N, 12), torch.int32).data_ptr()
+        nat.check(nat.lib().rlr_run_steps(h, 1, C.byref(rp), self._stream_ptr()))
+        self.launch_count += 1
+        self._last_rewards = None
+        self._raise_on_status(self._status.cpu().numpy())
+
+    def sample_route_time(self, size, lambd, slot=1, freq=1, lr={}):
+        raise NotImplementedError("sample_route_time (SURVEY §8 row f2) is not implemented on the device")
 
     # ------------------------------------------------------------------ the hot path (env.py:367-414)
     def train(self, duration, lambd, slot=1, freq=1, lr={}, droprate=False, hop=False, *, lrq=None, lrp=None,
@@ -555,6 +693,8 @@ class Network:
     # ------------------------------------------------------------------ counters (env.py:271-276, 440-450)
     def _ctr(self, name):
         v = self._counters[:, nat.CTR[name]].cpu().numpy()
+        if name == "all_packets" and self.__dict__.get("_pending"):
+            v = v + np.array([len(pk) for pk in self._pending], dtype=np.int64)     # injected, joining at the next step
         return int(v[0]) if self.replicas == 1 else v
 
     all_packets = property(lambda self: self._ctr("all_packets"))

@@ -55,6 +55,11 @@ class Qroute(Policy):
 
     Qtable = property(lambda self: self._get_table("Qtable"), lambda self, v: self._set_table("Qtable", v))
 
+    def learn(self, rewards, lr={}):
+        """qroute.py:51-53 / hybrid.py:55-62 / multi_agent.py:17-43 on the device, for the rewards of the latest
+        Network.step() (Network.train fuses this call into the step kernel)."""
+        self._network._learn(self, rewards, lr)
+
     def choose(self, source, dest, idx=False):
         scores = self.Qtable[source][..., dest, :]
         if idx:

@@ -90,3 +90,45 @@ def test_unsupported_policies_and_calls_raise(compat_path):
         nw.train(10, 1.0)                       # no device policy bound
     with pytest.raises(NotImplementedError):
         nw.step(1)
+
+
+@pytest.mark.parametrize("policy,rng,R", [("Qroute", "trace", 1), ("Shortest", "trace", 1), ("HybridQ", "philox", 3),
+                                          ("MaHybridQ", "philox", 2), ("Qroute", "philox", 4)])
+def test_manual_loop_equals_fused_train(policy, rng, R):
+    """The reference's own loop body (env.py:400-408) spelled out by the caller — inject(new_packet(l)); r = step(1);
+    agent.learn(r) — must leave exactly the state Network.train leaves, and the rewards must be the send list."""
+    import rlrouting_b200 as rb
+    T, lam = 120, 2.0
+    lr = {"q": 0.1, "p": 0.001, "e": 0.1} if policy == "MaHybridQ" else {}
+    kw = dict(replicas=R, rng=rng, seed=5)
+    fused = rb.Network("6x6.net", **kw)
+    fa = getattr(rb, policy)(fused)
+    fused.agent = fa
+    fused.train(T, lam, lr=lr, sendlog=True)
+    manual = rb.Network("6x6.net", **kw)
+    ma = getattr(rb, policy)(manual)
+    manual.agent = ma
+    sends = [[] for _ in range(R)]
+    for i in range(T):
+        pk = manual.new_packet(lam)
+        manual.inject(pk)
+        assert np.all(manual.active_packets >= 0)
+        r = manual.step(1)
+        for rr, lst in enumerate([r] if R == 1 else r):
+            sends[rr] += [(manual.clock, w.source, w.action, w.dest) for w in lst]
+            for w in lst:
+                assert w.agent_info["t_y"] == 1 and w.agent_info["q_y"] >= 0 and w.packet.dest == w.dest
+        ma.learn(r, lr=lr) if lr else ma.learn(r)
+    cf, cm = fused.counters(), manual.counters()
+    for k in cf:
+        assert np.array_equal(cf[k], cm[k]), k
+    for name in fa._dev:
+        if name in ("Qtable", "Theta", "Trace"):
+            assert np.array_equal(fa.table_array(name).view(np.int64), ma.table_array(name).view(np.int64)), name
+    for rr in range(R):
+        assert np.array_equal(np.array(sends[rr], dtype=np.int32).reshape(-1, 4), fused.sendlog_rows(rr))
+        for x in range(36):
+            assert np.array_equal(fused.queue_array(x, rr), manual.queue_array(x, rr))
+    if policy != "Shortest":                           # Shortest.learn is the base class's no-op, as in the reference
+        with pytest.raises(NotImplementedError):
+            ma.learn([])                               # not the list of the latest step
