@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "librlr_oracle.so")
 
-POLICY_ID = {"Shortest": 0, "Qroute": 1, "HybridQ": 2, "MaHybridQ": 3}
+POLICY_ID = {"Shortest": 0, "Qroute": 1, "HybridQ": 2, "MaHybridQ": 3, "CQ": 4, "CDRQ": 5}
 _lib = None
 
 
@@ -36,6 +36,8 @@ def lib():
         L.orc_destroy.argtypes = [p]
         L.orc_set_hparams.argtypes = [p, f64, f64, i32]
         L.orc_set_stream.argtypes = [p, C.c_uint64, C.c_uint64]
+        L.orc_set_decay.argtypes = [p, f64]
+        L.orc_cq_clean.argtypes = [p]
         L.orc_table_size.restype = i64
         L.orc_table_size.argtypes = [p]
         L.orc_table.restype = C.POINTER(C.c_double)
@@ -75,8 +77,10 @@ COUNTER_NAMES = ("clock", "all_packets", "end_packets", "drop_packets", "active_
 class OracleEnv:
     """One environment replica + its agent (reference `Network` + `Policy`)."""
 
-    def __init__(self, links, policy, discount=0.99, discount_trace=0.6, add_entropy=True,
-                 seed=0, replica=0):
+    def __init__(self, links, policy, discount=None, discount_trace=0.6, add_entropy=True,
+                 seed=0, replica=0, decay=0.9):
+        if discount is None:
+            discount = 0.9 if policy in ("CQ", "CDRQ") else 0.99          # qroute.py:59 vs qroute.py:9
         L = lib()
         self.N = len(links)
         self.deg = np.array([len(links[x]) for x in range(self.N)], dtype=np.int32)
@@ -87,10 +91,12 @@ class OracleEnv:
         self.h = L.orc_create(self.N, _ptr(self.row_ptr), _ptr(self.col), POLICY_ID[policy])
         L.orc_set_hparams(self.h, discount, discount_trace, int(add_entropy))
         L.orc_set_stream(self.h, seed, replica)
+        L.orc_set_decay(self.h, decay)
         self.tsize = L.orc_table_size(self.h)
         self.toff = self.row_ptr.astype(np.int64) * self.N
         self.Q = np.ctypeslib.as_array(L.orc_table(self.h, 0), shape=(self.tsize,))
         self.Theta = np.ctypeslib.as_array(L.orc_table(self.h, 1), shape=(self.tsize,))
+        self.Conf = self.Theta                          # CQ.confidence shares the storage
         self.Trace = np.ctypeslib.as_array(L.orc_table(self.h, 2), shape=(self.tsize,))
         self.choice = np.ctypeslib.as_array(L.orc_choice(self.h), shape=(self.tsize,))
         self.distance = np.ctypeslib.as_array(L.orc_distance(self.h), shape=(self.N, self.N))
@@ -108,6 +114,8 @@ class OracleEnv:
         lib().orc_qtable_structure(self.h)
         self.Theta[:] = initP
         self.Trace[:] = 0.0
+        if self.policy in ("CQ", "CDRQ"):
+            lib().orc_cq_clean(self.h)                  # CQ.__init__ -> clean(), qroute.py:64
 
     def reset(self):
         lib().orc_reset(self.h)

@@ -29,7 +29,7 @@ def load():
     import env, qroute, shortest, hybrid, multi_agent  # noqa: E401
     return {"env": env, "Network": env.Network, "Qroute": qroute.Qroute,
             "Shortest": shortest.Shortest, "HybridQ": hybrid.HybridQ,
-            "MaHybridQ": multi_agent.MaHybridQ}
+            "MaHybridQ": multi_agent.MaHybridQ, "CQ": qroute.CQ, "CDRQ": qroute.CDRQ}
 
 
 def sendlog_hash(log):
@@ -165,7 +165,7 @@ def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, repl
     })
     if keep_sendlog:
         out["sendlog"] = log
-    for name in ("Qtable", "Theta", "Trace"):
+    for name in ("Qtable", "Theta", "Trace", "confidence"):
         if hasattr(agent, name):
             out[name] = pack_tables(getattr(agent, name), N)
     if policy == "Shortest":

@@ -27,7 +27,7 @@
 #include <omp.h>
 #endif
 
-enum { POL_SHORTEST = 0, POL_QROUTE = 1, POL_HYBRIDQ = 2, POL_MAHYBRIDQ = 3 };
+enum { POL_SHORTEST = 0, POL_QROUTE = 1, POL_HYBRIDQ = 2, POL_MAHYBRIDQ = 3, POL_CQ = 4, POL_CDRQ = 5 };
 enum { INJ_TRACE = 0, INJ_PHILOX = 1 };
 enum { ST_OK = 0, ST_NAN_PROB = 1 };
 
@@ -41,7 +41,11 @@ typedef struct { pkt_t *buf; int64_t head, len, cap; } fifo_t;
 typedef struct { pkt_t p; int32_t from, to; int64_t arrive; } event_t;
 
 /* env.py:52-70 Reward + the agent_info dict flattened. */
-typedef struct { int32_t x, y, d, k; int64_t q_y; double max_Q_y, max_Q_x_d; } reward_t;
+typedef struct {
+    int32_t x, y, d, k, src; int64_t q_y, q_x;
+    double max_Q_y, max_Q_x_d;          /* for CQ/CDRQ max_Q_y holds max_Q_f */
+    double C_f, C_b, max_Q_b;           /* qroute.py:72-78, 107-115 */
+} reward_t;
 
 typedef struct orc {
     int N, sdeg, policy;
@@ -49,6 +53,8 @@ typedef struct orc {
     int *aidx;                /* action_idx[x][y] (N*N, -1 if absent)          base_policy.py:21-23 */
     int64_t *toff, tsize;     /* table[x] is (N, deg_x) at toff[x]             qroute.py:13-15      */
     double *Q, *Theta, *Trace;
+    double *Conf;             /* CQ.confidence (qroute.py:62-63); shares storage with Theta (never both) */
+    double decay;             /* CQ(decay=0.9), qroute.py:59 */
     uint8_t *choice;          /* shortest.py:26, same packing as the tables */
     double *distance;         /* shortest.py:24 */
     fifo_t *queue;
@@ -156,6 +162,9 @@ orc_t *orc_create(int N, const int *row_ptr, const int *col, int policy)
     o->discount = 0.99;        /* qroute.py:9, hybrid.py:44, multi_agent.py:10 */
     o->discount_trace = 0.6;   /* multi_agent.py:10 */
     o->add_entropy = 1;        /* hybrid.py:44 */
+    o->Conf = o->Theta;
+    o->decay = 0.9;
+    if (policy == POL_CQ || policy == POL_CDRQ) o->discount = 0.9;     /* qroute.py:59 */
     return o;
 }
 
@@ -172,6 +181,8 @@ void orc_set_hparams(orc_t *o, double discount, double discount_trace, int add_e
 {
     o->discount = discount; o->discount_trace = discount_trace; o->add_entropy = add_entropy;
 }
+
+void orc_set_decay(orc_t *o, double decay) { o->decay = decay; }
 
 void orc_set_stream(orc_t *o, uint64_t seed, uint64_t replica) { o->seed = seed; o->replica = replica; }
 
@@ -212,6 +223,19 @@ void orc_qtable_structure(orc_t *o)
     }
 }
 
+/* CQ.clean (qroute.py:66-71): confidence = 0, then conf[links[x]] = eye(deg_x). */
+void orc_cq_clean(orc_t *o)
+{
+    memset(o->Conf, 0, sizeof(double) * (size_t)o->tsize);
+    for (int x = 0; x < o->N; ++x) {
+        int deg = o->row_ptr[x + 1] - o->row_ptr[x];
+        for (int j = 0; j < deg; ++j) {
+            int y = o->col[o->row_ptr[x] + j];
+            o->Conf[o->toff[x] + (int64_t)y * deg + j] = 1.0;
+        }
+    }
+}
+
 /* Network.reset (env.py:267-280) + Node.reset (env.py:99-101) + agent.clean():
  * Policy.clean is a no-op (base_policy.py:37-39); MaHybridQ.clean zeroes the traces
  * (multi_agent.py:48-50).  Tables are NOT reset. */
@@ -222,6 +246,7 @@ void orc_reset(orc_t *o)
     o->heap_len = 0; o->status = ST_OK; o->status_clock = 0;
     for (int x = 0; x < o->N; ++x) { o->queue[x].head = 0; o->queue[x].len = 0; }
     if (o->policy == POL_MAHYBRIDQ) memset(o->Trace, 0, sizeof(double) * (size_t)o->tsize);
+    if (o->policy == POL_CQ || o->policy == POL_CDRQ) orc_cq_clean(o);
 }
 
 /* Shortest.__init__ + _calc_distance (shortest.py:20-58), multiway=False.
@@ -496,7 +521,7 @@ static void send_phase(orc_t *o)
         if (o->policy == POL_SHORTEST) {
             const uint8_t *c = o->choice + o->toff[x] + (int64_t)d * deg;
             while (k < deg && !c[k]) k++;
-        } else if (o->policy == POL_QROUTE) {
+        } else if (o->policy == POL_QROUTE || o->policy == POL_CQ || o->policy == POL_CDRQ) {
             const double *row = o->Q + o->toff[x] + (int64_t)d * deg;
             for (int j = 1; j < deg; ++j) if (row[j] > row[k]) k = j;
         } else {
@@ -518,9 +543,27 @@ static void send_phase(orc_t *o)
         hq_push(o, &e);
         o->sends += 1;
         reward_t *r = &o->rewards[o->n_rewards++];
-        r->x = x; r->y = y; r->d = d; r->k = k; r->q_y = o->clock - p.start_queue;
+        r->x = x; r->y = y; r->d = d; r->k = k; r->src = p.source; r->q_y = o->clock - p.start_queue;
         r->max_Q_y = r->max_Q_x_d = 0.0;
-        if (o->policy != POL_SHORTEST) {
+        r->q_x = 0; r->C_f = r->C_b = r->max_Q_b = 0.0;
+        if (o->policy == POL_CQ || o->policy == POL_CDRQ) {
+            /* CQ.get_info (qroute.py:72-78): z_idx, max_Q_f = choose(y, dest, idx=True); C_f = conf[y][dest][z_idx] */
+            int degy = o->row_ptr[y + 1] - o->row_ptr[y];
+            const double *ry = o->Q + o->toff[y] + (int64_t)d * degy;
+            int z = 0; for (int j = 1; j < degy; ++j) if (ry[j] > ry[z]) z = j;
+            r->max_Q_y = ry[z];
+            r->C_f = o->Conf[o->toff[y] + (int64_t)d * degy + z];
+            if (o->policy == POL_CDRQ) {
+                /* CDRQ.get_info (qroute.py:107-115) + Node._build_info_dual (env.py:154-160): queue lengths as they
+                 * are at this point of the sequential node loop (own packet already popped) */
+                const double *rb = o->Q + o->toff[x] + (int64_t)p.source * deg;
+                int w = 0; for (int j = 1; j < deg; ++j) if (rb[j] > rb[w]) w = j;
+                r->max_Q_b = rb[w];
+                r->C_b = o->Conf[o->toff[x] + (int64_t)p.source * deg + w];
+                r->q_y = o->queue[y].len > 1 ? o->queue[y].len : 1;
+                r->q_x = q->len > 1 ? q->len : 1;
+            }
+        } else if (o->policy != POL_SHORTEST) {
             int degy = o->row_ptr[y + 1] - o->row_ptr[y];
             const double *ry = o->Q + o->toff[y] + (int64_t)d * degy;
             double m = ry[0]; for (int j = 1; j < degy; ++j) if (ry[j] > m) m = ry[j];
@@ -562,6 +605,33 @@ static void learn_phase(orc_t *o, double lr_q, double lr_p, double lr_e)
 {
     int n = o->n_rewards;
     if (o->policy == POL_SHORTEST) return;                       /* Policy.learn: no-op */
+    if (o->policy == POL_CQ || o->policy == POL_CDRQ) {          /* qroute.py:80-101, 117-122 */
+        for (int i = 0; i < n; ++i) {
+            const reward_t *rw = &o->rewards[i];
+            for (int pass = 0; pass < (o->policy == POL_CDRQ ? 2 : 1); ++pass) {
+                /* forward: table x, row dest, column idx(y); backward (CDRQ): table y, row packet.source, column idx(x) */
+                int tx = pass == 0 ? rw->x : rw->y, ty = pass == 0 ? rw->y : rw->x, row = pass == 0 ? rw->d : rw->src;
+                double C = pass == 0 ? rw->C_f : rw->C_b, maxQ = pass == 0 ? rw->max_Q_y : rw->max_Q_b;
+                double r = pass == 0 ? (double)(-rw->q_y - (o->policy == POL_CDRQ ? 0 : 1)) : (double)(-rw->q_x);
+                int deg = o->row_ptr[tx + 1] - o->row_ptr[tx];
+                int64_t cell = o->toff[tx] + (int64_t)row * deg + o->aidx[tx * o->N + ty];
+                double old_Q = o->Q[cell], old_conf = o->Conf[cell];
+                double one_minus = 1.0 - old_conf;
+                double eta = (one_minus > C) ? one_minus : C;            /* max(C, 1 - old_conf) */
+                double t = o->discount * maxQ;
+                double u = r + t;
+                double v = u - old_Q;
+                double w = eta * v;
+                o->Q[cell] = old_Q + w;
+                double dc = C - old_conf;
+                double ec = eta * dc;
+                double nc = old_conf + ec;
+                o->Conf[cell] = nc / o->decay;
+            }
+        }
+        for (int64_t i = 0; i < o->tsize; ++i) o->Conf[i] = o->Conf[i] * o->decay;   /* confidence_decay, qroute.py:99-101 */
+        return;
+    }
     if (o->policy == POL_QROUTE) {                               /* qroute.py:32-53 */
         for (int i = 0; i < n; ++i) {
             const reward_t *rw = &o->rewards[i];

@@ -53,6 +53,15 @@ CASES = [
     dict(net="6x6.net", policy="MaHybridQ", T=3000, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3, det_math=True),  # F7: NaN at 2526
     dict(net="6x6-modified.net", policy="MaHybridQ", T=1500, lambd=1.0, seed=1, rng="philox", philox_seed=7, replica=3,
          det_math=True, lr={"q": 0.1, "p": 0.001}),
+    # confidence-based and dual Q-routing (qroute.py:56-122; CDRQ runs the network in 'dual' mode)
+    dict(net="6x6.net", policy="CQ", T=3000, lambd=2.0, seed=1),
+    dict(net="lata.net", policy="CQ", T=800, lambd=2.0, seed=1),
+    dict(net="6x6.net", policy="CQ", T=1500, lambd=1.0, seed=1, rng="philox", philox_seed=7, replica=3,
+         agent_kwargs={"decay": 0.8, "discount": 0.95}),
+    dict(net="6x6.net", policy="CDRQ", T=3000, lambd=2.0, seed=1),
+    dict(net="6x6-modified.net", policy="CDRQ", T=2000, lambd=1.0, seed=1),
+    dict(net="lata.net", policy="CDRQ", T=800, lambd=3.0, seed=1),
+    dict(net="6x6.net", policy="CDRQ", T=1500, lambd=3.0, seed=1, rng="philox", philox_seed=7, replica=3),
     # sampled policies with NumPy's own exp/log2: short horizon, tables compared with a tolerance
     dict(net="6x6.net", policy="HybridQ", T=300, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3, keep_tables=True),
     dict(net="6x6.net", policy="MaHybridQ", T=300, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3,
@@ -77,7 +86,7 @@ def main():
             "queues_sha256": h(np.concatenate([q.reshape(-1) for q in r["queues"]] + [np.array([len(q) for q in r["queues"]])]), "<i4"),
             "error": r["error"],
         }
-        for name in ("Q0", "Qtable", "Theta", "Trace"):
+        for name in ("Q0", "Qtable", "Theta", "Trace", "confidence"):
             if name in r:
                 rec["expect"][name + "_sha256"] = h(r[name], "<f8")
                 rec["expect"][name + "_sum"] = float(r[name].sum())

@@ -49,8 +49,8 @@ def lr_of(case):
 def run_oracle(case, sendlog=True):
     topo = topo_of(case["net"])
     kw = case.get("agent_kwargs") or {}
-    env = O.OracleEnv(topo.links, case["policy"], discount=kw.get("discount", 0.99),
-                      add_entropy=kw.get("add_entropy", True),
+    env = O.OracleEnv(topo.links, case["policy"], discount=kw.get("discount"),
+                      add_entropy=kw.get("add_entropy", True), decay=kw.get("decay", 0.9),
                       seed=case.get("philox_seed", 0), replica=case.get("replica", 0))
     q0, inj = case_inputs(case, topo)
     if q0 is not None:
