@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--replicas-per-gpu", type=int, default=8192)
     ap.add_argument("--sim-steps", type=int, default=500, help="simulator steps per bench step (one launch)")
     ap.add_argument("--net", default="6x6.net")
-    ap.add_argument("--policy", default="Qroute", choices=["Shortest", "Qroute", "HybridQ", "MaHybridQ"])
+    ap.add_argument("--policy", default="Qroute", choices=["Shortest", "Qroute", "HybridQ", "MaHybridQ", "CQ", "CDRQ"])
     ap.add_argument("--load", type=float, default=2.0)
     ap.add_argument("--queue-capacity", type=int, default=0, help="ring slots per (replica, node); 0 = from the run length")
     ap.add_argument("--replicas-per-block", type=int, default=0)
@@ -201,8 +201,10 @@ def algorithmic_bytes(a, topo, hops, injections, replica_steps):
     per_hop = {"Shortest": 16 + 2 + 16,
                "Qroute": 16 + w * dbar + w * dbar + w + 16,
                "HybridQ": 16 + w * dbar + w * dbar + w + 16 + 2 * w * dbar,
-               "MaHybridQ": 16 + w * dbar + w * dbar + w + 16 + w * dbar}[a.policy]
-    dense = 4 * w * topo.tsize if a.policy == "MaHybridQ" else 0
+               "MaHybridQ": 16 + w * dbar + w * dbar + w + 16 + w * dbar,
+               "CQ": 16 + w * dbar + w * dbar + w + 16 + 4 * w,                       # + C_f read, C[x][d][k] read+write, Q read
+               "CDRQ": 16 + 2 * w * dbar + w * dbar + 2 * w + 16 + 8 * w}[a.policy]  # + backward row, cell reads/writes
+    dense = {"MaHybridQ": 4 * w * topo.tsize, "CQ": 2 * w * topo.tsize, "CDRQ": 2 * w * topo.tsize}.get(a.policy, 0)
     return hops * per_hop + replica_steps * (16 * topo.N + dense) + injections * 16, per_hop
 
 
@@ -217,7 +219,7 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     R = a.replicas_per_gpu
-    cls = {"Shortest": rb.Shortest, "Qroute": rb.Qroute, "HybridQ": rb.HybridQ, "MaHybridQ": rb.MaHybridQ}[a.policy]
+    cls = getattr(rb, a.policy)
 
     def make():
         nw = rb.Network(a.net, replicas=R, rng="philox", seed=1, replica_base=rank * R, queue_capacity=a.queue_capacity,

@@ -34,7 +34,11 @@ enum { RLR_OK = 0, RLR_E_INVALID = -1, RLR_E_UNSUPPORTED = -2, RLR_E_CUDA = -3, 
 
 /* Policy ids: Shortest (shortest.py:6-58), Qroute (qroute.py:6-53), HybridQ (hybrid.py:41-62),
  * MaHybridQ (multi_agent.py:6-50). */
-enum { RLR_POLICY_SHORTEST = 0, RLR_POLICY_QROUTE = 1, RLR_POLICY_HYBRIDQ = 2, RLR_POLICY_MAHYBRIDQ = 3 };
+enum {
+    RLR_POLICY_SHORTEST = 0, RLR_POLICY_QROUTE = 1, RLR_POLICY_HYBRIDQ = 2, RLR_POLICY_MAHYBRIDQ = 3,
+    RLR_POLICY_CQ = 4,      /* qroute.py:56-101  confidence-based Q-routing                              */
+    RLR_POLICY_CDRQ = 5     /* qroute.py:104-122 + Node 'dual' mode env.py:92-94,154-160                  */
+};
 
 /* Injection: RLR_INJECT_TRACE replays host-generated draws of the reference's NumPy legacy stream
  * (env.py:307-310); RLR_INJECT_PHILOX draws on the device (Philox4x32-10 keyed per replica, clock,
@@ -78,7 +82,7 @@ typedef struct {
  * (N, deg_x) arrays of qroute.py:13-15 packed back to back). */
 typedef struct {
     double *q_table;          /* [R][TS]  Qroute.Qtable            (NULL for Shortest)       */
-    double *theta;            /* [R][TS]  PolicyGradient.Theta     (HybridQ, MaHybridQ)      */
+    double *theta;            /* [R][TS]  PolicyGradient.Theta (HybridQ, MaHybridQ) or CQ.confidence (CQ, CDRQ) */
     double *trace;            /* [R][TS]  MaHybridQ.Trace                                     */
     void *ring;               /* [R][N][cap] 16-byte packet records (Node.queue, env.py:100) */
     uint32_t *q_head;         /* [R][N] monotonically increasing pop counter                 */
@@ -112,6 +116,7 @@ typedef struct {
     double lr_q, lr_p, lr_e;
     double discount;          /* qroute.py:9 / hybrid.py:44                                  */
     double discount_trace;    /* multi_agent.py:10                                           */
+    double conf_decay;        /* CQ(decay=...) qroute.py:59                                  */
     int32_t clock0;           /* Network.clock before the first step                         */
     int32_t phase;            /* 0 or 3: fused inject+step+learn (Network.train); 1: Network.step only (env.py:333-365,
                                  rewards saved, nothing learned); 2: agent.learn of the rewards saved by phase 1.

@@ -13,9 +13,9 @@ from .base_policy import Policy
 from .env import Network, Node, Packet, Reward
 from .hybrid import HybridQ, PolicyGradient
 from .multi_agent import MaHybridQ
-from .qroute import Qroute
+from .qroute import CDRQ, CQ, Qroute
 from .shortest import Shortest
 from .topology import Topology
 
-__all__ = ["Network", "Node", "Packet", "Reward", "Policy", "Qroute", "Shortest", "PolicyGradient", "HybridQ",
+__all__ = ["Network", "Node", "Packet", "Reward", "Policy", "Qroute", "CQ", "CDRQ", "Shortest", "PolicyGradient", "HybridQ",
            "MaHybridQ", "Topology"]

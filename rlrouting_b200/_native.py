@@ -17,7 +17,7 @@ SO = os.environ.get("RLR_LIB") or os.path.join(HERE, "csrc", "librlrouting_b200.
 ABI_VERSION = 1
 NUM_COUNTERS = 8
 CTR = {"all_packets": 0, "end_packets": 1, "drop_packets": 2, "hops": 3, "route_time": 4, "sends": 5}
-POLICY_SHORTEST, POLICY_QROUTE, POLICY_HYBRIDQ, POLICY_MAHYBRIDQ = 0, 1, 2, 3
+POLICY_SHORTEST, POLICY_QROUTE, POLICY_HYBRIDQ, POLICY_MAHYBRIDQ, POLICY_CQ, POLICY_CDRQ = 0, 1, 2, 3, 4, 5
 INJECT_TRACE, INJECT_PHILOX = 0, 1
 STATUS_OK, STATUS_NAN_PROB, STATUS_QUEUE_OVERFLOW, STATUS_INJECT_OVERFLOW = 0, 1, 2, 3
 
@@ -59,7 +59,7 @@ class RunParams(C.Structure):
                 ("inj_events", C.c_void_p), ("inj_cap", C.c_int32), ("reserved0", C.c_int32),
                 ("enlam", C.c_void_p), ("inj_thr", C.c_void_p), ("seed", C.c_uint64),
                 ("lr_q", C.c_double), ("lr_p", C.c_double), ("lr_e", C.c_double),
-                ("discount", C.c_double), ("discount_trace", C.c_double),
+                ("discount", C.c_double), ("discount_trace", C.c_double), ("conf_decay", C.c_double),
                 ("clock0", C.c_int32), ("phase", C.c_int32), ("rewards", C.c_void_p),
                 ("metrics", C.c_void_p), ("route_time_out", C.c_void_p), ("hop_out", C.c_void_p),
                 ("sendlog", C.c_void_p)]

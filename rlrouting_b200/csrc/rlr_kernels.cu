@@ -71,7 +71,7 @@ struct StepParams {
     const unsigned *inj_events;
     unsigned long long seed;
     long long replica_base;
-    double lr_q, lr_p, lr_e, discount, discount_trace;
+    double lr_q, lr_p, lr_e, discount, discount_trace, conf_decay;
     uint4 *metrics;
     unsigned *sendlog;
 };
@@ -311,7 +311,8 @@ struct SmemLayout {
         size_t o = 0;
         tables = o; o += smem_tables ? align16((size_t)G * ntab * tsize * 8) : 0;
         rec = o; o += align16((size_t)GN * 16);
-        f64 = o; o += (policy == RLR_POLICY_MAHYBRIDQ) ? align16((size_t)(3 * GN + 4 * G) * 8) : 0;
+        f64 = o; o += (policy == RLR_POLICY_MAHYBRIDQ) ? align16((size_t)(3 * GN + 4 * G) * 8)
+                       : (policy == RLR_POLICY_CDRQ) ? align16((size_t)GN * 32) : 0;   // CDRQ: {C_b, max_Q_b}, len, q_x, d|k, src
         ull = o; o += align16((size_t)G * 3 * 8);            // route_time, sends, injected
         u32 = o; o += align16((size_t)G * 4 * 4);            // end, hops, dead
         wmask = o; o += align16((size_t)(threads / 32 + 1) * 4);
@@ -367,6 +368,15 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     unsigned *s_end = s_u32, *s_hops = s_u32 + G, *s_dead = s_u32 + 2 * G;
     // MaHybridQ scratch: r, max_Q_y, max_Q_x_d per node; three sums + spare per replica
     double *s_r = s_f64, *s_qy = s_f64 + GN, *s_qx = s_f64 + 2 * GN, *s_sum = s_f64 + 3 * GN;
+    // CDRQ scratch (same region): backward-update inputs of each sender and the queue lengths of 'dual' mode
+    double2 *s_bk = reinterpret_cast<double2 *>(s_f64);                          // {C_b, max_Q_b}
+    unsigned *s_len = reinterpret_cast<unsigned *>(s_f64 + 2 * GN);              // queue length after injection
+    int *s_qxi = reinterpret_cast<int *>(s_f64 + 2 * GN) + GN;                   // q_x = max(1, own length after the pop)
+    unsigned short *s_dk = reinterpret_cast<unsigned short *>(s_f64 + 3 * GN);   // dest | action index << 8
+    unsigned short *s_src = s_dk + GN;                                           // packet.source
+    constexpr bool IS_PG = POLICY == RLR_POLICY_HYBRIDQ || POLICY == RLR_POLICY_MAHYBRIDQ;   // softmax-sampled
+    constexpr bool IS_CQ = POLICY == RLR_POLICY_CQ || POLICY == RLR_POLICY_CDRQ;             // confidence tables
+    constexpr bool DUAL = POLICY == RLR_POLICY_CDRQ;                                         // Node mode 'dual'
 
     const long long rblock = (long long)blockIdx.x * G;            // first replica of this CTA
     const int g = t / N, x = t - g * N;
@@ -473,11 +483,11 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     const bool do_env = !SPLIT || (p.phase & 1) != 0, do_learn = !SPLIT || (p.phase & 2) != 0;
     for (int s = 0; s < p.K; ++s) {
         const int clock = p.clock0 + s;
-        if (POLICY >= RLR_POLICY_HYBRIDQ && is_node) dead = (s_dead[g] != 0u);
+        if (IS_PG && is_node) dead = (s_dead[g] != 0u);
         const bool live = !dead;
         bool sending = false;
         int d = 0, k = 0, y = 0;
-        double oldq = 0.0, max_qy = 0.0, max_qxd = 0.0, rwd = 0.0;
+        double oldq = 0.0, max_qy = 0.0, max_qxd = 0.0, rwd = 0.0, c_f = 0.0;
         double sm[MAXD];
         if (live && !do_env) {
             // learn-only call (agent.learn after Network.step): restore this node's Reward of that step
@@ -490,7 +500,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 const double2 mq = *reinterpret_cast<const double2 *>(rw + 2);
                 max_qy = mq.x; max_qxd = mq.y;
                 if (POLICY != RLR_POLICY_SHORTEST) oldq = Qx[d * deg + k];
-                if (POLICY >= RLR_POLICY_HYBRIDQ) softmax_row<MAXD>(Thx + d * deg, deg, sm);
+                if (IS_PG) softmax_row<MAXD>(Thx + d * deg, deg, sm);
                 if (POLICY == RLR_POLICY_MAHYBRIDQ) { s_r[t] = rwd; s_qy[t] = max_qy; s_qx[t] = max_qxd; }
             }
         }
@@ -503,6 +513,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 if (ev != 0xFFFFFFFFu) ev_next = *++evp;
             }
             // ---- B. Node._send_default (env.py:162-191): pop the head, choose, get_info ----
+            if (DUAL) s_len[t] = tail - head;                                   // len(queue) before this node's own send
             if (head != tail) {
                 sending = true;
                 uint4 rec = use_fresh ? fresh : pref;
@@ -512,7 +523,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 d = (int)(rec.x & 0xFFFFu);
                 if (POLICY == RLR_POLICY_SHORTEST) {
                     k = s_nexthop[x * N + d];                                   // shortest.py:38-41
-                } else if (POLICY == RLR_POLICY_QROUTE) {
+                } else if (POLICY == RLR_POLICY_QROUTE || IS_CQ) {
                     const double *row = Qx + d * deg;                           // qroute.py:22-27
                     double best = row[0];
 #pragma unroll
@@ -551,7 +562,30 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 y = s_col[rp + k];
                 rec.y += 1u;                                                    // p.hops += 1, env.py:141
                 rwd = (double)(-(clock - (int)rec.w) - 1);                      // r = -q_y - t_y, qroute.py:37
-                if (POLICY != RLR_POLICY_SHORTEST) {                            // max_Q_y, qroute.py:29-30
+                if (IS_CQ) {                        // CQ.get_info (qroute.py:72-78): z = argmax Q[y][d], max_Q_f, C_f
+                    const int rpy = s_rowptr[y], degy = s_rowptr[y + 1] - rpy;
+                    const double *ry = Qr + N * rpy + d * degy;
+                    double m = ry[0];
+                    int z = 0;
+#pragma unroll
+                    for (int j = 1; j < MAXD; ++j)
+                        if (j < degy) { const double v = ry[j]; if (v > m) { m = v; z = j; } }
+                    max_qy = m;
+                    c_f = Thr[N * rpy + d * degy + z];
+                    if (DUAL) {                     // CDRQ.get_info (qroute.py:107-115) + _build_info_dual (env.py:154-160)
+                        const int src = (int)(rec.x >> 16);
+                        const double *rb = Qx + src * deg;
+                        double mb = rb[0];
+                        int w = 0;
+#pragma unroll
+                        for (int j = 1; j < MAXD; ++j)
+                            if (j < deg) { const double v = rb[j]; if (v > mb) { mb = v; w = j; } }
+                        s_bk[t] = make_double2(Thx[src * deg + w], mb);
+                        s_qxi[t] = (int)max(1u, tail - head);
+                        s_dk[t] = (unsigned short)(d | (k << 8));
+                        s_src[t] = (unsigned short)src;
+                    }
+                } else if (POLICY != RLR_POLICY_SHORTEST) {                     // max_Q_y, qroute.py:29-30
                     const int rpy = s_rowptr[y], degy = s_rowptr[y + 1] - rpy;
                     const double *ry = Qr + N * rpy + d * degy;
                     double m = ry[0];
@@ -688,6 +722,68 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                         th[j] = __dadd_rn(th[j], __dmul_rn(__dmul_rn(p.lr_p, gj), adv));
                     }
             }
+        } else if (IS_CQ) {
+            // CQ._update_qtable (qroute.py:80-93): eta = max(C, 1 - old_conf); Q += eta * (r + discount * max_Q - Q);
+            // conf += eta * (C - conf); conf /= decay.  CDRQ (qroute.py:117-122) adds the backward update of
+            // Q[y][packet.source][idx(x)] with r_b = -q_x; rewards are applied in sender order, forward then backward.
+            auto cq_update = [&](double &q, double &c, double rr, double C, double maxQ) {
+                const double one_minus = __dsub_rn(1.0, c);
+                const double eta = (one_minus > C) ? one_minus : C;
+                q = __dadd_rn(q, __dmul_rn(eta, __dsub_rn(__dadd_rn(rr, __dmul_rn(p.discount, maxQ)), q)));
+                c = __ddiv_rn(__dadd_rn(c, __dmul_rn(eta, __dsub_rn(C, c))), p.conf_decay);
+            };
+            if (sending) {
+                const int cell = d * deg + k;
+                double q = oldq, c = Thx[cell];
+                if (!DUAL) {
+                    cq_update(q, c, rwd, c_f, max_qy);
+                } else {
+                    const int yt = gbase + y;                                   // my next hop's thread slot
+                    const unsigned ly = s_len[yt];
+                    const double r_f = -(double)(int)max(1u, ly - ((y < x && ly > 0u) ? 1u : 0u));
+                    // does y's backward update land on this very cell?  (y sends to me a packet whose source is my dest)
+                    const unsigned tpy = s_tp[yt];
+                    const bool hit = tpy != kNoSend && (tpy & 0xFFu) == (unsigned)x && s_src[yt] == (unsigned short)d;
+                    const double2 bk = s_bk[yt];
+                    const double r_by = -(double)s_qxi[yt];
+                    if (hit && y < x) cq_update(q, c, r_by, bk.x, bk.y);        // reward y precedes reward x
+                    cq_update(q, c, r_f, c_f, max_qy);
+                    if (hit && y > x) cq_update(q, c, r_by, bk.x, bk.y);
+                }
+                Qx[cell] = q;
+                Thx[cell] = c;
+                if (DUAL) {                                                     // my backward update on y's table
+                    const int src = (int)s_src[t];
+                    const int rpy = s_rowptr[y], degy = s_rowptr[y + 1] - rpy;
+                    int idx = 0;
+                    for (int j = 1; j < degy; ++j)
+                        if (s_col[rpy + j] == (unsigned short)x) idx = j;
+                    const unsigned tpy = s_tp[gbase + y];
+                    const bool owned_by_y = tpy != kNoSend && s_dk[gbase + y] == (unsigned short)(src | (idx << 8));
+                    if (!owned_by_y) {                                          // else y applies it with its own forward update
+                        const int cb = N * rpy + src * degy + idx;
+                        double qb = Qr[cb], cbv = Thr[cb];
+                        const double2 bk = s_bk[t];
+                        cq_update(qb, cbv, -(double)s_qxi[t], bk.x, bk.y);
+                        Qr[cb] = qb;
+                        Thr[cb] = cbv;
+                    }
+                }
+            }
+            __syncthreads();
+            // CQ.confidence_decay (qroute.py:99-101): every confidence entry *= decay, every step
+            for (int gg = 0; gg < G; ++gg) {
+                if (rblock + gg >= p.R || s_dead[gg]) continue;
+                double2 *cf = reinterpret_cast<double2 *>(SMEM_TABLES ? s_tables + gg * tstride + p.tsize
+                                                                      : p.Theta + (rblock + gg) * p.tsize);
+                const int n2 = (int)(p.tsize >> 1);
+                for (int i = t; i < n2; i += blockDim.x) {
+                    double2 v = cf[i];
+                    v.x = __dmul_rn(v.x, p.conf_decay);
+                    v.y = __dmul_rn(v.y, p.conf_decay);
+                    cf[i] = v;
+                }
+            }
         } else if (POLICY == RLR_POLICY_MAHYBRIDQ) {
             // MaHybridQ.learn (multi_agent.py:17-43).  Trace was decayed by the helper threads before barrier 1.
             if (sending) {                                                      // multi_agent.py:35-40
@@ -778,8 +874,9 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
 // ------------------------------------------------------------------------------------------------
 // Qroute.__init__ structure overrides (qroute.py:16-20), Theta = initP, Trace = 0.
 // ------------------------------------------------------------------------------------------------
+// conf_mode: Theta is CQ.confidence and receives CQ.clean's structure (qroute.py:66-71: 0, conf[links[x]] = eye).
 __global__ void rlr_init_tables_kernel(double *Q, double *Theta, double *Trace, const int *row_ptr, const int *col,
-                                       int N, int sdeg, long long R, double initP)
+                                       int N, int sdeg, long long R, double initP, int conf_mode)
 {
     const long long tsize = (long long)N * sdeg;
     const long long total = R * sdeg;
@@ -789,14 +886,27 @@ __global__ void rlr_init_tables_kernel(double *Q, double *Theta, double *Trace, 
         int x = 0;
         while (row_ptr[x + 1] <= e) ++x;          // small N: linear search
         const int rp = row_ptr[x], deg = row_ptr[x + 1] - rp, j = e - rp, y = col[e];
-        double *tab = Q + r * tsize + (long long)N * rp;
-        for (int k = 0; k < deg; ++k) tab[(long long)y * deg + k] = (j == k) ? -1.0 : -0.0;   // -eye
-        if (j == 0)
-            for (int k = 0; k < deg; ++k) tab[(long long)x * deg + k] = 0.0;                  // table[x] = 0
+        if (Q) {
+            double *tab = Q + r * tsize + (long long)N * rp;
+            for (int k = 0; k < deg; ++k) tab[(long long)y * deg + k] = (j == k) ? -1.0 : -0.0;   // -eye
+            if (j == 0)
+                for (int k = 0; k < deg; ++k) tab[(long long)x * deg + k] = 0.0;                  // table[x] = 0
+        }
     }
     const long long tot2 = R * tsize;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tot2; i += (long long)gridDim.x * blockDim.x) {
-        if (Theta) Theta[i] = initP;
+        if (Theta) {
+            double v = initP;
+            if (conf_mode) {                       // element i = (r, x, d, k): 1 where d is x's k-th neighbour
+                const long long e = i % tsize;
+                int x = 0;
+                while ((long long)N * row_ptr[x + 1] <= e) ++x;
+                const int rp = row_ptr[x], deg = row_ptr[x + 1] - rp;
+                const int dd = (int)((e - (long long)N * rp) / deg), k = (int)((e - (long long)N * rp) % deg);
+                v = (col[rp + k] == dd) ? 1.0 : 0.0;
+            }
+            Theta[i] = v;
+        }
         if (Trace) Trace[i] = 0.0;
     }
 }
@@ -952,7 +1062,9 @@ StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables)
     case RLR_POLICY_SHORTEST: return pick_deg<RLR_POLICY_SHORTEST, SPLIT>(n_nodes, max_deg, false);
     case RLR_POLICY_QROUTE: return pick_deg<RLR_POLICY_QROUTE, SPLIT>(n_nodes, max_deg, smem_tables);
     case RLR_POLICY_HYBRIDQ: return pick_deg<RLR_POLICY_HYBRIDQ, SPLIT>(n_nodes, max_deg, smem_tables);
-    default: return pick_deg<RLR_POLICY_MAHYBRIDQ, SPLIT>(n_nodes, max_deg, smem_tables);
+    case RLR_POLICY_MAHYBRIDQ: return pick_deg<RLR_POLICY_MAHYBRIDQ, SPLIT>(n_nodes, max_deg, smem_tables);
+    case RLR_POLICY_CQ: return pick_deg<RLR_POLICY_CQ, SPLIT>(n_nodes, max_deg, smem_tables);
+    default: return pick_deg<RLR_POLICY_CDRQ, SPLIT>(n_nodes, max_deg, smem_tables);
     }
 }
 
@@ -1089,7 +1201,7 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
         if (dg < 1 || dg > topo->max_deg) return fail(RLR_E_INVALID, "rlr_create: node degree outside [1, max_deg]");
     }
     if (cfg->replicas < 1) return fail(RLR_E_INVALID, "rlr_create: replicas must be >= 1");
-    if (cfg->policy < RLR_POLICY_SHORTEST || cfg->policy > RLR_POLICY_MAHYBRIDQ)
+    if (cfg->policy < RLR_POLICY_SHORTEST || cfg->policy > RLR_POLICY_CDRQ)
         return fail(RLR_E_UNSUPPORTED, "rlr_create: unknown policy id");
     const int cap = cfg->queue_capacity;
     if (cap < 2 || (cap & (cap - 1))) return fail(RLR_E_INVALID, "rlr_create: queue_capacity must be a power of two >= 2");
@@ -1097,7 +1209,8 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     RLR_CUDA(cudaSetDevice(cfg->device));
     rlr_handle *h = new rlr_handle();
     h->N = N; h->sdeg = topo->sum_deg; h->max_deg = topo->max_deg; h->policy = cfg->policy;
-    h->ntab = cfg->policy;                       // Shortest 0, Qroute 1 (Q), HybridQ 2 (+Theta), MaHybridQ 3 (+Trace)
+    // tables per replica: Shortest 0, Qroute 1 (Q), HybridQ 2 (+Theta), MaHybridQ 3 (+Trace), CQ/CDRQ 2 (Q + confidence)
+    h->ntab = cfg->policy >= RLR_POLICY_CQ ? 2 : cfg->policy;
     h->R = cfg->replicas; h->replica_base = cfg->replica_base;
     h->tsize = (long long)N * topo->sum_deg;
     h->cap = cap; h->bound = false; h->device = cfg->device;
@@ -1119,7 +1232,7 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     int threads = cfg->threads_per_block;
     if (threads <= 0) {
         threads = ((G * N + 31) / 32) * 32;
-        if (h->policy == RLR_POLICY_MAHYBRIDQ) {           // + helper warps for the dense passes and the reductions
+        if (h->policy == RLR_POLICY_MAHYBRIDQ || h->policy >= RLR_POLICY_CQ) {   // + helper warps for the dense passes / reductions
             threads = ((G * N + 31) / 32) * 32 + 128;
             if (threads < 256) threads = 256;
             if (threads > kMaxThreads) threads = kMaxThreads;
@@ -1167,7 +1280,7 @@ int rlr_bind_buffers(rlr_handle_t *h, const rlr_buffers_t *b)
         return fail(RLR_E_INVALID, "rlr_bind_buffers: Shortest needs next_hop, distance and choice");
     if (h->policy >= RLR_POLICY_QROUTE && !b->q_table) return fail(RLR_E_INVALID, "rlr_bind_buffers: q_table required");
     if (h->policy >= RLR_POLICY_HYBRIDQ && !b->theta) return fail(RLR_E_INVALID, "rlr_bind_buffers: theta required");
-    if (h->policy >= RLR_POLICY_MAHYBRIDQ && !b->trace) return fail(RLR_E_INVALID, "rlr_bind_buffers: trace required");
+    if (h->policy == RLR_POLICY_MAHYBRIDQ && !b->trace) return fail(RLR_E_INVALID, "rlr_bind_buffers: trace required");
     if (((uintptr_t)b->ring & 15) || ((uintptr_t)b->q_table & 15) || ((uintptr_t)b->theta & 15) || ((uintptr_t)b->trace & 15))
         return fail(RLR_E_INVALID, "rlr_bind_buffers: ring and tables must be 16-byte aligned");
     h->bufs = *b;
@@ -1197,6 +1310,13 @@ int rlr_reset(rlr_handle_t *h, void *stream)
     RLR_CUDA(cudaMemsetAsync(h->bufs.counters, 0, (size_t)h->R * RLR_NUM_COUNTERS * 8, st));
     RLR_CUDA(cudaMemsetAsync(h->bufs.status, 0, (size_t)h->R * 2 * 4, st));
     if (h->policy == RLR_POLICY_MAHYBRIDQ) RLR_CUDA(cudaMemsetAsync(h->bufs.trace, 0, (size_t)h->R * h->tsize * 8, st));
+    if (h->policy >= RLR_POLICY_CQ) {              // CQ.clean (qroute.py:66-71)
+        const long long total = h->R * h->tsize;
+        int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        rlr_init_tables_kernel<<<blocks, 256, 0, st>>>(nullptr, h->bufs.theta, nullptr, h->bufs.topo_row_ptr, h->bufs.topo_col,
+                                                       h->N, h->sdeg, h->R, 0.0, 1);
+        RLR_CUDA(cudaGetLastError());
+    }
     return RLR_OK;
 }
 
@@ -1209,7 +1329,7 @@ int rlr_init_tables(rlr_handle_t *h, double initP, void *stream)
     int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     rlr_init_tables_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->bufs.q_table, h->bufs.theta, h->bufs.trace,
                                                                       h->bufs.topo_row_ptr, h->bufs.topo_col, h->N, h->sdeg,
-                                                                      h->R, initP);
+                                                                      h->R, initP, h->policy >= RLR_POLICY_CQ ? 1 : 0);
     RLR_CUDA(cudaGetLastError());
     return RLR_OK;
 }
@@ -1255,6 +1375,8 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     }
     if (n_steps >= (1 << 24) - 1) return fail(RLR_E_INVALID, "rlr_run_steps: at most 2^24 - 2 steps per call");
     if (rp->phase < 0 || rp->phase > 3) return fail(RLR_E_INVALID, "rlr_run_steps: phase must be 0 (= 3), 1, 2 or 3");
+    if ((rp->phase == 1 || rp->phase == 2) && h->policy >= RLR_POLICY_CQ)
+        return fail(RLR_E_UNSUPPORTED, "rlr_run_steps: the split Network.step / agent.learn phases are not available for CQ / CDRQ");
     if ((rp->phase == 1 || rp->phase == 2) && (n_steps != 1 || !rp->rewards))
         return fail(RLR_E_INVALID, "rlr_run_steps: the split phases (Network.step / agent.learn) run one step and need the rewards buffer");
     if ((rp->route_time_out || rp->hop_out) && !rp->metrics)
@@ -1273,7 +1395,7 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     p.inj_cap = rp->inj_cap; p.add_entropy = rp->add_entropy;
     p.phase = rp->phase == 0 ? 3 : rp->phase; p.rewards = (uint4 *)rp->rewards;
     p.inj_events = rp->inj_events; p.seed = rp->seed; p.replica_base = h->replica_base;
-    p.lr_q = rp->lr_q; p.lr_p = rp->lr_p; p.lr_e = rp->lr_e; p.discount = rp->discount; p.discount_trace = rp->discount_trace;
+    p.lr_q = rp->lr_q; p.lr_p = rp->lr_p; p.lr_e = rp->lr_e; p.discount = rp->discount; p.discount_trace = rp->discount_trace; p.conf_decay = rp->conf_decay;
     p.metrics = (uint4 *)rp->metrics; p.sendlog = rp->sendlog;
     if (rp->inject_mode == RLR_INJECT_PHILOX) {
         const int rc = rlr_build_inject_schedule(h, n_steps, rp, stream);

@@ -173,7 +173,8 @@ class Network:
         h = C.c_void_p()
         nat.check(nat.lib().rlr_create(C.byref(t), C.byref(cfg), C.byref(h)))
         d = agent._dev
-        ptr = lambda name: d[name].data_ptr() if name in d else None  # noqa: E731
+        alias = getattr(agent, "_dev_alias", {})
+        ptr = lambda name: d[alias.get(name, name)].data_ptr() if alias.get(name, name) in d else None  # noqa: E731
         b = nat.Buffers(ptr("Qtable"), ptr("Theta"), ptr("Trace"), self._ring.data_ptr(), self._q_head.data_ptr(),
                         self._q_tail.data_ptr(), self._counters.data_ptr(), self._status.data_ptr(), ptr("next_hop"),
                         ptr("distance"), ptr("choice"), self._row_ptr.data_ptr(), self._col.data_ptr(),
@@ -294,7 +295,7 @@ class Network:
             raise NotImplementedError(f"{type(new_agent).__name__} is not one of the device policies (Shortest, Qroute, "
                                       "HybridQ, MaHybridQ); custom Python policies would need a CPU path, which this "
                                       "package does not have")
-        if new_agent.mode is not None:
+        if new_agent.mode is not None and not (new_agent.mode == "dual" and new_agent._kernel_policy == nat.POLICY_CDRQ):
             raise NotImplementedError(f"mode {new_agent.mode!r} is not implemented on the device (SURVEY §8 rows f1/f2)")
         if new_agent._network is not self:
             raise ValueError("the agent was constructed for a different Network")
@@ -384,6 +385,7 @@ class Network:
         rp.lr_q, rp.lr_p, rp.lr_e = float(lrd.get("q", 0.1)), float(lrd.get("p", 0.1)), float(lrd.get("e", 0.1))
         rp.discount = float(getattr(agent, "discount", 0.99))
         rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
+        rp.conf_decay = float(getattr(agent, "decay", 0.9))
         rp.seed = self.seed
         return rp
 
@@ -394,6 +396,9 @@ class Network:
         if duration != 1:
             raise NotImplementedError("step(duration != 1) (SURVEY §8 row f2) is not implemented on the device")
         h = self._handle_or_raise()
+        if self._agent._kernel_policy >= nat.POLICY_CQ:
+            raise NotImplementedError("Network.step / agent.learn as separate calls are not implemented for CQ / CDRQ; "
+                                      "use Network.train")
         R, N = self.replicas, self.topology.N
         pend = self.__dict__.get("_pending") or [[] for _ in range(R)]
         per_node = np.zeros((R, N), dtype=np.int64)
@@ -509,6 +514,7 @@ class Network:
         rp.lr_q, rp.lr_p, rp.lr_e = float(lrd.get("q", 0.1)), float(lrd.get("p", 0.1)), float(lrd.get("e", 0.1))
         rp.discount = float(getattr(agent, "discount", 0.99))
         rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
+        rp.conf_decay = float(getattr(agent, "decay", 0.9))
         rp.seed = self.seed
         keep = []
         h2d = 0
@@ -640,6 +646,7 @@ class Network:
         rp.lr_q, rp.lr_p, rp.lr_e = float(lrd.get("q", 0.1)), float(lrd.get("p", 0.1)), float(lrd.get("e", 0.1))
         rp.discount = float(getattr(agent, "discount", 0.99))
         rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
+        rp.conf_decay = float(getattr(agent, "decay", 0.9))
         rp.seed = self.seed
         rp.enlam = self._resident["enlam"].data_ptr()
         rp.inj_thr = self._resident["inj_thr"].data_ptr()

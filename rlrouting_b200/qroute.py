@@ -65,3 +65,36 @@ class Qroute(Policy):
         if idx:
             return np.argmax(scores, axis=-1), scores.max(axis=-1)
         return self.links[source][np.argmax(scores, axis=-1)]
+
+
+class CQ(Qroute):
+    """Confidence-based Q-routing (reference qroute.py:56-101).  `confidence` has the shape of `Qtable`; the
+    learning rate of an update is max(C_f, 1 - C_old) and every confidence entry decays by `decay` each step."""
+    attrs = Qroute.attrs | set(['decay', 'confidence'])
+    _kernel_policy = nat.POLICY_CQ
+    _table_names = ('Qtable', 'confidence')
+    _lr_default = {}                                                               # qroute.py:95
+    _dev_alias = {"Theta": "confidence"}        # the C ABI's `theta` slot carries the confidence table
+
+    def __init__(self, network, decay=0.9, initQ=0, discount=0.9):
+        Policy.__init__(self, network)
+        self.discount = discount
+        self.threshold = 0.1
+        self.decay = decay
+        self._alloc_tables(network, initQ, 0.0)      # rlr_init_tables also applies CQ.clean's structure (qroute.py:66-71)
+
+    confidence = property(lambda self: self._get_table("confidence"), lambda self, v: self._set_table("confidence", v))
+
+    def clean(self):
+        pass        # Network.reset re-initialises the confidence table on the device (rlr_reset), qroute.py:66-71
+
+    def learn(self, rewards, lr={}):
+        raise NotImplementedError("CQ / CDRQ learn inside Network.train on the device; the split Network.step / "
+                                  "agent.learn path is not implemented for them")
+
+
+class CDRQ(CQ):
+    """Confidence-based dual reinforcement Q-routing (reference qroute.py:104-122): runs the network in 'dual' mode
+    (env.py:92-94,154-160: rewards are queue lengths) and adds a backward update of Q[y][packet.source]."""
+    mode = 'dual'
+    _kernel_policy = nat.POLICY_CDRQ

@@ -15,7 +15,8 @@ POLICIES = {}
 
 def _classes():
     import rlrouting_b200 as rb
-    return {"Shortest": rb.Shortest, "Qroute": rb.Qroute, "HybridQ": rb.HybridQ, "MaHybridQ": rb.MaHybridQ}
+    return {"Shortest": rb.Shortest, "Qroute": rb.Qroute, "HybridQ": rb.HybridQ, "MaHybridQ": rb.MaHybridQ,
+            "CQ": rb.CQ, "CDRQ": rb.CDRQ}
 
 
 def device_run(case, **net_kw):
@@ -70,12 +71,12 @@ def test_device_matches_reference_known_answers(case):
         ohp = np.where(ores["end_packets"] > 0, ores["hops"] / np.maximum(ores["end_packets"], 1), 0.0)
     assert np.array_equal(res["route_time"], ort)
     assert np.array_equal(res["hop"], ohp)
-    bit_exact = case.get("rng", "trace") == "trace" or case.get("det_math") or case["policy"] == "Qroute"
+    bit_exact = case.get("rng", "trace") == "trace" or case.get("det_math") or case["policy"] in ("Qroute", "CQ", "CDRQ")
     if case["policy"] == "Shortest":
         assert sha(agent.distance, "<f8") == exp["distance_sha256"]
         assert sha(np.concatenate([agent.choice[x].reshape(-1) for x in range(topo.N)]).astype(np.uint8), "u1") == exp["choice_sha256"]
         return
-    for name, oarr in (("Qtable", env.Q), ("Theta", env.Theta), ("Trace", env.Trace)):
+    for name, oarr in (("Qtable", env.Q), ("Theta", env.Theta), ("Trace", env.Trace), ("confidence", env.Conf)):
         if name not in agent._dev:
             continue
         dev = agent.table_array(name)[0]
@@ -94,7 +95,7 @@ def _oracle_batch(net, policy, R, T, lam, seed, base, q0, lr, agent_kw=None):
     kw = agent_kw or {}
     envs = []
     for r in range(R):
-        e = O.OracleEnv(topo.links, policy, discount=kw.get("discount", 0.99), discount_trace=kw.get("discount_trace", 0.6),
+        e = O.OracleEnv(topo.links, policy, discount=kw.get("discount"), discount_trace=kw.get("discount_trace", 0.6),
                         add_entropy=kw.get("add_entropy", True), seed=seed, replica=base + r)
         if policy != "Shortest":
             e.set_qtable(q0[r], initP=kw.get("initP", 0.0))
@@ -112,7 +113,7 @@ def _compare_batch(nw, agent, envs, rt, en, res):
     with np.errstate(divide="ignore", invalid="ignore"):
         ort = np.where(en > 0, rt / np.maximum(en, 1), 0.0)
     assert np.array_equal(np.atleast_2d(res["route_time"]), ort)
-    for name, attr in (("Qtable", "Q"), ("Theta", "Theta"), ("Trace", "Trace")):
+    for name, attr in (("Qtable", "Q"), ("Theta", "Theta"), ("Trace", "Trace"), ("confidence", "Conf")):
         if name in agent._dev:
             dev = agent.table_array(name)
             for r, e in enumerate(envs):
@@ -138,6 +139,11 @@ BATCH = [
     ("6x6.net", "MaHybridQ", 10, 300, 2.0, dict(replicas_per_block=2, threads_per_block=192)),
     ("6x6-modified.net", "MaHybridQ", 5, 200, 1.0, dict(tables_in_smem=0)),
     ("lata.net", "MaHybridQ", 2, 100, 2.0, {}),
+    ("6x6.net", "CQ", 12, 400, 2.0, {}),
+    ("6x6-modified.net", "CQ", 7, 300, 1.0, dict(replicas_per_block=2, tables_in_smem=0)),
+    ("6x6.net", "CDRQ", 12, 500, 2.5, {}),
+    ("6x6.net", "CDRQ", 9, 400, 1.0, dict(replicas_per_block=3, threads_per_block=256)),
+    ("lata.net", "CDRQ", 3, 250, 3.0, {}),
 ]
 
 
