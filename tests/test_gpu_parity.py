@@ -339,3 +339,51 @@ def test_full_size_conservation_properties():
         oc = e.counters()
         assert all(int(c[k][r]) == oc[k] for k in ("all_packets", "end_packets", "hops", "route_time", "sends"))
         assert np.array_equal(q[r].view(np.int64), e.Q.view(np.int64))
+
+
+def _random_net(rng, n, extra, max_deg):
+    deg = np.zeros(n, dtype=int)
+    edges = []
+    for i in range(1, n):                                   # random spanning tree with a degree cap
+        cand = [j for j in range(i) if deg[j] < max(max_deg - 1, 1)] or [j for j in range(i) if deg[j] < max_deg]
+        j = cand[int(rng.integers(0, len(cand)))]
+        edges.append((i, j)); deg[i] += 1; deg[j] += 1
+    have = set(edges) | {(b, a) for a, b in edges}
+    for _ in range(extra):
+        a, b = (int(v) for v in rng.integers(0, n, 2))
+        if a != b and (a, b) not in have and deg[a] < max_deg and deg[b] < max_deg:
+            edges.append((a, b)); have |= {(a, b), (b, a)}; deg[a] += 1; deg[b] += 1
+    return "".join(f"1000 {i} 0 0 0\n" for i in range(n)) + "".join(f"2000 {a} {b} 0\n" for a, b in edges)
+
+
+@pytest.mark.parametrize("policy,n,extra,max_deg,R,T,lam", [
+    ("Qroute", 255, 700, 16, 3, 150, 6.0),          # maximum node count and degree: MAXD = 16, MAXW = 9 code paths
+    ("Shortest", 255, 300, 12, 2, 200, 8.0),
+    ("CDRQ", 97, 200, 9, 2, 150, 4.0),
+    ("HybridQ", 70, 120, 7, 3, 120, 3.0),
+    ("MaHybridQ", 127, 200, 10, 2, 60, 3.0),        # MaHybridQ's limit (NumPy single pairwise block: n < 128 senders)
+    ("Qroute", 2, 0, 1, 5, 300, 0.8),               # smallest graph
+    ("CQ", 33, 40, 6, 4, 200, 2.0),
+])
+def test_random_topologies_match_oracle(policy, n, extra, max_deg, R, T, lam, tmp_path):
+    """Random graphs written as .net text (degree-1 leaves, hubs, up to the supported maxima): device == oracle."""
+    import rlrouting_b200 as rb
+    rng = np.random.default_rng(n * 1000 + extra)
+    path = tmp_path / "g.net"
+    path.write_text(_random_net(rng, n, extra, max_deg))
+    nw = rb.Network(str(path), replicas=R, rng="philox", seed=17, replica_base=5, queue_capacity=1024)
+    agent = _classes()[policy](nw)
+    nw.agent = agent
+    topo = nw.topology
+    lr = {"q": 0.1, "p": 0.001 if policy == "MaHybridQ" else 0.1, "e": 0.1}
+    q0 = agent.table_array("Qtable") if policy != "Shortest" else None
+    res = nw.train(T, lam, lr=lr)
+    envs = []
+    for r in range(R):
+        e = O.OracleEnv(topo.links, policy, seed=17, replica=5 + r)
+        if q0 is not None:
+            e.set_qtable(q0[r])
+        envs.append(e)
+    sends, rt, en = O.run_many(envs, T, lam, lr_q=lr["q"], lr_p=lr["p"], lr_e=lr["e"], metrics=True)
+    assert sends > 0 or lam == 0
+    _compare_batch(nw, agent, envs, rt, en, res)

@@ -142,3 +142,15 @@ def test_native_trace_replay_equals_numpy_legacy_stream():
     rs = np.random.RandomState(0)
     cnt, pairs = trace.draw_injections(rs, 36, 100, 12.0)     # lambda >= 10: NumPy's PTRS branch, falls back to NumPy
     assert cnt.sum() == len(pairs) and np.all(pairs[:, 0] != pairs[:, 1])
+
+
+def test_integration_doc_ctypes_stub_matches_the_library():
+    """The binding shown in INTEGRATION.md must describe the structs the shipped library was built with."""
+    src = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = src[src.index("class Topology(C.Structure)"):src.index("sizes = (C.c_int32 * 4)()")]
+    ns = {"C": C}
+    exec(code, ns)
+    sizes = (C.c_int32 * 4)()
+    nat.lib().rlr_struct_sizes(sizes)
+    assert list(sizes) == [C.sizeof(ns[k]) for k in ("Topology", "Config", "Buffers", "RunParams")]
+    assert [f[0] for f in ns["RunParams"]._fields_] == [f[0] for f in nat.RunParams._fields_]
