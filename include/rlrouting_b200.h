@@ -107,7 +107,7 @@ typedef struct {
      *   a node with more than inj_cap - 1 injections sets RLR_STATUS_INJECT_OVERFLOW. */
     uint32_t *inj_events;
     int32_t inj_cap;
-    int32_t reserved0;
+    int32_t is_drop;          /* Network(is_drop=True): a packet arriving with hops >= N is dropped, env.py:355-360 */
     /* Philox mode */
     const double *enlam;      /* device [R]: exp(-lambda_r / N)                              */
     const uint64_t *inj_thr;  /* device [R]: smallest w in [0, 2^32] with (w + 0.5) * 2^-32 > enlam[r] */
@@ -130,6 +130,8 @@ typedef struct {
     double *route_time_out;   /* [n_steps][R] Network.ave_route_time after each step (env.py:409, 444-446); step-major
                                  so a chunk of steps is one contiguous block for the device->host copy */
     double *hop_out;          /* [n_steps][R] Network.ave_hops after each step (env.py:412-413, 440-442) */
+    void *metrics2;           /* [n_steps][R] {uint32 all_packets, uint32 drop_packets} after each step; for droprate_out */
+    double *droprate_out;     /* [n_steps][R] Network.drop_rate after each step (env.py:410-411, 448-450) */
     uint32_t *sendlog;        /* [R][n_steps][N]: y | dest << 16 for a send by node x, else 0xFFFFFFFF */
 } rlr_run_params_t;
 

@@ -58,7 +58,7 @@ def _det_math():
 
 
 def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, replica=0,
-        agent_kwargs=None, keep_sendlog=False, det_math=False):
+        agent_kwargs=None, keep_sendlog=False, det_math=False, net_kwargs=None):
     """Runs `Network(net); agent = policy(nw); nw.train(T, lambd, lr=lr)` step by step.
 
     rng='trace'  : np.random.seed(seed) and the reference's own legacy stream (bit-for-bit the
@@ -71,7 +71,7 @@ def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, repl
     R = load()
     path = net if os.path.isabs(net) else os.path.join(REF, net)
     np.random.seed(seed)
-    nw = R["Network"](path)
+    nw = R["Network"](path, **(net_kwargs or {}))
     agent = R[policy](nw, **(agent_kwargs or {}))
     nw.agent = agent
     N = len(nw.nodes)

@@ -14,8 +14,7 @@
  * Every function cites the reference lines it restates (paths relative to /root/reference).
  * One orc_t is one environment replica == one `Network` + one bound agent.
  *
- * Scope: default mode only — bandwidth=1, transtime=1, slot=1, freq=1,
- * is_drop=False.  Under those defaults every event of a step arrives inside the step
+ * Scope: default timing model — bandwidth=1, transtime=1, slot=1, freq=1 (is_drop optional).  Under those defaults every event of a step arrives inside the step
  * (env.py:349-353), `sent` returns to 0 and `avaliable_path` is all-True (env.py:171-174),
  * so the head of the queue is the packet sent (env.py:175-180).
  */
@@ -64,6 +63,7 @@ typedef struct orc {
     int64_t clock, all_packets, end_packets, drop_packets, active_packets, hops, route_time, sends;
     double discount, discount_trace, reward_shape;
     int add_entropy, status;
+    int is_drop;              /* Network(is_drop=True): env.py:355-360 */
     int64_t status_clock;
     uint64_t seed, replica;   /* Philox key / stream id */
 } orc_t;
@@ -183,6 +183,7 @@ void orc_set_hparams(orc_t *o, double discount, double discount_trace, int add_e
 }
 
 void orc_set_decay(orc_t *o, double decay) { o->decay = decay; }
+void orc_set_is_drop(orc_t *o, int is_drop) { o->is_drop = is_drop; }
 
 void orc_set_stream(orc_t *o, uint64_t seed, uint64_t replica) { o->seed = seed; o->replica = replica; }
 
@@ -581,6 +582,11 @@ static void drain_events(orc_t *o)
     int64_t end_time = o->clock + 1;
     while (o->heap_len > 0 && o->heap[0].arrive <= end_time) {
         event_t e = hq_pop(o);
+        if (o->is_drop && e.p.hops >= o->N) {          /* env.py:355-360; drop_penalty is a no-op for every in-scope agent */
+            o->drop_packets += 1;
+            o->active_packets -= 1;
+            continue;
+        }
         o->clock = e.arrive;
         node_receive(o, e.to, &e.p);
     }

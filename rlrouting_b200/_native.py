@@ -56,13 +56,13 @@ class Buffers(C.Structure):
 
 class RunParams(C.Structure):
     _fields_ = [("inject_mode", C.c_int32), ("add_entropy", C.c_int32),
-                ("inj_events", C.c_void_p), ("inj_cap", C.c_int32), ("reserved0", C.c_int32),
+                ("inj_events", C.c_void_p), ("inj_cap", C.c_int32), ("is_drop", C.c_int32),
                 ("enlam", C.c_void_p), ("inj_thr", C.c_void_p), ("seed", C.c_uint64),
                 ("lr_q", C.c_double), ("lr_p", C.c_double), ("lr_e", C.c_double),
                 ("discount", C.c_double), ("discount_trace", C.c_double), ("conf_decay", C.c_double),
                 ("clock0", C.c_int32), ("phase", C.c_int32), ("rewards", C.c_void_p),
                 ("metrics", C.c_void_p), ("route_time_out", C.c_void_p), ("hop_out", C.c_void_p),
-                ("sendlog", C.c_void_p)]
+                ("metrics2", C.c_void_p), ("droprate_out", C.c_void_p), ("sendlog", C.c_void_p)]
 
 
 EXPORTS = ("rlr_abi_version", "rlr_last_error_string", "rlr_struct_sizes", "rlr_create", "rlr_destroy", "rlr_bind_buffers",

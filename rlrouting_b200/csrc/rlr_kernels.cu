@@ -66,6 +66,7 @@ struct StepParams {
     long long *counters;
     int *status;
     int inj_cap, add_entropy;
+    int is_drop;                  // Network(is_drop=True), env.py:355-360
     int phase;                    // bit 0: inject + send + arrive (Network.step); bit 1: agent.learn
     uint4 *rewards;               // [R][N][3] saved Reward records (phase 1 writes, phase 2 reads)
     const unsigned *inj_events;
@@ -73,6 +74,7 @@ struct StepParams {
     long long replica_base;
     double lr_q, lr_p, lr_e, discount, discount_trace, conf_decay;
     uint4 *metrics;
+    uint2 *metrics2;              // [K][R] {all_packets, drop_packets} after each step (for the droprate vector)
     unsigned *sendlog;
 };
 
@@ -314,7 +316,7 @@ struct SmemLayout {
         f64 = o; o += (policy == RLR_POLICY_MAHYBRIDQ) ? align16((size_t)(3 * GN + 4 * G) * 8)
                        : (policy == RLR_POLICY_CDRQ) ? align16((size_t)GN * 32) : 0;   // CDRQ: {C_b, max_Q_b}, len, q_x, d|k, src
         ull = o; o += align16((size_t)G * 3 * 8);            // route_time, sends, injected
-        u32 = o; o += align16((size_t)G * 4 * 4);            // end, hops, dead
+        u32 = o; o += align16((size_t)G * 8 * 4);            // end, hops, dead, drop, injected-so-far
         wmask = o; o += align16((size_t)(threads / 32 + 1) * 4);
         rowptr = o; o += align16((size_t)(N + 1) * 4);
         col = o; o += align16((size_t)sdeg * 2);
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     unsigned char *s_nexthop = smem + L.nexthop;
     // per-replica accumulators of this launch
     unsigned long long *s_rt = s_ull, *s_sends = s_ull + G, *s_inj = s_ull + 2 * G;
-    unsigned *s_end = s_u32, *s_hops = s_u32 + G, *s_dead = s_u32 + 2 * G;
+    unsigned *s_end = s_u32, *s_hops = s_u32 + G, *s_dead = s_u32 + 2 * G, *s_drop = s_u32 + 3 * G, *s_injs = s_u32 + 4 * G;
     // MaHybridQ scratch: r, max_Q_y, max_Q_x_d per node; three sums + spare per replica
     double *s_r = s_f64, *s_qy = s_f64 + GN, *s_qx = s_f64 + 2 * GN, *s_sum = s_f64 + 3 * GN;
     // CDRQ scratch (same region): backward-update inputs of each sender and the queue lengths of 'dual' mode
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     if (POLICY == RLR_POLICY_SHORTEST)
         for (int i = t; i < N * N; i += blockDim.x) s_nexthop[i] = p.next_hop[i];
     for (int i = t; i < G; i += blockDim.x) {
-        s_rt[i] = 0; s_sends[i] = 0; s_inj[i] = 0; s_end[i] = 0; s_hops[i] = 0;
+        s_rt[i] = 0; s_sends[i] = 0; s_inj[i] = 0; s_end[i] = 0; s_hops[i] = 0; s_drop[i] = 0; s_injs[i] = 0;
         s_dead[i] = (rblock + i < p.R) ? (unsigned)(p.status[2 * (rblock + i)] != 0) : 1u;
     }
     if (SMEM_TABLES) {
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     uint4 *myring = nullptr;
     int rp = 0, deg = 0;
     unsigned my_sends = 0, my_inj = 0;
-    long long base_rt = 0, base_end = 0, base_hops = 0;
+    long long base_rt = 0, base_end = 0, base_hops = 0, base_all = 0, base_drop = 0;
     double *Qx = nullptr, *Thx = nullptr, *Trx = nullptr;          // table[x] of this node
     if (is_node) {
         head = p.qhead[r * N + x];
@@ -447,6 +449,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             base_rt = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_ROUTE_TIME];
             base_end = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_END_PACKETS];
             base_hops = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_HOPS];
+            base_all = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_ALL_PACKETS];
+            base_drop = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_DROP_PACKETS];
         }
     }
     const unsigned long long stream_id = (unsigned long long)(p.replica_base + r);
@@ -509,6 +513,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             while ((ev >> 8) == (unsigned)s) {
                 append(make_uint4((ev & 0xFFu) | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock));
                 ++my_inj;
+                if (p.metrics2) atomicAdd(&s_injs[g], 1u);
                 ev = ev_next;
                 if (ev != 0xFFFFFFFFu) ev_next = *++evp;
             }
@@ -680,6 +685,10 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 }
                 if (best == kNoKey) break;
                 uint4 rec = s_rec[best & 0xFFFFu];
+                if (p.is_drop && rec.y >= (unsigned)N) {                        // env.py:355-360: too many hops, dropped
+                    atomicAdd(&s_drop[g], 1u);
+                    continue;
+                }
                 if ((int)(rec.x & 0xFFFFu) == x) {                              // Network.end_packet, env.py:321-331
                     atomicAdd(&s_end[g], 1u);
                     atomicAdd(&s_rt[g], (unsigned long long)(clock + 1 - (int)rec.z));
@@ -838,6 +847,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             const long long rt = base_rt + (long long)s_rt[g];
             const unsigned en = (unsigned)(base_end + s_end[g]), hps = (unsigned)(base_hops + s_hops[g]);
             p.metrics[(long long)s * p.R + r] = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hps);
+            if (p.metrics2)
+                p.metrics2[(long long)s * p.R + r] = make_uint2((unsigned)(base_all + s_injs[g]), (unsigned)(base_drop + s_drop[g]));
         }
     }
 
@@ -853,6 +864,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         long long *c = p.counters + r * RLR_NUM_COUNTERS;
         c[RLR_CTR_ALL_PACKETS] += (long long)s_inj[g];
         c[RLR_CTR_END_PACKETS] += (long long)s_end[g];
+        c[RLR_CTR_DROP_PACKETS] += (long long)s_drop[g];
         c[RLR_CTR_HOPS] += (long long)s_hops[g];
         c[RLR_CTR_ROUTE_TIME] += (long long)s_rt[g];
         c[RLR_CTR_SENDS] += (long long)s_sends[g];
@@ -1022,7 +1034,8 @@ __global__ void rlr_inject_schedule_kernel(unsigned *events, int cap, long long 
 
 // ave_route_time / ave_hops after each step (env.py:440-446): route_time / end_packets if end_packets > 0 else 0.
 // IEEE division of two exactly converted integers is Python's correctly rounded int / int.
-__global__ void rlr_ratio_kernel(const uint4 *metrics, long long n, double *route_time_out, double *hop_out)
+__global__ void rlr_ratio_kernel(const uint4 *metrics, const uint2 *metrics2, long long n, double *route_time_out,
+                                 double *hop_out, double *droprate_out)
 {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const uint4 m = metrics[i];
@@ -1030,6 +1043,10 @@ __global__ void rlr_ratio_kernel(const uint4 *metrics, long long n, double *rout
         const double en = (double)m.z;
         if (route_time_out) route_time_out[i] = m.z ? __ddiv_rn((double)rt, en) : 0.0;
         if (hop_out) hop_out[i] = m.z ? __ddiv_rn((double)m.w, en) : 0.0;
+        if (droprate_out) {                          // drop_packets / all_packets if all_packets > 0 else 0, env.py:448-450
+            const uint2 m2 = metrics2[i];
+            droprate_out[i] = m2.x ? __ddiv_rn((double)m2.y, (double)m2.x) : 0.0;
+        }
     }
 }
 
@@ -1379,8 +1396,9 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
         return fail(RLR_E_UNSUPPORTED, "rlr_run_steps: the split Network.step / agent.learn phases are not available for CQ / CDRQ");
     if ((rp->phase == 1 || rp->phase == 2) && (n_steps != 1 || !rp->rewards))
         return fail(RLR_E_INVALID, "rlr_run_steps: the split phases (Network.step / agent.learn) run one step and need the rewards buffer");
-    if ((rp->route_time_out || rp->hop_out) && !rp->metrics)
-        return fail(RLR_E_INVALID, "rlr_run_steps: route_time_out / hop_out need the metrics record buffer");
+    if ((rp->route_time_out || rp->hop_out || rp->droprate_out) && !rp->metrics)
+        return fail(RLR_E_INVALID, "rlr_run_steps: route_time_out / hop_out / droprate_out need the metrics record buffer");
+    if (rp->droprate_out && !rp->metrics2) return fail(RLR_E_INVALID, "rlr_run_steps: droprate_out needs the metrics2 buffer");
     if ((long long)rp->clock0 + n_steps > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: clock overflows int32");
     RLR_CUDA(cudaSetDevice(h->device));
     StepParams p;
@@ -1392,11 +1410,11 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     p.Q = h->bufs.q_table; p.Theta = h->bufs.theta; p.Trace = h->bufs.trace;
     p.ring = (uint4 *)h->bufs.ring; p.qhead = h->bufs.q_head; p.qtail = h->bufs.q_tail;
     p.counters = (long long *)h->bufs.counters; p.status = h->bufs.status;
-    p.inj_cap = rp->inj_cap; p.add_entropy = rp->add_entropy;
+    p.inj_cap = rp->inj_cap; p.add_entropy = rp->add_entropy; p.is_drop = rp->is_drop;
     p.phase = rp->phase == 0 ? 3 : rp->phase; p.rewards = (uint4 *)rp->rewards;
     p.inj_events = rp->inj_events; p.seed = rp->seed; p.replica_base = h->replica_base;
     p.lr_q = rp->lr_q; p.lr_p = rp->lr_p; p.lr_e = rp->lr_e; p.discount = rp->discount; p.discount_trace = rp->discount_trace; p.conf_decay = rp->conf_decay;
-    p.metrics = (uint4 *)rp->metrics; p.sendlog = rp->sendlog;
+    p.metrics = (uint4 *)rp->metrics; p.metrics2 = (uint2 *)rp->metrics2; p.sendlog = rp->sendlog;
     if (rp->inject_mode == RLR_INJECT_PHILOX) {
         const int rc = rlr_build_inject_schedule(h, n_steps, rp, stream);
         if (rc != RLR_OK) return rc;
@@ -1405,10 +1423,11 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     if (blocks > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: too many blocks");
     (p.phase == 3 ? h->kernel : h->kernel_split)<<<(unsigned)blocks, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p);
     RLR_CUDA(cudaGetLastError());
-    if (rp->route_time_out || rp->hop_out) {
+    if (rp->route_time_out || rp->hop_out || rp->droprate_out) {
         const long long n = n_steps * h->R;
         const int rb = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-        rlr_ratio_kernel<<<rb, 256, 0, (cudaStream_t)stream>>>((const uint4 *)rp->metrics, n, rp->route_time_out, rp->hop_out);
+        rlr_ratio_kernel<<<rb, 256, 0, (cudaStream_t)stream>>>((const uint4 *)rp->metrics, (const uint2 *)rp->metrics2, n,
+                                                               rp->route_time_out, rp->hop_out, rp->droprate_out);
         RLR_CUDA(cudaGetLastError());
     }
     return RLR_OK;

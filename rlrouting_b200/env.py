@@ -6,7 +6,7 @@ the reference's numbers bit for bit.  The additive keywords (`replicas`, `rng`, 
 independent environments; every counter property then returns an array of length R.
 
 Unsupported reference options raise NotImplementedError when they are requested, never mid-run,
-and there is no CPU fallback: `bandwidth != 1`, `transtime != 1`, `is_drop`,
+and there is no CPU fallback: `bandwidth != 1`, `transtime != 1`,
 `slot != 1`, `freq != 1`, mode 'dual'/'bp', and agents that are not one of the built-in policies.
 """
 import ctypes as C
@@ -101,8 +101,6 @@ class Network:
         if bandwidth != 1 or transtime != 1:
             raise NotImplementedError("bandwidth != 1 / transtime != 1 need in-flight events that outlive a step "
                                       "(SURVEY §8 row f2); not implemented on the device and there is no CPU fallback")
-        if is_drop:
-            raise NotImplementedError("is_drop=True (SURVEY §8 row f2) is not implemented on the device")
         if rng not in ("trace", "philox"):
             raise ValueError("rng must be 'trace' or 'philox'")
         if replicas < 1:
@@ -386,6 +384,7 @@ class Network:
         rp.discount = float(getattr(agent, "discount", 0.99))
         rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
         rp.conf_decay = float(getattr(agent, "decay", 0.9))
+        rp.is_drop = int(bool(self.is_drop))
         rp.seed = self.seed
         return rp
 
@@ -515,6 +514,7 @@ class Network:
         rp.discount = float(getattr(agent, "discount", 0.99))
         rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
         rp.conf_decay = float(getattr(agent, "decay", 0.9))
+        rp.is_drop = int(bool(self.is_drop))
         rp.seed = self.seed
         keep = []
         h2d = 0
@@ -542,6 +542,8 @@ class Network:
         # results land in pooled page-locked buffers handed out zero-copy (rlrouting_b200.pinned)
         host_rt, out_rt = pinned.POOL.take((T, R)) if per_step else (None, None)       # step-major
         host_hop, out_hop = pinned.POOL.take((T, R)) if (per_step and hop) else (None, None)
+        want_drop = bool(per_step and droprate and self.is_drop)
+        host_drop, out_drop = pinned.POOL.take((T, R)) if want_drop else (None, None)
         log_chunks = []
         s0 = 0
         stream = self._stream_ptr()
@@ -569,6 +571,10 @@ class Network:
             d_hop = torch.empty((K, R), dtype=torch.float64, device=dev) if host_hop is not None else None
             rp.route_time_out = d_rt.data_ptr() if d_rt is not None else None
             rp.hop_out = d_hop.data_ptr() if d_hop is not None else None
+            d_rec2 = torch.empty((K, R, 2), dtype=torch.int32, device=dev) if want_drop else None
+            d_drop = torch.empty((K, R), dtype=torch.float64, device=dev) if want_drop else None
+            rp.metrics2 = d_rec2.data_ptr() if want_drop else None
+            rp.droprate_out = d_drop.data_ptr() if want_drop else None
             log = torch.empty((R, K, N), dtype=torch.int32, device=dev) if sendlog else None
             rp.sendlog = log.data_ptr() if log is not None else None
             nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), stream))
@@ -585,6 +591,9 @@ class Network:
                     if d_hop is not None:
                         host_hop[s0:s0 + K].copy_(d_hop, non_blocking=True)
                         d_hop.record_stream(copier)
+                    if d_drop is not None:
+                        host_drop[s0:s0 + K].copy_(d_drop, non_blocking=True)
+                        d_drop.record_stream(copier)
             if log is not None:
                 log_chunks.append(log)
             s0 += K
@@ -610,8 +619,14 @@ class Network:
             result["route_time"] = np.where(end > 0, rt / np.maximum(end, 1), 0.0)
             if hop:
                 result["hop"] = np.where(end > 0, hops / np.maximum(end, 1), 0.0)
-        if droprate:                                                                    # is_drop is off: env.py:448-450
-            result["droprate"] = np.broadcast_to(np.zeros((R, 1)), result["route_time"].shape)
+        if droprate:                                                                    # env.py:410-411, 448-450
+            if want_drop:
+                result["droprate"] = out_drop.T
+            elif self.is_drop:
+                c = self._counters.cpu().numpy()
+                result["droprate"] = np.where(c[:, 0:1] > 0, c[:, 2:3] / np.maximum(c[:, 0:1], 1), 0.0)
+            else:
+                result["droprate"] = np.broadcast_to(np.zeros((R, 1)), result["route_time"].shape)
         if sendlog:
             self.last_sendlog = torch.cat(log_chunks, dim=1).cpu().numpy().view(np.uint32)
         return self._finish(result, legacy, R)
@@ -647,6 +662,7 @@ class Network:
         rp.discount = float(getattr(agent, "discount", 0.99))
         rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
         rp.conf_decay = float(getattr(agent, "decay", 0.9))
+        rp.is_drop = int(bool(self.is_drop))
         rp.seed = self.seed
         rp.enlam = self._resident["enlam"].data_ptr()
         rp.inj_thr = self._resident["inj_thr"].data_ptr()

@@ -62,6 +62,11 @@ CASES = [
     dict(net="6x6-modified.net", policy="CDRQ", T=2000, lambd=1.0, seed=1),
     dict(net="lata.net", policy="CDRQ", T=800, lambd=3.0, seed=1),
     dict(net="6x6.net", policy="CDRQ", T=1500, lambd=3.0, seed=1, rng="philox", philox_seed=7, replica=3),
+    # is_drop=True — a packet arriving with hops >= N is dropped (env.py:355-360)
+    dict(net="6x6.net", policy="Qroute", T=3000, lambd=2.0, seed=1, net_kwargs={"is_drop": True}),
+    dict(net="6x6.net", policy="CDRQ", T=2000, lambd=3.0, seed=2, net_kwargs={"is_drop": True}),
+    dict(net="lata.net", policy="HybridQ", T=600, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3, det_math=True,
+         net_kwargs={"is_drop": True}),
     # sampled policies with NumPy's own exp/log2: short horizon, tables compared with a tolerance
     dict(net="6x6.net", policy="HybridQ", T=300, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3, keep_tables=True),
     dict(net="6x6.net", policy="MaHybridQ", T=300, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3,

@@ -25,6 +25,7 @@ def device_run(case, **net_kw):
     topo = topo_of(case["net"])
     kw = dict(case.get("agent_kwargs") or {})
     rng = case.get("rng", "trace")
+    net_kw = dict(net_kw, **(case.get("net_kwargs") or {}))
     if rng == "trace":
         nw = rb.Network(case["net"], rng="trace", seed=case["seed"], **net_kw)
         agent = _classes()[case["policy"]](nw, **kw)
@@ -41,7 +42,7 @@ def device_run(case, **net_kw):
         with pytest.raises(ValueError, match="probabilities contain NaN"):
             nw.train(case["T"], case["lambd"], lr=case.get("lr") or {}, hop=True, sendlog=True)
         return nw, agent, None
-    res = nw.train(case["T"], case["lambd"], lr=case.get("lr") or {}, hop=True, sendlog=True)
+    res = nw.train(case["T"], case["lambd"], lr=case.get("lr") or {}, hop=True, droprate=True, sendlog=True)
     return nw, agent, res
 
 
@@ -71,6 +72,8 @@ def test_device_matches_reference_known_answers(case):
         ohp = np.where(ores["end_packets"] > 0, ores["hops"] / np.maximum(ores["end_packets"], 1), 0.0)
     assert np.array_equal(res["route_time"], ort)
     assert np.array_equal(res["hop"], ohp)
+    assert res["droprate"][-1] == (got["drop_packets"] / got["all_packets"] if got["all_packets"] else 0)   # env.py:448-450
+    assert res["droprate"].shape == ort.shape and np.all(np.diff(res["droprate"] * 0 + np.arange(len(ort))) == 1)
     bit_exact = case.get("rng", "trace") == "trace" or case.get("det_math") or case["policy"] in ("Qroute", "CQ", "CDRQ")
     if case["policy"] == "Shortest":
         assert sha(agent.distance, "<f8") == exp["distance_sha256"]

@@ -88,7 +88,7 @@ def test_injection_threshold_is_exact():
 
 def test_unsupported_options_fail_before_touching_the_device():
     import rlrouting_b200 as rb
-    for kw in (dict(bandwidth=2), dict(transtime=2), dict(is_drop=True)):
+    for kw in (dict(bandwidth=2), dict(transtime=2), dict(bandwidth=3, is_drop=True)):
         with pytest.raises(NotImplementedError):
             rb.Network("6x6.net", **kw)
     with pytest.raises(ValueError):
