@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "librlr_oracle.so")
 
-POLICY_ID = {"Shortest": 0, "Qroute": 1, "HybridQ": 2, "MaHybridQ": 3, "CQ": 4, "CDRQ": 5}
+POLICY_ID = {"Shortest": 0, "Qroute": 1, "HybridQ": 2, "MaHybridQ": 3, "CQ": 4, "CDRQ": 5, "GlobalRoute": 6}
 _lib = None
 
 
@@ -56,6 +56,9 @@ def lib():
         L.orc_qtable_structure.argtypes = [p]
         L.orc_reset.argtypes = [p]
         L.orc_shortest_build.argtypes = [p]
+        L.orc_globalroute_init.argtypes = [p]
+        L.orc_queue_size.restype = C.POINTER(C.c_int64)
+        L.orc_queue_size.argtypes = [p]
         L.orc_heap_perm.argtypes = [i32, p]
         L.orc_philox4x32.argtypes = [p, p, p]
         L.orc_run.restype = i64
@@ -104,6 +107,9 @@ class OracleEnv:
         self.distance = np.ctypeslib.as_array(L.orc_distance(self.h), shape=(self.N, self.N))
         if policy == "Shortest":
             L.orc_shortest_build(self.h)
+        if policy == "GlobalRoute":
+            L.orc_globalroute_init(self.h)
+        self.queue_size = np.ctypeslib.as_array(L.orc_queue_size(self.h), shape=(self.N,))
 
     def __del__(self):
         if getattr(self, "h", None) and _lib is not None:

@@ -29,7 +29,7 @@ def load():
     import env, qroute, shortest, hybrid, multi_agent  # noqa: E401
     return {"env": env, "Network": env.Network, "Qroute": qroute.Qroute,
             "Shortest": shortest.Shortest, "HybridQ": hybrid.HybridQ,
-            "MaHybridQ": multi_agent.MaHybridQ, "CQ": qroute.CQ, "CDRQ": qroute.CDRQ}
+            "MaHybridQ": multi_agent.MaHybridQ, "CQ": qroute.CQ, "CDRQ": qroute.CDRQ, "GlobalRoute": shortest.GlobalRoute}
 
 
 def sendlog_hash(log):
@@ -168,7 +168,9 @@ def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, repl
     for name in ("Qtable", "Theta", "Trace", "confidence"):
         if hasattr(agent, name):
             out[name] = pack_tables(getattr(agent, name), N)
-    if policy == "Shortest":
+    if policy in ("Shortest", "GlobalRoute"):
         out["distance"] = agent.distance.copy()
         out["choice"] = np.concatenate([agent.choice[x].reshape(-1) for x in range(N)]).astype(np.uint8)
+    if policy == "GlobalRoute":
+        out["queue_size"] = np.asarray(agent.queue_size, dtype=np.int64).copy()
     return out

@@ -26,7 +26,7 @@
 #include <omp.h>
 #endif
 
-enum { POL_SHORTEST = 0, POL_QROUTE = 1, POL_HYBRIDQ = 2, POL_MAHYBRIDQ = 3, POL_CQ = 4, POL_CDRQ = 5 };
+enum { POL_SHORTEST = 0, POL_QROUTE = 1, POL_HYBRIDQ = 2, POL_MAHYBRIDQ = 3, POL_CQ = 4, POL_CDRQ = 5, POL_GLOBALROUTE = 6 };
 enum { INJ_TRACE = 0, INJ_PHILOX = 1 };
 enum { ST_OK = 0, ST_NAN_PROB = 1 };
 
@@ -64,6 +64,7 @@ typedef struct orc {
     double discount, discount_trace, reward_shape;
     int add_entropy, status;
     int is_drop;              /* Network(is_drop=True): env.py:355-360 */
+    int64_t *queue_size;      /* GlobalRoute.queue_size (shortest.py:89): +1 per receive callback, -1 per send callback */
     int64_t status_clock;
     uint64_t seed, replica;   /* Philox key / stream id */
 } orc_t;
@@ -158,6 +159,7 @@ orc_t *orc_create(int N, const int *row_ptr, const int *col, int policy)
     o->queue = (fifo_t *)calloc((size_t)N, sizeof(fifo_t));
     o->heap_cap = N + 8; o->heap = (event_t *)malloc(sizeof(event_t) * o->heap_cap);
     o->rewards = (reward_t *)malloc(sizeof(reward_t) * N);
+    o->queue_size = (int64_t *)calloc((size_t)N, sizeof(int64_t));
     o->scratch = (double *)malloc(sizeof(double) * 3 * N);
     o->discount = 0.99;        /* qroute.py:9, hybrid.py:44, multi_agent.py:10 */
     o->discount_trace = 0.6;   /* multi_agent.py:10 */
@@ -174,7 +176,7 @@ void orc_destroy(orc_t *o)
     for (int x = 0; x < o->N; ++x) free(o->queue[x].buf);
     free(o->row_ptr); free(o->col); free(o->aidx); free(o->toff); free(o->Q); free(o->Theta);
     free(o->Trace); free(o->choice); free(o->distance); free(o->queue); free(o->heap);
-    free(o->rewards); free(o->scratch); free(o);
+    free(o->rewards); free(o->scratch); free(o->queue_size); free(o);
 }
 
 void orc_set_hparams(orc_t *o, double discount, double discount_trace, int add_entropy)
@@ -288,6 +290,49 @@ void orc_shortest_build(orc_t *o)
         }
     }
 }
+
+/* GlobalRoute (shortest.py:84-104).  `_calc_distance` (shortest.py:43-58) with mask = everything off the diagonal
+ * (shortest.py:87-88: all distances restart from inf) and unit(y) = 1 + queue_size[y] (shortest.py:90).  The
+ * caller clears `choice` first, as GlobalRoute.learn does (shortest.py:101-103). */
+void orc_globalroute_calc(orc_t *o)
+{
+    int N = o->N;
+    for (int x = 0; x < N; ++x)
+        for (int z = 0; z < N; ++z)
+            if (x != z) o->distance[x * N + z] = INFINITY;               /* distance[mask] = inf */
+    int changing = 1;
+    while (changing) {
+        changing = 0;
+        for (int x = 0; x < N; ++x) {
+            int deg = o->row_ptr[x + 1] - o->row_ptr[x];
+            for (int j = 0; j < deg; ++j) {
+                int y = o->col[o->row_ptr[x] + j];
+                double unit = (double)(1 + o->queue_size[y]);
+                for (int z = 0; z < N; ++z) {
+                    double nd = o->distance[y * N + z] + unit;
+                    if (o->distance[x * N + z] > nd) {
+                        o->distance[x * N + z] = nd;
+                        uint8_t *c = o->choice + o->toff[x] + (int64_t)z * deg;
+                        memset(c, 0, (size_t)deg);
+                        c[j] = 1;
+                        changing = 1;
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* GlobalRoute.__init__ (shortest.py:85-91): Shortest.__init__ (tables with unit 1), then the mask is widened, the
+ * queue sizes zeroed and the distances recomputed WITHOUT clearing `choice` first. */
+void orc_globalroute_init(orc_t *o)
+{
+    orc_shortest_build(o);
+    memset(o->queue_size, 0, sizeof(int64_t) * (size_t)o->N);
+    orc_globalroute_calc(o);
+}
+
+int64_t *orc_queue_size(orc_t *o) { return o->queue_size; }
 
 /* ---- heapq with keys compared by arrive_time only (CPython Lib/heapq.py restated) ---- */
 static inline int ev_lt(const event_t *a, const event_t *b) { return a->arrive < b->arrive; }  /* env.py:48-49 */
@@ -461,6 +506,7 @@ static void node_receive(orc_t *o, int x, pkt_t *p)
     } else {
         p->start_queue = (int32_t)o->clock;
         fifo_push(&o->queue[x], p);
+        o->queue_size[x] += 1;                           /* agent.receive (env.py:131-133, shortest.py:93-94) */
     }
 }
 
@@ -519,7 +565,7 @@ static void send_phase(orc_t *o)
         int deg = o->row_ptr[x + 1] - o->row_ptr[x];
         pkt_t p = q->buf[q->head];
         int d = p.dest, k = 0;
-        if (o->policy == POL_SHORTEST) {
+        if (o->policy == POL_SHORTEST || o->policy == POL_GLOBALROUTE) {
             const uint8_t *c = o->choice + o->toff[x] + (int64_t)d * deg;
             while (k < deg && !c[k]) k++;
         } else if (o->policy == POL_QROUTE || o->policy == POL_CQ || o->policy == POL_CDRQ) {
@@ -539,6 +585,7 @@ static void send_phase(orc_t *o)
         }
         int y = o->col[o->row_ptr[x] + k];
         q->head++; q->len--;
+        o->queue_size[x] -= 1;                           /* agent.send (env.py:181, shortest.py:96-97) */
         p.hops += 1;
         event_t e; e.p = p; e.from = x; e.to = y; e.arrive = o->clock + 1;
         hq_push(o, &e);
@@ -564,7 +611,7 @@ static void send_phase(orc_t *o)
                 r->q_y = o->queue[y].len > 1 ? o->queue[y].len : 1;
                 r->q_x = q->len > 1 ? q->len : 1;
             }
-        } else if (o->policy != POL_SHORTEST) {
+        } else if (o->policy != POL_SHORTEST && o->policy != POL_GLOBALROUTE) {
             int degy = o->row_ptr[y + 1] - o->row_ptr[y];
             const double *ry = o->Q + o->toff[y] + (int64_t)d * degy;
             double m = ry[0]; for (int j = 1; j < degy; ++j) if (ry[j] > m) m = ry[j];
@@ -611,6 +658,11 @@ static void learn_phase(orc_t *o, double lr_q, double lr_p, double lr_e)
 {
     int n = o->n_rewards;
     if (o->policy == POL_SHORTEST) return;                       /* Policy.learn: no-op */
+    if (o->policy == POL_GLOBALROUTE) {                          /* shortest.py:99-104 */
+        memset(o->choice, 0, (size_t)o->tsize);
+        orc_globalroute_calc(o);
+        return;
+    }
     if (o->policy == POL_CQ || o->policy == POL_CDRQ) {          /* qroute.py:80-101, 117-122 */
         for (int i = 0; i < n; ++i) {
             const reward_t *rw = &o->rewards[i];

@@ -62,6 +62,11 @@ CASES = [
     dict(net="6x6-modified.net", policy="CDRQ", T=2000, lambd=1.0, seed=1),
     dict(net="lata.net", policy="CDRQ", T=800, lambd=3.0, seed=1),
     dict(net="6x6.net", policy="CDRQ", T=1500, lambd=3.0, seed=1, rng="philox", philox_seed=7, replica=3),
+    # GlobalRoute — all-pairs distances recomputed every step with node weights 1 + queue size
+    dict(net="6x6.net", policy="GlobalRoute", T=300, lambd=2.0, seed=1),
+    dict(net="6x6-modified.net", policy="GlobalRoute", T=200, lambd=3.0, seed=1),
+    dict(net="lata.net", policy="GlobalRoute", T=40, lambd=3.0, seed=1),
+    dict(net="6x6.net", policy="GlobalRoute", T=200, lambd=3.0, seed=1, rng="philox", philox_seed=7, replica=3),
     # is_drop=True — a packet arriving with hops >= N is dropped (env.py:355-360)
     dict(net="6x6.net", policy="Qroute", T=3000, lambd=2.0, seed=1, net_kwargs={"is_drop": True}),
     dict(net="6x6.net", policy="CDRQ", T=2000, lambd=3.0, seed=2, net_kwargs={"is_drop": True}),
@@ -100,6 +105,8 @@ def main():
         if "distance" in r:
             rec["expect"]["distance_sha256"] = h(r["distance"], "<f8")
             rec["expect"]["choice_sha256"] = h(r["choice"], "u1")
+        if "queue_size" in r:
+            rec["expect"]["queue_size"] = [int(v) for v in r["queue_size"]]
         out.append(rec)
         print(i, c["net"], c["policy"], r["counters"], r["error"], flush=True)
     with open(os.path.join(HERE, "kat.json"), "w") as f:

@@ -31,7 +31,7 @@ def case_inputs(case, topo):
     rs = np.random.RandomState(case["seed"])
     kw = case.get("agent_kwargs") or {}
     q0 = None
-    if case["policy"] != "Shortest":
+    if case["policy"] not in ("Shortest", "GlobalRoute"):
         times = 2 if case["policy"] in ("HybridQ", "MaHybridQ") else 1
         q0 = topo.pack(trace.draw_qtable_normals(rs, topo, kw.get("initQ", 0), times))
     inj = None
