@@ -37,7 +37,8 @@ enum { RLR_OK = 0, RLR_E_INVALID = -1, RLR_E_UNSUPPORTED = -2, RLR_E_CUDA = -3, 
 enum {
     RLR_POLICY_SHORTEST = 0, RLR_POLICY_QROUTE = 1, RLR_POLICY_HYBRIDQ = 2, RLR_POLICY_MAHYBRIDQ = 3,
     RLR_POLICY_CQ = 4,      /* qroute.py:56-101  confidence-based Q-routing                              */
-    RLR_POLICY_CDRQ = 5     /* qroute.py:104-122 + Node 'dual' mode env.py:92-94,154-160                  */
+    RLR_POLICY_CDRQ = 5,    /* qroute.py:104-122 + Node 'dual' mode env.py:92-94,154-160                  */
+    RLR_POLICY_GLOBALROUTE = 6 /* shortest.py:84-104 all-pairs distances recomputed every step, weights 1 + queue size */
 };
 
 /* Injection: RLR_INJECT_TRACE replays host-generated draws of the reference's NumPy legacy stream
@@ -95,6 +96,11 @@ typedef struct {
     int32_t *topo_row_ptr;    /* [N+1]   device copy of the CSR (uploaded by the caller)     */
     int32_t *topo_col;        /* [sum_deg]                                                   */
     uint8_t *heap_pos;        /* [(N+1)*N] heap_pos[k*N + rank]: pop position among k ties   */
+    /* GlobalRoute only (per replica, persist across calls) */
+    uint8_t *gr_next_hop;     /* [R][N*N] action index chosen at x for dest d (the single True of `choice`) */
+    int32_t *gr_distance;     /* [R][N*N] GlobalRoute.distance as integers, 0x3FFFFFFF = inf   */
+    int32_t *gr_qs_off;       /* [R][N] queue_size[x] - len(queue[x]): 0 until Network.reset, which clears the queues
+                                 but not the agent's queue_size (env.py:267-280, shortest.py:89) */
 } rlr_buffers_t;
 
 typedef struct {

@@ -14,8 +14,8 @@ from .env import Network, Node, Packet, Reward
 from .hybrid import HybridQ, PolicyGradient
 from .multi_agent import MaHybridQ
 from .qroute import CDRQ, CQ, Qroute
-from .shortest import Shortest
+from .shortest import GlobalRoute, Shortest
 from .topology import Topology
 
-__all__ = ["Network", "Node", "Packet", "Reward", "Policy", "Qroute", "CQ", "CDRQ", "Shortest", "PolicyGradient", "HybridQ",
+__all__ = ["Network", "Node", "Packet", "Reward", "Policy", "Qroute", "CQ", "CDRQ", "Shortest", "GlobalRoute", "PolicyGradient", "HybridQ",
            "MaHybridQ", "Topology"]

@@ -17,7 +17,7 @@ SO = os.environ.get("RLR_LIB") or os.path.join(HERE, "csrc", "librlrouting_b200.
 ABI_VERSION = 1
 NUM_COUNTERS = 8
 CTR = {"all_packets": 0, "end_packets": 1, "drop_packets": 2, "hops": 3, "route_time": 4, "sends": 5}
-POLICY_SHORTEST, POLICY_QROUTE, POLICY_HYBRIDQ, POLICY_MAHYBRIDQ, POLICY_CQ, POLICY_CDRQ = 0, 1, 2, 3, 4, 5
+POLICY_SHORTEST, POLICY_QROUTE, POLICY_HYBRIDQ, POLICY_MAHYBRIDQ, POLICY_CQ, POLICY_CDRQ, POLICY_GLOBALROUTE = 0, 1, 2, 3, 4, 5, 6
 INJECT_TRACE, INJECT_PHILOX = 0, 1
 STATUS_OK, STATUS_NAN_PROB, STATUS_QUEUE_OVERFLOW, STATUS_INJECT_OVERFLOW = 0, 1, 2, 3
 
@@ -51,7 +51,7 @@ class Config(C.Structure):
 class Buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "q_table", "theta", "trace", "ring", "q_head", "q_tail", "counters", "status", "next_hop",
-        "distance", "choice", "topo_row_ptr", "topo_col", "heap_pos")]
+        "distance", "choice", "topo_row_ptr", "topo_col", "heap_pos", "gr_next_hop", "gr_distance", "gr_qs_off")]
 
 
 class RunParams(C.Structure):

@@ -60,6 +60,9 @@ struct StepParams {
     const int *col;
     const unsigned char *heap_pos;
     const unsigned char *next_hop;
+    unsigned char *gr_next_hop;   // GlobalRoute: [R][N*N] per-replica next-hop tables (persist across launches)
+    int *gr_distance;             // GlobalRoute: [R][N*N] distances (0x3FFFFFFF = inf)
+    const int *gr_qs_off;         // GlobalRoute: [R][N] queue_size - len(queue) (non-zero only after Network.reset)
     double *Q, *Theta, *Trace;
     uint4 *ring;
     unsigned *qhead, *qtail;
@@ -306,7 +309,7 @@ __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t
 
 // Shared-memory carve-up, identical on host (sizing) and device (pointers).
 struct SmemLayout {
-    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, total;
+    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, gr, total;
     __host__ __device__ SmemLayout(int N, int sdeg, int G, int threads, int policy, bool smem_tables, long long tsize, int ntab)
     {
         const int GN = G * N;
@@ -322,7 +325,9 @@ struct SmemLayout {
         col = o; o += align16((size_t)sdeg * 2);
         tp = o; o += align16((size_t)GN * 2);
         heappos = o; o += align16((size_t)(N + 1) * N);
-        nexthop = o; o += (policy == RLR_POLICY_SHORTEST) ? align16((size_t)N * N) : 0;
+        nexthop = o; o += (policy == RLR_POLICY_SHORTEST) ? align16((size_t)N * N)
+                           : (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * N * N) : 0;
+        gr = o; o += (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * (N * N + N) * 4) : 0;   // distances + weights
         total = o;
     }
 };
@@ -337,6 +342,31 @@ __device__ __forceinline__ void softmax_row(const double *th, int deg, double (&
     const double ssum = np_sum_row<MAXD>(e, deg);
 #pragma unroll
     for (int j = 0; j < MAXD; ++j) sm[j] = (j < deg) ? __ddiv_rn(e[j], ssum) : 0.0;
+}
+
+constexpr int kGrInf = 0x3FFFFFFF;
+
+// GlobalRoute._calc_distance (shortest.py:43-58 with mask = all off-diagonal, unit(y) = 1 + queue_size[y]) for ONE
+// destination column z: the columns of the distance matrix are independent, so thread z replays the reference's
+// sequential Gauss-Seidel (x, y in links[x]) sweeps on its own column.  dist/nh are [N][N] in shared memory, w[y] the
+// node weights.  A next hop is (re)written only on a strict improvement, like `choice` in the reference.
+__device__ __forceinline__ void gr_column(int z, int N, const int *rowptr, const unsigned short *col, const int *w,
+                                          int *dist, unsigned char *nh)
+{
+    for (int x = 0; x < N; ++x) dist[x * N + z] = (x == z) ? 0 : kGrInf;
+    bool changing = true;
+    while (changing) {
+        changing = false;
+        for (int x = 0; x < N; ++x) {
+            const int rp = rowptr[x], deg = rowptr[x + 1] - rp;
+            int cur = dist[x * N + z];
+            for (int j = 0; j < deg; ++j) {
+                const int y = col[rp + j];
+                const int nd = dist[y * N + z] + w[y];
+                if (cur > nd) { cur = nd; dist[x * N + z] = nd; nh[x * N + z] = (unsigned char)j; changing = true; }
+            }
+        }
+    }
 }
 
 constexpr unsigned kNoKey = 0xFFFFFFFFu;   // "no arrival" sort key (real keys are heap position << 16 | send slot)
@@ -365,6 +395,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     unsigned short *s_tp = reinterpret_cast<unsigned short *>(smem + L.tp);   // target | warp-local rank << 8
     unsigned char *s_heappos = smem + L.heappos;
     unsigned char *s_nexthop = smem + L.nexthop;
+    int *s_grdist = reinterpret_cast<int *>(smem + L.gr);          // GlobalRoute: [G][N*N] distances, then [G][N] weights
+    int *s_grw = s_grdist + G * N * N;
     // per-replica accumulators of this launch
     unsigned long long *s_rt = s_ull, *s_sends = s_ull + G, *s_inj = s_ull + 2 * G;
     unsigned *s_end = s_u32, *s_hops = s_u32 + G, *s_dead = s_u32 + 2 * G, *s_drop = s_u32 + 3 * G, *s_injs = s_u32 + 4 * G;
@@ -393,6 +425,11 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     for (int i = t; i < (N + 1) * N; i += blockDim.x) s_heappos[i] = p.heap_pos[i];
     if (POLICY == RLR_POLICY_SHORTEST)
         for (int i = t; i < N * N; i += blockDim.x) s_nexthop[i] = p.next_hop[i];
+    if (POLICY == RLR_POLICY_GLOBALROUTE)
+        for (int i = t; i < G * N * N; i += blockDim.x) {
+            const long long rr = rblock + i / (N * N);
+            s_nexthop[i] = rr < p.R ? p.gr_next_hop[rr * N * N + i % (N * N)] : 0;
+        }
     for (int i = t; i < G; i += blockDim.x) {
         s_rt[i] = 0; s_sends[i] = 0; s_inj[i] = 0; s_end[i] = 0; s_hops[i] = 0; s_drop[i] = 0; s_injs[i] = 0;
         s_dead[i] = (rblock + i < p.R) ? (unsigned)(p.status[2 * (rblock + i)] != 0) : 1u;
@@ -413,7 +450,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
 
     // ---- per-thread state, constant over the launch ----
     double *Qr = nullptr, *Thr = nullptr, *Trr = nullptr;          // this replica's tables
-    if (POLICY != RLR_POLICY_SHORTEST && t < GN && r < p.R) {
+    if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE && t < GN && r < p.R) {
         if (SMEM_TABLES) {
             Qr = s_tables + g * tstride;
             Thr = Qr + p.tsize;
@@ -440,7 +477,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         if (head != tail) pref = myring[head & capmask];
         rp = s_rowptr[x];
         deg = s_rowptr[x + 1] - rp;
-        if (POLICY != RLR_POLICY_SHORTEST) {
+        if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) {
             Qx = Qr + (long long)N * rp;
             Thx = Thr ? Thr + (long long)N * rp : nullptr;
             Trx = Trr ? Trr + (long long)N * rp : nullptr;
@@ -473,6 +510,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     unsigned ev_next = (is_node && ev != 0xFFFFFFFFu) ? evp[1] : 0xFFFFFFFFu;    // read two entries ahead of its use
     evp += 1;
     bool dead = is_node ? (s_dead[g] != 0u) : true;                 // only sampled policies can die mid-launch
+    const int gr_off = (POLICY == RLR_POLICY_GLOBALROUTE && is_node) ? p.gr_qs_off[r * N + x] : 0;
     unsigned *sendlog = (p.sendlog && is_node) ? p.sendlog + r * (long long)p.K * N + x : nullptr;
 
     // Ring append.  Overflow is detected once per step (tail - head > cap) and reported through the sticky
@@ -503,7 +541,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 rwd = (double)(-(int)meta.y - 1);
                 const double2 mq = *reinterpret_cast<const double2 *>(rw + 2);
                 max_qy = mq.x; max_qxd = mq.y;
-                if (POLICY != RLR_POLICY_SHORTEST) oldq = Qx[d * deg + k];
+                if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) oldq = Qx[d * deg + k];
                 if (IS_PG) softmax_row<MAXD>(Thx + d * deg, deg, sm);
                 if (POLICY == RLR_POLICY_MAHYBRIDQ) { s_r[t] = rwd; s_qy[t] = max_qy; s_qx[t] = max_qxd; }
             }
@@ -526,7 +564,9 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 ++head;
                 if (head != tail) pref = myring[head & capmask];               // prefetch the next head
                 d = (int)(rec.x & 0xFFFFu);
-                if (POLICY == RLR_POLICY_SHORTEST) {
+                if (POLICY == RLR_POLICY_GLOBALROUTE) {
+                    k = s_nexthop[(g * N + x) * N + d];                         // shortest.py:38-41 on this replica's table
+                } else if (POLICY == RLR_POLICY_SHORTEST) {
                     k = s_nexthop[x * N + d];                                   // shortest.py:38-41
                 } else if (POLICY == RLR_POLICY_QROUTE || IS_CQ) {
                     const double *row = Qx + d * deg;                           // qroute.py:22-27
@@ -590,7 +630,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                         s_dk[t] = (unsigned short)(d | (k << 8));
                         s_src[t] = (unsigned short)src;
                     }
-                } else if (POLICY != RLR_POLICY_SHORTEST) {                     // max_Q_y, qroute.py:29-30
+                } else if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) {   // max_Q_y, qroute.py:29-30
                     const int rpy = s_rowptr[y], degy = s_rowptr[y + 1] - rpy;
                     const double *ry = Qr + N * rpy + d * degy;
                     double m = ry[0];
@@ -731,6 +771,11 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                         th[j] = __dadd_rn(th[j], __dmul_rn(__dmul_rn(p.lr_p, gj), adv));
                     }
             }
+        } else if (POLICY == RLR_POLICY_GLOBALROUTE) {
+            // GlobalRoute.learn (shortest.py:99-104): recompute every distance with node weights 1 + queue_size[y]
+            if (live) s_grw[gbase + x] = 1 + (int)(tail - head) + gr_off;
+            __syncthreads();
+            if (live) gr_column(x, N, s_rowptr, s_col, s_grw + gbase, s_grdist + g * N * N, s_nexthop + g * N * N);
         } else if (IS_CQ) {
             // CQ._update_qtable (qroute.py:80-93): eta = max(C, 1 - old_conf); Q += eta * (r + discount * max_Q - Q);
             // conf += eta * (C - conf); conf /= decay.  CDRQ (qroute.py:117-122) adds the backward update of
@@ -869,6 +914,15 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         c[RLR_CTR_ROUTE_TIME] += (long long)s_rt[g];
         c[RLR_CTR_SENDS] += (long long)s_sends[g];
     }
+    if (POLICY == RLR_POLICY_GLOBALROUTE && do_learn) {
+        for (int i = t; i < G * N * N; i += blockDim.x) {
+            const long long rr = rblock + i / (N * N);
+            if (rr < p.R) {
+                p.gr_next_hop[rr * N * N + i % (N * N)] = s_nexthop[i];
+                p.gr_distance[rr * N * N + i % (N * N)] = s_grdist[i];
+            }
+        }
+    }
     if (SMEM_TABLES) {
         const long long per = p.tsize / 2;
         for (int gg = 0; gg < G; ++gg) {
@@ -968,6 +1022,32 @@ __global__ void rlr_apsp_kernel(double *distance, unsigned char *choice, unsigne
     }
 }
 
+// GlobalRoute.__init__ (shortest.py:85-91): after Shortest.__init__ the mask is widened to everything off the diagonal
+// and the distances are recomputed from inf with queue_size = 0; every reachable (x, z) is strictly improved at least
+// once in that pass, so its `choice` entry is the one this kernel computes.  One CTA per replica, thread z = column z.
+__global__ void rlr_globalroute_init_kernel(unsigned char *gr_next_hop, int *gr_distance, const int *qs_off,
+                                            const int *row_ptr, const int *col, int N, int sdeg)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    int *dist = reinterpret_cast<int *>(smem);
+    int *w = dist + N * N;
+    int *rowptr = w + N;
+    unsigned short *scol = reinterpret_cast<unsigned short *>(rowptr + N + 1);
+    unsigned char *nh = reinterpret_cast<unsigned char *>(scol + sdeg);
+    const long long r = blockIdx.x;
+    for (int i = threadIdx.x; i <= N; i += blockDim.x) rowptr[i] = row_ptr[i];
+    for (int i = threadIdx.x; i < sdeg; i += blockDim.x) scol[i] = (unsigned short)col[i];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) w[i] = 1 + qs_off[r * N + i];
+    for (int i = threadIdx.x; i < N * N; i += blockDim.x) nh[i] = 0;
+    __syncthreads();
+    for (int z = threadIdx.x; z < N; z += blockDim.x) gr_column(z, N, rowptr, scol, w, dist, nh);
+    __syncthreads();
+    for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
+        gr_next_hop[r * N * N + i] = nh[i];
+        gr_distance[r * N * N + i] = dist[i];
+    }
+}
+
 __global__ void rlr_reduce_stats_kernel(const long long *counters, long long R, long long *out)
 {
     __shared__ long long acc[RLR_NUM_COUNTERS];
@@ -1055,7 +1135,8 @@ using StepKernel = void (*)(const StepParams);
 template <int POLICY, int MAXD, int MAXW, bool SPLIT>
 StepKernel pick_smem(bool smem_tables)
 {
-    if (POLICY == RLR_POLICY_SHORTEST) return (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT>;
+    if (POLICY == RLR_POLICY_SHORTEST || POLICY == RLR_POLICY_GLOBALROUTE)
+        return (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT>;
     return smem_tables ? (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, true, SPLIT>
                        : (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT>;
 }
@@ -1081,6 +1162,7 @@ StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables)
     case RLR_POLICY_HYBRIDQ: return pick_deg<RLR_POLICY_HYBRIDQ, SPLIT>(n_nodes, max_deg, smem_tables);
     case RLR_POLICY_MAHYBRIDQ: return pick_deg<RLR_POLICY_MAHYBRIDQ, SPLIT>(n_nodes, max_deg, smem_tables);
     case RLR_POLICY_CQ: return pick_deg<RLR_POLICY_CQ, SPLIT>(n_nodes, max_deg, smem_tables);
+    case RLR_POLICY_GLOBALROUTE: return pick_deg<RLR_POLICY_GLOBALROUTE, SPLIT>(n_nodes, max_deg, false);
     default: return pick_deg<RLR_POLICY_CDRQ, SPLIT>(n_nodes, max_deg, smem_tables);
     }
 }
@@ -1218,7 +1300,7 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
         if (dg < 1 || dg > topo->max_deg) return fail(RLR_E_INVALID, "rlr_create: node degree outside [1, max_deg]");
     }
     if (cfg->replicas < 1) return fail(RLR_E_INVALID, "rlr_create: replicas must be >= 1");
-    if (cfg->policy < RLR_POLICY_SHORTEST || cfg->policy > RLR_POLICY_CDRQ)
+    if (cfg->policy < RLR_POLICY_SHORTEST || cfg->policy > RLR_POLICY_GLOBALROUTE)
         return fail(RLR_E_UNSUPPORTED, "rlr_create: unknown policy id");
     const int cap = cfg->queue_capacity;
     if (cap < 2 || (cap & (cap - 1))) return fail(RLR_E_INVALID, "rlr_create: queue_capacity must be a power of two >= 2");
@@ -1227,7 +1309,7 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     rlr_handle *h = new rlr_handle();
     h->N = N; h->sdeg = topo->sum_deg; h->max_deg = topo->max_deg; h->policy = cfg->policy;
     // tables per replica: Shortest 0, Qroute 1 (Q), HybridQ 2 (+Theta), MaHybridQ 3 (+Trace), CQ/CDRQ 2 (Q + confidence)
-    h->ntab = cfg->policy >= RLR_POLICY_CQ ? 2 : cfg->policy;
+    h->ntab = cfg->policy == RLR_POLICY_GLOBALROUTE ? 0 : cfg->policy >= RLR_POLICY_CQ ? 2 : cfg->policy;
     h->R = cfg->replicas; h->replica_base = cfg->replica_base;
     h->tsize = (long long)N * topo->sum_deg;
     h->cap = cap; h->bound = false; h->device = cfg->device;
@@ -1239,7 +1321,7 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     const size_t table_bytes = (size_t)h->ntab * h->tsize * 8;
     int G = cfg->replicas_per_block;
     int smem_tables = cfg->tables_in_smem;
-    if (h->policy == RLR_POLICY_SHORTEST) smem_tables = 0;
+    if (h->policy == RLR_POLICY_SHORTEST || h->policy == RLR_POLICY_GLOBALROUTE) smem_tables = 0;
     auto smem_for = [&](int g, int thr, bool st) {
         return SmemLayout(N, h->sdeg, g, thr, h->policy, st, h->tsize, h->ntab).total;
     };
@@ -1249,7 +1331,7 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     int threads = cfg->threads_per_block;
     if (threads <= 0) {
         threads = ((G * N + 31) / 32) * 32;
-        if (h->policy == RLR_POLICY_MAHYBRIDQ || h->policy >= RLR_POLICY_CQ) {   // + helper warps for the dense passes / reductions
+        if (h->policy == RLR_POLICY_MAHYBRIDQ || h->policy == RLR_POLICY_CQ || h->policy == RLR_POLICY_CDRQ) {   // + helper warps for the dense passes / reductions
             threads = ((G * N + 31) / 32) * 32 + 128;
             if (threads < 256) threads = 256;
             if (threads > kMaxThreads) threads = kMaxThreads;
@@ -1295,8 +1377,11 @@ int rlr_bind_buffers(rlr_handle_t *h, const rlr_buffers_t *b)
         return fail(RLR_E_INVALID, "rlr_bind_buffers: ring, q_head, q_tail, counters, status, topo_* and heap_pos are required");
     if (h->policy == RLR_POLICY_SHORTEST && (!b->next_hop || !b->distance || !b->choice))
         return fail(RLR_E_INVALID, "rlr_bind_buffers: Shortest needs next_hop, distance and choice");
-    if (h->policy >= RLR_POLICY_QROUTE && !b->q_table) return fail(RLR_E_INVALID, "rlr_bind_buffers: q_table required");
-    if (h->policy >= RLR_POLICY_HYBRIDQ && !b->theta) return fail(RLR_E_INVALID, "rlr_bind_buffers: theta required");
+    const bool gr = h->policy == RLR_POLICY_GLOBALROUTE;
+    if (gr && (!b->gr_next_hop || !b->gr_distance || !b->gr_qs_off))
+        return fail(RLR_E_INVALID, "rlr_bind_buffers: GlobalRoute needs gr_next_hop, gr_distance and gr_qs_off");
+    if (!gr && h->policy >= RLR_POLICY_QROUTE && !b->q_table) return fail(RLR_E_INVALID, "rlr_bind_buffers: q_table required");
+    if (!gr && h->policy >= RLR_POLICY_HYBRIDQ && !b->theta) return fail(RLR_E_INVALID, "rlr_bind_buffers: theta required");
     if (h->policy == RLR_POLICY_MAHYBRIDQ && !b->trace) return fail(RLR_E_INVALID, "rlr_bind_buffers: trace required");
     if (((uintptr_t)b->ring & 15) || ((uintptr_t)b->q_table & 15) || ((uintptr_t)b->theta & 15) || ((uintptr_t)b->trace & 15))
         return fail(RLR_E_INVALID, "rlr_bind_buffers: ring and tables must be 16-byte aligned");
@@ -1327,7 +1412,7 @@ int rlr_reset(rlr_handle_t *h, void *stream)
     RLR_CUDA(cudaMemsetAsync(h->bufs.counters, 0, (size_t)h->R * RLR_NUM_COUNTERS * 8, st));
     RLR_CUDA(cudaMemsetAsync(h->bufs.status, 0, (size_t)h->R * 2 * 4, st));
     if (h->policy == RLR_POLICY_MAHYBRIDQ) RLR_CUDA(cudaMemsetAsync(h->bufs.trace, 0, (size_t)h->R * h->tsize * 8, st));
-    if (h->policy >= RLR_POLICY_CQ) {              // CQ.clean (qroute.py:66-71)
+    if (h->policy == RLR_POLICY_CQ || h->policy == RLR_POLICY_CDRQ) {              // CQ.clean (qroute.py:66-71)
         const long long total = h->R * h->tsize;
         int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
         rlr_init_tables_kernel<<<blocks, 256, 0, st>>>(nullptr, h->bufs.theta, nullptr, h->bufs.topo_row_ptr, h->bufs.topo_col,
@@ -1342,11 +1427,20 @@ int rlr_init_tables(rlr_handle_t *h, double initP, void *stream)
     if (!h || !h->bound) return fail(RLR_E_STATE, "rlr_init_tables: buffers not bound");
     if (h->policy == RLR_POLICY_SHORTEST) return RLR_OK;
     RLR_CUDA(cudaSetDevice(h->device));
+    if (h->policy == RLR_POLICY_GLOBALROUTE) {
+        const size_t sm = (size_t)(h->N * h->N + h->N + h->N + 1) * 4 + (size_t)h->sdeg * 2 + (size_t)h->N * h->N;
+        RLR_CUDA(cudaFuncSetAttribute((const void *)rlr_globalroute_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        rlr_globalroute_init_kernel<<<(unsigned)h->R, 128, sm, (cudaStream_t)stream>>>(h->bufs.gr_next_hop, h->bufs.gr_distance,
+                                                                                        h->bufs.gr_qs_off, h->bufs.topo_row_ptr,
+                                                                                        h->bufs.topo_col, h->N, h->sdeg);
+        RLR_CUDA(cudaGetLastError());
+        return RLR_OK;
+    }
     const long long total = h->R * h->tsize;
     int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     rlr_init_tables_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->bufs.q_table, h->bufs.theta, h->bufs.trace,
                                                                       h->bufs.topo_row_ptr, h->bufs.topo_col, h->N, h->sdeg,
-                                                                      h->R, initP, h->policy >= RLR_POLICY_CQ ? 1 : 0);
+                                                                      h->R, initP, (h->policy == RLR_POLICY_CQ || h->policy == RLR_POLICY_CDRQ) ? 1 : 0);
     RLR_CUDA(cudaGetLastError());
     return RLR_OK;
 }
@@ -1392,7 +1486,7 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     }
     if (n_steps >= (1 << 24) - 1) return fail(RLR_E_INVALID, "rlr_run_steps: at most 2^24 - 2 steps per call");
     if (rp->phase < 0 || rp->phase > 3) return fail(RLR_E_INVALID, "rlr_run_steps: phase must be 0 (= 3), 1, 2 or 3");
-    if ((rp->phase == 1 || rp->phase == 2) && h->policy >= RLR_POLICY_CQ)
+    if ((rp->phase == 1 || rp->phase == 2) && (h->policy == RLR_POLICY_CQ || h->policy == RLR_POLICY_CDRQ))
         return fail(RLR_E_UNSUPPORTED, "rlr_run_steps: the split Network.step / agent.learn phases are not available for CQ / CDRQ");
     if ((rp->phase == 1 || rp->phase == 2) && (n_steps != 1 || !rp->rewards))
         return fail(RLR_E_INVALID, "rlr_run_steps: the split phases (Network.step / agent.learn) run one step and need the rewards buffer");
@@ -1407,6 +1501,7 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     p.cap = h->cap; p.K = (int)n_steps; p.clock0 = rp->clock0; p.ntab = h->ntab;
     p.tsize = h->tsize;
     p.row_ptr = h->bufs.topo_row_ptr; p.col = h->bufs.topo_col; p.heap_pos = h->bufs.heap_pos; p.next_hop = h->bufs.next_hop;
+    p.gr_next_hop = h->bufs.gr_next_hop; p.gr_distance = h->bufs.gr_distance; p.gr_qs_off = h->bufs.gr_qs_off;
     p.Q = h->bufs.q_table; p.Theta = h->bufs.theta; p.Trace = h->bufs.trace;
     p.ring = (uint4 *)h->bufs.ring; p.qhead = h->bufs.q_head; p.qtail = h->bufs.q_tail;
     p.counters = (long long *)h->bufs.counters; p.status = h->bufs.status;

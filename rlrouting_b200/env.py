@@ -176,7 +176,7 @@ class Network:
         b = nat.Buffers(ptr("Qtable"), ptr("Theta"), ptr("Trace"), self._ring.data_ptr(), self._q_head.data_ptr(),
                         self._q_tail.data_ptr(), self._counters.data_ptr(), self._status.data_ptr(), ptr("next_hop"),
                         ptr("distance"), ptr("choice"), self._row_ptr.data_ptr(), self._col.data_ptr(),
-                        self._heap_pos.data_ptr())
+                        self._heap_pos.data_ptr(), ptr("gr_next_hop"), ptr("gr_distance"), ptr("gr_qs_off"))
         nat.check(nat.lib().rlr_bind_buffers(h, C.byref(b)))
         self._handles.append(h)
         return h
@@ -309,6 +309,8 @@ class Network:
         self._pending = [[] for _ in range(self.replicas)]
         self._last_rewards = None
         h = getattr(self._agent, "_handle", None)
+        if hasattr(self._agent, "_before_network_reset"):
+            self._agent._before_network_reset()
         if h is not None:
             nat.check(nat.lib().rlr_reset(h, self._stream_ptr()))
         else:
@@ -395,7 +397,7 @@ class Network:
         if duration != 1:
             raise NotImplementedError("step(duration != 1) (SURVEY §8 row f2) is not implemented on the device")
         h = self._handle_or_raise()
-        if self._agent._kernel_policy >= nat.POLICY_CQ:
+        if self._agent._kernel_policy in (nat.POLICY_CQ, nat.POLICY_CDRQ):
             raise NotImplementedError("Network.step / agent.learn as separate calls are not implemented for CQ / CDRQ; "
                                       "use Network.train")
         R, N = self.replicas, self.topology.N
@@ -435,9 +437,9 @@ class Network:
                 pkt = Packet(w0 >> 16, w0 & 0xFFFF, int(rec[2]), int(rec[1]), int(rec[3]))
                 mq = rec[8:12].view(np.float64)
                 info = {"q_y": int(rec[5]), "t_y": 1}
-                if self._agent._kernel_policy != nat.POLICY_SHORTEST:
+                if self._agent._kernel_policy in (nat.POLICY_QROUTE, nat.POLICY_HYBRIDQ, nat.POLICY_MAHYBRIDQ):
                     info["max_Q_y"] = float(mq[0])
-                if self._agent._kernel_policy >= nat.POLICY_HYBRIDQ:
+                if self._agent._kernel_policy in (nat.POLICY_HYBRIDQ, nat.POLICY_MAHYBRIDQ):
                     info["max_Q_x_d"] = float(mq[1])
                 lst.append(Reward(x, pkt, int(y), info))
             out.append(lst)

@@ -36,3 +36,69 @@ class Shortest(Policy):
 
     def choose(self, source, dest):
         return self.links[source][self.choice[source][dest]][0]                    # shortest.py:38-41
+
+
+class GlobalRoute(Shortest):
+    """Queue-aware global routing (reference shortest.py:84-104): after every step all distances are recomputed with
+    node weight 1 + queue_size[y] and packets follow the new next-hop tables.  Each replica has its own tables on the
+    device; `distance`, `choice` and `queue_size` read them back (one replica: the reference's shapes)."""
+    _kernel_policy = nat.POLICY_GLOBALROUTE
+
+    def __init__(self, network, multiway=False, random=False):
+        if multiway or random:
+            raise NotImplementedError("GlobalRoute(multiway=True / random=True) is not implemented on the device")
+        Policy.__init__(self, network)
+        self.multiway, self.random = multiway, random
+        import torch
+        topo, dev, R = network.topology, network.device, network.replicas
+        n = topo.N
+        self._dev = {"gr_next_hop": torch.zeros((R, n * n), dtype=torch.uint8, device=dev),
+                     "gr_distance": torch.zeros((R, n * n), dtype=torch.int32, device=dev),
+                     "gr_qs_off": torch.zeros((R, n), dtype=torch.int32, device=dev)}
+        self._handle = network._make_handle(self)
+        nat.check(nat.lib().rlr_init_tables(self._handle, 0.0, network._stream_ptr()))      # shortest.py:85-91
+        self.mask = ~np.eye(n, dtype=bool)                                                    # shortest.py:87-88
+
+    INF = 0x3FFFFFFF
+
+    def _one(self, a):
+        return a[0] if self._network.replicas == 1 else a
+
+    @property
+    def distance(self):
+        n = self._network.topology.N
+        d = self._dev["gr_distance"].cpu().numpy().reshape(-1, n, n).astype(np.float64)
+        d[d >= self.INF] = np.inf
+        return self._one(d)
+
+    @property
+    def choice(self):
+        topo = self._network.topology
+        n, R = topo.N, self._network.replicas
+        nh = self._dev["gr_next_hop"].cpu().numpy().reshape(R, n, n)
+        dist = self._dev["gr_distance"].cpu().numpy().reshape(R, n, n)
+        out = {}
+        for x in range(n):
+            c = np.zeros((R, n, int(topo.deg[x])), dtype=bool)
+            rr, zz = np.nonzero((dist[:, x, :] < self.INF) & (np.arange(n)[None, :] != x))
+            c[rr, zz, nh[rr, x, zz]] = True
+            out[x] = self._one(c)
+        return out
+
+    @property
+    def queue_size(self):
+        net = self._network
+        q = (net._q_tail - net._q_head + self._dev["gr_qs_off"]).cpu().numpy().astype(np.int64)
+        return self._one(q)
+
+    def choose(self, source, dest):
+        return self.links[source][self.choice[source][dest]][0]
+
+    def _before_network_reset(self):
+        """Network.reset empties the queues but GlobalRoute.queue_size is only ever changed by the receive / send
+        callbacks (shortest.py:93-97), so the reference keeps the stale counts; mirror that exactly."""
+        net = self._network
+        self._dev["gr_qs_off"] += (net._q_tail - net._q_head)
+
+    def learn(self, rewards, lr={}):
+        self._network._learn(self, rewards, lr)

@@ -16,7 +16,7 @@ POLICIES = {}
 def _classes():
     import rlrouting_b200 as rb
     return {"Shortest": rb.Shortest, "Qroute": rb.Qroute, "HybridQ": rb.HybridQ, "MaHybridQ": rb.MaHybridQ,
-            "CQ": rb.CQ, "CDRQ": rb.CDRQ}
+            "CQ": rb.CQ, "CDRQ": rb.CDRQ, "GlobalRoute": rb.GlobalRoute}
 
 
 def device_run(case, **net_kw):
@@ -75,6 +75,11 @@ def test_device_matches_reference_known_answers(case):
     assert res["droprate"][-1] == (got["drop_packets"] / got["all_packets"] if got["all_packets"] else 0)   # env.py:448-450
     assert res["droprate"].shape == ort.shape and np.all(np.diff(res["droprate"] * 0 + np.arange(len(ort))) == 1)
     bit_exact = case.get("rng", "trace") == "trace" or case.get("det_math") or case["policy"] in ("Qroute", "CQ", "CDRQ")
+    if case["policy"] == "GlobalRoute":
+        assert sha(agent.distance, "<f8") == exp["distance_sha256"]
+        assert sha(np.concatenate([agent.choice[x].reshape(-1) for x in range(topo.N)]).astype(np.uint8), "u1") == exp["choice_sha256"]
+        assert list(agent.queue_size) == exp["queue_size"]
+        return
     if case["policy"] == "Shortest":
         assert sha(agent.distance, "<f8") == exp["distance_sha256"]
         assert sha(np.concatenate([agent.choice[x].reshape(-1) for x in range(topo.N)]).astype(np.uint8), "u1") == exp["choice_sha256"]
@@ -100,7 +105,7 @@ def _oracle_batch(net, policy, R, T, lam, seed, base, q0, lr, agent_kw=None):
     for r in range(R):
         e = O.OracleEnv(topo.links, policy, discount=kw.get("discount"), discount_trace=kw.get("discount_trace", 0.6),
                         add_entropy=kw.get("add_entropy", True), seed=seed, replica=base + r)
-        if policy != "Shortest":
+        if policy not in ("Shortest", "GlobalRoute"):
             e.set_qtable(q0[r], initP=kw.get("initP", 0.0))
         envs.append(e)
     sends, rt, en = O.run_many(envs, T, lam, lr_q=lr["q"], lr_p=lr["p"], lr_e=lr["e"], metrics=True)
@@ -147,6 +152,9 @@ BATCH = [
     ("6x6.net", "CDRQ", 12, 500, 2.5, {}),
     ("6x6.net", "CDRQ", 9, 400, 1.0, dict(replicas_per_block=3, threads_per_block=256)),
     ("lata.net", "CDRQ", 3, 250, 3.0, {}),
+    ("6x6.net", "GlobalRoute", 11, 300, 3.0, {}),
+    ("6x6-modified.net", "GlobalRoute", 6, 250, 4.0, dict(replicas_per_block=2)),
+    ("lata.net", "GlobalRoute", 2, 80, 4.0, {}),
 ]
 
 
@@ -162,7 +170,7 @@ def test_device_batch_matches_oracle(net, policy, R, T, lam, cfg):
     agent = _classes()[policy](nw)
     nw.agent = agent
     lr = {"q": 0.1, "p": 0.001 if policy == "MaHybridQ" else 0.1, "e": 0.1}
-    q0 = agent.table_array("Qtable") if policy != "Shortest" else None
+    q0 = agent.table_array("Qtable") if policy not in ("Shortest", "GlobalRoute") else None
     # the device applied qroute.py:16-20 itself; hand the oracle the raw draws and let it do the same
     res = nw.train(T, lam, lr=lr)
     envs, sends, rt, en = _oracle_batch(net, policy, R, T, lam, seed, base, q0, lr)
@@ -367,6 +375,7 @@ def _random_net(rng, n, extra, max_deg):
     ("MaHybridQ", 127, 200, 10, 2, 60, 3.0),        # MaHybridQ's limit (NumPy single pairwise block: n < 128 senders)
     ("Qroute", 2, 0, 1, 5, 300, 0.8),               # smallest graph
     ("CQ", 33, 40, 6, 4, 200, 2.0),
+    ("GlobalRoute", 150, 250, 11, 2, 60, 6.0),
 ])
 def test_random_topologies_match_oracle(policy, n, extra, max_deg, R, T, lam, tmp_path):
     """Random graphs written as .net text (degree-1 leaves, hubs, up to the supported maxima): device == oracle."""
@@ -379,7 +388,7 @@ def test_random_topologies_match_oracle(policy, n, extra, max_deg, R, T, lam, tm
     nw.agent = agent
     topo = nw.topology
     lr = {"q": 0.1, "p": 0.001 if policy == "MaHybridQ" else 0.1, "e": 0.1}
-    q0 = agent.table_array("Qtable") if policy != "Shortest" else None
+    q0 = agent.table_array("Qtable") if policy not in ("Shortest", "GlobalRoute") else None
     res = nw.train(T, lam, lr=lr)
     envs = []
     for r in range(R):
@@ -390,3 +399,34 @@ def test_random_topologies_match_oracle(policy, n, extra, max_deg, R, T, lam, tm
     sends, rt, en = O.run_many(envs, T, lam, lr_q=lr["q"], lr_p=lr["p"], lr_e=lr["e"], metrics=True)
     assert sends > 0 or lam == 0
     _compare_batch(nw, agent, envs, rt, en, res)
+
+
+@pytest.mark.parametrize("policy", ["GlobalRoute", "MaHybridQ", "CQ", "Qroute"])
+def test_network_reset_semantics_match_oracle(policy):
+    """Network.reset (env.py:267-280) zeroes the environment and calls agent.clean(): tables survive, MaHybridQ's
+    traces and CQ's confidences are re-initialised, and GlobalRoute keeps its (now stale) queue_size like the
+    reference does.  Train, reset, train again on both sides."""
+    import rlrouting_b200 as rb
+    R, seed = 4, 21
+    nw = rb.Network("6x6.net", replicas=R, rng="philox", seed=seed)
+    agent = _classes()[policy](nw)
+    nw.agent = agent
+    lr = {"q": 0.1, "p": 0.001 if policy == "MaHybridQ" else 0.1, "e": 0.1}
+    q0 = agent.table_array("Qtable") if policy != "GlobalRoute" else None
+    nw.train(150, 3.0, lr=lr)
+    nw.reset()
+    assert nw.clock == 0
+    res = nw.train(200, 2.0, lr=lr)
+    envs = []
+    for r in range(R):
+        e = O.OracleEnv(nw.topology.links, policy, seed=seed, replica=r)
+        if q0 is not None:
+            e.set_qtable(q0[r])
+        e.run(150, lambd=3.0, lr_q=lr["q"], lr_p=lr["p"], lr_e=lr["e"])
+        e.reset()
+        envs.append(e)
+    sends, rt, en = O.run_many(envs, 200, 2.0, lr_q=lr["q"], lr_p=lr["p"], lr_e=lr["e"], metrics=True)
+    _compare_batch(nw, agent, envs, rt, en, res)
+    if policy == "GlobalRoute":
+        for r in range(R):
+            assert list(agent.queue_size[r]) == list(envs[r].queue_size)
