@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--replicas-per-gpu", type=int, default=8192)
     ap.add_argument("--sim-steps", type=int, default=500, help="simulator steps per bench step (one launch)")
     ap.add_argument("--net", default="6x6.net")
-    ap.add_argument("--policy", default="Qroute", choices=["Shortest", "Qroute", "HybridQ", "MaHybridQ", "CQ", "CDRQ"])
+    ap.add_argument("--policy", default="Qroute", choices=["Shortest", "Qroute", "HybridQ", "MaHybridQ", "CQ", "CDRQ", "GlobalRoute"])
     ap.add_argument("--load", type=float, default=2.0)
     ap.add_argument("--queue-capacity", type=int, default=0, help="ring slots per (replica, node); 0 = from the run length")
     ap.add_argument("--replicas-per-block", type=int, default=0)
@@ -85,7 +85,7 @@ def oracle_envs(a, n, base=0, seed=1):
     envs = []
     for r in range(n):
         e = O.OracleEnv(topo.links, a.policy, seed=seed, replica=base + r)
-        if a.policy != "Shortest":
+        if a.policy not in ("Shortest", "GlobalRoute"):
             g = np.random.Generator(np.random.Philox(key=[seed, base + r]))
             e.set_qtable(g.standard_normal(topo.tsize))
         envs.append(e)
@@ -198,13 +198,14 @@ def algorithmic_bytes(a, topo, hops, injections, replica_steps):
     """per node-step head+tail 16 B; per injection a 16 B record; per hop a 16 B record read,
     the policy's rows, its writes and a 16 B record write (counted for every hop)."""
     w, dbar = 8, 4 if topo.max_deg <= 4 else topo.max_deg          # padded-row convention of SURVEY §8(d)
-    per_hop = {"Shortest": 16 + 2 + 16,
+    per_hop = {"Shortest": 16 + 2 + 16, "GlobalRoute": 16 + 1 + 16,
                "Qroute": 16 + w * dbar + w * dbar + w + 16,
                "HybridQ": 16 + w * dbar + w * dbar + w + 16 + 2 * w * dbar,
                "MaHybridQ": 16 + w * dbar + w * dbar + w + 16 + w * dbar,
                "CQ": 16 + w * dbar + w * dbar + w + 16 + 4 * w,                       # + C_f read, C[x][d][k] read+write, Q read
                "CDRQ": 16 + 2 * w * dbar + w * dbar + 2 * w + 16 + 8 * w}[a.policy]  # + backward row, cell reads/writes
-    dense = {"MaHybridQ": 4 * w * topo.tsize, "CQ": 2 * w * topo.tsize, "CDRQ": 2 * w * topo.tsize}.get(a.policy, 0)
+    dense = {"GlobalRoute": 5 * topo.N * topo.N,      # distance (int32) + next-hop (u8) tables rewritten every step
+             "MaHybridQ": 4 * w * topo.tsize, "CQ": 2 * w * topo.tsize, "CDRQ": 2 * w * topo.tsize}.get(a.policy, 0)
     return hops * per_hop + replica_steps * (16 * topo.N + dense) + injections * 16, per_hop
 
 
