@@ -344,6 +344,13 @@ __device__ __forceinline__ void softmax_row(const double *th, int deg, double (&
     for (int j = 0; j < MAXD; ++j) sm[j] = (j < deg) ? __ddiv_rn(e[j], ssum) : 0.0;
 }
 
+#ifdef RLR_EXP_TIMING
+__device__ unsigned long long g_phase_cycles[8];
+#define RLR_T(i) do { const long long now_ = clock64(); tacc_[i] += now_ - tmark_; tmark_ = now_; } while (0)
+#else
+#define RLR_T(i) do { } while (0)
+#endif
+
 constexpr int kGrInf = 0x3FFFFFFF;
 
 // GlobalRoute._calc_distance (shortest.py:43-58 with mask = all off-diagonal, unit(y) = 1 + queue_size[y]) for ONE
@@ -398,8 +405,9 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     int *s_grdist = reinterpret_cast<int *>(smem + L.gr);          // GlobalRoute: [G][N*N] distances, then [G][N] weights
     int *s_grw = s_grdist + G * N * N;
     // per-replica accumulators of this launch
-    unsigned long long *s_rt = s_ull, *s_sends = s_ull + G, *s_inj = s_ull + 2 * G;
-    unsigned *s_end = s_u32, *s_hops = s_u32 + G, *s_dead = s_u32 + 2 * G, *s_drop = s_u32 + 3 * G, *s_injs = s_u32 + 4 * G;
+    unsigned long long *s_sends = s_ull + G, *s_inj = s_ull + 2 * G;
+    unsigned *s_end = s_u32, *s_hops = s_u32 + G, *s_dead = s_u32 + 2 * G, *s_drop = s_u32 + 3 * G, *s_injs = s_u32 + 4 * G,
+             *s_rt32 = s_u32 + 5 * G;        // delivery latencies of the current step (drained every step by the metric thread)
     // MaHybridQ scratch: r, max_Q_y, max_Q_x_d per node; three sums + spare per replica
     double *s_r = s_f64, *s_qy = s_f64 + GN, *s_qx = s_f64 + 2 * GN, *s_sum = s_f64 + 3 * GN;
     // CDRQ scratch (same region): backward-update inputs of each sender and the queue lengths of 'dual' mode
@@ -431,7 +439,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             s_nexthop[i] = rr < p.R ? p.gr_next_hop[rr * N * N + i % (N * N)] : 0;
         }
     for (int i = t; i < G; i += blockDim.x) {
-        s_rt[i] = 0; s_sends[i] = 0; s_inj[i] = 0; s_end[i] = 0; s_hops[i] = 0; s_drop[i] = 0; s_injs[i] = 0;
+        s_rt32[i] = 0; s_sends[i] = 0; s_inj[i] = 0; s_end[i] = 0; s_hops[i] = 0; s_drop[i] = 0; s_injs[i] = 0;
         s_dead[i] = (rblock + i < p.R) ? (unsigned)(p.status[2 * (rblock + i)] != 0) : 1u;
     }
     if (SMEM_TABLES) {
@@ -468,7 +476,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     uint4 *myring = nullptr;
     int rp = 0, deg = 0;
     unsigned my_sends = 0, my_inj = 0;
-    long long base_rt = 0, base_end = 0, base_hops = 0, base_all = 0, base_drop = 0;
+    long long base_rt = 0, base_end = 0, base_hops = 0, base_all = 0, base_drop = 0, run_rt = 0;
     double *Qx = nullptr, *Thx = nullptr, *Trx = nullptr;          // table[x] of this node
     if (is_node) {
         head = p.qhead[r * N + x];
@@ -523,6 +531,10 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
 
     // SPLIT = false is the fused Network.train path (both phases, no flag tests in the loop)
     const bool do_env = !SPLIT || (p.phase & 1) != 0, do_learn = !SPLIT || (p.phase & 2) != 0;
+#ifdef RLR_EXP_TIMING
+    long long tacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tmark_ = clock64();
+#endif
     for (int s = 0; s < p.K; ++s) {
         const int clock = p.clock0 + s;
         if (IS_PG && is_node) dead = (s_dead[g] != 0u);
@@ -564,6 +576,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 ++head;
                 if (head != tail) pref = myring[head & capmask];               // prefetch the next head
                 d = (int)(rec.x & 0xFFFFu);
+                RLR_T(6);                           // A + pop
                 if (POLICY == RLR_POLICY_GLOBALROUTE) {
                     k = s_nexthop[(g * N + x) * N + d];                         // shortest.py:38-41 on this replica's table
                 } else if (POLICY == RLR_POLICY_SHORTEST) {
@@ -670,12 +683,15 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 }
             }
         }
+        RLR_T(0);                                   // A + B
         if (sendlog) sendlog[(long long)s * N] = sending ? ((unsigned)y | ((unsigned)d << 16)) : 0xFFFFFFFFu;
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, sending);
         if (lane == 0) s_wmask[warp] = bal;
         if (t < GN) s_tp[t] = sending ? (unsigned short)(y | (__popc(bal & prank_mask) << 8)) : (unsigned short)kNoSend;
         __syncthreads();                                                        // ---- barrier 1 ----
+        RLR_T(1);
 
+#ifndef RLR_EXP_SKIP_C
         if (live && do_env) {
             // ---- C. event drain (env.py:349-364): gather arrivals from neighbours in heap-tie order ----
             unsigned cum[MAXW + 1];         // senders of this replica in the window words before word i
@@ -712,6 +728,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 RLR_CE(0, 1) RLR_CE(2, 3) RLR_CE(0, 2) RLR_CE(1, 3) RLR_CE(1, 2)
 #undef RLR_CE
             }
+            RLR_T(5);                               // C: window + keys + sort
             for (;;) {
                 unsigned best = key[0];
                 if (MAXD == 4) {
@@ -731,7 +748,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 }
                 if ((int)(rec.x & 0xFFFFu) == x) {                              // Network.end_packet, env.py:321-331
                     atomicAdd(&s_end[g], 1u);
-                    atomicAdd(&s_rt[g], (unsigned long long)(clock + 1 - (int)rec.z));
+                    atomicAdd(&s_rt32[g], (unsigned)(clock + 1 - (int)rec.z));
                     atomicAdd(&s_hops[g], rec.y);
                 } else {                                                        // Node.receive, env.py:127-130
                     rec.w = (unsigned)(clock + 1);
@@ -740,6 +757,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             }
             if (tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
         }
+#endif
+        RLR_T(2);                                   // C
         // ---- D. agent.learn ----
         if (!do_learn) {
         } else if (POLICY == RLR_POLICY_QROUTE) {
@@ -887,9 +906,15 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 }
             }
         }
+        RLR_T(3);                                   // D
         __syncthreads();                                                        // ---- barrier 2 ----
+        RLR_T(4);
+        if (is_node && x == N - 1) {                // the metric thread: 64-bit running route_time, per-step record
+            run_rt += (long long)s_rt32[g];
+            s_rt32[g] = 0u;                         // next deliveries come after the next barrier 1
+        }
         if (is_node && x == N - 1 && p.metrics) {                               // env.py:409-413 (cumulative counters)
-            const long long rt = base_rt + (long long)s_rt[g];
+            const long long rt = base_rt + run_rt;
             const unsigned en = (unsigned)(base_end + s_end[g]), hps = (unsigned)(base_hops + s_hops[g]);
             p.metrics[(long long)s * p.R + r] = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hps);
             if (p.metrics2)
@@ -897,6 +922,10 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         }
     }
 
+#ifdef RLR_EXP_TIMING
+    if (t == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)tacc_[i]);
+#endif
     // ---- write back ----
     if (is_node) {
         p.qhead[r * N + x] = head;
@@ -905,13 +934,13 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         if (my_inj) atomicAdd(&s_inj[g], (unsigned long long)my_inj);
     }
     __syncthreads();
-    if (is_node && x == 0) {
+    if (is_node && x == N - 1) {
         long long *c = p.counters + r * RLR_NUM_COUNTERS;
         c[RLR_CTR_ALL_PACKETS] += (long long)s_inj[g];
         c[RLR_CTR_END_PACKETS] += (long long)s_end[g];
         c[RLR_CTR_DROP_PACKETS] += (long long)s_drop[g];
         c[RLR_CTR_HOPS] += (long long)s_hops[g];
-        c[RLR_CTR_ROUTE_TIME] += (long long)s_rt[g];
+        c[RLR_CTR_ROUTE_TIME] += run_rt;
         c[RLR_CTR_SENDS] += (long long)s_sends[g];
     }
     if (POLICY == RLR_POLICY_GLOBALROUTE && do_learn) {
@@ -1156,6 +1185,10 @@ StepKernel pick_deg(int n_nodes, int max_deg, bool smem_tables)
 template <bool SPLIT>
 StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables)
 {
+#ifdef RLR_FAST_BUILD       // kernel-tuning builds: only the 6x6 Qroute instantiations (seconds instead of a minute)
+    (void)policy; (void)n_nodes; (void)max_deg;
+    return pick_smem<RLR_POLICY_QROUTE, 4, 3, false>(smem_tables);
+#else
     switch (policy) {
     case RLR_POLICY_SHORTEST: return pick_deg<RLR_POLICY_SHORTEST, SPLIT>(n_nodes, max_deg, false);
     case RLR_POLICY_QROUTE: return pick_deg<RLR_POLICY_QROUTE, SPLIT>(n_nodes, max_deg, smem_tables);
@@ -1165,6 +1198,7 @@ StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables)
     case RLR_POLICY_GLOBALROUTE: return pick_deg<RLR_POLICY_GLOBALROUTE, SPLIT>(n_nodes, max_deg, false);
     default: return pick_deg<RLR_POLICY_CDRQ, SPLIT>(n_nodes, max_deg, smem_tables);
     }
+#endif
 }
 
 }  // namespace
@@ -1221,6 +1255,15 @@ struct Mt19937 {
     }
 };
 }  // namespace
+
+#ifdef RLR_EXP_TIMING
+extern "C" int rlr_debug_phase_cycles(unsigned long long *out, int reset)
+{
+    cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 extern "C" int rlr_trace_replay(uint32_t *mt_key, int32_t *mt_pos, int32_t n_nodes, int64_t n_steps, double lam,
                                 int32_t *cnt_out, uint32_t *pairs_out, int64_t pairs_cap, int64_t *n_pairs_out)
