@@ -99,6 +99,8 @@ typedef struct {
     /* GlobalRoute only (per replica, persist across calls) */
     uint8_t *gr_next_hop;     /* [R][N*N] action index chosen at x for dest d (the single True of `choice`) */
     int32_t *gr_distance;     /* [R][N*N] GlobalRoute.distance as integers, 0x3FFFFFFF = inf   */
+    uint16_t *choice_mask;    /* [N][N] Shortest: bit j = choice[x][d][j] (all optimal neighbours with multiway=True);
+                                 needed when shortest_random is set */
     int32_t *gr_qs_off;       /* [R][N] queue_size[x] - len(queue[x]): 0 until Network.reset, which clears the queues
                                  but not the agent's queue_size (env.py:267-280, shortest.py:89) */
 } rlr_buffers_t;
@@ -124,6 +126,8 @@ typedef struct {
     double discount_trace;    /* multi_agent.py:10                                           */
     double conf_decay;        /* CQ(decay=...) qroute.py:59                                  */
     int32_t clock0;           /* Network.clock before the first step                         */
+    int32_t shortest_random;  /* Shortest(random=True): next hop drawn uniformly from the choice mask (shortest.py:40-41) */
+    int32_t reserved1;
     int32_t phase;            /* 0 or 3: fused inject+step+learn (Network.train); 1: Network.step only (env.py:333-365,
                                  rewards saved, nothing learned); 2: agent.learn of the rewards saved by phase 1.
                                  Phases 1 and 2 need n_steps == 1 and `rewards`. */
@@ -167,9 +171,9 @@ int rlr_reset(rlr_handle_t *h, void *stream);
  *      the N(initQ,1) draws; Theta = initP (hybrid.py:13-14); Trace = 0 (multi_agent.py:14-15) ---- */
 int rlr_init_tables(rlr_handle_t *h, double initP, void *stream);
 
-/* ---- Shortest.__init__ + _calc_distance (shortest.py:20-58, multiway=False): fills distance,
- *      choice and next_hop ---- */
-int rlr_build_shortest_tables(rlr_handle_t *h, void *stream);
+/* ---- Shortest.__init__ + _calc_distance (shortest.py:20-58): fills distance, choice, next_hop (first True of the
+ *      mask) and, if bound, choice_mask; multiway != 0 keeps every optimal neighbour (shortest.py:57-58) ---- */
+int rlr_build_shortest_tables(rlr_handle_t *h, int32_t multiway, void *stream);
 
 /* ---- host helper (no device work): replays NumPy's legacy RandomState stream for n_steps calls of
  *      Network.new_packet(lam) (env.py:298-312; np.random.poisson + np.random.randint) on the MT19937 state

@@ -38,6 +38,7 @@ def lib():
         L.orc_set_stream.argtypes = [p, C.c_uint64, C.c_uint64]
         L.orc_set_decay.argtypes = [p, f64]
         L.orc_set_is_drop.argtypes = [p, i32]
+        L.orc_set_shortest_flags.argtypes = [p, i32, i32]
         L.orc_cq_clean.argtypes = [p]
         L.orc_table_size.restype = i64
         L.orc_table_size.argtypes = [p]
@@ -82,7 +83,7 @@ class OracleEnv:
     """One environment replica + its agent (reference `Network` + `Policy`)."""
 
     def __init__(self, links, policy, discount=None, discount_trace=0.6, add_entropy=True,
-                 seed=0, replica=0, decay=0.9, is_drop=False):
+                 seed=0, replica=0, decay=0.9, is_drop=False, multiway=False, random=False):
         if discount is None:
             discount = 0.9 if policy in ("CQ", "CDRQ") else 0.99          # qroute.py:59 vs qroute.py:9
         L = lib()
@@ -97,6 +98,7 @@ class OracleEnv:
         L.orc_set_stream(self.h, seed, replica)
         L.orc_set_decay(self.h, decay)
         L.orc_set_is_drop(self.h, int(is_drop))
+        L.orc_set_shortest_flags(self.h, int(multiway), int(random))
         self.tsize = L.orc_table_size(self.h)
         self.toff = self.row_ptr.astype(np.int64) * self.N
         self.Q = np.ctypeslib.as_array(L.orc_table(self.h, 0), shape=(self.tsize,))

@@ -108,6 +108,13 @@ def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, repl
         def choice(a, size=None, replace=True, p=None):
             # legacy RandomState.choice with p (numpy/random/mtrand.pyx): validate p, then
             # cdf = p.cumsum(); cdf /= cdf[-1]; idx = cdf.searchsorted(u, side='right')
+            if p is None:
+                # legacy RandomState.choice(a) without p = a[randint(0, len(a))]; here the index comes from the Philox
+                # stream as mulhi(word, count) (Shortest(random=True), shortest.py:40-41); one choice draws nothing
+                if len(a) == 1:
+                    return a[0]
+                w = philox_twin.Stream(philox_seed, replica, nw.clock, state["node"], 1).next()
+                return a[(w * len(a)) >> 32]
             p = np.asarray(p, dtype=np.float64)
             if np.isnan(p.sum()):
                 raise ValueError("probabilities contain NaN")

@@ -64,6 +64,7 @@ typedef struct orc {
     double discount, discount_trace, reward_shape;
     int add_entropy, status;
     int is_drop;              /* Network(is_drop=True): env.py:355-360 */
+    int multiway, random_choice; /* Shortest(multiway=..., random=...), shortest.py:20-23,38-41 */
     int64_t *queue_size;      /* GlobalRoute.queue_size (shortest.py:89): +1 per receive callback, -1 per send callback */
     int64_t status_clock;
     uint64_t seed, replica;   /* Philox key / stream id */
@@ -186,6 +187,7 @@ void orc_set_hparams(orc_t *o, double discount, double discount_trace, int add_e
 
 void orc_set_decay(orc_t *o, double decay) { o->decay = decay; }
 void orc_set_is_drop(orc_t *o, int is_drop) { o->is_drop = is_drop; }
+void orc_set_shortest_flags(orc_t *o, int multiway, int random_choice) { o->multiway = multiway; o->random_choice = random_choice; }
 
 void orc_set_stream(orc_t *o, uint64_t seed, uint64_t replica) { o->seed = seed; o->replica = replica; }
 
@@ -285,6 +287,8 @@ void orc_shortest_build(orc_t *o)
                         c[j] = 1;
                         changing = 1;
                     }
+                    if (o->multiway && isfinite(nd) && o->distance[x * N + z] == nd)      /* shortest.py:57-58 */
+                        o->choice[o->toff[x] + (int64_t)z * deg + j] = 1;
                 }
             }
         }
@@ -568,6 +572,17 @@ static void send_phase(orc_t *o)
         if (o->policy == POL_SHORTEST || o->policy == POL_GLOBALROUTE) {
             const uint8_t *c = o->choice + o->toff[x] + (int64_t)d * deg;
             while (k < deg && !c[k]) k++;
+            if (o->random_choice) {
+                /* shortest.py:40-41 np.random.choice(choices): a uniform index into the True entries; the index comes
+                 * from the Philox stream (purpose 1) as mulhi(word, count), nothing is drawn for a single choice */
+                int cnt = 0;
+                for (int j = 0; j < deg; ++j) cnt += c[j];
+                if (cnt > 1) {
+                    pstream_t s; ps_init(&s, o->seed, o->replica, o->clock, x, 1);
+                    int idx = (int)(((uint64_t)ps_next(&s) * (uint32_t)cnt) >> 32);
+                    for (k = 0; k < deg; ++k) if (c[k] && idx-- == 0) break;
+                }
+            }
         } else if (o->policy == POL_QROUTE || o->policy == POL_CQ || o->policy == POL_CDRQ) {
             const double *row = o->Q + o->toff[x] + (int64_t)d * deg;
             for (int j = 1; j < deg; ++j) if (row[j] > row[k]) k = j;

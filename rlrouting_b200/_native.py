@@ -51,7 +51,7 @@ class Config(C.Structure):
 class Buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "q_table", "theta", "trace", "ring", "q_head", "q_tail", "counters", "status", "next_hop",
-        "distance", "choice", "topo_row_ptr", "topo_col", "heap_pos", "gr_next_hop", "gr_distance", "gr_qs_off")]
+        "distance", "choice", "topo_row_ptr", "topo_col", "heap_pos", "gr_next_hop", "gr_distance", "choice_mask", "gr_qs_off")]
 
 
 class RunParams(C.Structure):
@@ -60,7 +60,8 @@ class RunParams(C.Structure):
                 ("enlam", C.c_void_p), ("inj_thr", C.c_void_p), ("seed", C.c_uint64),
                 ("lr_q", C.c_double), ("lr_p", C.c_double), ("lr_e", C.c_double),
                 ("discount", C.c_double), ("discount_trace", C.c_double), ("conf_decay", C.c_double),
-                ("clock0", C.c_int32), ("phase", C.c_int32), ("rewards", C.c_void_p),
+                ("clock0", C.c_int32), ("shortest_random", C.c_int32), ("reserved1", C.c_int32), ("phase", C.c_int32),
+                ("rewards", C.c_void_p),
                 ("metrics", C.c_void_p), ("route_time_out", C.c_void_p), ("hop_out", C.c_void_p),
                 ("metrics2", C.c_void_p), ("droprate_out", C.c_void_p), ("sendlog", C.c_void_p)]
 
@@ -93,7 +94,7 @@ def lib():
     L.rlr_launch_info.argtypes = [p] + [C.POINTER(C.c_int32)] * 4
     L.rlr_reset.argtypes = [p, p]
     L.rlr_init_tables.argtypes = [p, C.c_double, p]
-    L.rlr_build_shortest_tables.argtypes = [p, p]
+    L.rlr_build_shortest_tables.argtypes = [p, C.c_int32, p]
     L.rlr_run_steps.argtypes = [p, C.c_int64, C.POINTER(RunParams), p]
     L.rlr_build_inject_schedule.argtypes = [p, C.c_int64, C.POINTER(RunParams), p]
     L.rlr_reduce_stats.argtypes = [p, p, p]

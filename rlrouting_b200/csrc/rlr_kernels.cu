@@ -60,6 +60,8 @@ struct StepParams {
     const int *col;
     const unsigned char *heap_pos;
     const unsigned char *next_hop;
+    const unsigned short *choice_mask;    // Shortest(random=True): [N*N] bit j = choice[x][d][j]
+    int shortest_random;
     unsigned char *gr_next_hop;   // GlobalRoute: [R][N*N] per-replica next-hop tables (persist across launches)
     int *gr_distance;             // GlobalRoute: [R][N*N] distances (0x3FFFFFFF = inf)
     const int *gr_qs_off;         // GlobalRoute: [R][N] queue_size - len(queue) (non-zero only after Network.reset)
@@ -325,7 +327,7 @@ struct SmemLayout {
         col = o; o += align16((size_t)sdeg * 2);
         tp = o; o += align16((size_t)GN * 2);
         heappos = o; o += align16((size_t)(N + 1) * N);
-        nexthop = o; o += (policy == RLR_POLICY_SHORTEST) ? align16((size_t)N * N)
+        nexthop = o; o += (policy == RLR_POLICY_SHORTEST) ? align16((size_t)N * N * 2)      // u8 next hops or u16 choice masks
                            : (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * N * N) : 0;
         gr = o; o += (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * (N * N + N) * 4) : 0;   // distances + weights
         total = o;
@@ -431,8 +433,12 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     for (int i = t; i <= N; i += blockDim.x) s_rowptr[i] = p.row_ptr[i];
     for (int i = t; i < p.sdeg; i += blockDim.x) s_col[i] = (unsigned short)p.col[i];
     for (int i = t; i < (N + 1) * N; i += blockDim.x) s_heappos[i] = p.heap_pos[i];
-    if (POLICY == RLR_POLICY_SHORTEST)
-        for (int i = t; i < N * N; i += blockDim.x) s_nexthop[i] = p.next_hop[i];
+    if (POLICY == RLR_POLICY_SHORTEST) {
+        if (p.shortest_random)
+            for (int i = t; i < N * N; i += blockDim.x) reinterpret_cast<unsigned short *>(s_nexthop)[i] = p.choice_mask[i];
+        else
+            for (int i = t; i < N * N; i += blockDim.x) s_nexthop[i] = p.next_hop[i];
+    }
     if (POLICY == RLR_POLICY_GLOBALROUTE)
         for (int i = t; i < G * N * N; i += blockDim.x) {
             const long long rr = rblock + i / (N * N);
@@ -580,7 +586,18 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 if (POLICY == RLR_POLICY_GLOBALROUTE) {
                     k = s_nexthop[(g * N + x) * N + d];                         // shortest.py:38-41 on this replica's table
                 } else if (POLICY == RLR_POLICY_SHORTEST) {
-                    k = s_nexthop[x * N + d];                                   // shortest.py:38-41
+                    if (!p.shortest_random) {
+                        k = s_nexthop[x * N + d];                               // shortest.py:38-41, choices[0]
+                    } else {                                                    // np.random.choice(choices), shortest.py:40-41
+                        const unsigned cm = reinterpret_cast<const unsigned short *>(s_nexthop)[x * N + d];
+                        const int cnt = __popc(cm);
+                        int idx = 0;
+                        if (cnt > 1) {
+                            PhiloxStream ps(p.seed, stream_id, clock, x, 1);
+                            idx = (int)__umulhi(ps.next(), (unsigned)cnt);
+                        }
+                        k = __fns(cm, 0, idx + 1);
+                    }
                 } else if (POLICY == RLR_POLICY_QROUTE || IS_CQ) {
                     const double *row = Qx + d * deg;                           // qroute.py:22-27
                     double best = row[0];
@@ -1011,8 +1028,8 @@ __global__ void rlr_init_tables_kernel(double *Q, double *Theta, double *Trace, 
 // distance matrix are mutually independent (distance[.,z] reads only distance[.,z]), so one thread
 // replays the reference's sequential Gauss-Seidel (x, y in links[x]) sweeps for its destination z.
 // ------------------------------------------------------------------------------------------------
-__global__ void rlr_apsp_kernel(double *distance, unsigned char *choice, unsigned char *next_hop, const int *row_ptr,
-                                const int *col, int N)
+__global__ void rlr_apsp_kernel(double *distance, unsigned char *choice, unsigned char *next_hop, unsigned short *choice_mask,
+                                const int *row_ptr, const int *col, int N, int multiway)
 {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     if (z >= N) return;
@@ -1039,6 +1056,7 @@ __global__ void rlr_apsp_kernel(double *distance, unsigned char *choice, unsigne
                     c[j] = 1;
                     changing = true;
                 }
+                if (multiway && nd < CUDART_INF && distance[x * N + z] == nd) c[j] = 1;         // shortest.py:57-58
             }
         }
     }
@@ -1048,6 +1066,9 @@ __global__ void rlr_apsp_kernel(double *distance, unsigned char *choice, unsigne
         int k = 0;
         while (k < deg - 1 && !c[k]) ++k;
         next_hop[x * N + z] = (unsigned char)k;
+        unsigned m = 0;
+        for (int j = 0; j < deg; ++j) m |= (unsigned)(c[j] != 0) << j;
+        if (choice_mask) choice_mask[x * N + z] = (unsigned short)m;
     }
 }
 
@@ -1488,14 +1509,15 @@ int rlr_init_tables(rlr_handle_t *h, double initP, void *stream)
     return RLR_OK;
 }
 
-int rlr_build_shortest_tables(rlr_handle_t *h, void *stream)
+int rlr_build_shortest_tables(rlr_handle_t *h, int32_t multiway, void *stream)
 {
     if (!h || !h->bound) return fail(RLR_E_STATE, "rlr_build_shortest_tables: buffers not bound");
     if (!h->bufs.next_hop || !h->bufs.distance || !h->bufs.choice)
         return fail(RLR_E_INVALID, "rlr_build_shortest_tables: next_hop, distance and choice are required");
     RLR_CUDA(cudaSetDevice(h->device));
     rlr_apsp_kernel<<<(h->N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(h->bufs.distance, h->bufs.choice, h->bufs.next_hop,
-                                                                        h->bufs.topo_row_ptr, h->bufs.topo_col, h->N);
+                                                                        h->bufs.choice_mask, h->bufs.topo_row_ptr,
+                                                                        h->bufs.topo_col, h->N, multiway ? 1 : 0);
     RLR_CUDA(cudaGetLastError());
     return RLR_OK;
 }
@@ -1544,6 +1566,9 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     p.cap = h->cap; p.K = (int)n_steps; p.clock0 = rp->clock0; p.ntab = h->ntab;
     p.tsize = h->tsize;
     p.row_ptr = h->bufs.topo_row_ptr; p.col = h->bufs.topo_col; p.heap_pos = h->bufs.heap_pos; p.next_hop = h->bufs.next_hop;
+    p.choice_mask = h->bufs.choice_mask; p.shortest_random = rp->shortest_random;
+    if (p.shortest_random && (h->policy != RLR_POLICY_SHORTEST || !p.choice_mask))
+        return fail(RLR_E_INVALID, "rlr_run_steps: shortest_random needs the Shortest policy and the choice_mask buffer");
     p.gr_next_hop = h->bufs.gr_next_hop; p.gr_distance = h->bufs.gr_distance; p.gr_qs_off = h->bufs.gr_qs_off;
     p.Q = h->bufs.q_table; p.Theta = h->bufs.theta; p.Trace = h->bufs.trace;
     p.ring = (uint4 *)h->bufs.ring; p.qhead = h->bufs.q_head; p.qtail = h->bufs.q_tail;

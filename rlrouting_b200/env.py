@@ -176,7 +176,8 @@ class Network:
         b = nat.Buffers(ptr("Qtable"), ptr("Theta"), ptr("Trace"), self._ring.data_ptr(), self._q_head.data_ptr(),
                         self._q_tail.data_ptr(), self._counters.data_ptr(), self._status.data_ptr(), ptr("next_hop"),
                         ptr("distance"), ptr("choice"), self._row_ptr.data_ptr(), self._col.data_ptr(),
-                        self._heap_pos.data_ptr(), ptr("gr_next_hop"), ptr("gr_distance"), ptr("gr_qs_off"))
+                        self._heap_pos.data_ptr(), ptr("gr_next_hop"), ptr("gr_distance"), ptr("choice_mask"),
+                        ptr("gr_qs_off"))
         nat.check(nat.lib().rlr_bind_buffers(h, C.byref(b)))
         self._handles.append(h)
         return h
@@ -387,6 +388,7 @@ class Network:
         rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
         rp.conf_decay = float(getattr(agent, "decay", 0.9))
         rp.is_drop = int(bool(self.is_drop))
+        rp.shortest_random = int(agent._kernel_policy == nat.POLICY_SHORTEST and bool(getattr(agent, "random", False)))
         rp.seed = self.seed
         return rp
 
@@ -517,6 +519,7 @@ class Network:
         rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
         rp.conf_decay = float(getattr(agent, "decay", 0.9))
         rp.is_drop = int(bool(self.is_drop))
+        rp.shortest_random = int(agent._kernel_policy == nat.POLICY_SHORTEST and bool(getattr(agent, "random", False)))
         rp.seed = self.seed
         keep = []
         h2d = 0
@@ -665,6 +668,7 @@ class Network:
         rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
         rp.conf_decay = float(getattr(agent, "decay", 0.9))
         rp.is_drop = int(bool(self.is_drop))
+        rp.shortest_random = int(agent._kernel_policy == nat.POLICY_SHORTEST and bool(getattr(agent, "random", False)))
         rp.seed = self.seed
         rp.enlam = self._resident["enlam"].data_ptr()
         rp.inj_thr = self._resident["inj_thr"].data_ptr()

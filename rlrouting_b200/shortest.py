@@ -12,9 +12,6 @@ class Shortest(Policy):
     _kernel_policy = nat.POLICY_SHORTEST
 
     def __init__(self, network, multiway=False, random=False):
-        if multiway or random:
-            raise NotImplementedError("Shortest(multiway=True / random=True) is not implemented on the device "
-                                      "(SURVEY §8 row f3); there is no CPU fallback")
         super().__init__(network)
         self.multiway = multiway
         self.random = random
@@ -22,9 +19,10 @@ class Shortest(Policy):
         topo, dev = network.topology, network.device
         self._dev = {"next_hop": torch.zeros(topo.N * topo.N, dtype=torch.uint8, device=dev),
                      "distance": torch.zeros(topo.N * topo.N, dtype=torch.float64, device=dev),
-                     "choice": torch.zeros(topo.tsize, dtype=torch.uint8, device=dev)}
+                     "choice": torch.zeros(topo.tsize, dtype=torch.uint8, device=dev),
+                     "choice_mask": torch.zeros(topo.N * topo.N, dtype=torch.int16, device=dev)}
         self._handle = network._make_handle(self)
-        nat.check(nat.lib().rlr_build_shortest_tables(self._handle, network._stream_ptr()))
+        nat.check(nat.lib().rlr_build_shortest_tables(self._handle, int(bool(multiway)), network._stream_ptr()))
         n = topo.N
         self.distance = self._dev["distance"].cpu().numpy().reshape(n, n)
         flat = self._dev["choice"].cpu().numpy().astype(bool)
@@ -35,7 +33,8 @@ class Shortest(Policy):
             self.mask[x, neighbors] = False
 
     def choose(self, source, dest):
-        return self.links[source][self.choice[source][dest]][0]                    # shortest.py:38-41
+        choices = self.links[source][self.choice[source][dest]]                    # shortest.py:38-41
+        return np.random.choice(choices) if self.random else choices[0]
 
 
 class GlobalRoute(Shortest):

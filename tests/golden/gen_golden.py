@@ -67,6 +67,13 @@ CASES = [
     dict(net="6x6-modified.net", policy="GlobalRoute", T=200, lambd=3.0, seed=1),
     dict(net="lata.net", policy="GlobalRoute", T=40, lambd=3.0, seed=1),
     dict(net="6x6.net", policy="GlobalRoute", T=200, lambd=3.0, seed=1, rng="philox", philox_seed=7, replica=3),
+    # Shortest(multiway=True) keeps every optimal neighbour, random=True samples among them
+    dict(net="6x6.net", policy="Shortest", T=1500, lambd=2.0, seed=1, agent_kwargs={"multiway": True}),
+    dict(net="lata.net", policy="Shortest", T=500, lambd=3.0, seed=1, agent_kwargs={"multiway": True}),
+    dict(net="6x6.net", policy="Shortest", T=1500, lambd=3.0, seed=1, rng="philox", philox_seed=7, replica=3,
+         agent_kwargs={"multiway": True, "random": True}),
+    dict(net="lata.net", policy="Shortest", T=500, lambd=3.0, seed=1, rng="philox", philox_seed=7, replica=3,
+         agent_kwargs={"multiway": True, "random": True}),
     # is_drop=True — a packet arriving with hops >= N is dropped (env.py:355-360)
     dict(net="6x6.net", policy="Qroute", T=3000, lambd=2.0, seed=1, net_kwargs={"is_drop": True}),
     dict(net="6x6.net", policy="CDRQ", T=2000, lambd=3.0, seed=2, net_kwargs={"is_drop": True}),

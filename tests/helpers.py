@@ -52,6 +52,7 @@ def run_oracle(case, sendlog=True):
     env = O.OracleEnv(topo.links, case["policy"], discount=kw.get("discount"),
                       add_entropy=kw.get("add_entropy", True), decay=kw.get("decay", 0.9),
                       is_drop=(case.get("net_kwargs") or {}).get("is_drop", False),
+                      multiway=kw.get("multiway", False), random=kw.get("random", False),
                       seed=case.get("philox_seed", 0), replica=case.get("replica", 0))
     q0, inj = case_inputs(case, topo)
     if q0 is not None:
