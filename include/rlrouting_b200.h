@@ -142,6 +142,14 @@ typedef struct {
     double *hop_out;          /* [n_steps][R] Network.ave_hops after each step (env.py:412-413, 440-442) */
     void *metrics2;           /* [n_steps][R] {uint32 all_packets, uint32 drop_packets} after each step; for droprate_out */
     double *droprate_out;     /* [n_steps][R] Network.drop_rate after each step (env.py:410-411, 448-450) */
+    /* Network.sample_route_time (env.py:416-438): when `sample` is set, every delivery files its routing time at
+     * sample[r][min(sample_idx[r], sample_size-1)] in the reference's delivery order, and a replica stops stepping
+     * (sample_clock[r] = its clock) once sample_idx[r] >= sample_size */
+    int32_t *sample;          /* [R][sample_size] */
+    int32_t *sample_idx;      /* [R], persists across calls */
+    int32_t *sample_clock;    /* [R] */
+    int32_t sample_size;
+    int32_t reserved2;
     uint32_t *sendlog;        /* [R][n_steps][N]: y | dest << 16 for a send by node x, else 0xFFFFFFFF */
 } rlr_run_params_t;
 

@@ -64,6 +64,8 @@ def lib():
         L.orc_philox4x32.argtypes = [p, p, p]
         L.orc_run.restype = i64
         L.orc_run.argtypes = [p, i64, i32, p, p, f64, f64, f64, f64, p, p, p, p, i64, p]
+        L.orc_sample_route_time.restype = i64
+        L.orc_sample_route_time.argtypes = [p, i64, i64, p, p, f64, f64, f64, f64, p]
         L.orc_run_many.restype = i64
         L.orc_run_many.argtypes = [p, i32, i64, p, f64, f64, f64, i32, p, p]
         L.orc_max_threads.restype = i32
@@ -169,6 +171,20 @@ class OracleEnv:
         if sendlog:
             res["sendlog"] = log[:nlog.value].copy()
         return res
+
+
+def sample_route_time(env, size, lambd=None, inj=None, lr_q=0.1, lr_p=0.1, lr_e=0.1, max_steps=1 << 20):
+    """Network.sample_route_time on one OracleEnv; returns (sample[int64 size], steps_run)."""
+    out = np.zeros(size, dtype=np.int64)
+    if inj is not None:
+        cnt = np.ascontiguousarray(inj[0], dtype=np.int32)
+        pairs = np.ascontiguousarray(inj[1], dtype=np.int32)
+        max_steps, enlam = min(max_steps, len(cnt)), 0.0
+    else:
+        cnt = pairs = None
+        enlam = float(np.exp(-np.float64(lambd) / np.float64(env.N)))
+    steps = lib().orc_sample_route_time(env.h, size, max_steps, _ptr(cnt), _ptr(pairs), enlam, lr_q, lr_p, lr_e, _ptr(out))
+    return out, int(steps)
 
 
 def run_many(envs, n_steps, lambd, lr_q=0.1, lr_p=0.1, lr_e=0.1, nthreads=0, metrics=False):

@@ -58,7 +58,7 @@ def _det_math():
 
 
 def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, replica=0,
-        agent_kwargs=None, keep_sendlog=False, det_math=False, net_kwargs=None):
+        agent_kwargs=None, keep_sendlog=False, det_math=False, net_kwargs=None, sample_size=0):
     """Runs `Network(net); agent = policy(nw); nw.train(T, lambd, lr=lr)` step by step.
 
     rng='trace'  : np.random.seed(seed) and the reference's own legacy stream (bit-for-bit the
@@ -136,7 +136,11 @@ def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, repl
     hp = np.zeros(T, dtype=np.int64)
     sends = 0
     err = None
+    sample = None
     try:
+        if sample_size:                          # Network.sample_route_time (env.py:416-438) instead of the train loop
+            sample = nw.sample_route_time(sample_size, lambd, lr=lr or {})
+            T = 0
         for i in range(T):                       # Network.train's loop, env.py:400-413, freq=1
             nw.inject(nw.new_packet(lambd))
             r = nw.step(1)
@@ -172,6 +176,8 @@ def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, repl
     })
     if keep_sendlog:
         out["sendlog"] = log
+    if sample is not None:
+        out["sample"] = np.asarray(sample, dtype=np.int64)
     for name in ("Qtable", "Theta", "Trace", "confidence"):
         if hasattr(agent, name):
             out[name] = pack_tables(getattr(agent, name), N)

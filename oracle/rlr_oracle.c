@@ -65,6 +65,7 @@ typedef struct orc {
     int add_entropy, status;
     int is_drop;              /* Network(is_drop=True): env.py:355-360 */
     int multiway, random_choice; /* Shortest(multiway=..., random=...), shortest.py:20-23,38-41 */
+    int64_t *sample; int64_t sample_size, sample_idx;   /* Network.sample / _sample_idx (env.py:242, 325-328, 424-425) */
     int64_t *queue_size;      /* GlobalRoute.queue_size (shortest.py:89): +1 per receive callback, -1 per send callback */
     int64_t status_clock;
     uint64_t seed, replica;   /* Philox key / stream id */
@@ -505,6 +506,11 @@ static void node_receive(orc_t *o, int x, pkt_t *p)
     if (x == p->dest) {
         o->active_packets -= 1;
         o->end_packets += 1;
+        if (o->sample_size > 0) {                       /* env.py:325-328 */
+            int64_t at = o->sample_idx < o->sample_size - 1 ? o->sample_idx : o->sample_size - 1;
+            o->sample[at] = o->clock - p->birth;
+            o->sample_idx += 1;
+        }
         o->route_time += o->clock - p->birth;
         o->hops += p->hops;
     } else {
@@ -807,6 +813,31 @@ int64_t orc_run(orc_t *o, int64_t n_steps, int inj_mode, const int32_t *inj_cnt,
     }
     if (n_sendlog) *n_sendlog = nlog;
     return n_steps;
+}
+
+/* Network.sample_route_time (env.py:416-438), slot = freq = 1: runs whole steps until `size` packets have been
+ * delivered; sample[i] is the routing time of the i-th delivery (deliveries past `size` in the last step overwrite the
+ * last entry).  Philox mode if inj_cnt is NULL; in trace mode the caller supplies at least `max_steps` steps of draws.
+ * Returns the number of steps run (or -1 if max_steps was not enough). */
+int64_t orc_sample_route_time(orc_t *o, int64_t size, int64_t max_steps, const int32_t *inj_cnt, const int32_t *inj_pairs,
+                              double enlam, double lr_q, double lr_p, double lr_e, int64_t *sample_out)
+{
+    o->sample = sample_out; o->sample_size = size; o->sample_idx = 0;
+    for (int64_t i = 0; i < size; ++i) sample_out[i] = 0;
+    int64_t off = 0, steps = 0;
+    while (o->sample_idx < size) {
+        if (steps >= max_steps) { o->sample_size = 0; o->sample = NULL; return -1; }
+        int cnt = inj_cnt ? inj_cnt[steps] : 0;
+        inject_step(o, inj_cnt ? INJ_TRACE : INJ_PHILOX, inj_pairs ? inj_pairs + 2 * off : NULL, cnt, enlam);
+        off += cnt;
+        send_phase(o);
+        if (o->status != ST_OK) break;
+        drain_events(o);
+        learn_phase(o, lr_q, lr_p, lr_e);
+        steps++;
+    }
+    o->sample_size = 0; o->sample = NULL;
+    return steps;
 }
 
 /* Runs `nrep` independent replicas (one orc_t each) for n_steps in Philox mode, one OpenMP

@@ -63,7 +63,9 @@ class RunParams(C.Structure):
                 ("clock0", C.c_int32), ("shortest_random", C.c_int32), ("reserved1", C.c_int32), ("phase", C.c_int32),
                 ("rewards", C.c_void_p),
                 ("metrics", C.c_void_p), ("route_time_out", C.c_void_p), ("hop_out", C.c_void_p),
-                ("metrics2", C.c_void_p), ("droprate_out", C.c_void_p), ("sendlog", C.c_void_p)]
+                ("metrics2", C.c_void_p), ("droprate_out", C.c_void_p),
+                ("sample", C.c_void_p), ("sample_idx", C.c_void_p), ("sample_clock", C.c_void_p),
+                ("sample_size", C.c_int32), ("reserved2", C.c_int32), ("sendlog", C.c_void_p)]
 
 
 EXPORTS = ("rlr_abi_version", "rlr_last_error_string", "rlr_struct_sizes", "rlr_create", "rlr_destroy", "rlr_bind_buffers",

@@ -79,6 +79,10 @@ struct StepParams {
     long long replica_base;
     double lr_q, lr_p, lr_e, discount, discount_trace, conf_decay;
     uint4 *metrics;
+    int *sample;                  // Network.sample_route_time: [R][sample_size] routing times in delivery order
+    int *sample_idx;              // [R] Network._sample_idx (persists across calls)
+    int *sample_clock;            // [R] clock at which the replica reached sample_size deliveries
+    int sample_size;
     uint2 *metrics2;              // [K][R] {all_packets, drop_packets} after each step (for the droprate vector)
     unsigned *sendlog;
 };
@@ -311,7 +315,7 @@ __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t
 
 // Shared-memory carve-up, identical on host (sizing) and device (pointers).
 struct SmemLayout {
-    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, gr, total;
+    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, gr, samp, total;
     __host__ __device__ SmemLayout(int N, int sdeg, int G, int threads, int policy, bool smem_tables, long long tsize, int ntab)
     {
         const int GN = G * N;
@@ -329,6 +333,7 @@ struct SmemLayout {
         heappos = o; o += align16((size_t)(N + 1) * N);
         nexthop = o; o += (policy == RLR_POLICY_SHORTEST) ? align16((size_t)N * N * 2)      // u8 next hops or u16 choice masks
                            : (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * N * N) : 0;
+        samp = o; o += align16((size_t)GN * 8);             // sample_route_time staging: (heap position, routing time) per delivery
         gr = o; o += (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * (N * N + N) * 4) : 0;   // distances + weights
         total = o;
     }
@@ -404,12 +409,14 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     unsigned short *s_tp = reinterpret_cast<unsigned short *>(smem + L.tp);   // target | warp-local rank << 8
     unsigned char *s_heappos = smem + L.heappos;
     unsigned char *s_nexthop = smem + L.nexthop;
+    int *s_samp_lat = reinterpret_cast<int *>(smem + L.samp);        // [GN] routing times of this step's deliveries
+    unsigned *s_samp_pos = reinterpret_cast<unsigned *>(smem + L.samp) + GN;   // [GN] their heap pop positions
     int *s_grdist = reinterpret_cast<int *>(smem + L.gr);          // GlobalRoute: [G][N*N] distances, then [G][N] weights
     int *s_grw = s_grdist + G * N * N;
     // per-replica accumulators of this launch
     unsigned long long *s_sends = s_ull + G, *s_inj = s_ull + 2 * G;
     unsigned *s_end = s_u32, *s_hops = s_u32 + G, *s_dead = s_u32 + 2 * G, *s_drop = s_u32 + 3 * G, *s_injs = s_u32 + 4 * G,
-             *s_rt32 = s_u32 + 5 * G;        // delivery latencies of the current step (drained every step by the metric thread)
+             *s_rt32 = s_u32 + 5 * G, *s_nsamp = s_u32 + 6 * G, *s_sidx = s_u32 + 7 * G;        // delivery latencies of the current step (drained every step by the metric thread)
     // MaHybridQ scratch: r, max_Q_y, max_Q_x_d per node; three sums + spare per replica
     double *s_r = s_f64, *s_qy = s_f64 + GN, *s_qx = s_f64 + 2 * GN, *s_sum = s_f64 + 3 * GN;
     // CDRQ scratch (same region): backward-update inputs of each sender and the queue lengths of 'dual' mode
@@ -447,6 +454,9 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     for (int i = t; i < G; i += blockDim.x) {
         s_rt32[i] = 0; s_sends[i] = 0; s_inj[i] = 0; s_end[i] = 0; s_hops[i] = 0; s_drop[i] = 0; s_injs[i] = 0;
         s_dead[i] = (rblock + i < p.R) ? (unsigned)(p.status[2 * (rblock + i)] != 0) : 1u;
+        s_nsamp[i] = 0;
+        s_sidx[i] = (p.sample && rblock + i < p.R) ? (unsigned)p.sample_idx[rblock + i] : 0u;
+        if (p.sample && s_sidx[i] >= (unsigned)p.sample_size) s_dead[i] = 2u;     // already has its samples: frozen
     }
     if (SMEM_TABLES) {
         const long long per = p.tsize / 2;                          // double2 per table
@@ -543,7 +553,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
 #endif
     for (int s = 0; s < p.K; ++s) {
         const int clock = p.clock0 + s;
-        if (IS_PG && is_node) dead = (s_dead[g] != 0u);
+        if ((IS_PG || p.sample) && is_node) dead = (s_dead[g] != 0u);
         const bool live = !dead;
         bool sending = false;
         int d = 0, k = 0, y = 0;
@@ -764,6 +774,11 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                     continue;
                 }
                 if ((int)(rec.x & 0xFFFFu) == x) {                              // Network.end_packet, env.py:321-331
+                    if (p.sample) {                                             // env.py:325-328, ordered later by pop position
+                        const unsigned slot = atomicAdd(&s_nsamp[g], 1u);
+                        s_samp_pos[gbase + slot] = best >> 16;
+                        s_samp_lat[gbase + slot] = clock + 1 - (int)rec.z;
+                    }
                     atomicAdd(&s_end[g], 1u);
                     atomicAdd(&s_rt32[g], (unsigned)(clock + 1 - (int)rec.z));
                     atomicAdd(&s_hops[g], rec.y);
@@ -930,6 +945,30 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             run_rt += (long long)s_rt32[g];
             s_rt32[g] = 0u;                         // next deliveries come after the next barrier 1
         }
+        if (p.sample) {                             // Network.sample_route_time (env.py:416-438): file this step's deliveries
+            if (is_node && x == N - 1 && !dead) {
+                const int n = (int)s_nsamp[g];
+                for (int i = 1; i < n; ++i) {       // insertion sort by heap pop position = the reference's delivery order
+                    const unsigned kp = s_samp_pos[gbase + i];
+                    const int kl = s_samp_lat[gbase + i];
+                    int j = i - 1;
+                    while (j >= 0 && s_samp_pos[gbase + j] > kp) {
+                        s_samp_pos[gbase + j + 1] = s_samp_pos[gbase + j];
+                        s_samp_lat[gbase + j + 1] = s_samp_lat[gbase + j];
+                        --j;
+                    }
+                    s_samp_pos[gbase + j + 1] = kp;
+                    s_samp_lat[gbase + j + 1] = kl;
+                }
+                int idx = (int)s_sidx[g];
+                for (int i = 0; i < n; ++i, ++idx)
+                    p.sample[r * (long long)p.sample_size + (idx < p.sample_size - 1 ? idx : p.sample_size - 1)] = s_samp_lat[gbase + i];
+                s_sidx[g] = (unsigned)idx;
+                s_nsamp[g] = 0u;
+                if (idx >= p.sample_size) { s_dead[g] = 2u; p.sample_clock[r] = clock + 1; }
+            }
+            __syncthreads();
+        }
         if (is_node && x == N - 1 && p.metrics) {                               // env.py:409-413 (cumulative counters)
             const long long rt = base_rt + run_rt;
             const unsigned en = (unsigned)(base_end + s_end[g]), hps = (unsigned)(base_hops + s_hops[g]);
@@ -958,6 +997,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         c[RLR_CTR_DROP_PACKETS] += (long long)s_drop[g];
         c[RLR_CTR_HOPS] += (long long)s_hops[g];
         c[RLR_CTR_ROUTE_TIME] += run_rt;
+        if (p.sample) p.sample_idx[r] = (int)s_sidx[g];
         c[RLR_CTR_SENDS] += (long long)s_sends[g];
     }
     if (POLICY == RLR_POLICY_GLOBALROUTE && do_learn) {
@@ -1578,6 +1618,9 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     p.inj_events = rp->inj_events; p.seed = rp->seed; p.replica_base = h->replica_base;
     p.lr_q = rp->lr_q; p.lr_p = rp->lr_p; p.lr_e = rp->lr_e; p.discount = rp->discount; p.discount_trace = rp->discount_trace; p.conf_decay = rp->conf_decay;
     p.metrics = (uint4 *)rp->metrics; p.metrics2 = (uint2 *)rp->metrics2; p.sendlog = rp->sendlog;
+    p.sample = rp->sample; p.sample_idx = rp->sample_idx; p.sample_clock = rp->sample_clock; p.sample_size = rp->sample_size;
+    if (p.sample && (!p.sample_idx || !p.sample_clock || p.sample_size < 1))
+        return fail(RLR_E_INVALID, "rlr_run_steps: sample needs sample_idx, sample_clock and sample_size >= 1");
     if (rp->inject_mode == RLR_INJECT_PHILOX) {
         const int rc = rlr_build_inject_schedule(h, n_steps, rp, stream);
         if (rc != RLR_OK) return rc;

@@ -307,6 +307,7 @@ class Network:
     # ------------------------------------------------------------------ reset (env.py:267-280)
     def reset(self):
         self.clock = 0
+        self._desync = False
         self._pending = [[] for _ in range(self.replicas)]
         self._last_rewards = None
         h = getattr(self._agent, "_handle", None)
@@ -470,7 +471,65 @@ class Network:
         self._raise_on_status(self._status.cpu().numpy())
 
     def sample_route_time(self, size, lambd, slot=1, freq=1, lr={}):
-        raise NotImplementedError("sample_route_time (SURVEY §8 row f2) is not implemented on the device")
+        """env.py:416-438: runs like `train` until `size` packets have been delivered and returns their routing times
+        in delivery order (one replica: [size]; R replicas: [R, size], each replica stopping at its own clock).
+        After a multi-replica call the replicas' clocks differ, so the network must be `reset()` before it is used
+        again."""
+        import torch
+        if slot != 1 or freq != 1:
+            raise NotImplementedError("slot != 1 / freq != 1 (SURVEY §8 row f2) are not implemented on the device")
+        self._check_sync()
+        agent = self._agent
+        h = self._handle_or_raise()
+        R, N, dev = self.replicas, self.topology.N, self.device
+        size = int(size)
+        lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (R,))
+        rp = self._run_params(agent, lr)
+        samp = torch.zeros((R, size), dtype=torch.int32, device=dev)
+        sidx = torch.zeros(R, dtype=torch.int32, device=dev)
+        sclk = torch.zeros(R, dtype=torch.int32, device=dev)
+        rp.sample, rp.sample_idx, rp.sample_clock, rp.sample_size = samp.data_ptr(), sidx.data_ptr(), sclk.data_ptr(), size
+        keep = []
+        if self.rng == "philox":
+            lam_key = lam.tobytes() if lam.strides[0] else float(lam[0])
+            en_host = np.exp(-lam / np.float64(N))
+            enlam = torch.from_numpy(en_host).to(dev)
+            thr = torch.from_numpy(injection_threshold(en_host).view(np.int64)).to(dev)
+            rp.enlam, rp.inj_thr = enlam.data_ptr(), thr.data_ptr()
+            keep += [enlam, thr]
+        # trace mode advances one step per launch so the host RNG stream stops exactly where the reference's would
+        K = 1 if self.rng == "trace" else 128
+        while True:
+            if self.rng == "trace":
+                traces = trace.draw_injections_many(self._rs, N, K, lam)
+                evs = [trace_schedule(c, pr, N, 0, K) for c, pr in traces]
+                per_node = [np.bincount(node, minlength=N) for _, node in evs]
+                cap = int(max(pn.max() for pn in per_node)) + 2
+                sched = np.full((R, N, cap), 0xFFFFFFFF, dtype=np.uint32)
+                for r, ((e, node), pn) in enumerate(zip(evs, per_node)):
+                    start = np.concatenate([[0], np.cumsum(pn)[:-1]])
+                    sched[r, node, np.arange(len(e)) - start[node]] = e
+                d_sched = torch.from_numpy(sched.view(np.int32)).to(dev)
+                rp.inject_mode, rp.inj_events, rp.inj_cap, rp.clock0 = nat.INJECT_TRACE, d_sched.data_ptr(), cap, self.clock
+            else:
+                self._schedule(h, rp, self.clock, K, lam_key, lam.max(), (self.clock + K, K))
+            nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), self._stream_ptr()))
+            self.launch_count += 1
+            if self.rng == "philox":
+                self._schedule_done(h, rp)
+            self.clock += K
+            self._raise_on_status(self._status.cpu().numpy())
+            if bool((sidx >= size).all().item()):
+                break
+        clocks = sclk.cpu().numpy().astype(np.int64)
+        self.clock = int(clocks.max())
+        self._desync = bool((clocks != clocks[0]).any())
+        out = samp.cpu().numpy().astype(np.float64)
+        return out[0] if R == 1 else out
+
+    def _check_sync(self):
+        if self.__dict__.get("_desync"):
+            raise RuntimeError("the replicas stopped at different clocks in sample_route_time; call reset() first")
 
     # ------------------------------------------------------------------ the hot path (env.py:367-414)
     def train(self, duration, lambd, slot=1, freq=1, lr={}, droprate=False, hop=False, *, lrq=None, lrp=None,
@@ -485,6 +544,7 @@ class Network:
         """
         import time
         import torch
+        self._check_sync()
         _t = [time.perf_counter()]
         if slot != 1 or freq != 1:
             raise NotImplementedError("slot != 1 / freq != 1 (SURVEY §8 row f2) are not implemented on the device")
@@ -557,7 +617,7 @@ class Network:
             if traces is not None:                      # host replay of env.py:307-310 -> per-node event lists
                 evs = [trace_schedule(c, pr, N, s0, s0 + K) for c, pr in traces]
                 per_node = [np.bincount(node, minlength=N) for _, node in evs]
-                cap = int(max(pn.max() for pn in per_node)) + 1
+                cap = int(max(pn.max() for pn in per_node)) + 2
                 sched = np.full((R, N, cap), 0xFFFFFFFF, dtype=np.uint32)
                 for r, ((e, node), pn) in enumerate(zip(evs, per_node)):
                     start = np.concatenate([[0], np.cumsum(pn)[:-1]])

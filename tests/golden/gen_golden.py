@@ -74,6 +74,13 @@ CASES = [
          agent_kwargs={"multiway": True, "random": True}),
     dict(net="lata.net", policy="Shortest", T=500, lambd=3.0, seed=1, rng="philox", philox_seed=7, replica=3,
          agent_kwargs={"multiway": True, "random": True}),
+    # Network.sample_route_time — run until `sample_size` deliveries, routing times in delivery order
+    dict(net="6x6.net", policy="Shortest", T=0, lambd=2.0, seed=1, sample_size=500),
+    dict(net="6x6.net", policy="Qroute", T=0, lambd=2.0, seed=1, sample_size=300),
+    dict(net="6x6.net", policy="CDRQ", T=0, lambd=3.0, seed=1, sample_size=200),
+    dict(net="lata.net", policy="Qroute", T=0, lambd=3.0, seed=1, rng="philox", philox_seed=7, replica=3, sample_size=40),
+    dict(net="6x6.net", policy="MaHybridQ", T=0, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3, det_math=True,
+         lr={"q": 0.1, "p": 0.001}, sample_size=60),
     # is_drop=True — a packet arriving with hops >= N is dropped (env.py:355-360)
     dict(net="6x6.net", policy="Qroute", T=3000, lambd=2.0, seed=1, net_kwargs={"is_drop": True}),
     dict(net="6x6.net", policy="CDRQ", T=2000, lambd=3.0, seed=2, net_kwargs={"is_drop": True}),
@@ -112,6 +119,8 @@ def main():
         if "distance" in r:
             rec["expect"]["distance_sha256"] = h(r["distance"], "<f8")
             rec["expect"]["choice_sha256"] = h(r["choice"], "u1")
+        if "sample" in r:
+            rec["expect"]["sample"] = [int(v) for v in r["sample"]]
         if "queue_size" in r:
             rec["expect"]["queue_size"] = [int(v) for v in r["queue_size"]]
         out.append(rec)

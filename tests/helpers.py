@@ -36,7 +36,7 @@ def case_inputs(case, topo):
         q0 = topo.pack(trace.draw_qtable_normals(rs, topo, kw.get("initQ", 0), times))
     inj = None
     if case.get("rng", "trace") == "trace":
-        inj = trace.draw_injections(rs, topo.N, case["T"], case["lambd"])
+        inj = trace.draw_injections(rs, topo.N, case["T"] or 4000, case["lambd"])   # sample cases stop on their own
     return q0, inj
 
 
@@ -58,6 +58,10 @@ def run_oracle(case, sendlog=True):
     if q0 is not None:
         env.set_qtable(q0, initP=kw.get("initP", 0.0))
     lr = lr_of(case)
+    if case.get("sample_size"):
+        smp, steps = O.sample_route_time(env, case["sample_size"], lambd=case["lambd"], inj=inj, lr_q=lr["q"], lr_p=lr["p"],
+                                         lr_e=lr["e"])
+        return topo, env, q0, inj, {"sample": smp, "steps_done": steps}
     res = env.run(case["T"], lambd=case["lambd"], inj=inj, lr_q=lr["q"], lr_p=lr["p"], lr_e=lr["e"],
                   sendlog=sendlog)
     return topo, env, q0, inj, res

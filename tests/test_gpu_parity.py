@@ -37,6 +37,8 @@ def device_run(case, **net_kw):
         if q0 is not None:
             agent.set_initial_q(q0, initP=kw.get("initP", 0.0))
     nw.agent = agent
+    if case.get("sample_size"):
+        return nw, agent, nw.sample_route_time(case["sample_size"], case["lambd"], lr=case.get("lr") or {})
     exp_err = case["expect"]["error"]
     if exp_err is not None:
         with pytest.raises(ValueError, match="probabilities contain NaN"):
@@ -50,6 +52,17 @@ def device_run(case, **net_kw):
 def test_device_matches_reference_known_answers(case):
     nw, agent, res = device_run(case)
     exp = case["expect"]
+    if case.get("sample_size"):                       # Network.sample_route_time (env.py:416-438)
+        assert [int(v) for v in res] == exp["sample"] and res.dtype == np.float64
+        c = nw.counters()
+        for k in ("clock", "all_packets", "end_packets", "drop_packets", "active_packets", "hops", "route_time"):
+            assert int(c[k][0]) == exp["counters"][k], k
+        qs = [nw.queue_array(x) for x in range(nw.topology.N)]
+        assert sha(np.concatenate([q.reshape(-1) for q in qs] + [np.array([len(q) for q in qs])]), "<i4") == exp["queues_sha256"]
+        for name in ("Qtable", "Theta", "Trace", "confidence"):
+            if name in agent._dev and name + "_sha256" in exp:
+                assert sha(agent.table_array(name)[0], "<f8") == exp[name + "_sha256"], name
+        return
     if exp["error"] is not None:
         st = nw._status.cpu().numpy()[0]
         assert (int(st[0]), int(st[1])) == (1, exp["error"][1])
@@ -430,3 +443,30 @@ def test_network_reset_semantics_match_oracle(policy):
     if policy == "GlobalRoute":
         for r in range(R):
             assert list(agent.queue_size[r]) == list(envs[r].queue_size)
+
+
+def test_sample_route_time_many_replicas_and_desync_guard():
+    """R replicas sample until each has its deliveries; every replica equals its own oracle run, and the network
+    refuses further training until reset() because the replicas stopped at different clocks."""
+    import rlrouting_b200 as rb
+    R, size, lam, seed = 9, 150, 2.0, 4
+    nw = rb.Network("6x6.net", replicas=R, rng="philox", seed=seed)
+    agent = rb.Qroute(nw)
+    nw.agent = agent
+    q0 = agent.table_array("Qtable")
+    out = nw.sample_route_time(size, lam)
+    assert out.shape == (R, size)
+    clocks = []
+    for r in range(R):
+        e = O.OracleEnv(nw.topology.links, "Qroute", seed=seed, replica=r)
+        e.set_qtable(q0[r])
+        smp, steps = O.sample_route_time(e, size, lambd=lam)
+        assert np.array_equal(out[r].astype(np.int64), smp), r
+        assert np.array_equal(agent.table_array("Qtable")[r].view(np.int64), e.Q.view(np.int64)), r
+        clocks.append(steps)
+    assert nw.clock == max(clocks)
+    if len(set(clocks)) > 1:
+        with pytest.raises(RuntimeError, match="different clocks"):
+            nw.train(10, lam)
+    nw.reset()
+    nw.train(10, lam)
