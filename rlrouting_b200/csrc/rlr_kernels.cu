@@ -547,13 +547,14 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
 
     // SPLIT = false is the fused Network.train path (both phases, no flag tests in the loop)
     const bool do_env = !SPLIT || (p.phase & 1) != 0, do_learn = !SPLIT || (p.phase & 2) != 0;
+    const bool sampling = SPLIT && p.sample != nullptr;      // sample_route_time also runs on the SPLIT instantiation
 #ifdef RLR_EXP_TIMING
     long long tacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tmark_ = clock64();
 #endif
     for (int s = 0; s < p.K; ++s) {
         const int clock = p.clock0 + s;
-        if ((IS_PG || p.sample) && is_node) dead = (s_dead[g] != 0u);
+        if ((IS_PG || sampling) && is_node) dead = (s_dead[g] != 0u);
         const bool live = !dead;
         bool sending = false;
         int d = 0, k = 0, y = 0;
@@ -774,7 +775,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                     continue;
                 }
                 if ((int)(rec.x & 0xFFFFu) == x) {                              // Network.end_packet, env.py:321-331
-                    if (p.sample) {                                             // env.py:325-328, ordered later by pop position
+                    if (sampling) {                                             // env.py:325-328, ordered later by pop position
                         const unsigned slot = atomicAdd(&s_nsamp[g], 1u);
                         s_samp_pos[gbase + slot] = best >> 16;
                         s_samp_lat[gbase + slot] = clock + 1 - (int)rec.z;
@@ -945,7 +946,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             run_rt += (long long)s_rt32[g];
             s_rt32[g] = 0u;                         // next deliveries come after the next barrier 1
         }
-        if (p.sample) {                             // Network.sample_route_time (env.py:416-438): file this step's deliveries
+        if (sampling) {                             // Network.sample_route_time (env.py:416-438): file this step's deliveries
             if (is_node && x == N - 1 && !dead) {
                 const int n = (int)s_nsamp[g];
                 for (int i = 1; i < n; ++i) {       // insertion sort by heap pop position = the reference's delivery order
@@ -997,7 +998,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         c[RLR_CTR_DROP_PACKETS] += (long long)s_drop[g];
         c[RLR_CTR_HOPS] += (long long)s_hops[g];
         c[RLR_CTR_ROUTE_TIME] += run_rt;
-        if (p.sample) p.sample_idx[r] = (int)s_sidx[g];
+        if (sampling) p.sample_idx[r] = (int)s_sidx[g];
         c[RLR_CTR_SENDS] += (long long)s_sends[g];
     }
     if (POLICY == RLR_POLICY_GLOBALROUTE && do_learn) {
@@ -1627,7 +1628,7 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     }
     const long long blocks = (h->R + h->G - 1) / h->G;
     if (blocks > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: too many blocks");
-    (p.phase == 3 ? h->kernel : h->kernel_split)<<<(unsigned)blocks, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p);
+    ((p.phase == 3 && !p.sample) ? h->kernel : h->kernel_split)<<<(unsigned)blocks, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p);
     RLR_CUDA(cudaGetLastError());
     if (rp->route_time_out || rp->hop_out || rp->droprate_out) {
         const long long n = n_steps * h->R;
