@@ -535,7 +535,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     evp += 1;
     bool dead = is_node ? (s_dead[g] != 0u) : true;                 // only sampled policies can die mid-launch
     const int gr_off = (POLICY == RLR_POLICY_GLOBALROUTE && is_node) ? p.gr_qs_off[r * N + x] : 0;
-    unsigned *sendlog = (p.sendlog && is_node) ? p.sendlog + r * (long long)p.K * N + x : nullptr;
+    // rarely used options (send log, is_drop, droprate records, sampling, split phases) live in the SPLIT instantiation only
+    unsigned *sendlog = (SPLIT && p.sendlog && is_node) ? p.sendlog + r * (long long)p.K * N + x : nullptr;
 
     // Ring append.  Overflow is detected once per step (tail - head > cap) and reported through the sticky
     // status word; the masked index keeps a wrapped write inside this node's own ring.
@@ -580,7 +581,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             while ((ev >> 8) == (unsigned)s) {
                 append(make_uint4((ev & 0xFFu) | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock));
                 ++my_inj;
-                if (p.metrics2) atomicAdd(&s_injs[g], 1u);
+                if (SPLIT && p.metrics2) atomicAdd(&s_injs[g], 1u);
                 ev = ev_next;
                 if (ev != 0xFFFFFFFFu) ev_next = *++evp;
             }
@@ -770,7 +771,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 }
                 if (best == kNoKey) break;
                 uint4 rec = s_rec[best & 0xFFFFu];
-                if (p.is_drop && rec.y >= (unsigned)N) {                        // env.py:355-360: too many hops, dropped
+                if (SPLIT && p.is_drop && rec.y >= (unsigned)N) {                        // env.py:355-360: too many hops, dropped
                     atomicAdd(&s_drop[g], 1u);
                     continue;
                 }
@@ -974,7 +975,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             const long long rt = base_rt + run_rt;
             const unsigned en = (unsigned)(base_end + s_end[g]), hps = (unsigned)(base_hops + s_hops[g]);
             p.metrics[(long long)s * p.R + r] = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hps);
-            if (p.metrics2)
+            if (SPLIT && p.metrics2)
                 p.metrics2[(long long)s * p.R + r] = make_uint2((unsigned)(base_all + s_injs[g]), (unsigned)(base_drop + s_drop[g]));
         }
     }
@@ -1628,7 +1629,8 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     }
     const long long blocks = (h->R + h->G - 1) / h->G;
     if (blocks > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: too many blocks");
-    ((p.phase == 3 && !p.sample) ? h->kernel : h->kernel_split)<<<(unsigned)blocks, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p);
+    const bool plain = p.phase == 3 && !p.sample && !p.sendlog && !p.is_drop && !p.metrics2;
+    (plain ? h->kernel : h->kernel_split)<<<(unsigned)blocks, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p);
     RLR_CUDA(cudaGetLastError());
     if (rp->route_time_out || rp->hop_out || rp->droprate_out) {
         const long long n = n_steps * h->R;
