@@ -93,19 +93,19 @@ def oracle_envs(a, n, base=0, seed=1):
 
 
 def cpu_sample(a, seconds):
-    """Times the oracle on all host cores on a bounded sample of the workload; returns the dict."""
+    """Times the oracle on all host cores on a bounded sample of the workload (about `seconds` of CPU wall time)."""
     from oracle import oracle as O
     O.build()
     cores = os.cpu_count() or 1
-    n = 16 * cores
+    n = 32 * cores
     envs = oracle_envs(a, n)
-    t0 = time.perf_counter()
-    sends = O.run_many(envs, 200, a.load, LR["q"], LR["p"], LR["e"], nthreads=cores)      # probe (also warms queues)
-    dt = max(time.perf_counter() - t0, 1e-6)
-    steps = int(max(200, min(20000, 200 * seconds / dt)))
-    t0 = time.perf_counter()
-    sends = O.run_many(envs, steps, a.load, LR["q"], LR["p"], LR["e"], nthreads=cores)
-    dt = time.perf_counter() - t0
+    O.run_many(envs, 200, a.load, LR["q"], LR["p"], LR["e"], nthreads=cores)   # warm the queues like the GPU's warm-up
+    sends, steps, dt = 0, 0, 0.0
+    while dt < seconds and steps < 20000:                                       # chunks of the same continuing run
+        t0 = time.perf_counter()
+        sends += O.run_many(envs, 500, a.load, LR["q"], LR["p"], LR["e"], nthreads=cores)
+        dt += time.perf_counter() - t0
+        steps += 500
     return {"value": sends / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} replicas x {steps} simulator steps (after 200 warm-up steps) of the same workload, "
                       f"oracle/rlr_oracle.c via OpenMP on {cores} threads, {dt:.1f} s"}
@@ -154,7 +154,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -338,6 +338,15 @@ def run_b200(a):
     print(json.dumps(line))
 
 
+def _finalize():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 def main():
     a = parse()
     plan_capacity(a)
@@ -345,6 +354,7 @@ def main():
         run_reference(a)
         return
     run_b200(a)
+    _finalize()
 
 
 if __name__ == "__main__":
