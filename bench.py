@@ -97,11 +97,11 @@ def cpu_sample(a, seconds):
     from oracle import oracle as O
     O.build()
     cores = os.cpu_count() or 1
-    n = 32 * cores
+    n = 128 * cores
     envs = oracle_envs(a, n)
     O.run_many(envs, 200, a.load, LR["q"], LR["p"], LR["e"], nthreads=cores)   # warm the queues like the GPU's warm-up
     sends, steps, dt = 0, 0, 0.0
-    while dt < seconds and steps < 20000:                                       # chunks of the same continuing run
+    while dt < seconds and steps < 10000:                                       # chunks of the same continuing run
         t0 = time.perf_counter()
         sends += O.run_many(envs, 500, a.load, LR["q"], LR["p"], LR["e"], nthreads=cores)
         dt += time.perf_counter() - t0
