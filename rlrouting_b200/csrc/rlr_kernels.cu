@@ -11,7 +11,14 @@
 //     they stay in HBM and the same code reads them through L1/L2;
 //   * arrivals are GATHERED by the receiving node from its neighbours' send slots and appended in
 //     the heap-tie order of the reference, so no atomics touch the queues and the
-//     result is deterministic.
+//     result is deterministic;
+//   * injections come from a precomputed per-node schedule (Philox kernel one chunk ahead on a side
+//     stream, or the host's replay of NumPy's legacy stream), so no RNG sits on the step's critical path;
+//   * the fused Network.train path and the rarely used options (split step/learn phases, send log,
+//     is_drop, droprate records, sample_route_time) are separate instantiations (SPLIT), because the
+//     fused loop is latency-bound and every extra test in it costs throughput.
+// Tuning aids: -DRLR_FAST_BUILD (only the 6x6 Qroute instantiations, seconds to build) and
+// -DRLR_EXP_TIMING (per-phase clock64 accounting read through rlr_debug_phase_cycles).
 //
 // All fp64 arithmetic on tables uses the explicitly rounded intrinsics (__dmul_rn/__dadd_rn/...),
 // never FMA, because the reference evaluates every NumPy scalar operation separately.
@@ -219,43 +226,9 @@ __device__ __forceinline__ double np_sum_row(const double (&a)[MAXD], int n)
     return res;
 }
 
-// Same order over the senders of one replica, values indexed by node (non-senders skipped):
-// MaHybridQ.learn's max_Q_y.sum() / max_Q_x_d.sum() (multi_agent.py:28-29).
-__device__ double np_sum_compacted(const double *v, const unsigned short *tp, int N, int n)
-{
-    if (n < 8) {
-        double r = 0.0;
-        for (int x = 0; x < N; ++x)
-            if (tp[x] != 0xFFFFu) r = __dadd_rn(r, v[x]);
-        return r;
-    }
-    double acc[8];
-    const int nb = n - (n % 8);
-    int idx = 0;
-    double res = 0.0;
-    for (int x = 0; x < N; ++x) {
-        if (tp[x] == 0xFFFFu) continue;
-        const double a = v[x];
-        if (idx < 8) {
-            acc[idx] = a;
-        } else if (idx < nb) {
-            acc[idx & 7] = __dadd_rn(acc[idx & 7], a);
-        } else {
-            if (idx == nb)
-                res = __dadd_rn(__dadd_rn(__dadd_rn(acc[0], acc[1]), __dadd_rn(acc[2], acc[3])),
-                                __dadd_rn(__dadd_rn(acc[4], acc[5]), __dadd_rn(acc[6], acc[7])));
-            res = __dadd_rn(res, a);
-        }
-        ++idx;
-    }
-    if (n == nb)
-        res = __dadd_rn(__dadd_rn(__dadd_rn(acc[0], acc[1]), __dadd_rn(acc[2], acc[3])),
-                        __dadd_rn(__dadd_rn(acc[4], acc[5]), __dadd_rn(acc[6], acc[7])));
-    return res;
-}
-
-// The same sum computed by one whole warp (MaHybridQ.learn's three reductions run on helper warps while the node
-// warps process arrivals).  v is indexed by thread slot; the replica's senders are the set bits of its window of the
+// ndarray.sum() in NumPy's order over the values of one replica's senders (MaHybridQ.learn's r.sum(), max_Q_y.sum(),
+// max_Q_x_d.sum(), multi_agent.py:28-29), computed by one whole warp: the three reductions run on helper warps while
+// the node warps process arrivals.  v is indexed by thread slot; the replica's senders are the set bits of its window of the
 // CTA-wide "sent" bit array (words wm[wlo .. wlo+nw), first/last word masked).  n < 128 (NumPy's single pairwise block).
 template <int MAXW>
 __device__ double np_sum_warp(const double *v, const unsigned *wm, int wlo, int nw, unsigned mfirst, unsigned mlast, int lane)
@@ -720,7 +693,6 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         __syncthreads();                                                        // ---- barrier 1 ----
         RLR_T(1);
 
-#ifndef RLR_EXP_SKIP_C
         if (live && do_env) {
             // ---- C. event drain (env.py:349-364): gather arrivals from neighbours in heap-tie order ----
             unsigned cum[MAXW + 1];         // senders of this replica in the window words before word i
@@ -791,7 +763,6 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             }
             if (tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
         }
-#endif
         RLR_T(2);                                   // C
         // ---- D. agent.learn ----
         if (!do_learn) {

@@ -13,6 +13,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _native_libraries_built():
+    """The CUDA library and the oracle are built in-tree and git-ignored; build them if a fresh checkout lacks them
+    (nvcc cross-compiles for sm_100a without a GPU)."""
+    from rlrouting_b200 import _native
+    if not os.path.exists(_native.SO):
+        _native.build()
+    from oracle import oracle as O
+    O.build()
+
+
 def pytest_collection_modifyitems(config, items):
     have_ref = os.path.isdir("/root/reference")
     for item in items:
