@@ -191,6 +191,12 @@ int rlr_build_shortest_tables(rlr_handle_t *h, int32_t multiway, void *stream);
 int rlr_trace_replay(uint32_t *mt_key, int32_t *mt_pos, int32_t n_nodes, int64_t n_steps, double lam,
                      int32_t *cnt_out, uint32_t *pairs_out, int64_t pairs_cap, int64_t *n_pairs_out);
 
+/* the same for n_streams independent RandomState streams (mt_keys[n_streams][624], mt_pos[n_streams], lam[n_streams];
+ * cnt_out[n_streams][n_steps], pairs_out[n_streams][pairs_cap], n_pairs_out[n_streams]) on nthreads host threads */
+int rlr_trace_replay_many(uint32_t *mt_keys, int32_t *mt_pos, int64_t n_streams, int32_t n_nodes, int64_t n_steps,
+                          const double *lam, int32_t *cnt_out, uint32_t *pairs_out, int64_t pairs_cap,
+                          int64_t *n_pairs_out, int32_t nthreads);
+
 /* ---- Network.new_packet (env.py:298-312) for n_steps steps ahead of time, Philox mode: fills params->inj_events
  *      from enlam / inj_thr / seed / clock0.  rlr_run_steps does this itself for RLR_INJECT_PHILOX; calling it
  *      separately (on another stream, then running with RLR_INJECT_TRACE) overlaps it with the previous chunk. ---- */

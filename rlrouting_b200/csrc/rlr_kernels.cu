@@ -28,7 +28,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rlrouting_b200.h"
@@ -1331,6 +1333,35 @@ extern "C" int rlr_trace_replay(uint32_t *mt_key, int32_t *mt_pos, int32_t n_nod
     }
     *mt_pos = mt.pos;
     *n_pairs_out = np;
+    return RLR_OK;
+}
+
+// The same replay for R independent streams on `nthreads` host threads (replica r uses lam[r], writes cnt_out[r][*]
+// and at most pairs_cap entries of pairs_out[r][*]).
+extern "C" int rlr_trace_replay_many(uint32_t *mt_keys, int32_t *mt_pos, int64_t n_streams, int32_t n_nodes, int64_t n_steps,
+                                     const double *lam, int32_t *cnt_out, uint32_t *pairs_out, int64_t pairs_cap,
+                                     int64_t *n_pairs_out, int32_t nthreads)
+{
+    if (!mt_keys || !mt_pos || !lam || !cnt_out || !pairs_out || !n_pairs_out || n_streams < 0)
+        return fail(RLR_E_INVALID, "rlr_trace_replay_many: null argument");
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int64_t> next(0);
+    std::atomic<int> rc(RLR_OK);
+    std::string msg;
+    auto work = [&]() {
+        for (;;) {
+            const int64_t r = next.fetch_add(1);
+            if (r >= n_streams) return;
+            const int one = rlr_trace_replay(mt_keys + r * 624, mt_pos + r, n_nodes, n_steps, lam[r], cnt_out + r * n_steps,
+                                             pairs_out + r * pairs_cap, pairs_cap, n_pairs_out + r);
+            if (one != RLR_OK) { int expect = RLR_OK; if (rc.compare_exchange_strong(expect, one)) msg = g_last_error; }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int i = 1; i < nthreads; ++i) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    if (rc.load() != RLR_OK) return fail(rc.load(), msg.empty() ? "rlr_trace_replay_many: a stream failed" : msg);
     return RLR_OK;
 }
 

@@ -69,15 +69,42 @@ def _draw_worker(args):
     return cnt, pairs, rs.get_state()
 
 
+def _draw_native_many(streams, n_nodes, n_steps, lambdas, workers):
+    """All replicas' streams through one call of rlr_trace_replay_many (C threads, no GIL)."""
+    import ctypes as C
+    from . import _native as nat
+    R = len(streams)
+    states = [rs.get_state() for rs in streams]
+    keys = np.ascontiguousarray(np.stack([st[1] for st in states]), dtype=np.uint32)
+    pos = np.array([st[2] for st in states], dtype=np.int32)
+    lam = np.ascontiguousarray(np.broadcast_to(lambdas, (R,)), dtype=np.float64)
+    m = float(lam.max()) * n_steps
+    cap = int(m + 12.0 * np.sqrt(m + 1.0) + 64)
+    cnt = np.zeros((R, n_steps), dtype=np.int32)
+    packed = np.zeros((R, cap), dtype=np.uint32)
+    n_out = np.zeros(R, dtype=np.int64)
+    nat.check(nat.lib().rlr_trace_replay_many(keys.ctypes.data, pos.ctypes.data, R, n_nodes, n_steps, lam.ctypes.data,
+                                               cnt.ctypes.data, packed.ctypes.data, cap, n_out.ctypes.data, workers))
+    out = []
+    for r, (rs, st) in enumerate(zip(streams, states)):
+        rs.set_state((st[0], keys[r], int(pos[r]), st[3], st[4]))
+        pk = packed[r, :n_out[r]]
+        out.append((cnt[r], np.stack([pk & 0xFFFF, pk >> 16], axis=1).astype(np.int32).reshape(-1, 2)))
+    return out
+
+
 def draw_injections_many(streams, n_nodes, n_steps, lambdas, workers=None):
-    """draw_injections for every replica's RandomState; replicas are independent streams, so with many of them
-    the replay is farmed out to worker processes (each stream's state is advanced exactly as in-process)."""
+    """draw_injections for every replica's RandomState.  Replicas are independent streams: the C replay releases the
+    GIL, so they are replayed on a thread pool; loads NumPy has to draw itself (lambda >= 10) go to worker processes."""
     import os
     R = len(streams)
     if workers is None:
-        workers = min(os.cpu_count() or 1, 16)
-    if R < 64 or workers < 2 or any(rs is np.random.mtrand._rand for rs in streams) or float(np.max(lambdas)) < 10.0:
+        workers = min(os.cpu_count() or 1, 32)
+    lam_max = float(np.max(lambdas)) if R else 0.0
+    if R < 64 or workers < 2 or any(rs is np.random.mtrand._rand for rs in streams):
         return [draw_injections(rs, n_nodes, n_steps, lambdas[r]) for r, rs in enumerate(streams)]
+    if lam_max < 10.0 and n_nodes <= 65535:
+        return _draw_native_many(streams, n_nodes, n_steps, np.asarray(lambdas, dtype=np.float64), workers)
     import multiprocessing as mp
     with mp.get_context("fork").Pool(workers) as pool:
         res = pool.map(_draw_worker, [(rs.get_state(), n_nodes, n_steps, float(lambdas[r])) for r, rs in enumerate(streams)],
