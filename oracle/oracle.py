@@ -38,6 +38,9 @@ def lib():
         L.orc_set_stream.argtypes = [p, C.c_uint64, C.c_uint64]
         L.orc_set_decay.argtypes = [p, f64]
         L.orc_set_is_drop.argtypes = [p, i32]
+        L.orc_set_timing.argtypes = [p, i32, i32, i32, i32]
+        L.orc_in_flight.restype = i32
+        L.orc_in_flight.argtypes = [p]
         L.orc_set_shortest_flags.argtypes = [p, i32, i32]
         L.orc_cq_clean.argtypes = [p]
         L.orc_table_size.restype = i64
@@ -85,7 +88,8 @@ class OracleEnv:
     """One environment replica + its agent (reference `Network` + `Policy`)."""
 
     def __init__(self, links, policy, discount=None, discount_trace=0.6, add_entropy=True,
-                 seed=0, replica=0, decay=0.9, is_drop=False, multiway=False, random=False):
+                 seed=0, replica=0, decay=0.9, is_drop=False, multiway=False, random=False,
+                 bandwidth=1, transtime=1):
         if discount is None:
             discount = 0.9 if policy in ("CQ", "CDRQ") else 0.99          # qroute.py:59 vs qroute.py:9
         L = lib()
@@ -100,6 +104,8 @@ class OracleEnv:
         L.orc_set_stream(self.h, seed, replica)
         L.orc_set_decay(self.h, decay)
         L.orc_set_is_drop(self.h, int(is_drop))
+        self.bandwidth, self.transtime = int(bandwidth), int(transtime)
+        L.orc_set_timing(self.h, self.bandwidth, self.transtime, 1, 1)
         L.orc_set_shortest_flags(self.h, int(multiway), int(random))
         self.tsize = L.orc_table_size(self.h)
         self.toff = self.row_ptr.astype(np.int64) * self.N
@@ -149,12 +155,18 @@ class OracleEnv:
         st = lib().orc_status(self.h, C.byref(clk))
         return st, clk.value
 
-    def run(self, n_steps, lambd=None, inj=None, lr_q=0.1, lr_p=0.1, lr_e=0.1, sendlog=False):
-        """inj=(cnt, pairs) -> trace mode; else Philox mode at rate `lambd`."""
+    def set_timing(self, slot=1, freq=1):
+        lib().orc_set_timing(self.h, self.bandwidth, self.transtime, int(slot), int(freq))
+        self.slot, self.freq = int(slot), int(freq)
+
+    def run(self, n_steps, lambd=None, inj=None, lr_q=0.1, lr_p=0.1, lr_e=0.1, sendlog=False, slot=1, freq=1):
+        """inj=(cnt, pairs) -> trace mode; else Philox mode at rate `lambd` (per unit time: Poisson(lambd * slot) per
+        iteration, env.py:401).  One iteration = one injection + `freq` calls of step(slot)."""
+        self.set_timing(slot, freq)
         rt = np.zeros(n_steps, dtype=np.int64)
         en = np.zeros(n_steps, dtype=np.int64)
         hp = np.zeros(n_steps, dtype=np.int64)
-        log = np.zeros((n_steps * self.N, 4), dtype=np.int32) if sendlog else None
+        log = np.zeros((n_steps * freq * self.N, 4), dtype=np.int32) if sendlog else None
         nlog = C.c_int64(0)
         if inj is not None:
             cnt = np.ascontiguousarray(inj[0], dtype=np.int32)
@@ -163,7 +175,7 @@ class OracleEnv:
             mode, enlam = 0, 0.0
         else:
             cnt = pairs = None
-            mode, enlam = 1, float(np.exp(-np.float64(lambd) / np.float64(self.N)))
+            mode, enlam = 1, float(np.exp(-(np.float64(lambd) * slot) / np.float64(self.N)))
         done = lib().orc_run(self.h, n_steps, mode, _ptr(cnt), _ptr(pairs), enlam, lr_q, lr_p,
                              lr_e, _ptr(rt), _ptr(en), _ptr(hp), _ptr(log),
                              0 if log is None else len(log), C.byref(nlog))
@@ -173,16 +185,17 @@ class OracleEnv:
         return res
 
 
-def sample_route_time(env, size, lambd=None, inj=None, lr_q=0.1, lr_p=0.1, lr_e=0.1, max_steps=1 << 20):
+def sample_route_time(env, size, lambd=None, inj=None, lr_q=0.1, lr_p=0.1, lr_e=0.1, max_steps=1 << 20, slot=1, freq=1):
     """Network.sample_route_time on one OracleEnv; returns (sample[int64 size], steps_run)."""
     out = np.zeros(size, dtype=np.int64)
+    env.set_timing(slot, freq)
     if inj is not None:
         cnt = np.ascontiguousarray(inj[0], dtype=np.int32)
         pairs = np.ascontiguousarray(inj[1], dtype=np.int32)
         max_steps, enlam = min(max_steps, len(cnt)), 0.0
     else:
         cnt = pairs = None
-        enlam = float(np.exp(-np.float64(lambd) / np.float64(env.N)))
+        enlam = float(np.exp(-(np.float64(lambd) * slot) / np.float64(env.N)))
     steps = lib().orc_sample_route_time(env.h, size, max_steps, _ptr(cnt), _ptr(pairs), enlam, lr_q, lr_p, lr_e, _ptr(out))
     return out, int(steps)
 

@@ -58,8 +58,9 @@ def _det_math():
 
 
 def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, replica=0,
-        agent_kwargs=None, keep_sendlog=False, det_math=False, net_kwargs=None, sample_size=0):
-    """Runs `Network(net); agent = policy(nw); nw.train(T, lambd, lr=lr)` step by step.
+        agent_kwargs=None, keep_sendlog=False, det_math=False, net_kwargs=None, sample_size=0, slot=1, freq=1):
+    """Runs `Network(net, **net_kwargs); agent = policy(nw); nw.train(T * slot, lambd, slot, freq, lr=lr)` step by
+    step (T = number of iterations of train's loop, env.py:400).
 
     rng='trace'  : np.random.seed(seed) and the reference's own legacy stream (bit-for-bit the
                    reference); injections are recorded by wrapping the instance's new_packet.
@@ -90,9 +91,8 @@ def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, repl
             inj_pairs.extend((p.source, p.dest) for p in ps)
             return ps
     else:
-        enlam = np.exp(-np.float64(lambd) / np.float64(N))
-
         def new_packet(l):
+            enlam = np.exp(-np.float64(l) / np.float64(N))
             pairs = philox_twin.new_packets(philox_seed, replica, nw.clock, N, enlam)
             inj_cnt.append(len(pairs))
             inj_pairs.extend(pairs)
@@ -105,6 +105,17 @@ def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, repl
         agent.choose = choose
         orig_choice = np.random.choice
 
+        streams = {}
+
+        def stream():
+            # node x's sampling stream of this step (purpose 1): a queue scan that calls choose more than once
+            # (env.py:174-190, links busy) keeps drawing from it
+            key = (nw.clock, state["node"])
+            if key not in streams:
+                streams.clear()
+                streams[key] = philox_twin.Stream(philox_seed, replica, nw.clock, state["node"], 1)
+            return streams[key]
+
         def choice(a, size=None, replace=True, p=None):
             # legacy RandomState.choice with p (numpy/random/mtrand.pyx): validate p, then
             # cdf = p.cumsum(); cdf /= cdf[-1]; idx = cdf.searchsorted(u, side='right')
@@ -113,14 +124,15 @@ def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, repl
                 # stream as mulhi(word, count) (Shortest(random=True), shortest.py:40-41); one choice draws nothing
                 if len(a) == 1:
                     return a[0]
-                w = philox_twin.Stream(philox_seed, replica, nw.clock, state["node"], 1).next()
-                return a[(w * len(a)) >> 32]
+                return a[(stream().next() * len(a)) >> 32]
             p = np.asarray(p, dtype=np.float64)
             if np.isnan(p.sum()):
                 raise ValueError("probabilities contain NaN")
             cdf = p.cumsum()
             cdf /= cdf[-1]
-            u = philox_twin.uniform53(philox_seed, replica, nw.clock, state["node"])
+            st = stream()
+            hi, lo = st.next() >> 5, st.next() >> 6
+            u = (hi * 67108864.0 + lo) / 9007199254740992.0
             return a[int(cdf.searchsorted(u, side="right"))]
         np.random.choice = choice
     nw.new_packet = new_packet
@@ -139,18 +151,19 @@ def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, repl
     sample = None
     try:
         if sample_size:                          # Network.sample_route_time (env.py:416-438) instead of the train loop
-            sample = nw.sample_route_time(sample_size, lambd, lr=lr or {})
+            sample = nw.sample_route_time(sample_size, lambd, slot=slot, freq=freq, lr=lr or {})
             T = 0
-        for i in range(T):                       # Network.train's loop, env.py:400-413, freq=1
-            nw.inject(nw.new_packet(lambd))
-            r = nw.step(1)
-            for rw in r:
-                log.append((nw.clock, rw.source, rw.action, rw.dest))
-            sends += len(r)
-            if lr:
-                agent.learn(r, lr=lr)
-            else:
-                agent.learn(r)
+        for i in range(T):                       # Network.train's loop, env.py:400-413
+            nw.inject(nw.new_packet(lambd * slot))
+            for _ in range(freq):
+                r = nw.step(slot)
+                for rw in r:
+                    log.append((nw.clock, rw.source, rw.action, rw.dest))
+                sends += len(r)
+                if lr:
+                    agent.learn(r, lr=lr)
+                else:
+                    agent.learn(r)
             rt[i], en[i], hp[i] = nw.route_time, nw.end_packets, nw.hops
     except ValueError as e:                      # F7: NaN probabilities
         err = (str(e), i)
@@ -173,6 +186,7 @@ def run(net, policy, T, lambd, seed=1, lr=None, rng="trace", philox_seed=0, repl
                              for p in nw.nodes[x].queue], dtype=np.int32).reshape(-1, 5)
                    for x in range(N)],
         "error": err,
+        "in_flight": len(nw.event_queue),
     })
     if keep_sendlog:
         out["sendlog"] = log

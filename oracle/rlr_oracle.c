@@ -14,9 +14,11 @@
  * Every function cites the reference lines it restates (paths relative to /root/reference).
  * One orc_t is one environment replica == one `Network` + one bound agent.
  *
- * Scope: default timing model — bandwidth=1, transtime=1, slot=1, freq=1 (is_drop optional).  Under those defaults every event of a step arrives inside the step
- * (env.py:349-353), `sent` returns to 0 and `avaliable_path` is all-True (env.py:171-174),
- * so the head of the queue is the packet sent (env.py:175-180).
+ * Scope (SURVEY §8a + row f2): the reference's full timing model with INTEGER bandwidth, transtime, slot and freq
+ * (orc_set_timing; defaults 1).  Under the defaults every event of a step arrives inside the step (env.py:349-353),
+ * `sent` returns to 0 and `avaliable_path` is all-True (env.py:171-174), so the head of the queue is the packet sent
+ * (env.py:175-180).  With transtime > slot events outlive the step: the literal event heap persists, links stay busy
+ * (env.py:115-116) and the send loop scans the queue for the first packet whose chosen link is free (env.py:174-190).
  */
 #include <math.h>
 #include <stdint.h>
@@ -37,7 +39,7 @@ typedef struct { int32_t dest, source, hops, birth, start_queue; } pkt_t;
 typedef struct { pkt_t *buf; int64_t head, len, cap; } fifo_t;
 
 /* env.py:30-49 Event; ordered by arrive_time ONLY (env.py:48-49). */
-typedef struct { pkt_t p; int32_t from, to; int64_t arrive; } event_t;
+typedef struct { pkt_t p; int32_t from, to, link; int64_t arrive; } event_t;   /* link = row_ptr[from] + action index */
 
 /* env.py:52-70 Reward + the agent_info dict flattened. */
 typedef struct {
@@ -64,6 +66,9 @@ typedef struct orc {
     double discount, discount_trace, reward_shape;
     int add_entropy, status;
     int is_drop;              /* Network(is_drop=True): env.py:355-360 */
+    int bandwidth, transtime; /* Network(bandwidth=1, transtime=1), env.py:237-239 (integers) */
+    int slot, freq;           /* Network.train(slot=1, freq=1), env.py:367-373 (integers) */
+    int *sent;                /* Node.sent[y] per directed link (env.py:100,115-116,142,352) */
     int multiway, random_choice; /* Shortest(multiway=..., random=...), shortest.py:20-23,38-41 */
     int64_t *sample; int64_t sample_size, sample_idx;   /* Network.sample / _sample_idx (env.py:242, 325-328, 424-425) */
     int64_t *queue_size;      /* GlobalRoute.queue_size (shortest.py:89): +1 per receive callback, -1 per send callback */
@@ -163,6 +168,8 @@ orc_t *orc_create(int N, const int *row_ptr, const int *col, int policy)
     o->rewards = (reward_t *)malloc(sizeof(reward_t) * N);
     o->queue_size = (int64_t *)calloc((size_t)N, sizeof(int64_t));
     o->scratch = (double *)malloc(sizeof(double) * 3 * N);
+    o->sent = (int *)calloc((size_t)o->sdeg, sizeof(int));
+    o->bandwidth = o->transtime = o->slot = o->freq = 1;
     o->discount = 0.99;        /* qroute.py:9, hybrid.py:44, multi_agent.py:10 */
     o->discount_trace = 0.6;   /* multi_agent.py:10 */
     o->add_entropy = 1;        /* hybrid.py:44 */
@@ -178,7 +185,7 @@ void orc_destroy(orc_t *o)
     for (int x = 0; x < o->N; ++x) free(o->queue[x].buf);
     free(o->row_ptr); free(o->col); free(o->aidx); free(o->toff); free(o->Q); free(o->Theta);
     free(o->Trace); free(o->choice); free(o->distance); free(o->queue); free(o->heap);
-    free(o->rewards); free(o->scratch); free(o->queue_size); free(o);
+    free(o->rewards); free(o->scratch); free(o->queue_size); free(o->sent); free(o);
 }
 
 void orc_set_hparams(orc_t *o, double discount, double discount_trace, int add_entropy)
@@ -188,6 +195,11 @@ void orc_set_hparams(orc_t *o, double discount, double discount_trace, int add_e
 
 void orc_set_decay(orc_t *o, double decay) { o->decay = decay; }
 void orc_set_is_drop(orc_t *o, int is_drop) { o->is_drop = is_drop; }
+void orc_set_timing(orc_t *o, int bandwidth, int transtime, int slot, int freq)
+{
+    o->bandwidth = bandwidth; o->transtime = transtime; o->slot = slot; o->freq = freq;
+}
+int orc_in_flight(const orc_t *o) { return o->heap_len; }
 void orc_set_shortest_flags(orc_t *o, int multiway, int random_choice) { o->multiway = multiway; o->random_choice = random_choice; }
 
 void orc_set_stream(orc_t *o, uint64_t seed, uint64_t replica) { o->seed = seed; o->replica = replica; }
@@ -251,6 +263,7 @@ void orc_reset(orc_t *o)
     o->active_packets = o->hops = o->route_time = o->sends = 0;
     o->heap_len = 0; o->status = ST_OK; o->status_clock = 0;
     for (int x = 0; x < o->N; ++x) { o->queue[x].head = 0; o->queue[x].len = 0; }
+    memset(o->sent, 0, sizeof(int) * (size_t)o->sdeg);
     if (o->policy == POL_MAHYBRIDQ) memset(o->Trace, 0, sizeof(double) * (size_t)o->tsize);
     if (o->policy == POL_CQ || o->policy == POL_CDRQ) orc_cq_clean(o);
 }
@@ -566,6 +579,44 @@ static void inject_step(orc_t *o, int mode, const int32_t *pairs, int cnt, doubl
  *       u comes from the Philox stream (purpose 1) instead of the global MT19937)
  *   Qroute.get_info  qroute.py:29-30 ; HybridQ.get_info hybrid.py:49-53
  *   _build_info_default env.py:147-152 ; _send_packet env.py:135-145                        */
+/* agent.choose(x, d) for the built-in policies; returns the action index, or -1 when the softmax row holds a NaN
+ * (np.random.choice raises ValueError).  `s` is node x's sampling stream of this step (purpose 1), opened on first
+ * use: a scan that calls choose several times (env.py:174-190) keeps drawing from the same stream. */
+static int choose_action(orc_t *o, int x, int d, pstream_t *s, int *s_open)
+{
+    int deg = o->row_ptr[x + 1] - o->row_ptr[x], k = 0;
+    if (o->policy == POL_SHORTEST || o->policy == POL_GLOBALROUTE) {
+        const uint8_t *c = o->choice + o->toff[x] + (int64_t)d * deg;
+        while (k < deg && !c[k]) k++;
+        if (o->random_choice) {
+            /* shortest.py:40-41 np.random.choice(choices): a uniform index into the True entries; the index comes
+             * from the Philox stream (purpose 1) as mulhi(word, count), nothing is drawn for a single choice */
+            int cnt = 0;
+            for (int j = 0; j < deg; ++j) cnt += c[j];
+            if (cnt > 1) {
+                if (!*s_open) { ps_init(s, o->seed, o->replica, o->clock, x, 1); *s_open = 1; }
+                int idx = (int)(((uint64_t)ps_next(s) * (uint32_t)cnt) >> 32);
+                for (k = 0; k < deg; ++k) if (c[k] && idx-- == 0) break;
+            }
+        }
+    } else if (o->policy == POL_QROUTE || o->policy == POL_CQ || o->policy == POL_CDRQ) {
+        const double *row = o->Q + o->toff[x] + (int64_t)d * deg;
+        for (int j = 1; j < deg; ++j) if (row[j] > row[k]) k = j;
+    } else {
+        double sm[MAXDEG], cdf[MAXDEG];
+        softmax_row(o->Theta + o->toff[x] + (int64_t)d * deg, deg, sm);
+        int bad = 0; double c = 0.0;
+        for (int j = 0; j < deg; ++j) { if (isnan(sm[j])) bad = 1; c += sm[j]; cdf[j] = c; }
+        if (bad) return -1;
+        for (int j = 0; j < deg; ++j) cdf[j] /= c;
+        if (!*s_open) { ps_init(s, o->seed, o->replica, o->clock, x, 1); *s_open = 1; }
+        uint32_t a = ps_next(s) >> 5, b = ps_next(s) >> 6;
+        double u = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+        k = 0; while (k < deg - 1 && cdf[k] <= u) k++;
+    }
+    return k;
+}
+
 static void send_phase(orc_t *o)
 {
     o->n_rewards = 0;
@@ -573,42 +624,28 @@ static void send_phase(orc_t *o)
         fifo_t *q = &o->queue[x];
         if (q->len == 0) continue;
         int deg = o->row_ptr[x + 1] - o->row_ptr[x];
-        pkt_t p = q->buf[q->head];
-        int d = p.dest, k = 0;
-        if (o->policy == POL_SHORTEST || o->policy == POL_GLOBALROUTE) {
-            const uint8_t *c = o->choice + o->toff[x] + (int64_t)d * deg;
-            while (k < deg && !c[k]) k++;
-            if (o->random_choice) {
-                /* shortest.py:40-41 np.random.choice(choices): a uniform index into the True entries; the index comes
-                 * from the Philox stream (purpose 1) as mulhi(word, count), nothing is drawn for a single choice */
-                int cnt = 0;
-                for (int j = 0; j < deg; ++j) cnt += c[j];
-                if (cnt > 1) {
-                    pstream_t s; ps_init(&s, o->seed, o->replica, o->clock, x, 1);
-                    int idx = (int)(((uint64_t)ps_next(&s) * (uint32_t)cnt) >> 32);
-                    for (k = 0; k < deg; ++k) if (c[k] && idx-- == 0) break;
-                }
-            }
-        } else if (o->policy == POL_QROUTE || o->policy == POL_CQ || o->policy == POL_CDRQ) {
-            const double *row = o->Q + o->toff[x] + (int64_t)d * deg;
-            for (int j = 1; j < deg; ++j) if (row[j] > row[k]) k = j;
-        } else {
-            double sm[MAXDEG], cdf[MAXDEG];
-            softmax_row(o->Theta + o->toff[x] + (int64_t)d * deg, deg, sm);
-            int bad = 0; double c = 0.0;
-            for (int j = 0; j < deg; ++j) { if (isnan(sm[j])) bad = 1; c += sm[j]; cdf[j] = c; }
-            if (bad) { o->status = ST_NAN_PROB; o->status_clock = o->clock; return; }
-            for (int j = 0; j < deg; ++j) cdf[j] /= c;
-            pstream_t s; ps_init(&s, o->seed, o->replica, o->clock, x, 1);
-            uint32_t a = ps_next(&s) >> 5, b = ps_next(&s) >> 6;
-            double u = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
-            k = 0; while (k < deg - 1 && cdf[k] <= u) k++;
+        /* env.py:171-190: avaliable_path is evaluated once; scan the queue in order for the first packet whose chosen
+         * link has sent[action] < bandwidth.  Under the default timing every link is free and i stays 0. */
+        int any_free = 0;
+        for (int j = 0; j < deg; ++j) any_free |= (o->sent[o->row_ptr[x] + j] < o->bandwidth);
+        pstream_t ps; int ps_open = 0;
+        int64_t i = 0; int k = -1;
+        while (i < q->len && any_free) {
+            k = choose_action(o, x, q->buf[q->head + i].dest, &ps, &ps_open);
+            if (k < 0) { o->status = ST_NAN_PROB; o->status_clock = o->clock; return; }
+            if (o->sent[o->row_ptr[x] + k] < o->bandwidth) break;
+            k = -1; i++;
         }
+        if (k < 0) continue;
+        pkt_t p = q->buf[q->head + i];
+        int d = p.dest;
         int y = o->col[o->row_ptr[x] + k];
+        if (i > 0) memmove(q->buf + q->head + 1, q->buf + q->head, (size_t)i * sizeof(pkt_t));   /* queue.pop(i) */
         q->head++; q->len--;
         o->queue_size[x] -= 1;                           /* agent.send (env.py:181, shortest.py:96-97) */
         p.hops += 1;
-        event_t e; e.p = p; e.from = x; e.to = y; e.arrive = o->clock + 1;
+        o->sent[o->row_ptr[x] + k] += 1;                 /* env.py:142 */
+        event_t e; e.p = p; e.from = x; e.to = y; e.link = o->row_ptr[x] + k; e.arrive = o->clock + o->transtime;
         hq_push(o, &e);
         o->sends += 1;
         reward_t *r = &o->rewards[o->n_rewards++];
@@ -647,9 +684,10 @@ static void send_phase(orc_t *o)
 /* Event drain of Network.step (env.py:349-364). */
 static void drain_events(orc_t *o)
 {
-    int64_t end_time = o->clock + 1;
+    int64_t end_time = o->clock + o->slot;
     while (o->heap_len > 0 && o->heap[0].arrive <= end_time) {
         event_t e = hq_pop(o);
+        o->sent[e.link] -= 1;                            /* env.py:352 */
         if (o->is_drop && e.p.hops >= o->N) {          /* env.py:355-360; drop_penalty is a no-op for every in-scope agent */
             o->drop_packets += 1;
             o->active_packets -= 1;
@@ -777,7 +815,7 @@ static void learn_phase(orc_t *o, double lr_q, double lr_p, double lr_e)
     }
 }
 
-/* Network.train (env.py:367-414) for `n_steps` steps of slot=1, freq=1.
+/* Network.train (env.py:367-414) for `n_steps` iterations (inject once, then `freq` calls of step(slot) + learn).
  *   inj_cnt[n_steps], inj_pairs[2*sum(cnt)]  trace-mode injections (NULL in Philox mode)
  *   enlam                                     exp(-lambda/N) for Philox mode
  *   m_route_time/m_end/m_hops[n_steps]        cumulative counters after each step (env.py:409-413)
@@ -794,19 +832,21 @@ int64_t orc_run(orc_t *o, int64_t n_steps, int inj_mode, const int32_t *inj_cnt,
         int cnt = inj_mode == INJ_TRACE ? inj_cnt[s] : 0;
         inject_step(o, inj_mode, inj_pairs ? inj_pairs + 2 * off : NULL, cnt, enlam);
         off += cnt;
-        int64_t sends_before = o->sends;
-        send_phase(o);
-        if (o->status != ST_OK) { o->sends = sends_before; if (n_sendlog) *n_sendlog = nlog; return s; }
-        if (sendlog) {
-            for (int i = 0; i < o->n_rewards && nlog < sendlog_cap; ++i, ++nlog) {
-                sendlog[4 * nlog + 0] = (int32_t)(o->clock + 1);
-                sendlog[4 * nlog + 1] = o->rewards[i].x;
-                sendlog[4 * nlog + 2] = o->rewards[i].y;
-                sendlog[4 * nlog + 3] = o->rewards[i].d;
+        for (int f = 0; f < o->freq; ++f) {              /* env.py:402-408: freq calls of step(slot) + learn per injection */
+            int64_t sends_before = o->sends;
+            send_phase(o);
+            if (o->status != ST_OK) { o->sends = sends_before; if (n_sendlog) *n_sendlog = nlog; return s; }
+            if (sendlog) {
+                for (int i = 0; i < o->n_rewards && nlog < sendlog_cap; ++i, ++nlog) {
+                    sendlog[4 * nlog + 0] = (int32_t)(o->clock + o->slot);
+                    sendlog[4 * nlog + 1] = o->rewards[i].x;
+                    sendlog[4 * nlog + 2] = o->rewards[i].y;
+                    sendlog[4 * nlog + 3] = o->rewards[i].d;
+                }
             }
+            drain_events(o);
+            learn_phase(o, lr_q, lr_p, lr_e);
         }
-        drain_events(o);
-        learn_phase(o, lr_q, lr_p, lr_e);
         if (m_route_time) m_route_time[s] = o->route_time;
         if (m_end) m_end[s] = o->end_packets;
         if (m_hops) m_hops[s] = o->hops;
@@ -815,7 +855,7 @@ int64_t orc_run(orc_t *o, int64_t n_steps, int inj_mode, const int32_t *inj_cnt,
     return n_steps;
 }
 
-/* Network.sample_route_time (env.py:416-438), slot = freq = 1: runs whole steps until `size` packets have been
+/* Network.sample_route_time (env.py:416-438): runs whole iterations until `size` packets have been
  * delivered; sample[i] is the routing time of the i-th delivery (deliveries past `size` in the last step overwrite the
  * last entry).  Philox mode if inj_cnt is NULL; in trace mode the caller supplies at least `max_steps` steps of draws.
  * Returns the number of steps run (or -1 if max_steps was not enough). */
@@ -830,10 +870,13 @@ int64_t orc_sample_route_time(orc_t *o, int64_t size, int64_t max_steps, const i
         int cnt = inj_cnt ? inj_cnt[steps] : 0;
         inject_step(o, inj_cnt ? INJ_TRACE : INJ_PHILOX, inj_pairs ? inj_pairs + 2 * off : NULL, cnt, enlam);
         off += cnt;
-        send_phase(o);
+        for (int f = 0; f < o->freq && o->status == ST_OK; ++f) {
+            send_phase(o);
+            if (o->status != ST_OK) break;
+            drain_events(o);
+            learn_phase(o, lr_q, lr_p, lr_e);
+        }
         if (o->status != ST_OK) break;
-        drain_events(o);
-        learn_phase(o, lr_q, lr_p, lr_e);
         steps++;
     }
     o->sample_size = 0; o->sample = NULL;

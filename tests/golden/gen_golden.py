@@ -90,6 +90,30 @@ CASES = [
     dict(net="6x6.net", policy="HybridQ", T=300, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3, keep_tables=True),
     dict(net="6x6.net", policy="MaHybridQ", T=300, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3,
          lr={"q": 0.1, "p": 0.001}, keep_tables=True),
+    # the general timing model — integer slot / freq / transtime / bandwidth.  transtime > slot
+    # keeps events in flight across steps: links stay busy and the send loop scans past packets whose link is full
+    dict(net="6x6.net", policy="Qroute", T=600, lambd=1.0, seed=1, slot=2),
+    dict(net="6x6.net", policy="Qroute", T=600, lambd=2.0, seed=1, freq=2),
+    dict(net="6x6.net", policy="Qroute", T=500, lambd=1.0, seed=2, net_kwargs={"transtime": 2, "bandwidth": 3}, slot=3, freq=2),
+    dict(net="6x6.net", policy="Qroute", T=800, lambd=2.0, seed=1, net_kwargs={"transtime": 2}),
+    dict(net="6x6.net", policy="Qroute", T=800, lambd=2.0, seed=1, net_kwargs={"transtime": 3, "bandwidth": 2}),
+    dict(net="6x6.net", policy="Qroute", T=500, lambd=1.0, seed=2, net_kwargs={"transtime": 5, "bandwidth": 2}, slot=2, freq=2),
+    dict(net="6x6.net", policy="Shortest", T=800, lambd=1.0, seed=1, net_kwargs={"transtime": 2}),
+    dict(net="lata.net", policy="Shortest", T=300, lambd=3.0, seed=1, net_kwargs={"transtime": 3, "bandwidth": 3}, freq=2),
+    dict(net="6x6.net", policy="HybridQ", T=500, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3, det_math=True,
+         net_kwargs={"transtime": 2}),
+    dict(net="6x6.net", policy="MaHybridQ", T=500, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3, det_math=True,
+         lr={"q": 0.1, "p": 0.001}, net_kwargs={"transtime": 3, "bandwidth": 2}),
+    dict(net="6x6.net", policy="CQ", T=500, lambd=2.0, seed=1, net_kwargs={"transtime": 2}),
+    dict(net="6x6.net", policy="CDRQ", T=500, lambd=2.0, seed=1, net_kwargs={"transtime": 2}),
+    dict(net="6x6.net", policy="GlobalRoute", T=150, lambd=2.0, seed=1, net_kwargs={"transtime": 2}),
+    dict(net="6x6.net", policy="Shortest", T=500, lambd=3.0, seed=1, rng="philox", philox_seed=7, replica=3,
+         agent_kwargs={"multiway": True, "random": True}, net_kwargs={"transtime": 2}),
+    dict(net="6x6.net", policy="Qroute", T=600, lambd=2.0, seed=1, net_kwargs={"transtime": 2, "is_drop": True}),
+    dict(net="6x6.net", policy="Qroute", T=0, lambd=2.0, seed=1, sample_size=200, net_kwargs={"transtime": 2}),
+    dict(net="lata.net", policy="Qroute", T=300, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3,
+         net_kwargs={"transtime": 2, "bandwidth": 2}),
+    dict(net="6x6.net", policy="Qroute", T=400, lambd=2.0, seed=1, net_kwargs={"bandwidth": 0}),
 ]
 
 
@@ -108,7 +132,7 @@ def main():
             "route_time_sha256": h(r["route_time"], "<i8"), "end_packets_sha256": h(r["end_packets"], "<i8"),
             "hops_sha256": h(r["hops"], "<i8"),
             "queues_sha256": h(np.concatenate([q.reshape(-1) for q in r["queues"]] + [np.array([len(q) for q in r["queues"]])]), "<i4"),
-            "error": r["error"],
+            "error": r["error"], "in_flight": r["in_flight"],
         }
         for name in ("Q0", "Qtable", "Theta", "Trace", "confidence"):
             if name in r:

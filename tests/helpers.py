@@ -36,7 +36,7 @@ def case_inputs(case, topo):
         q0 = topo.pack(trace.draw_qtable_normals(rs, topo, kw.get("initQ", 0), times))
     inj = None
     if case.get("rng", "trace") == "trace":
-        inj = trace.draw_injections(rs, topo.N, case["T"] or 4000, case["lambd"])   # sample cases stop on their own
+        inj = trace.draw_injections(rs, topo.N, case["T"] or 4000, case["lambd"] * case.get("slot", 1))   # sample cases stop on their own
     return q0, inj
 
 
@@ -52,6 +52,8 @@ def run_oracle(case, sendlog=True):
     env = O.OracleEnv(topo.links, case["policy"], discount=kw.get("discount"),
                       add_entropy=kw.get("add_entropy", True), decay=kw.get("decay", 0.9),
                       is_drop=(case.get("net_kwargs") or {}).get("is_drop", False),
+                      bandwidth=(case.get("net_kwargs") or {}).get("bandwidth", 1),
+                      transtime=(case.get("net_kwargs") or {}).get("transtime", 1),
                       multiway=kw.get("multiway", False), random=kw.get("random", False),
                       seed=case.get("philox_seed", 0), replica=case.get("replica", 0))
     q0, inj = case_inputs(case, topo)
@@ -60,8 +62,8 @@ def run_oracle(case, sendlog=True):
     lr = lr_of(case)
     if case.get("sample_size"):
         smp, steps = O.sample_route_time(env, case["sample_size"], lambd=case["lambd"], inj=inj, lr_q=lr["q"], lr_p=lr["p"],
-                                         lr_e=lr["e"])
+                                         lr_e=lr["e"], slot=case.get("slot", 1), freq=case.get("freq", 1))
         return topo, env, q0, inj, {"sample": smp, "steps_done": steps}
     res = env.run(case["T"], lambd=case["lambd"], inj=inj, lr_q=lr["q"], lr_p=lr["p"], lr_e=lr["e"],
-                  sendlog=sendlog)
+                  sendlog=sendlog, slot=case.get("slot", 1), freq=case.get("freq", 1))
     return topo, env, q0, inj, res
