@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RLR_ABI_VERSION 1
+#define RLR_ABI_VERSION 2
 
 enum { RLR_OK = 0, RLR_E_INVALID = -1, RLR_E_UNSUPPORTED = -2, RLR_E_CUDA = -3, RLR_E_STATE = -4 };
 
@@ -76,6 +76,9 @@ typedef struct {
     int32_t threads_per_block;  /* 0 = choose; >= replicas_per_block * N, multiple of 32    */
     int32_t tables_in_smem;   /* -1 = choose, 0 = tables stay in HBM, 1 = staged in smem    */
     int32_t device;           /* CUDA device ordinal the buffers live on                    */
+    int32_t event_capacity;   /* events that can be in flight per replica when they outlive a step (transtime > slot,
+                                 env.py:143-145): N * (transtime + 1); 0 = the default timing model only */
+    int32_t reserved;
 } rlr_config_t;
 
 /* Raw DEVICE pointers borrowed from the caller.  R = replicas, N = n_nodes,
@@ -103,6 +106,15 @@ typedef struct {
                                  needed when shortest_random is set */
     int32_t *gr_qs_off;       /* [R][N] queue_size[x] - len(queue[x]): 0 until Network.reset, which clears the queues
                                  but not the agent's queue_size (env.py:267-280, shortest.py:89) */
+    /* general timing model only (event_capacity > 0; all persist across calls, zeroed by rlr_reset) */
+    int32_t *link_sent;       /* [R][sum_deg] Node.sent[y] per directed link (env.py:100,115-116,142,352)       */
+    uint64_t *event_heap;     /* [R][event_capacity] Network.event_queue as the heapq array (env.py:144,349-353):
+                                 arrive_time << 32 | link << 16 | record slot, ordered by arrive_time only      */
+    int32_t *event_count;     /* [R] len(event_queue)                                                           */
+    void *event_rec;          /* [R][event_capacity] 16-byte packet records of the events in flight, at slot
+                                 (arrive_time mod (transtime + 1)) * N + sender                                 */
+    int32_t *q_dead;          /* [R][N] ring entries between head and tail already sent out of order (queue.pop(i),
+                                 env.py:177): len(queue) = tail - head - q_dead                                 */
 } rlr_buffers_t;
 
 typedef struct {
@@ -151,6 +163,17 @@ typedef struct {
     int32_t sample_size;
     int32_t reserved2;
     uint32_t *sendlog;        /* [R][n_steps][N]: y | dest << 16 for a send by node x, else 0xFFFFFFFF */
+    /* timing model, integers; 0 means 1.  n_steps counts Network.step calls: one injection
+     * (Poisson(lambda * slot), the caller folds slot into enlam / inj_thr) every `freq` steps, each step advancing the
+     * clock by `slot`; a packet sent at clock c arrives at c + transtime; a link carries at most `bandwidth` packets.
+     * transtime > slot or bandwidth < 1 needs a handle created with event_capacity > 0 and `general` set. */
+    int32_t slot;             /* Network.train(slot=...) / Network.step(duration), env.py:333,372,403 */
+    int32_t freq;             /* Network.train(freq=...), env.py:373,402 */
+    int32_t transtime;        /* Network(transtime=...), env.py:143 */
+    int32_t bandwidth;        /* Network(bandwidth=...), env.py:115-116 */
+    int32_t general;          /* 1: events persist in event_heap, links can be busy, the send loop scans the queue
+                                 (env.py:171-190); 0: every event arrives inside its step (transtime <= slot) */
+    int32_t reserved3;
 } rlr_run_params_t;
 
 /* ---- introspection ---- */
@@ -202,8 +225,8 @@ int rlr_trace_replay_many(uint32_t *mt_keys, int32_t *mt_pos, int64_t n_streams,
  *      separately (on another stream, then running with RLR_INJECT_TRACE) overlaps it with the previous chunk. ---- */
 int rlr_build_inject_schedule(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *params, void *stream);
 
-/* ---- the hot path: n_steps iterations of Network.train's loop body (env.py:400-413) with
- *      slot=1, freq=1: new_packet + inject, step (send phase + event drain), agent.learn ---- */
+/* ---- the hot path: n_steps calls of Network.step + agent.learn inside Network.train's loop (env.py:400-413),
+ *      with new_packet + inject before every freq-th of them (slot = freq = transtime = bandwidth = 1 by default) ---- */
 int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *params, void *stream);
 
 /* ---- sums the per-replica counters into out[RLR_NUM_COUNTERS] (device pointer, int64) so a

@@ -200,12 +200,14 @@ def sample_route_time(env, size, lambd=None, inj=None, lr_q=0.1, lr_p=0.1, lr_e=
     return out, int(steps)
 
 
-def run_many(envs, n_steps, lambd, lr_q=0.1, lr_p=0.1, lr_e=0.1, nthreads=0, metrics=False):
+def run_many(envs, n_steps, lambd, lr_q=0.1, lr_p=0.1, lr_e=0.1, nthreads=0, metrics=False, slot=1, freq=1):
     """Philox-mode batch over independent OracleEnv objects on `nthreads` host threads."""
     n = len(envs)
+    for e in envs:
+        e.set_timing(slot, freq)
     hs = (C.c_void_p * n)(*[e.h for e in envs])
     lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (n,))
-    enlam = np.exp(-lam / np.float64(envs[0].N))
+    enlam = np.exp(-(lam * slot) / np.float64(envs[0].N))
     rt = np.zeros((n, n_steps), dtype=np.int64) if metrics else None
     en = np.zeros((n, n_steps), dtype=np.int64) if metrics else None
     sends = lib().orc_run_many(hs, n, n_steps, _ptr(np.ascontiguousarray(enlam)), lr_q, lr_p,

@@ -14,7 +14,7 @@ SRC = os.path.join(HERE, "csrc", "rlr_kernels.cu")
 HDR = os.path.join(ROOT, "include", "rlrouting_b200.h")
 SO = os.environ.get("RLR_LIB") or os.path.join(HERE, "csrc", "librlrouting_b200.so")   # RLR_LIB: experiment builds
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NUM_COUNTERS = 8
 CTR = {"all_packets": 0, "end_packets": 1, "drop_packets": 2, "hops": 3, "route_time": 4, "sends": 5}
 POLICY_SHORTEST, POLICY_QROUTE, POLICY_HYBRIDQ, POLICY_MAHYBRIDQ, POLICY_CQ, POLICY_CDRQ, POLICY_GLOBALROUTE = 0, 1, 2, 3, 4, 5, 6
@@ -45,13 +45,15 @@ class Topology(C.Structure):
 class Config(C.Structure):
     _fields_ = [("replicas", C.c_int64), ("replica_base", C.c_int64), ("policy", C.c_int32),
                 ("queue_capacity", C.c_int32), ("replicas_per_block", C.c_int32),
-                ("threads_per_block", C.c_int32), ("tables_in_smem", C.c_int32), ("device", C.c_int32)]
+                ("threads_per_block", C.c_int32), ("tables_in_smem", C.c_int32), ("device", C.c_int32),
+                ("event_capacity", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "q_table", "theta", "trace", "ring", "q_head", "q_tail", "counters", "status", "next_hop",
-        "distance", "choice", "topo_row_ptr", "topo_col", "heap_pos", "gr_next_hop", "gr_distance", "choice_mask", "gr_qs_off")]
+        "distance", "choice", "topo_row_ptr", "topo_col", "heap_pos", "gr_next_hop", "gr_distance", "choice_mask", "gr_qs_off",
+        "link_sent", "event_heap", "event_count", "event_rec", "q_dead")]
 
 
 class RunParams(C.Structure):
@@ -65,7 +67,9 @@ class RunParams(C.Structure):
                 ("metrics", C.c_void_p), ("route_time_out", C.c_void_p), ("hop_out", C.c_void_p),
                 ("metrics2", C.c_void_p), ("droprate_out", C.c_void_p),
                 ("sample", C.c_void_p), ("sample_idx", C.c_void_p), ("sample_clock", C.c_void_p),
-                ("sample_size", C.c_int32), ("reserved2", C.c_int32), ("sendlog", C.c_void_p)]
+                ("sample_size", C.c_int32), ("reserved2", C.c_int32), ("sendlog", C.c_void_p),
+                ("slot", C.c_int32), ("freq", C.c_int32), ("transtime", C.c_int32), ("bandwidth", C.c_int32),
+                ("general", C.c_int32), ("reserved3", C.c_int32)]
 
 
 EXPORTS = ("rlr_abi_version", "rlr_last_error_string", "rlr_struct_sizes", "rlr_create", "rlr_destroy", "rlr_bind_buffers",

@@ -94,6 +94,15 @@ struct StepParams {
     int sample_size;
     uint2 *metrics2;              // [K][R] {all_packets, drop_packets} after each step (for the droprate vector)
     unsigned *sendlog;
+    // timing model (SPLIT instantiation only): clock advances `slot` per step, arrivals at clock + transtime
+    int slot, freq, transtime, bandwidth;
+    int general;                  // events outlive a step: persistent heap, busy links, queue scan (env.py:171-190)
+    int ecap;                     // event capacity per replica = N * (transtime + 1)
+    int *link_sent;               // [R][sdeg]
+    unsigned long long *event_heap;   // [R][ecap]
+    int *event_count;             // [R]
+    uint4 *event_rec;             // [R][ecap]
+    int *q_dead;                  // [R][N]
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -290,8 +299,9 @@ __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t
 
 // Shared-memory carve-up, identical on host (sizing) and device (pointers).
 struct SmemLayout {
-    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, gr, samp, total;
-    __host__ __device__ SmemLayout(int N, int sdeg, int G, int threads, int policy, bool smem_tables, long long tsize, int ntab)
+    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, gr, samp, evheap, evorder, evsent, evlen, total;
+    __host__ __device__ SmemLayout(int N, int sdeg, int G, int threads, int policy, bool smem_tables, long long tsize, int ntab,
+                                   int ecap = 0)
     {
         const int GN = G * N;
         size_t o = 0;
@@ -308,8 +318,13 @@ struct SmemLayout {
         heappos = o; o += align16((size_t)(N + 1) * N);
         nexthop = o; o += (policy == RLR_POLICY_SHORTEST) ? align16((size_t)N * N * 2)      // u8 next hops or u16 choice masks
                            : (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * N * N) : 0;
-        samp = o; o += align16((size_t)GN * 8);             // sample_route_time staging: (heap position, routing time) per delivery
+        samp = o; o += align16((size_t)G * (ecap > N ? ecap : N) * 8);   // sample_route_time staging: (heap position, routing time) per delivery
         gr = o; o += (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * (N * N + N) * 4) : 0;   // distances + weights
+        // general timing model: the event heap, this step's popped events, Node.sent per link, heap length + pop count
+        evheap = o; o += align16((size_t)G * ecap * 8);
+        evorder = o; o += align16((size_t)G * ecap * 8);
+        evsent = o; o += ecap ? align16((size_t)G * sdeg * 4) : 0;
+        evlen = o; o += ecap ? align16((size_t)G * 2 * 4) : 0;
         total = o;
     }
 };
@@ -360,6 +375,7 @@ __device__ __forceinline__ void gr_column(int z, int N, const int *rowptr, const
 
 constexpr unsigned kNoKey = 0xFFFFFFFFu;   // "no arrival" sort key (real keys are heap position << 16 | send slot)
 constexpr unsigned kNoSend = 0xFFFFu;      // s_tp entry of a node that did not send this step
+constexpr unsigned kDeadRec = 0xFFFFFFFFu; // word 0 of a ring entry that was sent from the middle of the queue (general timing)
 
 // ------------------------------------------------------------------------------------------------
 // The step kernel: n_steps iterations of Network.train's loop body (env.py:400-413, slot=freq=1).
@@ -372,7 +388,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     extern __shared__ __align__(16) unsigned char smem[];
     const int N = p.N, G = p.G, GN = G * N;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const SmemLayout L(N, p.sdeg, G, blockDim.x, POLICY, SMEM_TABLES, p.tsize, p.ntab);
+    const SmemLayout L(N, p.sdeg, G, blockDim.x, POLICY, SMEM_TABLES, p.tsize, p.ntab, SPLIT ? p.ecap : 0);
     double *s_tables = reinterpret_cast<double *>(smem + L.tables);
     uint4 *s_rec = reinterpret_cast<uint4 *>(smem + L.rec);
     double *s_f64 = reinterpret_cast<double *>(smem + L.f64);
@@ -384,8 +400,17 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     unsigned short *s_tp = reinterpret_cast<unsigned short *>(smem + L.tp);   // target | warp-local rank << 8
     unsigned char *s_heappos = smem + L.heappos;
     unsigned char *s_nexthop = smem + L.nexthop;
-    int *s_samp_lat = reinterpret_cast<int *>(smem + L.samp);        // [GN] routing times of this step's deliveries
-    unsigned *s_samp_pos = reinterpret_cast<unsigned *>(smem + L.samp) + GN;   // [GN] their heap pop positions
+    // timing model (compile-time defaults in the fused instantiation)
+    const bool general = SPLIT && p.general != 0;
+    const int slotw = SPLIT ? p.slot : 1, ttime = SPLIT ? p.transtime : 1, freq = SPLIT ? p.freq : 1;
+    const int ecap = SPLIT ? p.ecap : 0, ecap1 = ecap > 0 ? ecap : 1;
+    const int sstride = ecap > N ? ecap : N;                        // deliveries one step can stage per replica
+    int *s_samp_lat = reinterpret_cast<int *>(smem + L.samp);        // [G][sstride] routing times of this step's deliveries
+    unsigned *s_samp_pos = reinterpret_cast<unsigned *>(smem + L.samp) + G * sstride;   // their heap pop positions
+    unsigned long long *s_evheap = reinterpret_cast<unsigned long long *>(smem + L.evheap);    // [G][ecap] heapq array
+    unsigned long long *s_evorder = reinterpret_cast<unsigned long long *>(smem + L.evorder);  // [G][ecap] popped this step
+    int *s_evsent = reinterpret_cast<int *>(smem + L.evsent);        // [G][sdeg] Node.sent per directed link
+    int *s_evlen = reinterpret_cast<int *>(smem + L.evlen);          // [G] {len(event_queue), pops of this step}
     int *s_grdist = reinterpret_cast<int *>(smem + L.gr);          // GlobalRoute: [G][N*N] distances, then [G][N] weights
     int *s_grw = s_grdist + G * N * N;
     // per-replica accumulators of this launch
@@ -433,6 +458,20 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         s_sidx[i] = (p.sample && rblock + i < p.R) ? (unsigned)p.sample_idx[rblock + i] : 0u;
         if (p.sample && s_sidx[i] >= (unsigned)p.sample_size) s_dead[i] = 2u;     // already has its samples: frozen
     }
+    if (general) {
+        for (int i = t; i < G * ecap; i += blockDim.x) {
+            const long long rr = rblock + i / ecap1;
+            s_evheap[i] = rr < p.R ? p.event_heap[rr * ecap + i % ecap1] : 0ull;
+        }
+        for (int i = t; i < G * p.sdeg; i += blockDim.x) {
+            const long long rr = rblock + i / p.sdeg;
+            s_evsent[i] = rr < p.R ? p.link_sent[rr * p.sdeg + i % p.sdeg] : 0;
+        }
+        for (int i = t; i < G; i += blockDim.x) {
+            s_evlen[2 * i] = rblock + i < p.R ? p.event_count[rblock + i] : 0;
+            s_evlen[2 * i + 1] = 0;
+        }
+    }
     if (SMEM_TABLES) {
         const long long per = p.tsize / 2;                          // double2 per table
         for (int gg = 0; gg < G; ++gg) {
@@ -467,6 +506,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     uint4 *myring = nullptr;
     int rp = 0, deg = 0;
     unsigned my_sends = 0, my_inj = 0;
+    unsigned ndead = 0;                 // general timing: ring entries in [head, tail) already sent out of order
     long long base_rt = 0, base_end = 0, base_hops = 0, base_all = 0, base_drop = 0, run_rt = 0;
     double *Qx = nullptr, *Thx = nullptr, *Trx = nullptr;          // table[x] of this node
     if (is_node) {
@@ -474,6 +514,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         tail = p.qtail[r * N + x];
         myring = p.ring + ((size_t)r * N + x) * (size_t)p.cap;
         if (head != tail) pref = myring[head & capmask];
+        if (general) ndead = (unsigned)p.q_dead[r * N + x];
         rp = s_rowptr[x];
         deg = s_rowptr[x + 1] - rp;
         if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) {
@@ -529,7 +570,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     long long tmark_ = clock64();
 #endif
     for (int s = 0; s < p.K; ++s) {
-        const int clock = p.clock0 + s;
+        const int clock = p.clock0 + s * slotw;
         if ((IS_PG || sampling) && is_node) dead = (s_dead[g] != 0u);
         const bool live = !dead;
         bool sending = false;
@@ -561,16 +602,99 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 if (ev != 0xFFFFFFFFu) ev_next = *++evp;
             }
             // ---- B. Node._send_default (env.py:162-191): pop the head, choose, get_info ----
-            if (DUAL) s_len[t] = tail - head;                                   // len(queue) before this node's own send
-            if (head != tail) {
+            if (DUAL) s_len[t] = tail - head - ndead;                           // len(queue) before this node's own send
+            bool have = false;
+            uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+            if (!general) {
+                if (head != tail) {
+                    have = true;
+                    rec = use_fresh ? fresh : pref;
+                    use_fresh = false;
+                    ++head;
+                    if (head != tail) pref = myring[head & capmask];           // prefetch the next head
+                }
+            } else if (head != tail) {
+                // env.py:171-190 with busy links: avaliable_path is evaluated once, then the queue is scanned in order
+                // for the first packet whose chosen link is free; agent.choose runs (and, for the sampled policies,
+                // draws from this node's stream of the step) once per packet looked at.
+                unsigned am = 0u;
+#pragma unroll
+                for (int j = 0; j < MAXD; ++j)
+                    if (j < deg && s_evsent[g * p.sdeg + rp + j] < p.bandwidth) am |= 1u << j;
+                PhiloxStream ps(p.seed, stream_id, clock, x, 1);
+                unsigned pos = head;
+                while (am != 0u && pos != tail) {
+                    const uint4 cand = myring[pos & capmask];
+                    if (cand.x != kDeadRec) {
+                        const int dd = (int)(cand.x & 0xFFFFu);
+                        int kk = 0;
+                        if (POLICY == RLR_POLICY_GLOBALROUTE) {
+                            kk = s_nexthop[(g * N + x) * N + dd];
+                        } else if (POLICY == RLR_POLICY_SHORTEST) {
+                            if (!p.shortest_random) {
+                                kk = s_nexthop[x * N + dd];
+                            } else {
+                                const unsigned cm = reinterpret_cast<const unsigned short *>(s_nexthop)[x * N + dd];
+                                const int cnt = __popc(cm);
+                                const int idx = cnt > 1 ? (int)__umulhi(ps.next(), (unsigned)cnt) : 0;
+                                kk = __fns(cm, 0, idx + 1);
+                            }
+                        } else if (POLICY == RLR_POLICY_QROUTE || IS_CQ) {
+                            const double *row = Qx + dd * deg;
+                            double best = row[0];
+#pragma unroll
+                            for (int j = 1; j < MAXD; ++j)
+                                if (j < deg) { const double v = row[j]; if (v > best) { best = v; kk = j; } }
+                        } else {
+                            softmax_row<MAXD>(Thx + dd * deg, deg, sm);
+                            bool bad = false;
+                            double c = 0.0, cdf[MAXD];
+#pragma unroll
+                            for (int j = 0; j < MAXD; ++j) {
+                                if (j < deg) { bad |= (sm[j] != sm[j]); c = __dadd_rn(c, sm[j]); }
+                                cdf[j] = c;
+                            }
+                            if (bad) {
+                                set_status(p.status, r, RLR_STATUS_NAN_PROB, clock);
+                                s_dead[g] = 1u;
+                                break;
+                            }
+                            const unsigned a = ps.next() >> 5, b = ps.next() >> 6;
+                            const double u = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+#pragma unroll
+                            for (int j = 0; j < MAXD - 1; ++j)
+                                if (j < deg - 1 && kk == j && __ddiv_rn(cdf[j], c) <= u) kk = j + 1;
+                        }
+                        if ((am >> kk) & 1u) { have = true; rec = cand; k = kk; break; }
+                    }
+                    ++pos;
+                }
+                if (have) {                                                     // queue.pop(i), env.py:177
+                    if (pos == head) {
+                        ++head;
+                        while (head != tail && myring[head & capmask].x == kDeadRec) { ++head; --ndead; }
+                    } else {
+                        reinterpret_cast<unsigned *>(myring + (pos & capmask))[0] = kDeadRec;
+                        ++ndead;
+                    }
+                }
+            }
+            if (have) {
                 sending = true;
-                uint4 rec = use_fresh ? fresh : pref;
-                use_fresh = false;
-                ++head;
-                if (head != tail) pref = myring[head & capmask];               // prefetch the next head
                 d = (int)(rec.x & 0xFFFFu);
                 RLR_T(6);                           // A + pop
-                if (POLICY == RLR_POLICY_GLOBALROUTE) {
+                if (general) {
+                    // k was chosen by the scan; pick up the values Qroute/HybridQ.get_info and learn need
+                    if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) {
+                        const double *row = Qx + d * deg;
+                        double best = row[0];
+                        oldq = row[0];
+#pragma unroll
+                        for (int j = 1; j < MAXD; ++j)
+                            if (j < deg) { const double v = row[j]; if (v > best) best = v; if (j == k) oldq = v; }
+                        max_qxd = best;
+                    }
+                } else if (POLICY == RLR_POLICY_GLOBALROUTE) {
                     k = s_nexthop[(g * N + x) * N + d];                         // shortest.py:38-41 on this replica's table
                 } else if (POLICY == RLR_POLICY_SHORTEST) {
                     if (!p.shortest_random) {
@@ -643,7 +767,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                         for (int j = 1; j < MAXD; ++j)
                             if (j < deg) { const double v = rb[j]; if (v > mb) { mb = v; w = j; } }
                         s_bk[t] = make_double2(Thx[src * deg + w], mb);
-                        s_qxi[t] = (int)max(1u, tail - head);
+                        s_qxi[t] = (int)max(1u, tail - head - ndead);
                         s_dk[t] = (unsigned short)(d | (k << 8));
                         s_src[t] = (unsigned short)src;
                     }
@@ -657,6 +781,10 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                     max_qy = m;
                 }
                 s_rec[t] = rec;
+                if (general) {                      // Node._send_packet (env.py:135-145): the event outlives the step
+                    p.event_rec[(size_t)r * ecap + ((unsigned)(clock + ttime) % (unsigned)(ttime + 1)) * N + x] = rec;
+                    s_evsent[g * p.sdeg + rp + k] += 1;
+                }
                 if (POLICY == RLR_POLICY_MAHYBRIDQ) { s_r[t] = rwd; s_qy[t] = max_qy; s_qx[t] = max_qxd; }
                 ++my_sends;
                 if (!do_learn && p.rewards) {                                   // Network.step(): hand the Reward to the host
@@ -691,11 +819,88 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         if (sendlog) sendlog[(long long)s * N] = sending ? ((unsigned)y | ((unsigned)d << 16)) : 0xFFFFFFFFu;
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, sending);
         if (lane == 0) s_wmask[warp] = bal;
-        if (t < GN) s_tp[t] = sending ? (unsigned short)(y | (__popc(bal & prank_mask) << 8)) : (unsigned short)kNoSend;
+        if (t < GN) s_tp[t] = sending ? (unsigned short)(y | ((general ? k : __popc(bal & prank_mask)) << 8)) : (unsigned short)kNoSend;
         __syncthreads();                                                        // ---- barrier 1 ----
         RLR_T(1);
 
-        if (live && do_env) {
+        if (general) {
+            // ---- C (general timing). Network.event_queue restated literally (heapq on arrive_time only, env.py:48-49):
+            // one thread per replica pushes this step's events in node order and pops everything due by clock + slot;
+            // the receivers then take their arrivals from the popped list in pop order.
+            if (live && do_env && x == 0) {
+                unsigned long long *hp = s_evheap + g * ecap, *ord = s_evorder + g * ecap;
+                int len = s_evlen[2 * g], npop = 0;
+                const unsigned at = (unsigned)(clock + ttime);
+                for (int z = 0; z < N; ++z) {                                   // heappush, env.py:144
+                    const unsigned tp = s_tp[gbase + z];
+                    if (tp == kNoSend) continue;
+                    const unsigned link = (unsigned)s_rowptr[z] + (tp >> 8);
+                    const unsigned long long item = ((unsigned long long)at << 32) | (link << 16) | ((at % (unsigned)(ttime + 1)) * N + z);
+                    int pos = len++;
+                    while (pos > 0) {                                           // heapq._siftdown
+                        const int parent = (pos - 1) >> 1;
+                        if ((unsigned)(item >> 32) < (unsigned)(hp[parent] >> 32)) { hp[pos] = hp[parent]; pos = parent; continue; }
+                        break;
+                    }
+                    hp[pos] = item;
+                }
+                const unsigned end_time = (unsigned)(clock + slotw);
+                while (len > 0 && (unsigned)(hp[0] >> 32) <= end_time) {        // heappop, env.py:350-353
+                    const unsigned long long last = hp[--len];
+                    unsigned long long ret = last;
+                    if (len > 0) {
+                        ret = hp[0];
+                        int pos = 0, child = 1;                                 // heapq._siftup: bubble the smaller child up to a leaf
+                        while (child < len) {
+                            const int right = child + 1;
+                            if (right < len && !((unsigned)(hp[child] >> 32) < (unsigned)(hp[right] >> 32))) child = right;
+                            hp[pos] = hp[child];
+                            pos = child;
+                            child = 2 * pos + 1;
+                        }
+                        while (pos > 0) {                                       // then _siftdown(heap, 0, pos) of the moved item
+                            const int parent = (pos - 1) >> 1;
+                            if ((unsigned)(last >> 32) < (unsigned)(hp[parent] >> 32)) { hp[pos] = hp[parent]; pos = parent; continue; }
+                            break;
+                        }
+                        hp[pos] = last;
+                    }
+                    ord[npop++] = ret;
+                }
+                s_evlen[2 * g] = len;
+                s_evlen[2 * g + 1] = npop;
+            }
+            __syncthreads();
+            if (live && do_env) {
+                const int npop = s_evlen[2 * g + 1];
+                for (int i = 0; i < npop; ++i) {
+                    const unsigned long long e = s_evorder[g * ecap + i];
+                    const unsigned link = (unsigned)(e >> 16) & 0xFFFFu;
+                    if ((int)s_col[link] != x) continue;
+                    s_evsent[g * p.sdeg + link] -= 1;                           // env.py:352
+                    uint4 rec = p.event_rec[(size_t)r * ecap + (unsigned)(e & 0xFFFFu)];
+                    const int at = (int)(unsigned)(e >> 32);
+                    if (p.is_drop && rec.y >= (unsigned)N) {                    // env.py:355-360
+                        atomicAdd(&s_drop[g], 1u);
+                        continue;
+                    }
+                    if ((int)(rec.x & 0xFFFFu) == x) {                          // Network.end_packet, env.py:321-331
+                        if (sampling) {
+                            const unsigned slot = atomicAdd(&s_nsamp[g], 1u);
+                            s_samp_pos[g * sstride + slot] = (unsigned)i;
+                            s_samp_lat[g * sstride + slot] = at - (int)rec.z;
+                        }
+                        atomicAdd(&s_end[g], 1u);
+                        atomicAdd(&s_rt32[g], (unsigned)(at - (int)rec.z));
+                        atomicAdd(&s_hops[g], rec.y);
+                    } else {                                                    // Node.receive, env.py:127-130
+                        rec.w = (unsigned)at;
+                        append(rec);
+                    }
+                }
+                if (tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
+            }
+        } else if (live && do_env) {
             // ---- C. event drain (env.py:349-364): gather arrivals from neighbours in heap-tie order ----
             unsigned cum[MAXW + 1];         // senders of this replica in the window words before word i
             cum[0] = 0;
@@ -752,14 +957,14 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 if ((int)(rec.x & 0xFFFFu) == x) {                              // Network.end_packet, env.py:321-331
                     if (sampling) {                                             // env.py:325-328, ordered later by pop position
                         const unsigned slot = atomicAdd(&s_nsamp[g], 1u);
-                        s_samp_pos[gbase + slot] = best >> 16;
-                        s_samp_lat[gbase + slot] = clock + 1 - (int)rec.z;
+                        s_samp_pos[g * sstride + slot] = best >> 16;
+                        s_samp_lat[g * sstride + slot] = clock + ttime - (int)rec.z;
                     }
                     atomicAdd(&s_end[g], 1u);
-                    atomicAdd(&s_rt32[g], (unsigned)(clock + 1 - (int)rec.z));
+                    atomicAdd(&s_rt32[g], (unsigned)(clock + ttime - (int)rec.z));
                     atomicAdd(&s_hops[g], rec.y);
                 } else {                                                        // Node.receive, env.py:127-130
-                    rec.w = (unsigned)(clock + 1);
+                    rec.w = (unsigned)(clock + ttime);
                     append(rec);
                 }
             }
@@ -799,7 +1004,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             }
         } else if (POLICY == RLR_POLICY_GLOBALROUTE) {
             // GlobalRoute.learn (shortest.py:99-104): recompute every distance with node weights 1 + queue_size[y]
-            if (live) s_grw[gbase + x] = 1 + (int)(tail - head) + gr_off;
+            if (live) s_grw[gbase + x] = 1 + (int)(tail - head - ndead) + gr_off;
             __syncthreads();
             if (live) gr_column(x, N, s_rowptr, s_col, s_grw + gbase, s_grdist + g * N * N, s_nexthop + g * N * N);
         } else if (IS_CQ) {
@@ -820,9 +1025,11 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 } else {
                     const int yt = gbase + y;                                   // my next hop's thread slot
                     const unsigned ly = s_len[yt];
-                    const double r_f = -(double)(int)max(1u, ly - ((y < x && ly > 0u) ? 1u : 0u));
-                    // does y's backward update land on this very cell?  (y sends to me a packet whose source is my dest)
                     const unsigned tpy = s_tp[yt];
+                    // len(nodes[y].queue) as the sequential node loop sees it: y already popped its packet if y < x and y sent
+                    // (with busy links a non-empty queue does not imply a send)
+                    const double r_f = -(double)(int)max(1u, ly - ((y < x && tpy != kNoSend) ? 1u : 0u));
+                    // does y's backward update land on this very cell?  (y sends to me a packet whose source is my dest)
                     const bool hit = tpy != kNoSend && (tpy & 0xFFu) == (unsigned)x && s_src[yt] == (unsigned short)d;
                     const double2 bk = s_bk[yt];
                     const double r_by = -(double)s_qxi[yt];
@@ -924,23 +1131,24 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             if (is_node && x == N - 1 && !dead) {
                 const int n = (int)s_nsamp[g];
                 for (int i = 1; i < n; ++i) {       // insertion sort by heap pop position = the reference's delivery order
-                    const unsigned kp = s_samp_pos[gbase + i];
-                    const int kl = s_samp_lat[gbase + i];
+                    const unsigned kp = s_samp_pos[g * sstride + i];
+                    const int kl = s_samp_lat[g * sstride + i];
                     int j = i - 1;
-                    while (j >= 0 && s_samp_pos[gbase + j] > kp) {
-                        s_samp_pos[gbase + j + 1] = s_samp_pos[gbase + j];
-                        s_samp_lat[gbase + j + 1] = s_samp_lat[gbase + j];
+                    while (j >= 0 && s_samp_pos[g * sstride + j] > kp) {
+                        s_samp_pos[g * sstride + j + 1] = s_samp_pos[g * sstride + j];
+                        s_samp_lat[g * sstride + j + 1] = s_samp_lat[g * sstride + j];
                         --j;
                     }
-                    s_samp_pos[gbase + j + 1] = kp;
-                    s_samp_lat[gbase + j + 1] = kl;
+                    s_samp_pos[g * sstride + j + 1] = kp;
+                    s_samp_lat[g * sstride + j + 1] = kl;
                 }
                 int idx = (int)s_sidx[g];
                 for (int i = 0; i < n; ++i, ++idx)
-                    p.sample[r * (long long)p.sample_size + (idx < p.sample_size - 1 ? idx : p.sample_size - 1)] = s_samp_lat[gbase + i];
+                    p.sample[r * (long long)p.sample_size + (idx < p.sample_size - 1 ? idx : p.sample_size - 1)] = s_samp_lat[g * sstride + i];
                 s_sidx[g] = (unsigned)idx;
                 s_nsamp[g] = 0u;
-                if (idx >= p.sample_size) { s_dead[g] = 2u; p.sample_clock[r] = clock + 1; }
+                // the reference finishes the iteration (all `freq` steps) in which the sample filled up, env.py:426-428
+                if (idx >= p.sample_size && (s + 1) % freq == 0) { s_dead[g] = 2u; p.sample_clock[r] = clock + slotw; }
             }
             __syncthreads();
         }
@@ -961,6 +1169,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     if (is_node) {
         p.qhead[r * N + x] = head;
         p.qtail[r * N + x] = tail;
+        if (general) p.q_dead[r * N + x] = (int)ndead;
         if (my_sends) atomicAdd(&s_sends[g], (unsigned long long)my_sends);
         if (my_inj) atomicAdd(&s_inj[g], (unsigned long long)my_inj);
     }
@@ -974,6 +1183,18 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         c[RLR_CTR_ROUTE_TIME] += run_rt;
         if (sampling) p.sample_idx[r] = (int)s_sidx[g];
         c[RLR_CTR_SENDS] += (long long)s_sends[g];
+    }
+    if (general) {
+        for (int i = t; i < G * ecap; i += blockDim.x) {
+            const long long rr = rblock + i / ecap1;
+            if (rr < p.R) p.event_heap[rr * ecap + i % ecap1] = s_evheap[i];
+        }
+        for (int i = t; i < G * p.sdeg; i += blockDim.x) {
+            const long long rr = rblock + i / p.sdeg;
+            if (rr < p.R) p.link_sent[rr * p.sdeg + i % p.sdeg] = s_evsent[i];
+        }
+        for (int i = t; i < G; i += blockDim.x)
+            if (rblock + i < p.R) p.event_count[rblock + i] = s_evlen[2 * i];
     }
     if (POLICY == RLR_POLICY_GLOBALROUTE && do_learn) {
         for (int i = t; i < G * N * N; i += blockDim.x) {
@@ -1143,7 +1364,7 @@ __global__ void rlr_reduce_stats_kernel(const long long *counters, long long R, 
 // compare; each packet's destination is uniform over the other N-1 nodes.  Same word stream as the oracle.
 // Output: per (replica, node) an ascending list of events (local step << 8 | dest), 0xFFFFFFFF-terminated.
 // ------------------------------------------------------------------------------------------------
-__global__ void rlr_inject_schedule_kernel(unsigned *events, int cap, long long R, int N, int K, int clock0,
+__global__ void rlr_inject_schedule_kernel(unsigned *events, int cap, long long R, int N, int K, int clock0, int freq, int slot,
                                            const double *enlam, const unsigned long long *thr, unsigned long long seed,
                                            long long replica_base, int *status)
 {
@@ -1156,8 +1377,8 @@ __global__ void rlr_inject_schedule_kernel(unsigned *events, int cap, long long 
     unsigned *ev = events + idx * cap;
     int n_ev = 0;
     bool overflow = false;
-    for (int s = 0; s < K; ++s) {
-        PhiloxStream ps(seed, (unsigned long long)(replica_base + r), clock0 + s, x, 0);
+    for (int s = 0; s < K; s += freq) {                 // one new_packet per `freq` steps, each step `slot` long (env.py:400-403)
+        PhiloxStream ps(seed, (unsigned long long)(replica_base + r), clock0 + s * slot, x, 0);
         const unsigned w0 = ps.next();
         if ((unsigned long long)w0 < th) continue;
         int n = 1;
@@ -1371,7 +1592,7 @@ extern "C" int rlr_trace_replay_many(uint32_t *mt_keys, int32_t *mt_pos, int64_t
 struct rlr_handle {
     int N, sdeg, max_deg, policy, ntab;
     long long R, replica_base, tsize;
-    int cap, G, threads, smem_bytes, device;
+    int cap, G, threads, smem_bytes, device, ecap;
     bool smem_tables, bound;
     std::vector<int> row_ptr, col;
     rlr_buffers_t bufs;
@@ -1414,13 +1635,15 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     if (cap < 2 || (cap & (cap - 1))) return fail(RLR_E_INVALID, "rlr_create: queue_capacity must be a power of two >= 2");
 
     RLR_CUDA(cudaSetDevice(cfg->device));
+    if (cfg->event_capacity < 0 || cfg->event_capacity > 65535 || topo->sum_deg > 65535)
+        return fail(RLR_E_UNSUPPORTED, "rlr_create: event_capacity must be in [0, 65535] (N * (transtime + 1)) and sum_deg <= 65535");
     rlr_handle *h = new rlr_handle();
     h->N = N; h->sdeg = topo->sum_deg; h->max_deg = topo->max_deg; h->policy = cfg->policy;
     // tables per replica: Shortest 0, Qroute 1 (Q), HybridQ 2 (+Theta), MaHybridQ 3 (+Trace), CQ/CDRQ 2 (Q + confidence)
     h->ntab = cfg->policy == RLR_POLICY_GLOBALROUTE ? 0 : cfg->policy >= RLR_POLICY_CQ ? 2 : cfg->policy;
     h->R = cfg->replicas; h->replica_base = cfg->replica_base;
     h->tsize = (long long)N * topo->sum_deg;
-    h->cap = cap; h->bound = false; h->device = cfg->device;
+    h->cap = cap; h->bound = false; h->device = cfg->device; h->ecap = cfg->event_capacity;
     h->row_ptr.assign(topo->row_ptr, topo->row_ptr + N + 1);
     h->col.assign(topo->col, topo->col + topo->sum_deg);
     memset(&h->bufs, 0, sizeof(h->bufs));
@@ -1431,7 +1654,7 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     int smem_tables = cfg->tables_in_smem;
     if (h->policy == RLR_POLICY_SHORTEST || h->policy == RLR_POLICY_GLOBALROUTE) smem_tables = 0;
     auto smem_for = [&](int g, int thr, bool st) {
-        return SmemLayout(N, h->sdeg, g, thr, h->policy, st, h->tsize, h->ntab).total;
+        return SmemLayout(N, h->sdeg, g, thr, h->policy, st, h->tsize, h->ntab, h->ecap).total;
     };
     if (smem_tables < 0) smem_tables = (table_bytes > 0 && smem_for(1, 256, true) <= (size_t)kSmemLimit) ? 1 : 0;
     if (G <= 0) G = smem_tables ? 1 : (N >= 96 ? 1 : (128 / N > 0 ? 128 / N : 1));
@@ -1491,6 +1714,10 @@ int rlr_bind_buffers(rlr_handle_t *h, const rlr_buffers_t *b)
     if (!gr && h->policy >= RLR_POLICY_QROUTE && !b->q_table) return fail(RLR_E_INVALID, "rlr_bind_buffers: q_table required");
     if (!gr && h->policy >= RLR_POLICY_HYBRIDQ && !b->theta) return fail(RLR_E_INVALID, "rlr_bind_buffers: theta required");
     if (h->policy == RLR_POLICY_MAHYBRIDQ && !b->trace) return fail(RLR_E_INVALID, "rlr_bind_buffers: trace required");
+    if (h->ecap > 0 && (!b->link_sent || !b->event_heap || !b->event_count || !b->event_rec || !b->q_dead))
+        return fail(RLR_E_INVALID, "rlr_bind_buffers: event_capacity > 0 needs link_sent, event_heap, event_count, event_rec and q_dead");
+    if (((uintptr_t)b->event_rec & 15) || ((uintptr_t)b->event_heap & 7))
+        return fail(RLR_E_INVALID, "rlr_bind_buffers: event_rec must be 16-byte and event_heap 8-byte aligned");
     if (((uintptr_t)b->ring & 15) || ((uintptr_t)b->q_table & 15) || ((uintptr_t)b->theta & 15) || ((uintptr_t)b->trace & 15))
         return fail(RLR_E_INVALID, "rlr_bind_buffers: ring and tables must be 16-byte aligned");
     h->bufs = *b;
@@ -1520,6 +1747,11 @@ int rlr_reset(rlr_handle_t *h, void *stream)
     RLR_CUDA(cudaMemsetAsync(h->bufs.counters, 0, (size_t)h->R * RLR_NUM_COUNTERS * 8, st));
     RLR_CUDA(cudaMemsetAsync(h->bufs.status, 0, (size_t)h->R * 2 * 4, st));
     if (h->policy == RLR_POLICY_MAHYBRIDQ) RLR_CUDA(cudaMemsetAsync(h->bufs.trace, 0, (size_t)h->R * h->tsize * 8, st));
+    if (h->ecap > 0) {                                   // event_queue = [], Node.sent = 0 (env.py:269, 100-101)
+        RLR_CUDA(cudaMemsetAsync(h->bufs.link_sent, 0, (size_t)h->R * h->sdeg * 4, st));
+        RLR_CUDA(cudaMemsetAsync(h->bufs.event_count, 0, (size_t)h->R * 4, st));
+        RLR_CUDA(cudaMemsetAsync(h->bufs.q_dead, 0, RN * 4, st));
+    }
     if (h->policy == RLR_POLICY_CQ || h->policy == RLR_POLICY_CDRQ) {              // CQ.clean (qroute.py:66-71)
         const long long total = h->R * h->tsize;
         int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
@@ -1575,7 +1807,7 @@ int rlr_build_inject_schedule(rlr_handle_t *h, int64_t n_steps, const rlr_run_pa
     RLR_CUDA(cudaSetDevice(h->device));
     const long long nthr = h->R * h->N;
     rlr_inject_schedule_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        rp->inj_events, rp->inj_cap, h->R, h->N, (int)n_steps, rp->clock0, rp->enlam,
+        rp->inj_events, rp->inj_cap, h->R, h->N, (int)n_steps, rp->clock0, rp->freq > 0 ? rp->freq : 1, rp->slot > 0 ? rp->slot : 1, rp->enlam,
         (const unsigned long long *)rp->inj_thr, rp->seed, h->replica_base, h->bufs.status);
     RLR_CUDA(cudaGetLastError());
     return RLR_OK;
@@ -1602,7 +1834,21 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     if ((rp->route_time_out || rp->hop_out || rp->droprate_out) && !rp->metrics)
         return fail(RLR_E_INVALID, "rlr_run_steps: route_time_out / hop_out / droprate_out need the metrics record buffer");
     if (rp->droprate_out && !rp->metrics2) return fail(RLR_E_INVALID, "rlr_run_steps: droprate_out needs the metrics2 buffer");
-    if ((long long)rp->clock0 + n_steps > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: clock overflows int32");
+    const int slot = rp->slot > 0 ? rp->slot : 1, freq = rp->freq > 0 ? rp->freq : 1;
+    const int transtime = (rp->slot == 0 && rp->transtime == 0) ? 1 : rp->transtime;     // an all-zero block means the defaults
+    const int bandwidth = (rp->slot == 0 && rp->bandwidth == 0) ? 1 : rp->bandwidth;
+    if (rp->slot < 0 || rp->freq < 0 || transtime < 0) return fail(RLR_E_INVALID, "rlr_run_steps: slot, freq and transtime must be >= 0");
+    if ((long long)rp->clock0 + n_steps * slot + transtime > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: clock overflows int32");
+    if (rp->inject_mode == RLR_INJECT_PHILOX && n_steps % freq != 0)
+        return fail(RLR_E_INVALID, "rlr_run_steps: n_steps must be a multiple of freq (whole iterations of Network.train's loop)");
+    const bool need_general = transtime > slot || bandwidth < 1;
+    if (need_general && !rp->general)
+        return fail(RLR_E_INVALID, "rlr_run_steps: transtime > slot or bandwidth < 1 needs `general` (events outlive the step)");
+    if (rp->general) {
+        if (h->ecap < h->N * (transtime + 1))
+            return fail(RLR_E_INVALID, "rlr_run_steps: `general` needs a handle created with event_capacity >= N * (transtime + 1)");
+        if (h->max_deg > 32) return fail(RLR_E_UNSUPPORTED, "rlr_run_steps: the general timing model supports degrees up to 32");
+    }
     RLR_CUDA(cudaSetDevice(h->device));
     StepParams p;
     memset(&p, 0, sizeof(p));
@@ -1622,6 +1868,9 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     p.inj_events = rp->inj_events; p.seed = rp->seed; p.replica_base = h->replica_base;
     p.lr_q = rp->lr_q; p.lr_p = rp->lr_p; p.lr_e = rp->lr_e; p.discount = rp->discount; p.discount_trace = rp->discount_trace; p.conf_decay = rp->conf_decay;
     p.metrics = (uint4 *)rp->metrics; p.metrics2 = (uint2 *)rp->metrics2; p.sendlog = rp->sendlog;
+    p.slot = slot; p.freq = freq; p.transtime = transtime; p.bandwidth = bandwidth; p.general = rp->general != 0; p.ecap = h->ecap;
+    p.link_sent = h->bufs.link_sent; p.event_heap = (unsigned long long *)h->bufs.event_heap; p.event_count = h->bufs.event_count;
+    p.event_rec = (uint4 *)h->bufs.event_rec; p.q_dead = h->bufs.q_dead;
     p.sample = rp->sample; p.sample_idx = rp->sample_idx; p.sample_clock = rp->sample_clock; p.sample_size = rp->sample_size;
     if (p.sample && (!p.sample_idx || !p.sample_clock || p.sample_size < 1))
         return fail(RLR_E_INVALID, "rlr_run_steps: sample needs sample_idx, sample_clock and sample_size >= 1");
@@ -1631,7 +1880,8 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     }
     const long long blocks = (h->R + h->G - 1) / h->G;
     if (blocks > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: too many blocks");
-    const bool plain = p.phase == 3 && !p.sample && !p.sendlog && !p.is_drop && !p.metrics2;
+    const bool plain = p.phase == 3 && !p.sample && !p.sendlog && !p.is_drop && !p.metrics2 && !p.general && slot == 1 &&
+                       freq == 1 && transtime == 1;
     (plain ? h->kernel : h->kernel_split)<<<(unsigned)blocks, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p);
     RLR_CUDA(cudaGetLastError());
     if (rp->route_time_out || rp->hop_out || rp->droprate_out) {

@@ -80,14 +80,22 @@ def schedule_capacity(lam_max, n_nodes, n_steps):
     return int(m + 12.0 * np.sqrt(m) + 24) + 1
 
 
-def trace_schedule(cnt, pairs, n_nodes, s0, s1):
-    """Per-node event lists of steps [s0, s1) of one replica's trace: (events[int], node_of_event[int]) with
-    events = (local_step << 8 | dest) in (node, step, draw order)."""
+def trace_schedule(cnt, pairs, n_nodes, s0, s1, freq=1):
+    """Per-node event lists of iterations [s0, s1) of one replica's trace: (events[int], node_of_event[int]) with
+    events = (local_step << 8 | dest) in (node, step, draw order); iteration i injects at local step (i - s0) * freq."""
     steps = np.repeat(np.arange(len(cnt), dtype=np.int64), cnt)
     sel = (steps >= s0) & (steps < s1)
-    src, dst, st = pairs[sel, 0].astype(np.int64), pairs[sel, 1].astype(np.int64), steps[sel] - s0
+    src, dst, st = pairs[sel, 0].astype(np.int64), pairs[sel, 1].astype(np.int64), (steps[sel] - s0) * freq
     order = np.argsort(src, kind="stable")                       # stable: keeps (step, draw) order inside a node
     return ((st[order] << 8) | dst[order]).astype(np.uint32), src[order]
+
+
+def _as_int(v, name):
+    """The device clock is an integer: slot, freq, transtime and bandwidth must be integer-valued."""
+    if isinstance(v, (bool, np.bool_)) or int(v) != v:
+        raise NotImplementedError(f"{name}={v!r}: the device timing model is integer-valued (the reference's float "
+                                  "clock would make route_time a float sum); there is no CPU fallback")
+    return int(v)
 
 
 def _floor_pow2(v):
@@ -98,9 +106,9 @@ class Network:
     def __init__(self, file, bandwidth=1, transtime=1, is_drop=False, *, replicas=1, device=None,
                  rng="trace", seed=None, replica_base=0, queue_capacity=None,
                  replicas_per_block=0, threads_per_block=0, tables_in_smem=-1):
-        if bandwidth != 1 or transtime != 1:
-            raise NotImplementedError("bandwidth != 1 / transtime != 1 need in-flight events that outlive a step "
-                                      "(SURVEY §8 row f2); not implemented on the device and there is no CPU fallback")
+        bandwidth, transtime = _as_int(bandwidth, "bandwidth"), _as_int(transtime, "transtime")
+        if bandwidth < 0 or transtime < 0:
+            raise ValueError("bandwidth and transtime must be >= 0")
         if rng not in ("trace", "philox"):
             raise ValueError("rng must be 'trace' or 'philox'")
         if replicas < 1:
@@ -142,6 +150,18 @@ class Network:
         self._col = torch.from_numpy(topo.col).to(dev)
         self._heap_pos = torch.from_numpy(np.ascontiguousarray(topo.heap_pos, dtype=np.uint8)).to(dev)
         self._stats = torch.zeros(nat.NUM_COUNTERS, dtype=torch.int64, device=dev)
+        # General timing model: with transtime > 1 an event can outlive a step of slot 1, so the event
+        # heap, the per-link in-flight counts and out-of-order queue removals become persistent device state.
+        self._general = transtime > 1 or bandwidth < 1
+        self._ecap = N * (transtime + 1) if self._general else 0
+        if self._ecap > 65535:
+            raise NotImplementedError(f"N * (transtime + 1) = {self._ecap} in-flight event slots exceed the device limit of 65535")
+        if self._general:
+            self._link_sent = torch.zeros((R, topo.sum_deg), dtype=torch.int32, device=dev)
+            self._event_heap = torch.zeros((R, self._ecap), dtype=torch.int64, device=dev)
+            self._event_count = torch.zeros(R, dtype=torch.int32, device=dev)
+            self._event_rec = torch.zeros((R, self._ecap, 4), dtype=torch.int32, device=dev)
+            self._q_dead = torch.zeros((R, N), dtype=torch.int32, device=dev)
         self._handles = []
         self.launch_count = 0          # rlr_run_steps launches issued (bench.py reports it as gpu_launches)
         self.last_h2d_bytes = self.last_d2h_bytes = 0
@@ -167,7 +187,7 @@ class Network:
         t = nat.Topology(topo.N, topo.sum_deg, topo.max_deg, topo.row_ptr.ctypes.data, topo.col.ctypes.data)
         rpb, tpb, tis = self._launch_cfg
         cfg = nat.Config(self.replicas, self.replica_base, agent._kernel_policy, self.queue_capacity, rpb, tpb, tis,
-                         self.device.index or 0)
+                         self.device.index or 0, self._ecap, 0)
         h = C.c_void_p()
         nat.check(nat.lib().rlr_create(C.byref(t), C.byref(cfg), C.byref(h)))
         d = agent._dev
@@ -177,7 +197,9 @@ class Network:
                         self._q_tail.data_ptr(), self._counters.data_ptr(), self._status.data_ptr(), ptr("next_hop"),
                         ptr("distance"), ptr("choice"), self._row_ptr.data_ptr(), self._col.data_ptr(),
                         self._heap_pos.data_ptr(), ptr("gr_next_hop"), ptr("gr_distance"), ptr("choice_mask"),
-                        ptr("gr_qs_off"))
+                        ptr("gr_qs_off"), *([t.data_ptr() for t in (self._link_sent, self._event_heap, self._event_count,
+                                                                     self._event_rec, self._q_dead)]
+                                             if self._general else [None] * 5))
         nat.check(nat.lib().rlr_bind_buffers(h, C.byref(b)))
         self._handles.append(h)
         return h
@@ -318,6 +340,9 @@ class Network:
         else:
             for t in (self._q_head, self._q_tail, self._counters, self._status):
                 t.zero_()
+            if self._general:
+                for t in (self._link_sent, self._event_count, self._q_dead):
+                    t.zero_()
         self._agent.clean()
 
     def clean(self):
@@ -379,6 +404,14 @@ class Network:
             raise NotImplementedError("bind one of the device policies first (nw.agent = Qroute(nw) ...)")
         return h
 
+    def _timing(self, rp, slot=1, freq=1):
+        """Fills the timing block of the run parameters (env.py:237-239 bandwidth / transtime, env.py:372-373 slot / freq)."""
+        slot, freq = _as_int(slot, "slot"), _as_int(freq, "freq")
+        if slot < 1 or freq < 1:
+            raise ValueError("slot and freq must be >= 1")
+        rp.slot, rp.freq, rp.transtime, rp.bandwidth, rp.general = slot, freq, self.transtime, self.bandwidth, int(self._general)
+        return slot, freq
+
     def _run_params(self, agent, lr):
         lrd = dict(getattr(agent, "_lr_default", {}))
         lrd.update(lr or {})
@@ -391,14 +424,14 @@ class Network:
         rp.is_drop = int(bool(self.is_drop))
         rp.shortest_random = int(agent._kernel_policy == nat.POLICY_SHORTEST and bool(getattr(agent, "random", False)))
         rp.seed = self.seed
+        self._timing(rp)
         return rp
 
     def step(self, duration=1):
         """env.py:333-365: one send phase + event drain, nothing learned.  Returns the List[Reward] (one replica)
         or a list of R lists, to be passed to `agent.learn`."""
         import torch
-        if duration != 1:
-            raise NotImplementedError("step(duration != 1) (SURVEY §8 row f2) is not implemented on the device")
+        duration = _as_int(duration, "duration")
         h = self._handle_or_raise()
         if self._agent._kernel_policy in (nat.POLICY_CQ, nat.POLICY_CDRQ):
             raise NotImplementedError("Network.step / agent.learn as separate calls are not implemented for CQ / CDRQ; "
@@ -419,11 +452,13 @@ class Network:
         d_sched = torch.from_numpy(sched.view(np.int32)).to(self.device)
         rew = self._scratch("rewards", (R, N, 12), torch.int32)
         rp = self._run_params(self._agent, {})
+        self._timing(rp, duration, 1)
         rp.inject_mode, rp.inj_events, rp.inj_cap = nat.INJECT_TRACE, d_sched.data_ptr(), cap
         rp.clock0, rp.phase, rp.rewards = self.clock, 1, rew.data_ptr()
         nat.check(nat.lib().rlr_run_steps(h, 1, C.byref(rp), self._stream_ptr()))
         self.launch_count += 1
-        self.clock += 1
+        self.clock += duration
+        self._last_duration = duration
         self._pending = [[] for _ in range(R)]
         raw = rew.cpu().numpy()
         self._raise_on_status(self._status.cpu().numpy())
@@ -464,7 +499,8 @@ class Network:
             empty = self._resident["empty_sched"] = torch.full((R, N, 2), -1, dtype=torch.int32, device=self.device)
         rp = self._run_params(agent, lr)
         rp.inject_mode, rp.inj_events, rp.inj_cap = nat.INJECT_TRACE, empty.data_ptr(), 2
-        rp.clock0, rp.phase, rp.rewards = self.clock - 1, 2, self._scratch("rewards", (R, N, 12), torch.int32).data_ptr()
+        self._timing(rp, self.__dict__.get("_last_duration", 1), 1)
+        rp.clock0, rp.phase, rp.rewards = self.clock - rp.slot, 2, self._scratch("rewards", (R, N, 12), torch.int32).data_ptr()
         nat.check(nat.lib().rlr_run_steps(h, 1, C.byref(rp), self._stream_ptr()))
         self.launch_count += 1
         self._last_rewards = None
@@ -476,15 +512,14 @@ class Network:
         After a multi-replica call the replicas' clocks differ, so the network must be `reset()` before it is used
         again."""
         import torch
-        if slot != 1 or freq != 1:
-            raise NotImplementedError("slot != 1 / freq != 1 (SURVEY §8 row f2) are not implemented on the device")
         self._check_sync()
         agent = self._agent
         h = self._handle_or_raise()
         R, N, dev = self.replicas, self.topology.N, self.device
         size = int(size)
-        lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (R,))
         rp = self._run_params(agent, lr)
+        slot, freq = self._timing(rp, slot, freq)
+        lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (R,)) * slot          # env.py:427
         samp = torch.zeros((R, size), dtype=torch.int32, device=dev)
         sidx = torch.zeros(R, dtype=torch.int32, device=dev)
         sclk = torch.zeros(R, dtype=torch.int32, device=dev)
@@ -497,12 +532,12 @@ class Network:
             thr = torch.from_numpy(injection_threshold(en_host).view(np.int64)).to(dev)
             rp.enlam, rp.inj_thr = enlam.data_ptr(), thr.data_ptr()
             keep += [enlam, thr]
-        # trace mode advances one step per launch so the host RNG stream stops exactly where the reference's would
-        K = 1 if self.rng == "trace" else 128
+        # trace mode advances one iteration per launch so the host RNG stream stops exactly where the reference's would
+        K = freq * (1 if self.rng == "trace" else 128)                  # Network.step calls per launch
         while True:
             if self.rng == "trace":
-                traces = trace.draw_injections_many(self._rs, N, K, lam)
-                evs = [trace_schedule(c, pr, N, 0, K) for c, pr in traces]
+                traces = trace.draw_injections_many(self._rs, N, 1, lam)
+                evs = [trace_schedule(c, pr, N, 0, 1) for c, pr in traces]
                 per_node = [np.bincount(node, minlength=N) for _, node in evs]
                 cap = int(max(pn.max() for pn in per_node)) + 2
                 sched = np.full((R, N, cap), 0xFFFFFFFF, dtype=np.uint32)
@@ -512,12 +547,12 @@ class Network:
                 d_sched = torch.from_numpy(sched.view(np.int32)).to(dev)
                 rp.inject_mode, rp.inj_events, rp.inj_cap, rp.clock0 = nat.INJECT_TRACE, d_sched.data_ptr(), cap, self.clock
             else:
-                self._schedule(h, rp, self.clock, K, lam_key, lam.max(), (self.clock + K, K))
+                self._schedule(h, rp, self.clock, K, lam_key, lam.max(), (self.clock + K * slot, K))
             nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), self._stream_ptr()))
             self.launch_count += 1
             if self.rng == "philox":
                 self._schedule_done(h, rp)
-            self.clock += K
+            self.clock += K * slot
             self._raise_on_status(self._status.cpu().numpy())
             if bool((sidx >= size).all().item()):
                 break
@@ -546,8 +581,6 @@ class Network:
         import torch
         self._check_sync()
         _t = [time.perf_counter()]
-        if slot != 1 or freq != 1:
-            raise NotImplementedError("slot != 1 / freq != 1 (SURVEY §8 row f2) are not implemented on the device")
         agent = self._agent
         h = getattr(agent, "_handle", None)
         if h is None:
@@ -559,8 +592,8 @@ class Network:
             lrd["q"] = lrq
         if lrp is not None:
             lrd["p"] = lrp
-        T, R, N, dev = int(duration / slot), self.replicas, self.topology.N, self.device
-        lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (R,)) * slot
+        T, R, N, dev = int(duration / _as_int(slot, "slot")), self.replicas, self.topology.N, self.device
+        lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (R,)) * slot         # Poisson(lambd * slot), env.py:401
         if per_step is None:
             per_step = R * T <= (1 << 26)
         result = {}
@@ -581,6 +614,7 @@ class Network:
         rp.is_drop = int(bool(self.is_drop))
         rp.shortest_random = int(agent._kernel_policy == nat.POLICY_SHORTEST and bool(getattr(agent, "random", False)))
         rp.seed = self.seed
+        slot, freq = self._timing(rp, slot, freq)
         keep = []
         h2d = 0
         traces = None
@@ -600,7 +634,7 @@ class Network:
         # Launch in chunks and stream each chunk's per-step vectors to pinned host memory on a side stream
         # while the next chunk computes, so the device->host copy of [R, T] doubles hides behind the kernel.
         if steps_per_launch is None:
-            steps_per_launch = T if not per_step else max(1, min(max(-(-T // 4), 32), (1 << 25) // R))
+            steps_per_launch = T if not per_step else max(1, min(max(-(-T // 4), 32), (1 << 25) // (R * freq)))
         _t.append(time.perf_counter())
         compute = torch.cuda.current_stream(dev)
         copier = self._copy_stream()
@@ -615,7 +649,7 @@ class Network:
         while s0 < T:
             K = min(steps_per_launch, T - s0)
             if traces is not None:                      # host replay of env.py:307-310 -> per-node event lists
-                evs = [trace_schedule(c, pr, N, s0, s0 + K) for c, pr in traces]
+                evs = [trace_schedule(c, pr, N, s0, s0 + K, freq) for c, pr in traces]
                 per_node = [np.bincount(node, minlength=N) for _, node in evs]
                 cap = int(max(pn.max() for pn in per_node)) + 2
                 sched = np.full((R, N, cap), 0xFFFFFFFF, dtype=np.uint32)
@@ -626,23 +660,29 @@ class Network:
                 h2d += sched.nbytes
                 rp.inj_events, rp.inj_cap = d_sched.data_ptr(), cap
                 keep.append(d_sched)
-                rp.clock0 = self.clock + s0
+                rp.clock0 = self.clock + s0 * freq * slot
             else:                                       # device Philox schedule, prefetched one chunk ahead
-                nxt = (self.clock + s0 + K, min(steps_per_launch, T - s0 - K)) if s0 + K < T else None
-                self._schedule(h, rp, self.clock + s0, K, lam_key, lam.max(), nxt)
-            d_rec = torch.empty((K, R, 2), dtype=torch.int64, device=dev) if per_step else None
+                nxt = ((self.clock + (s0 + K) * freq * slot, min(steps_per_launch, T - s0 - K) * freq)
+                       if s0 + K < T else None)
+                self._schedule(h, rp, self.clock + s0 * freq * slot, K * freq, lam_key, lam.max(), nxt)
+            KS = K * freq                               # Network.step calls of this launch (K iterations of the loop)
+            d_rec = torch.empty((KS, R, 2), dtype=torch.int64, device=dev) if per_step else None
             rp.metrics = d_rec.data_ptr() if d_rec is not None else None
-            d_rt = torch.empty((K, R), dtype=torch.float64, device=dev) if per_step else None
-            d_hop = torch.empty((K, R), dtype=torch.float64, device=dev) if host_hop is not None else None
+            d_rt = torch.empty((KS, R), dtype=torch.float64, device=dev) if per_step else None
+            d_hop = torch.empty((KS, R), dtype=torch.float64, device=dev) if host_hop is not None else None
             rp.route_time_out = d_rt.data_ptr() if d_rt is not None else None
             rp.hop_out = d_hop.data_ptr() if d_hop is not None else None
-            d_rec2 = torch.empty((K, R, 2), dtype=torch.int32, device=dev) if want_drop else None
-            d_drop = torch.empty((K, R), dtype=torch.float64, device=dev) if want_drop else None
+            d_rec2 = torch.empty((KS, R, 2), dtype=torch.int32, device=dev) if want_drop else None
+            d_drop = torch.empty((KS, R), dtype=torch.float64, device=dev) if want_drop else None
             rp.metrics2 = d_rec2.data_ptr() if want_drop else None
             rp.droprate_out = d_drop.data_ptr() if want_drop else None
-            log = torch.empty((R, K, N), dtype=torch.int32, device=dev) if sendlog else None
+            log = torch.empty((R, KS, N), dtype=torch.int32, device=dev) if sendlog else None
             rp.sendlog = log.data_ptr() if log is not None else None
-            nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), stream))
+            nat.check(nat.lib().rlr_run_steps(h, KS, C.byref(rp), stream))
+            if freq > 1 and per_step:                   # the vectors hold one entry per iteration (env.py:409-413)
+                d_rt = d_rt[freq - 1::freq].contiguous()
+                d_hop = d_hop[freq - 1::freq].contiguous() if d_hop is not None else None
+                d_drop = d_drop[freq - 1::freq].contiguous() if d_drop is not None else None
             self.launch_count += 1
             if traces is None:
                 self._schedule_done(h, rp)
@@ -662,7 +702,8 @@ class Network:
             if log is not None:
                 log_chunks.append(log)
             s0 += K
-        self.clock += T
+        self.clock += T * freq * slot
+        self._last_slot = slot
         _t.append(time.perf_counter())
         status = self._status.cpu().numpy()                     # device -> host: synchronises the compute stream
         _t.append(time.perf_counter())
@@ -733,6 +774,7 @@ class Network:
         rp.enlam = self._resident["enlam"].data_ptr()
         rp.inj_thr = self._resident["inj_thr"].data_ptr()
         rp.metrics = self._resident["metrics"].data_ptr()
+        self._timing(rp)
         self._schedule(h, rp, self.clock, K, key[1], lam.max(), (self.clock + K, K))    # next call's schedule is prefetched
         nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), self._stream_ptr()))
         self.launch_count += 1
@@ -776,8 +818,9 @@ class Network:
         K, N = log.shape
         s, x = np.nonzero(log != 0xFFFFFFFF)
         v = log[s, x]
-        clock0 = self.clock - K
-        return np.stack([clock0 + s + 1, x, v & 0xFFFF, v >> 16], axis=1).astype(np.int32)
+        slot = self.__dict__.get("_last_slot", 1)
+        clock0 = self.clock - K * slot
+        return np.stack([clock0 + (s + 1) * slot, x, v & 0xFFFF, v >> 16], axis=1).astype(np.int32)
 
     # ------------------------------------------------------------------ counters (env.py:271-276, 440-450)
     def _ctr(self, name):
@@ -824,6 +867,11 @@ class Network:
         nat.check(nat.lib().rlr_reduce_stats(h, self._stats.data_ptr(), self._stream_ptr()))
         return self._stats
 
+    def _queue_len_device(self):
+        """len(Node.queue) per (replica, node) as a device tensor."""
+        n = self._q_tail - self._q_head
+        return n - self._q_dead if self._general else n
+
     def queue_array(self, x, r=0):
         """Queue of node x of replica r, head first: rows (dest, source, hops, birth, start_queue)."""
         head = int(self._q_head[r, x].item()) & 0xFFFFFFFF
@@ -835,4 +883,4 @@ class Network:
         out[:, 0] = rec[:, 0] & 0xFFFF
         out[:, 1] = rec[:, 0] >> 16
         out[:, 2:] = rec[:, 1:].view(np.int32)
-        return out
+        return out[rec[:, 0] != 0xFFFFFFFF]             # general timing: entries sent from the middle of the queue

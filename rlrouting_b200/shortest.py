@@ -87,7 +87,7 @@ class GlobalRoute(Shortest):
     @property
     def queue_size(self):
         net = self._network
-        q = (net._q_tail - net._q_head + self._dev["gr_qs_off"]).cpu().numpy().astype(np.int64)
+        q = (net._queue_len_device() + self._dev["gr_qs_off"]).cpu().numpy().astype(np.int64)
         return self._one(q)
 
     def choose(self, source, dest):
@@ -97,7 +97,7 @@ class GlobalRoute(Shortest):
         """Network.reset empties the queues but GlobalRoute.queue_size is only ever changed by the receive / send
         callbacks (shortest.py:93-97), so the reference keeps the stale counts; mirror that exactly."""
         net = self._network
-        self._dev["gr_qs_off"] += (net._q_tail - net._q_head)
+        self._dev["gr_qs_off"] += net._queue_len_device()
 
     def learn(self, rewards, lr={}):
         self._network._learn(self, rewards, lr)

@@ -37,14 +37,16 @@ def device_run(case, **net_kw):
         if q0 is not None:
             agent.set_initial_q(q0, initP=kw.get("initP", 0.0))
     nw.agent = agent
+    slot, freq = case.get("slot", 1), case.get("freq", 1)        # T counts iterations of train's loop: duration = T * slot
     if case.get("sample_size"):
-        return nw, agent, nw.sample_route_time(case["sample_size"], case["lambd"], lr=case.get("lr") or {})
+        return nw, agent, nw.sample_route_time(case["sample_size"], case["lambd"], slot=slot, freq=freq, lr=case.get("lr") or {})
     exp_err = case["expect"]["error"]
     if exp_err is not None:
         with pytest.raises(ValueError, match="probabilities contain NaN"):
-            nw.train(case["T"], case["lambd"], lr=case.get("lr") or {}, hop=True, sendlog=True)
+            nw.train(case["T"] * slot, case["lambd"], slot=slot, freq=freq, lr=case.get("lr") or {}, hop=True, sendlog=True)
         return nw, agent, None
-    res = nw.train(case["T"], case["lambd"], lr=case.get("lr") or {}, hop=True, droprate=True, sendlog=True)
+    res = nw.train(case["T"] * slot, case["lambd"], slot=slot, freq=freq, lr=case.get("lr") or {}, hop=True, droprate=True,
+                   sendlog=True)
     return nw, agent, res
 
 
@@ -470,3 +472,88 @@ def test_sample_route_time_many_replicas_and_desync_guard():
             nw.train(10, lam)
     nw.reset()
     nw.train(10, lam)
+
+
+TIMING = [
+    # net, policy, R, T (iterations), lambda, Network kwargs, slot, freq, launch config
+    ("6x6.net", "Qroute", 19, 300, 2.0, dict(transtime=2), 1, 1, {}),
+    ("6x6.net", "Qroute", 16, 200, 1.0, dict(transtime=5, bandwidth=2), 2, 2, dict(replicas_per_block=3, threads_per_block=128)),
+    ("6x6.net", "Qroute", 9, 200, 1.5, dict(transtime=1), 3, 2, {}),                 # slot > transtime: nothing outlives a step
+    ("6x6.net", "Qroute", 8, 250, 2.0, dict(transtime=3, bandwidth=2, is_drop=True), 1, 1, dict(tables_in_smem=0, replicas_per_block=2)),
+    ("6x6-modified.net", "Shortest", 12, 300, "sweep", dict(transtime=2), 1, 1, dict(replicas_per_block=4)),
+    ("lata.net", "Shortest", 3, 200, 3.0, dict(transtime=3, bandwidth=3), 1, 2, {}),
+    ("6x6.net", "HybridQ", 10, 250, 2.0, dict(transtime=2), 1, 1, {}),
+    ("6x6.net", "MaHybridQ", 6, 200, 2.0, dict(transtime=3, bandwidth=2), 1, 1, {}),
+    ("6x6.net", "CQ", 7, 250, 2.0, dict(transtime=2), 1, 1, {}),
+    ("6x6.net", "CDRQ", 7, 300, 2.5, dict(transtime=2), 1, 1, {}),
+    ("6x6.net", "CDRQ", 5, 200, 1.0, dict(transtime=4, bandwidth=2), 2, 1, dict(replicas_per_block=2, threads_per_block=256)),
+    ("6x6.net", "GlobalRoute", 6, 200, 3.0, dict(transtime=2), 1, 1, {}),
+    ("lata.net", "Qroute", 3, 150, 2.0, dict(transtime=2, bandwidth=2), 1, 1, {}),
+]
+
+
+@pytest.mark.parametrize("net,policy,R,T,lam,nkw,slot,freq,cfg", TIMING,
+                         ids=lambda v: str(v) if not isinstance(v, dict) else "-".join(f"{k}{x}" for k, x in v.items()) or "auto")
+def test_general_timing_model_matches_oracle(net, policy, R, T, lam, nkw, slot, freq, cfg):
+    """integer bandwidth / transtime / slot / freq.  With transtime > slot events stay in flight across
+    steps and launches (persistent heapq array, busy links, queue scan); R device replicas == R oracle replicas, bit for
+    bit, across a chunked run (3 launches), followed by a second train call that continues from the in-flight state."""
+    import rlrouting_b200 as rb
+    base, seed = 500, 11
+    if lam == "sweep":
+        lam = np.linspace(1.0, 3.0, R)
+    nw = rb.Network(net, replicas=R, rng="philox", seed=seed, replica_base=base, **nkw, **cfg)
+    agent = _classes()[policy](nw)
+    nw.agent = agent
+    lr = {"q": 0.1, "p": 0.001 if policy == "MaHybridQ" else 0.1, "e": 0.1}
+    q0 = agent.table_array("Qtable") if policy not in ("Shortest", "GlobalRoute") else None
+    T1 = (2 * T) // 3
+    res1 = nw.train(T1 * slot, lam, slot=slot, freq=freq, lr=lr, steps_per_launch=max(1, T1 // 3))
+    res2 = nw.train((T - T1) * slot, lam, slot=slot, freq=freq, lr=lr)
+    res = {"route_time": np.concatenate([np.atleast_2d(res1["route_time"]), np.atleast_2d(res2["route_time"])], axis=1)}
+    topo = topo_of(net)
+    envs = []
+    for r in range(R):
+        e = O.OracleEnv(topo.links, policy, seed=seed, replica=base + r, is_drop=nkw.get("is_drop", False),
+                        bandwidth=nkw.get("bandwidth", 1), transtime=nkw.get("transtime", 1))
+        if q0 is not None:
+            e.set_qtable(q0[r])
+        envs.append(e)
+    sends, rt, en = O.run_many(envs, T, lam, lr_q=lr["q"], lr_p=lr["p"], lr_e=lr["e"], metrics=True, slot=slot, freq=freq)
+    assert int(nw.counters()["sends"].sum()) == sends
+    assert nw.clock == T * slot * freq == envs[0].counters()["clock"]
+    _compare_batch(nw, agent, envs, rt, en, res)
+    c = nw.counters()
+    for r, e in enumerate(envs):
+        assert int(c["drop_packets"][r]) == e.counters()["drop_packets"]
+        if nw._general:
+            assert int(nw._event_count[r].item()) == O.lib().orc_in_flight(e.h)
+    # Network.reset clears the events in flight and the busy links too (env.py:267-280)
+    nw.reset()
+    for e in envs:
+        e.reset()
+    res3 = nw.train(40 * slot, lam, slot=slot, freq=freq, lr=lr)
+    sends, rt, en = O.run_many(envs, 40, lam, lr_q=lr["q"], lr_p=lr["p"], lr_e=lr["e"], metrics=True, slot=slot, freq=freq)
+    _compare_batch(nw, agent, envs, rt, en, res3)
+
+
+def test_general_timing_manual_step_loop_equals_train():
+    """The reference's own loop body (inject(new_packet) / step(duration) / agent.learn) under transtime > duration."""
+    import rlrouting_b200 as rb
+    out = []
+    for manual in (False, True):
+        nw = rb.Network("6x6.net", transtime=3, bandwidth=2, replicas=3, rng="philox", seed=4)
+        ag = rb.HybridQ(nw)
+        nw.agent = ag
+        if manual:
+            for _ in range(60):
+                nw.inject(nw.new_packet(2.0 * 2))
+                r = nw.step(2)
+                ag.learn(r)
+        else:
+            nw.train(120, 2.0, slot=2)
+        out.append((nw.counters(), ag.table_array("Theta"), ag.table_array("Qtable"), [nw.queue_array(x, 2) for x in range(36)]))
+    assert all(np.array_equal(out[0][0][k], out[1][0][k]) for k in out[0][0])
+    assert np.array_equal(out[0][1].view(np.int64), out[1][1].view(np.int64))
+    assert np.array_equal(out[0][2].view(np.int64), out[1][2].view(np.int64))
+    assert all(np.array_equal(a, b) for a, b in zip(out[0][3], out[1][3]))

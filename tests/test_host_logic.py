@@ -25,7 +25,7 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
     assert lib.rlr_abi_version() == nat.ABI_VERSION
     # argument validation happens before any CUDA call, so it is testable without a GPU
     t = nat.Topology(1, 0, 0, None, None)
-    cfg = nat.Config(1, 0, 1, 64, 0, 0, -1, 0)
+    cfg = nat.Config(1, 0, 1, 64, 0, 0, -1, 0, 0, 0)
     h = C.c_void_p()
     assert lib.rlr_create(C.byref(t), C.byref(cfg), C.byref(h)) < 0
     assert b"n_nodes" in lib.rlr_last_error_string()
@@ -36,7 +36,7 @@ def test_struct_sizes_match_header_layout():
     sizes = (C.c_int32 * 4)()
     assert nat.lib().rlr_struct_sizes(sizes) == 0
     assert list(sizes) == [C.sizeof(nat.Topology), C.sizeof(nat.Config), C.sizeof(nat.Buffers), C.sizeof(nat.RunParams)]
-    assert C.sizeof(nat.Buffers) == 18 * 8
+    assert C.sizeof(nat.Buffers) == 23 * 8
 
 
 def test_builtin_topologies_layout():
@@ -88,7 +88,7 @@ def test_injection_threshold_is_exact():
 
 def test_unsupported_options_fail_before_touching_the_device():
     import rlrouting_b200 as rb
-    for kw in (dict(bandwidth=2), dict(transtime=2), dict(bandwidth=3, is_drop=True)):
+    for kw in (dict(bandwidth=1.5), dict(transtime=0.5), dict(transtime=2.25, is_drop=True)):     # float clocks
         with pytest.raises(NotImplementedError):
             rb.Network("6x6.net", **kw)
     with pytest.raises(ValueError):
