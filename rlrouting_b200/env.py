@@ -266,6 +266,9 @@ class Network:
         cap = schedule_capacity(lam_max, self.topology.N, K)
         self._sched_buf(st, other, (self.replicas, self.topology.N, cap))
         side = st["stream"]
+        lam_st = self._resident.get("lam")
+        if lam_st is not None and lam_st.get("uploaded") is not None:
+            side.wait_event(lam_st["uploaded"])                      # the load vectors were copied on the compute stream
         if st["used"][other] is not None:
             side.wait_event(st["used"][other])                       # the step kernel that last read that slot
         rp2 = nat.RunParams()
@@ -275,6 +278,34 @@ class Network:
         done = torch.cuda.Event()
         done.record(side)
         st["ready"][other] = ((clock0, K, lam_key, cap), done)
+
+    def _lam_tensors(self, lam, upload=True):
+        """exp(-lambda_r / N) and the exact integer injection thresholds as device tensors.  The host values are cached
+        per load vector in page-locked staging buffers; `upload` copies them to the device again (they are the inputs of
+        a train call), otherwise the resident copies are reused.  Returns (key, enlam, thr, bytes uploaded)."""
+        import torch
+        key = lam.tobytes() if lam.strides[0] else float(lam[0])
+        st = self._resident.get("lam")
+        fresh = st is None or st["key"] != key
+        if fresh:
+            if st is None:
+                st = self._resident["lam"] = {
+                    "h_en": torch.empty(self.replicas, dtype=torch.float64).pin_memory(),
+                    "h_thr": torch.empty(self.replicas, dtype=torch.int64).pin_memory(),
+                    "d_en": torch.empty(self.replicas, dtype=torch.float64, device=self.device),
+                    "d_thr": torch.empty(self.replicas, dtype=torch.int64, device=self.device)}
+            en_host = np.exp(-lam / np.float64(self.topology.N))
+            st["h_en"].numpy()[:] = en_host
+            st["h_thr"].numpy()[:] = injection_threshold(en_host).view(np.int64)
+            st["key"] = key
+        sent = 0
+        if fresh or upload:
+            st["d_en"].copy_(st["h_en"], non_blocking=True)
+            st["d_thr"].copy_(st["h_thr"], non_blocking=True)
+            st["uploaded"] = torch.cuda.Event()                  # the side stream that prefetches schedules waits for it
+            st["uploaded"].record(torch.cuda.current_stream(self.device))
+            sent = self.replicas * 16
+        return key, st["d_en"], st["d_thr"], sent
 
     def _copy_stream(self):
         import torch
@@ -623,18 +654,25 @@ class Network:
             traces = trace.draw_injections_many(self._rs, N, T, lam)
         else:
             rp.inject_mode = nat.INJECT_PHILOX
-            lam_key = lam.tobytes() if lam.strides[0] else float(lam[0])
-            en_host = np.exp(-lam / np.float64(N))
-            enlam = torch.from_numpy(en_host).to(dev)
-            thr = torch.from_numpy(injection_threshold(en_host).view(np.int64)).to(dev)
+            lam_key, enlam, thr, sent = self._lam_tensors(lam)
             rp.enlam, rp.inj_thr = enlam.data_ptr(), thr.data_ptr()
             keep += [enlam, thr]
-            h2d += R * 16
+            h2d += sent
 
         # Launch in chunks and stream each chunk's per-step vectors to pinned host memory on a side stream
         # while the next chunk computes, so the device->host copy of [R, T] doubles hides behind the kernel.
-        if steps_per_launch is None:
-            steps_per_launch = T if not per_step else max(1, min(max(-(-T // 4), 32), (1 << 25) // (R * freq)))
+        # Every launch re-stages the tables in shared memory, so the default is two launches, 3/4 + 1/4 of the run:
+        # only the copy of the short last chunk is exposed.
+        cap = max(1, (1 << 25) // (R * freq))                   # per-launch device buffers stay under ~1 GB
+        if steps_per_launch is not None:
+            cap = max(1, int(steps_per_launch))
+        elif not per_step:
+            cap = T
+        plan = [cap] * (T // cap) + ([T % cap] if T % cap else [])
+        if steps_per_launch is None and per_step and plan[-1] >= 64:
+            last = plan.pop()
+            plan += [last - last // 4, last // 4]
+        starts = np.concatenate([[0], np.cumsum(plan)]).astype(np.int64)
         _t.append(time.perf_counter())
         compute = torch.cuda.current_stream(dev)
         copier = self._copy_stream()
@@ -644,10 +682,9 @@ class Network:
         want_drop = bool(per_step and droprate and self.is_drop)
         host_drop, out_drop = pinned.POOL.take((T, R)) if want_drop else (None, None)
         log_chunks = []
-        s0 = 0
         stream = self._stream_ptr()
-        while s0 < T:
-            K = min(steps_per_launch, T - s0)
+        for ci, K in enumerate(plan):
+            s0 = int(starts[ci])
             if traces is not None:                      # host replay of env.py:307-310 -> per-node event lists
                 evs = [trace_schedule(c, pr, N, s0, s0 + K, freq) for c, pr in traces]
                 per_node = [np.bincount(node, minlength=N) for _, node in evs]
@@ -662,8 +699,7 @@ class Network:
                 keep.append(d_sched)
                 rp.clock0 = self.clock + s0 * freq * slot
             else:                                       # device Philox schedule, prefetched one chunk ahead
-                nxt = ((self.clock + (s0 + K) * freq * slot, min(steps_per_launch, T - s0 - K) * freq)
-                       if s0 + K < T else None)
+                nxt = (self.clock + (s0 + K) * freq * slot, plan[ci + 1] * freq) if ci + 1 < len(plan) else None
                 self._schedule(h, rp, self.clock + s0 * freq * slot, K * freq, lam_key, lam.max(), nxt)
             KS = K * freq                               # Network.step calls of this launch (K iterations of the loop)
             d_rec = torch.empty((KS, R, 2), dtype=torch.int64, device=dev) if per_step else None
@@ -701,7 +737,6 @@ class Network:
                         d_drop.record_stream(copier)
             if log is not None:
                 log_chunks.append(log)
-            s0 += K
         self.clock += T * freq * slot
         self._last_slot = slot
         _t.append(time.perf_counter())
@@ -750,12 +785,7 @@ class Network:
             raise NotImplementedError("bind one of the device policies first")
         R, N, K = self.replicas, self.topology.N, int(n_steps)
         lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (R,))
-        key = ("enlam", lam.tobytes() if lam.strides[0] else float(lam[0]))
-        if self._resident.get("enlam_key") != key:
-            en_host = np.exp(-lam / np.float64(N))
-            self._resident["enlam"] = torch.from_numpy(en_host).to(self.device)
-            self._resident["inj_thr"] = torch.from_numpy(injection_threshold(en_host).view(np.int64)).to(self.device)
-            self._resident["enlam_key"] = key
+        key, d_en, d_thr, _ = self._lam_tensors(lam, upload=False)
         if self._resident.get("metrics_shape") != (R, K):
             self._resident["metrics"] = torch.empty((K, R, 2), dtype=torch.int64, device=self.device)
             self._resident["metrics_shape"] = (R, K)
@@ -771,11 +801,11 @@ class Network:
         rp.is_drop = int(bool(self.is_drop))
         rp.shortest_random = int(agent._kernel_policy == nat.POLICY_SHORTEST and bool(getattr(agent, "random", False)))
         rp.seed = self.seed
-        rp.enlam = self._resident["enlam"].data_ptr()
-        rp.inj_thr = self._resident["inj_thr"].data_ptr()
+        rp.enlam = d_en.data_ptr()
+        rp.inj_thr = d_thr.data_ptr()
         rp.metrics = self._resident["metrics"].data_ptr()
         self._timing(rp)
-        self._schedule(h, rp, self.clock, K, key[1], lam.max(), (self.clock + K, K))    # next call's schedule is prefetched
+        self._schedule(h, rp, self.clock, K, key, lam.max(), (self.clock + K, K))    # next call's schedule is prefetched
         nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), self._stream_ptr()))
         self.launch_count += 1
         self._schedule_done(h, rp)
