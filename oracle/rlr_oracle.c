@@ -69,6 +69,7 @@ typedef struct orc {
     int bandwidth, transtime; /* Network(bandwidth=1, transtime=1), env.py:237-239 (integers) */
     int slot, freq;           /* Network.train(slot=1, freq=1), env.py:367-373 (integers) */
     int *sent;                /* Node.sent[y] per directed link (env.py:100,115-116,142,352) */
+    int64_t probes;           /* diagnostic: agent.choose calls made by the send loops (queue entries looked at) */
     int multiway, random_choice; /* Shortest(multiway=..., random=...), shortest.py:20-23,38-41 */
     int64_t *sample; int64_t sample_size, sample_idx;   /* Network.sample / _sample_idx (env.py:242, 325-328, 424-425) */
     int64_t *queue_size;      /* GlobalRoute.queue_size (shortest.py:89): +1 per receive callback, -1 per send callback */
@@ -200,6 +201,7 @@ void orc_set_timing(orc_t *o, int bandwidth, int transtime, int slot, int freq)
     o->bandwidth = bandwidth; o->transtime = transtime; o->slot = slot; o->freq = freq;
 }
 int orc_in_flight(const orc_t *o) { return o->heap_len; }
+int64_t orc_probes(const orc_t *o) { return o->probes; }
 void orc_set_shortest_flags(orc_t *o, int multiway, int random_choice) { o->multiway = multiway; o->random_choice = random_choice; }
 
 void orc_set_stream(orc_t *o, uint64_t seed, uint64_t replica) { o->seed = seed; o->replica = replica; }
@@ -632,6 +634,7 @@ static void send_phase(orc_t *o)
         int64_t i = 0; int k = -1;
         while (i < q->len && any_free) {
             k = choose_action(o, x, q->buf[q->head + i].dest, &ps, &ps_open);
+            o->probes++;
             if (k < 0) { o->status = ST_NAN_PROB; o->status_clock = o->clock; return; }
             if (o->sent[o->row_ptr[x] + k] < o->bandwidth) break;
             k = -1; i++;

@@ -299,7 +299,7 @@ __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t
 
 // Shared-memory carve-up, identical on host (sizing) and device (pointers).
 struct SmemLayout {
-    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, gr, samp, evheap, evorder, evsent, evlen, total;
+    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, gr, samp, evheap, evorder, evsent, evlen, evfrom, total;
     __host__ __device__ SmemLayout(int N, int sdeg, int G, int threads, int policy, bool smem_tables, long long tsize, int ntab,
                                    int ecap = 0)
     {
@@ -321,10 +321,11 @@ struct SmemLayout {
         samp = o; o += align16((size_t)G * (ecap > N ? ecap : N) * 8);   // sample_route_time staging: (heap position, routing time) per delivery
         gr = o; o += (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * (N * N + N) * 4) : 0;   // distances + weights
         // general timing model: the event heap, this step's popped events, Node.sent per link, heap length + pop count
-        evheap = o; o += align16((size_t)G * ecap * 8);
-        evorder = o; o += align16((size_t)G * ecap * 8);
+        evheap = o; o += ecap ? align16((size_t)G * ((ecap + 3) & ~1) * 4) : 0;
+        evorder = o; o += align16((size_t)G * ecap * 4);
         evsent = o; o += ecap ? align16((size_t)G * sdeg * 4) : 0;
         evlen = o; o += ecap ? align16((size_t)G * 2 * 4) : 0;
+        evfrom = o; o += ecap ? align16((size_t)sdeg) : 0;
         total = o;
     }
 };
@@ -407,8 +408,12 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     const int sstride = ecap > N ? ecap : N;                        // deliveries one step can stage per replica
     int *s_samp_lat = reinterpret_cast<int *>(smem + L.samp);        // [G][sstride] routing times of this step's deliveries
     unsigned *s_samp_pos = reinterpret_cast<unsigned *>(smem + L.samp) + G * sstride;   // their heap pop positions
-    unsigned long long *s_evheap = reinterpret_cast<unsigned long long *>(smem + L.evheap);    // [G][ecap] heapq array
-    unsigned long long *s_evorder = reinterpret_cast<unsigned long long *>(smem + L.evorder);  // [G][ecap] popped this step
+    // general timing: Network.event_queue as the heapq array of 32-bit items (arrive_time - clock0) << 16 | link, item i
+    // of replica g at s_evheap[g * hstride + 1 + i] so that the children 2i+1, 2i+2 form one aligned 8-byte pair
+    unsigned *s_evheap = reinterpret_cast<unsigned *>(smem + L.evheap);
+    const int hstride = (ecap + 3) & ~1;
+    unsigned *s_evorder = reinterpret_cast<unsigned *>(smem + L.evorder);   // [G][ecap] items popped this step, in pop order
+    unsigned char *s_evfrom = smem + L.evfrom;                       // [sdeg] sender of each directed link
     int *s_evsent = reinterpret_cast<int *>(smem + L.evsent);        // [G][sdeg] Node.sent per directed link
     int *s_evlen = reinterpret_cast<int *>(smem + L.evlen);          // [G] {len(event_queue), pops of this step}
     int *s_grdist = reinterpret_cast<int *>(smem + L.gr);          // GlobalRoute: [G][N*N] distances, then [G][N] weights
@@ -460,9 +465,12 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     }
     if (general) {
         for (int i = t; i < G * ecap; i += blockDim.x) {
-            const long long rr = rblock + i / ecap1;
-            s_evheap[i] = rr < p.R ? p.event_heap[rr * ecap + i % ecap1] : 0ull;
+            const int gg = i / ecap1, j = i - gg * ecap1;
+            const unsigned long long e = rblock + gg < p.R ? p.event_heap[(rblock + gg) * ecap + j] : 0ull;
+            s_evheap[gg * hstride + 1 + j] = (((unsigned)(e >> 32) - (unsigned)p.clock0) << 16) | ((unsigned)(e >> 16) & 0xFFFFu);
         }
+        for (int i = t; i < N; i += blockDim.x)
+            for (int j = p.row_ptr[i]; j < p.row_ptr[i + 1]; ++j) s_evfrom[j] = (unsigned char)i;
         for (int i = t; i < G * p.sdeg; i += blockDim.x) {
             const long long rr = rblock + i / p.sdeg;
             s_evsent[i] = rr < p.R ? p.link_sent[rr * p.sdeg + i % p.sdeg] : 0;
@@ -624,7 +632,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 PhiloxStream ps(p.seed, stream_id, clock, x, 1);
                 unsigned pos = head;
                 while (am != 0u && pos != tail) {
-                    const uint4 cand = myring[pos & capmask];
+                    // the head record is kept in registers (prefetched when the head last moved, or just appended)
+                    const uint4 cand = (pos == head) ? (use_fresh ? fresh : pref) : myring[pos & capmask];
                     if (cand.x != kDeadRec) {
                         const int dd = (int)(cand.x & 0xFFFFu);
                         int kk = 0;
@@ -672,7 +681,13 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 if (have) {                                                     // queue.pop(i), env.py:177
                     if (pos == head) {
                         ++head;
-                        while (head != tail && myring[head & capmask].x == kDeadRec) { ++head; --ndead; }
+                        use_fresh = false;
+                        while (head != tail) {                                  // next live entry becomes the head
+                            pref = myring[head & capmask];
+                            if (pref.x != kDeadRec) break;
+                            ++head;
+                            --ndead;
+                        }
                     } else {
                         reinterpret_cast<unsigned *>(myring + (pos & capmask))[0] = kDeadRec;
                         ++ndead;
@@ -827,43 +842,50 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             // ---- C (general timing). Network.event_queue restated literally (heapq on arrive_time only, env.py:48-49):
             // one thread per replica pushes this step's events in node order and pops everything due by clock + slot;
             // the receivers then take their arrivals from the popped list in pop order.
-            if (live && do_env && x == 0) {
-                unsigned long long *hp = s_evheap + g * ecap, *ord = s_evorder + g * ecap;
-                int len = s_evlen[2 * g], npop = 0;
-                const unsigned at = (unsigned)(clock + ttime);
-                for (int z = 0; z < N; ++z) {                                   // heappush, env.py:144
-                    const unsigned tp = s_tp[gbase + z];
-                    if (tp == kNoSend) continue;
-                    const unsigned link = (unsigned)s_rowptr[z] + (tp >> 8);
-                    const unsigned long long item = ((unsigned long long)at << 32) | (link << 16) | ((at % (unsigned)(ttime + 1)) * N + z);
-                    int pos = len++;
-                    while (pos > 0) {                                           // heapq._siftdown
-                        const int parent = (pos - 1) >> 1;
-                        if ((unsigned)(item >> 32) < (unsigned)(hp[parent] >> 32)) { hp[pos] = hp[parent]; pos = parent; continue; }
-                        break;
-                    }
-                    hp[pos] = item;
+            // heappush (env.py:144) never sifts here: a new event's arrive_time is >= every one in the heap and `<` is strict,
+            // so this step's events are appended in node order — each sender writes its own item at its rank
+            unsigned *hp1 = s_evheap + g * hstride;                             // item i at hp1[i + 1]
+            unsigned nsend = 0;
+            if (live && do_env) {
+                unsigned rank = 0;
+#pragma unroll
+                for (int i = 0; i < MAXW; ++i) {
+                    unsigned m = (i < nw) ? s_wmask[wlo + i] : 0u;
+                    if (i == 0) m &= mfirst;
+                    if (i == nw - 1) m &= mlast;
+                    nsend += __popc(m);
+                    if (wlo + i < warp) rank += __popc(m);
+                    else if (wlo + i == warp) rank += __popc(m & ((1u << lane) - 1u));
                 }
-                const unsigned end_time = (unsigned)(clock + slotw);
-                while (len > 0 && (unsigned)(hp[0] >> 32) <= end_time) {        // heappop, env.py:350-353
-                    const unsigned long long last = hp[--len];
-                    unsigned long long ret = last;
+                if (sending) hp1[1 + s_evlen[2 * g] + rank] = ((unsigned)(clock + ttime - p.clock0) << 16) | (unsigned)(rp + k);
+            }
+            __syncthreads();
+            RLR_T(7);                               // general: parallel append + barrier
+            if (live && do_env && x == 0) {
+                unsigned *ord = s_evorder + g * ecap;
+                int len = s_evlen[2 * g] + (int)nsend, npop = 0;
+                const unsigned end_rel = (unsigned)(clock + slotw - p.clock0);
+                while (len > 0 && (hp1[1] >> 16) <= end_rel) {                  // heappop, env.py:350-353 (heapq restated)
+                    const unsigned last = hp1[len];
+                    --len;
+                    unsigned ret = last;
                     if (len > 0) {
-                        ret = hp[0];
-                        int pos = 0, child = 1;                                 // heapq._siftup: bubble the smaller child up to a leaf
+                        ret = hp1[1];
+                        int pos = 0, child = 1;                                 // _siftup: bubble the smaller child up to a leaf
                         while (child < len) {
-                            const int right = child + 1;
-                            if (right < len && !((unsigned)(hp[child] >> 32) < (unsigned)(hp[right] >> 32))) child = right;
-                            hp[pos] = hp[child];
-                            pos = child;
+                            const uint2 pr = *reinterpret_cast<const uint2 *>(hp1 + child + 1);    // items child, child + 1
+                            const bool right = (child + 1 < len) && !(pr.x < (pr.y & 0xFFFF0000u));   // not (left < right)
+                            hp1[pos + 1] = right ? pr.y : pr.x;
+                            pos = child + (right ? 1 : 0);
                             child = 2 * pos + 1;
                         }
-                        while (pos > 0) {                                       // then _siftdown(heap, 0, pos) of the moved item
+                        while (pos > 0) {                                       // _siftdown(heap, 0, pos) of the former last item
                             const int parent = (pos - 1) >> 1;
-                            if ((unsigned)(last >> 32) < (unsigned)(hp[parent] >> 32)) { hp[pos] = hp[parent]; pos = parent; continue; }
+                            const unsigned pv = hp1[parent + 1];
+                            if (last < (pv & 0xFFFF0000u)) { hp1[pos + 1] = pv; pos = parent; continue; }
                             break;
                         }
-                        hp[pos] = last;
+                        hp1[pos + 1] = last;
                     }
                     ord[npop++] = ret;
                 }
@@ -871,32 +893,57 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 s_evlen[2 * g + 1] = npop;
             }
             __syncthreads();
+            RLR_T(5);                               // general: heap pops + barrier
             if (live && do_env) {
+                // arrivals in pop order: first find this node's events in the popped list (shared-memory reads only), fetch
+                // their records together, then process them in order; a node with more than MAXD events (several arrival
+                // times due in one drain) repeats the pass from where it stopped
                 const int npop = s_evlen[2 * g + 1];
-                for (int i = 0; i < npop; ++i) {
-                    const unsigned long long e = s_evorder[g * ecap + i];
-                    const unsigned link = (unsigned)(e >> 16) & 0xFFFFu;
-                    if ((int)s_col[link] != x) continue;
-                    s_evsent[g * p.sdeg + link] -= 1;                           // env.py:352
-                    uint4 rec = p.event_rec[(size_t)r * ecap + (unsigned)(e & 0xFFFFu)];
-                    const int at = (int)(unsigned)(e >> 32);
-                    if (p.is_drop && rec.y >= (unsigned)N) {                    // env.py:355-360
-                        atomicAdd(&s_drop[g], 1u);
-                        continue;
+                for (int skip = 0;; skip += MAXD) {
+                    unsigned mine[MAXD];
+                    int nm = 0, seen = 0;
+#pragma unroll 4
+                    for (int i = 0; i < npop; ++i) {                            // branch-free: the list is the same for every lane
+                        const unsigned e = s_evorder[g * ecap + i];
+                        const bool m = (int)s_col[e & 0xFFFFu] == x;
+                        const bool take = m && seen >= skip && nm < MAXD;
+#pragma unroll
+                        for (int j = 0; j < MAXD; ++j)
+                            if (take && j == nm) mine[j] = (e & 0xFFFF0000u) | (unsigned)i;      // arrive offset | pop index
+                        nm += take ? 1 : 0;
+                        seen += m ? 1 : 0;
                     }
-                    if ((int)(rec.x & 0xFFFFu) == x) {                          // Network.end_packet, env.py:321-331
-                        if (sampling) {
-                            const unsigned slot = atomicAdd(&s_nsamp[g], 1u);
-                            s_samp_pos[g * sstride + slot] = (unsigned)i;
-                            s_samp_lat[g * sstride + slot] = at - (int)rec.z;
+                    uint4 recs[MAXD];
+#pragma unroll
+                    for (int j = 0; j < MAXD; ++j)
+                        if (j < nm) {
+                            const unsigned e = s_evorder[g * ecap + (mine[j] & 0xFFFFu)];
+                            const int at = p.clock0 + (int)(e >> 16);
+                            s_evsent[g * p.sdeg + (e & 0xFFFFu)] -= 1;         // env.py:352
+                            recs[j] = p.event_rec[(size_t)r * ecap + ((unsigned)at % (unsigned)(ttime + 1)) * N + s_evfrom[e & 0xFFFFu]];
                         }
-                        atomicAdd(&s_end[g], 1u);
-                        atomicAdd(&s_rt32[g], (unsigned)(at - (int)rec.z));
-                        atomicAdd(&s_hops[g], rec.y);
-                    } else {                                                    // Node.receive, env.py:127-130
-                        rec.w = (unsigned)at;
-                        append(rec);
-                    }
+#pragma unroll
+                    for (int j = 0; j < MAXD; ++j)
+                        if (j < nm) {
+                            uint4 rec = recs[j];
+                            const int at = p.clock0 + (int)(mine[j] >> 16);
+                            if (p.is_drop && rec.y >= (unsigned)N) {            // env.py:355-360
+                                atomicAdd(&s_drop[g], 1u);
+                            } else if ((int)(rec.x & 0xFFFFu) == x) {           // Network.end_packet, env.py:321-331
+                                if (sampling) {
+                                    const unsigned slot = atomicAdd(&s_nsamp[g], 1u);
+                                    s_samp_pos[g * sstride + slot] = mine[j] & 0xFFFFu;
+                                    s_samp_lat[g * sstride + slot] = at - (int)rec.z;
+                                }
+                                atomicAdd(&s_end[g], 1u);
+                                atomicAdd(&s_rt32[g], (unsigned)(at - (int)rec.z));
+                                atomicAdd(&s_hops[g], rec.y);
+                            } else {                                            // Node.receive, env.py:127-130
+                                rec.w = (unsigned)at;
+                                append(rec);
+                            }
+                        }
+                    if (seen <= skip + MAXD) break;
                 }
                 if (tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
             }
@@ -1186,8 +1233,13 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     }
     if (general) {
         for (int i = t; i < G * ecap; i += blockDim.x) {
-            const long long rr = rblock + i / ecap1;
-            if (rr < p.R) p.event_heap[rr * ecap + i % ecap1] = s_evheap[i];
+            const int gg = i / ecap1, j = i - gg * ecap1;
+            if (rblock + gg < p.R && j < s_evlen[2 * gg]) {
+                const unsigned e = s_evheap[gg * hstride + 1 + j], link = e & 0xFFFFu;
+                const unsigned at = (unsigned)p.clock0 + (e >> 16);
+                p.event_heap[(rblock + gg) * ecap + j] = ((unsigned long long)at << 32) | (link << 16) |
+                                                         ((at % (unsigned)(ttime + 1)) * N + s_evfrom[link]);
+            }
         }
         for (int i = t; i < G * p.sdeg; i += blockDim.x) {
             const long long rr = rblock + i / p.sdeg;
@@ -1444,7 +1496,7 @@ StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables)
 {
 #ifdef RLR_FAST_BUILD       // kernel-tuning builds: only the 6x6 Qroute instantiations (seconds instead of a minute)
     (void)policy; (void)n_nodes; (void)max_deg;
-    return pick_smem<RLR_POLICY_QROUTE, 4, 3, false>(smem_tables);
+    return pick_smem<RLR_POLICY_QROUTE, 4, 3, SPLIT>(smem_tables);
 #else
     switch (policy) {
     case RLR_POLICY_SHORTEST: return pick_deg<RLR_POLICY_SHORTEST, SPLIT>(n_nodes, max_deg, false);
@@ -1656,7 +1708,11 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     auto smem_for = [&](int g, int thr, bool st) {
         return SmemLayout(N, h->sdeg, g, thr, h->policy, st, h->tsize, h->ntab, h->ecap).total;
     };
+    // General timing model: one thread per replica replays the event heap serially and bounds the step, so what pays is
+    // more resident replicas, not faster table reads: tables stay in HBM/L2 and a CTA carries ~256 threads (measured).
+    if (smem_tables < 0 && h->ecap > 0) smem_tables = 0;
     if (smem_tables < 0) smem_tables = (table_bytes > 0 && smem_for(1, 256, true) <= (size_t)kSmemLimit) ? 1 : 0;
+    if (G <= 0 && h->ecap > 0 && !smem_tables) G = 256 / N > 0 ? 256 / N : 1;
     if (G <= 0) G = smem_tables ? 1 : (N >= 96 ? 1 : (128 / N > 0 ? 128 / N : 1));
     if ((long long)G > h->R) G = (int)h->R;
     int threads = cfg->threads_per_block;
@@ -1848,6 +1904,8 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
         if (h->ecap < h->N * (transtime + 1))
             return fail(RLR_E_INVALID, "rlr_run_steps: `general` needs a handle created with event_capacity >= N * (transtime + 1)");
         if (h->max_deg > 32) return fail(RLR_E_UNSUPPORTED, "rlr_run_steps: the general timing model supports degrees up to 32");
+        if (n_steps * slot + transtime > 65535)
+            return fail(RLR_E_INVALID, "rlr_run_steps: with `general`, n_steps * slot + transtime must stay below 65536 per call");
     }
     RLR_CUDA(cudaSetDevice(h->device));
     StepParams p;

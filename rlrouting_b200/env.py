@@ -668,6 +668,8 @@ class Network:
             cap = max(1, int(steps_per_launch))
         elif not per_step:
             cap = T
+        if self._general:                                       # event times are 16-bit offsets from the launch's clock
+            cap = max(1, min(cap, (65535 - self.transtime) // (slot * freq)))
         plan = [cap] * (T // cap) + ([T % cap] if T % cap else [])
         if steps_per_launch is None and per_step and plan[-1] >= 64:
             last = plan.pop()
