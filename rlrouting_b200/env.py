@@ -380,6 +380,84 @@ class Network:
         """Legacy spelling used by the reference's train.py:51."""
         self.reset()
 
+    # ------------------------------------------------------------------ checkpoint / resume (SURVEY §8 row f4)
+    # The reference can pickle an agent's tables (Policy.store / load) but not the environment; these snapshots hold
+    # both, so a long run can be stopped and continued bit for bit — also on another GPU, or with another ring capacity.
+    def snapshot(self):
+        """Environment and bound-agent state as a dict of host arrays: clock, counters, status words, every queue's
+        packets (head first), events in flight and busy links (general timing model), the agent's device tables and
+        the trace-mode RNG states."""
+        import torch
+        self._check_sync()
+        R, N, cap, dev = self.replicas, self.topology.N, self.queue_capacity, self.device
+        head = self._q_head.reshape(-1).to(torch.int64) & 0xFFFFFFFF
+        lens = (self._q_tail.reshape(-1).to(torch.int64) - head) & 0xFFFFFFFF          # ring entries, tombstones included
+        qid = torch.repeat_interleave(torch.arange(R * N, device=dev), lens)
+        j = torch.arange(int(lens.sum().item()), device=dev) - (torch.cumsum(lens, 0) - lens)[qid]
+        recs = self._ring.view(R * N, cap, 4)[qid, (head[qid] + j) & (cap - 1)]
+        snap = {"version": 1, "n_nodes": N, "sum_deg": self.topology.sum_deg, "replicas": R,
+                "replica_base": self.replica_base, "rng": self.rng, "seed": self.seed, "clock": int(self.clock),
+                "bandwidth": self.bandwidth, "transtime": self.transtime, "is_drop": bool(self.is_drop),
+                "queue_len": lens.cpu().numpy().reshape(R, N), "queue_rec": recs.cpu().numpy(),
+                "counters": self._counters.cpu().numpy(), "status": self._status.cpu().numpy(),
+                "pending": [list(pk) for pk in self.__dict__.get("_pending") or []],
+                "agent_class": type(self._agent).__name__,
+                "agent": {k: v.cpu().numpy() for k, v in self._agent._dev.items()}}
+        if self._general:
+            snap["general"] = {k: getattr(self, "_" + k).cpu().numpy()
+                               for k in ("link_sent", "event_heap", "event_count", "event_rec", "q_dead")}
+        if self.rng == "trace":
+            snap["rng_state"] = [rs.get_state() for rs in self._rs]
+        return snap
+
+    def restore(self, snap):
+        """Loads a `snapshot()` into this network and its bound agent (same topology, replica count, timing model and
+        agent class); the run then continues exactly as the snapshotted one would have."""
+        import torch
+        R, N, cap, dev = self.replicas, self.topology.N, self.queue_capacity, self.device
+        want = (N, self.topology.sum_deg, R, self.replica_base, self.rng, self.bandwidth, self.transtime,
+                type(self._agent).__name__)
+        got = (snap["n_nodes"], snap["sum_deg"], snap["replicas"], snap["replica_base"], snap["rng"], snap["bandwidth"],
+               snap["transtime"], snap["agent_class"])
+        if snap.get("version") != 1 or want != got:
+            raise ValueError(f"snapshot does not fit this network: {got} vs {want}")
+        lens = torch.from_numpy(np.ascontiguousarray(snap["queue_len"], dtype=np.int64)).reshape(-1).to(dev)
+        if int(lens.max().item()) > cap:
+            raise OverflowError(f"snapshot holds a queue of {int(lens.max().item())} entries; queue_capacity is {cap}")
+        qid = torch.repeat_interleave(torch.arange(R * N, device=dev), lens)
+        j = torch.arange(int(lens.sum().item()), device=dev) - (torch.cumsum(lens, 0) - lens)[qid]
+        self._ring.view(R * N, cap, 4)[qid, j] = torch.from_numpy(np.ascontiguousarray(snap["queue_rec"], dtype=np.int32)).to(dev)
+        self._q_head.zero_()
+        self._q_tail.copy_(lens.reshape(R, N).to(torch.int32))
+        self._counters.copy_(torch.from_numpy(np.ascontiguousarray(snap["counters"])))
+        self._status.copy_(torch.from_numpy(np.ascontiguousarray(snap["status"])))
+        if self._general:
+            for k, v in snap["general"].items():
+                getattr(self, "_" + k).copy_(torch.from_numpy(np.ascontiguousarray(v)))
+        for k, v in snap["agent"].items():
+            self._agent._dev[k].copy_(torch.from_numpy(np.ascontiguousarray(v)))
+        if self.rng == "trace":
+            for rs, st in zip(self._rs, snap["rng_state"]):
+                rs.set_state(st)
+        self.seed = int(snap["seed"])                               # Philox key of the runs that follow
+        self.clock = int(snap["clock"])
+        self._pending = [list(map(tuple, pk)) for pk in snap["pending"]] or [[] for _ in range(R)]
+        self._desync, self._last_rewards = False, None
+        if self.__dict__.get("_sched") is not None:                 # injection schedules prefetched for the old state
+            torch.cuda.synchronize(dev)
+            self._sched["ready"] = [None, None]
+
+    def save_state(self, filename):
+        """`snapshot()` pickled to a file."""
+        import pickle
+        with open(filename, "wb") as f:
+            pickle.dump(self.snapshot(), f, protocol=4)
+
+    def load_state(self, filename):
+        import pickle
+        with open(filename, "rb") as f:
+            self.restore(pickle.load(f))
+
     # ------------------------------------------------------------------ the loop's pieces, one call at a time
     # Network.train fuses these on the device; they are also available separately with the reference's
     # semantics (one kernel launch per call, so this path is for inspection and custom loops, not for speed).

@@ -132,3 +132,52 @@ def test_manual_loop_equals_fused_train(policy, rng, R):
     if policy != "Shortest":                           # Shortest.learn is the base class's no-op, as in the reference
         with pytest.raises(NotImplementedError):
             ma.learn([])                               # not the list of the latest step
+
+
+@pytest.mark.parametrize("policy,rng,nkw,akw", [
+    ("Qroute", "philox", {}, {}),
+    ("HybridQ", "philox", {}, {}),
+    ("MaHybridQ", "philox", {}, {}),
+    ("CDRQ", "trace", {}, {}),
+    ("GlobalRoute", "philox", {}, {}),
+    ("Shortest", "trace", {}, {"multiway": True}),
+    ("Qroute", "philox", {"transtime": 3, "bandwidth": 2, "is_drop": True}, {}),
+    ("Shortest", "trace", {"transtime": 2}, {}),
+])
+def test_snapshot_restore_continues_bit_for_bit(policy, rng, nkw, akw, tmp_path):
+    """environment-state snapshots.  run(T1) -> snapshot -> run(T2) must equal a fresh network that
+    loads the snapshot (from a file, into rings of another capacity) and runs T2."""
+    import rlrouting_b200 as rb
+    cls = getattr(rb, policy)
+    lr = {"q": 0.1, "p": 0.001 if policy == "MaHybridQ" else 0.1}
+    R, T1, T2, lam = 5, 150, 120, 2.0
+
+    def make(cap):
+        nw = rb.Network("6x6.net", replicas=R, rng=rng, seed=7, replica_base=40, queue_capacity=cap, **nkw)
+        ag = cls(nw, **akw)
+        nw.agent = ag
+        return nw, ag
+
+    a, ag_a = make(512)
+    a.train(T1, lam, lr=lr)
+    a.save_state(tmp_path / "state.pkl")
+    res_a = a.train(T2, lam, lr=lr, hop=True)
+    b, ag_b = make(1024)
+    b.load_state(tmp_path / "state.pkl")
+    assert b.clock == T1
+    res_b = b.train(T2, lam, lr=lr, hop=True)
+    assert np.array_equal(res_a["route_time"], res_b["route_time"]) and np.array_equal(res_a["hop"], res_b["hop"])
+    ca, cb = a.counters(), b.counters()
+    assert all(np.array_equal(ca[k], cb[k]) for k in ca)
+    for name in ag_a._dev:
+        assert np.array_equal(ag_a._dev[name].cpu().numpy(), ag_b._dev[name].cpu().numpy()), name
+    for r in (0, R - 1):
+        for x in range(36):
+            assert np.array_equal(a.queue_array(x, r), b.queue_array(x, r))
+    if a._general:
+        assert np.array_equal(a._event_count.cpu().numpy(), b._event_count.cpu().numpy())
+        assert np.array_equal(a._link_sent.cpu().numpy(), b._link_sent.cpu().numpy())
+    with pytest.raises(ValueError, match="does not fit"):
+        other = rb.Network("6x6.net", replicas=R + 1, rng=rng, seed=7, **nkw)
+        other.agent = cls(other, **akw)
+        other.load_state(tmp_path / "state.pkl")
