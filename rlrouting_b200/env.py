@@ -782,9 +782,17 @@ class Network:
                 nxt = (self.clock + (s0 + K) * freq * slot, plan[ci + 1] * freq) if ci + 1 < len(plan) else None
                 self._schedule(h, rp, self.clock + s0 * freq * slot, K * freq, lam_key, lam.max(), nxt)
             KS = K * freq                               # Network.step calls of this launch (K iterations of the loop)
-            d_rec = torch.empty((KS, R, 2), dtype=torch.int64, device=dev) if per_step else None
+            # per-chunk device buffers are kept across calls (a fresh 32 MB torch.empty costs ~0.2 ms each); the call
+            # ends with copier.synchronize(), so nothing still reads them when the next call writes them
+            keepbuf = len(plan) <= 2                    # long runs in many launches allocate per launch instead
+            d_rec = d_rt = None
+            if per_step and keepbuf:
+                d_rec = self._scratch(("rec", ci), (KS, R, 2), torch.int64)
+                d_rt = self._scratch(("rt", ci), (KS, R), torch.float64)
+            elif per_step:
+                d_rec = torch.empty((KS, R, 2), dtype=torch.int64, device=dev)
+                d_rt = torch.empty((KS, R), dtype=torch.float64, device=dev)
             rp.metrics = d_rec.data_ptr() if d_rec is not None else None
-            d_rt = torch.empty((KS, R), dtype=torch.float64, device=dev) if per_step else None
             d_hop = torch.empty((KS, R), dtype=torch.float64, device=dev) if host_hop is not None else None
             rp.route_time_out = d_rt.data_ptr() if d_rt is not None else None
             rp.hop_out = d_hop.data_ptr() if d_hop is not None else None
@@ -808,7 +816,8 @@ class Network:
                 copier.wait_event(done)
                 with torch.cuda.stream(copier):
                     host_rt[s0:s0 + K].copy_(d_rt, non_blocking=True)          # contiguous rows on both sides
-                    d_rt.record_stream(copier)
+                    if freq > 1 or not keepbuf:
+                        d_rt.record_stream(copier)
                     if d_hop is not None:
                         host_hop[s0:s0 + K].copy_(d_hop, non_blocking=True)
                         d_hop.record_stream(copier)
