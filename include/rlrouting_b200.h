@@ -143,8 +143,9 @@ typedef struct {
     int32_t phase;            /* 0 or 3: fused inject+step+learn (Network.train); 1: Network.step only (env.py:333-365,
                                  rewards saved, nothing learned); 2: agent.learn of the rewards saved by phase 1.
                                  Phases 1 and 2 need n_steps == 1 and `rewards`. */
-    void *rewards;            /* device [R][N] 48-byte Reward records (env.py:52-70): packet record (16 B);
-                                 {sending | k << 1 | y << 9 | dest << 17, q_y, 0, 0}; {max_Q_y, max_Q_x_d} */
+    void *rewards;            /* device [R][N] 64-byte Reward records (env.py:52-70): packet record (16 B);
+                                 {sending | k << 1 | y << 9 | dest << 17, q_y, q_x ('dual' mode), 0};
+                                 {max_Q_y (CQ/CDRQ: max_Q_f), max_Q_x_d (CQ/CDRQ: C_f)}; {C_b, max_Q_b} (CDRQ) */
     /* outputs (device pointers, may be NULL) */
     void *metrics;            /* [n_steps][R] 16-byte records {int64 route_time, uint32 end_packets, uint32 hops}:
                                  cumulative counters after each step (env.py:409-413); step-major so a chunk

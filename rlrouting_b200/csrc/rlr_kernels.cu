@@ -82,7 +82,7 @@ struct StepParams {
     int inj_cap, add_entropy;
     int is_drop;                  // Network(is_drop=True), env.py:355-360
     int phase;                    // bit 0: inject + send + arrive (Network.step); bit 1: agent.learn
-    uint4 *rewards;               // [R][N][3] saved Reward records (phase 1 writes, phase 2 reads)
+    uint4 *rewards;               // [R][N][4] saved Reward records (phase 1 writes, phase 2 reads)
     const unsigned *inj_events;
     unsigned long long seed;
     long long replica_base;
@@ -584,10 +584,11 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         bool sending = false;
         int d = 0, k = 0, y = 0;
         double oldq = 0.0, max_qy = 0.0, max_qxd = 0.0, rwd = 0.0, c_f = 0.0;
+        int qy_dual = 1;                            // 'dual' mode q_y = max(1, len(nodes[y].queue)), env.py:156
         double sm[MAXD];
         if (live && !do_env) {
             // learn-only call (agent.learn after Network.step): restore this node's Reward of that step
-            const uint4 *rw = p.rewards + ((size_t)r * N + x) * 3;
+            const uint4 *rw = p.rewards + ((size_t)r * N + x) * 4;
             const uint4 meta = rw[1];
             sending = (meta.x & 1u) != 0u;
             if (sending) {
@@ -595,6 +596,14 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 rwd = (double)(-(int)meta.y - 1);
                 const double2 mq = *reinterpret_cast<const double2 *>(rw + 2);
                 max_qy = mq.x; max_qxd = mq.y;
+                if (IS_CQ) c_f = mq.y;
+                if (DUAL) {                         // what CDRQ.learn reads from the other senders' rewards
+                    qy_dual = (int)meta.y;
+                    s_bk[t] = *reinterpret_cast<const double2 *>(rw + 3);
+                    s_qxi[t] = (int)meta.z;
+                    s_dk[t] = (unsigned short)(d | (k << 8));
+                    s_src[t] = (unsigned short)(rw[0].x >> 16);
+                }
                 if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) oldq = Qx[d * deg + k];
                 if (IS_PG) softmax_row<MAXD>(Thx + d * deg, deg, sm);
                 if (POLICY == RLR_POLICY_MAHYBRIDQ) { s_r[t] = rwd; s_qy[t] = max_qy; s_qx[t] = max_qxd; }
@@ -803,14 +812,15 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 if (POLICY == RLR_POLICY_MAHYBRIDQ) { s_r[t] = rwd; s_qy[t] = max_qy; s_qx[t] = max_qxd; }
                 ++my_sends;
                 if (!do_learn && p.rewards) {                                   // Network.step(): hand the Reward to the host
-                    uint4 *rw = p.rewards + ((size_t)r * N + x) * 3;
+                    uint4 *rw = p.rewards + ((size_t)r * N + x) * 4;
                     rw[0] = rec;
                     rw[1] = make_uint4(1u | ((unsigned)k << 1) | ((unsigned)y << 9) | ((unsigned)d << 17),
-                                       (unsigned)(clock - (int)rec.w), 0u, 0u);
-                    *reinterpret_cast<double2 *>(rw + 2) = make_double2(max_qy, max_qxd);
+                                       (unsigned)(clock - (int)rec.w), DUAL ? (unsigned)s_qxi[t] : 0u, 0u);
+                    *reinterpret_cast<double2 *>(rw + 2) = make_double2(max_qy, IS_CQ ? c_f : max_qxd);
+                    if (DUAL) *reinterpret_cast<double2 *>(rw + 3) = s_bk[t];
                 }
             } else if (!do_learn && p.rewards) {
-                p.rewards[((size_t)r * N + x) * 3 + 1] = make_uint4(0u, 0u, 0u, 0u);
+                p.rewards[((size_t)r * N + x) * 4 + 1] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
         if (POLICY == RLR_POLICY_MAHYBRIDQ && t >= GN && do_learn) {
@@ -1020,6 +1030,10 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         RLR_T(2);                                   // C
         // ---- D. agent.learn ----
         if (!do_learn) {
+            if (DUAL && live && sending && p.rewards) {     // Network.step() in 'dual' mode: q_y needs every node's send (env.py:156)
+                const unsigned ly = s_len[gbase + y], tpy = s_tp[gbase + y];
+                p.rewards[((size_t)r * N + x) * 4 + 1].y = max(1u, ly - ((y < x && tpy != kNoSend) ? 1u : 0u));
+            }
         } else if (POLICY == RLR_POLICY_QROUTE) {
             if (sending) {                                                      // qroute.py:40-44
                 const double tq = __dmul_rn(p.discount, max_qy);
@@ -1074,8 +1088,9 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                     const unsigned ly = s_len[yt];
                     const unsigned tpy = s_tp[yt];
                     // len(nodes[y].queue) as the sequential node loop sees it: y already popped its packet if y < x and y sent
-                    // (with busy links a non-empty queue does not imply a send)
-                    const double r_f = -(double)(int)max(1u, ly - ((y < x && tpy != kNoSend) ? 1u : 0u));
+                    // (with busy links a non-empty queue does not imply a send); a learn-only call gets it from the saved reward
+                    if (do_env) qy_dual = (int)max(1u, ly - ((y < x && tpy != kNoSend) ? 1u : 0u));
+                    const double r_f = -(double)qy_dual;
                     // does y's backward update land on this very cell?  (y sends to me a packet whose source is my dest)
                     const bool hit = tpy != kNoSend && (tpy & 0xFFu) == (unsigned)x && s_src[yt] == (unsigned short)d;
                     const double2 bk = s_bk[yt];
@@ -1883,8 +1898,6 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     }
     if (n_steps >= (1 << 24) - 1) return fail(RLR_E_INVALID, "rlr_run_steps: at most 2^24 - 2 steps per call");
     if (rp->phase < 0 || rp->phase > 3) return fail(RLR_E_INVALID, "rlr_run_steps: phase must be 0 (= 3), 1, 2 or 3");
-    if ((rp->phase == 1 || rp->phase == 2) && (h->policy == RLR_POLICY_CQ || h->policy == RLR_POLICY_CDRQ))
-        return fail(RLR_E_UNSUPPORTED, "rlr_run_steps: the split Network.step / agent.learn phases are not available for CQ / CDRQ");
     if ((rp->phase == 1 || rp->phase == 2) && (n_steps != 1 || !rp->rewards))
         return fail(RLR_E_INVALID, "rlr_run_steps: the split phases (Network.step / agent.learn) run one step and need the rewards buffer");
     if ((rp->route_time_out || rp->hop_out || rp->droprate_out) && !rp->metrics)

@@ -542,9 +542,6 @@ class Network:
         import torch
         duration = _as_int(duration, "duration")
         h = self._handle_or_raise()
-        if self._agent._kernel_policy in (nat.POLICY_CQ, nat.POLICY_CDRQ):
-            raise NotImplementedError("Network.step / agent.learn as separate calls are not implemented for CQ / CDRQ; "
-                                      "use Network.train")
         R, N = self.replicas, self.topology.N
         pend = self.__dict__.get("_pending") or [[] for _ in range(R)]
         per_node = np.zeros((R, N), dtype=np.int64)
@@ -559,7 +556,7 @@ class Network:
                 sched[r, sv, fill[r, sv]] = dv              # local step 0
                 fill[r, sv] += 1
         d_sched = torch.from_numpy(sched.view(np.int32)).to(self.device)
-        rew = self._scratch("rewards", (R, N, 12), torch.int32)
+        rew = self._scratch("rewards", (R, N, 16), torch.int32)
         rp = self._run_params(self._agent, {})
         self._timing(rp, duration, 1)
         rp.inject_mode, rp.inj_events, rp.inj_cap = nat.INJECT_TRACE, d_sched.data_ptr(), cap
@@ -582,12 +579,17 @@ class Network:
                 y, dest = (meta >> 9) & 0xFF, meta >> 17
                 w0 = int(rec[0]) & 0xFFFFFFFF
                 pkt = Packet(w0 >> 16, w0 & 0xFFFF, int(rec[2]), int(rec[1]), int(rec[3]))
-                mq = rec[8:12].view(np.float64)
+                mq = rec[8:16].view(np.float64)
+                pol = self._agent._kernel_policy
                 info = {"q_y": int(rec[5]), "t_y": 1}
-                if self._agent._kernel_policy in (nat.POLICY_QROUTE, nat.POLICY_HYBRIDQ, nat.POLICY_MAHYBRIDQ):
+                if pol in (nat.POLICY_QROUTE, nat.POLICY_HYBRIDQ, nat.POLICY_MAHYBRIDQ):
                     info["max_Q_y"] = float(mq[0])
-                if self._agent._kernel_policy in (nat.POLICY_HYBRIDQ, nat.POLICY_MAHYBRIDQ):
+                if pol in (nat.POLICY_HYBRIDQ, nat.POLICY_MAHYBRIDQ):
                     info["max_Q_x_d"] = float(mq[1])
+                if pol in (nat.POLICY_CQ, nat.POLICY_CDRQ):                     # qroute.py:72-78, 107-115
+                    info["max_Q_f"], info["C_f"] = float(mq[0]), float(mq[1])
+                if pol == nat.POLICY_CDRQ:                                      # env.py:154-160 ('dual' mode)
+                    info.update({"t_y": 0, "q_x": int(rec[6]), "t_x": 0, "C_b": float(mq[2]), "max_Q_b": float(mq[3])})
                 lst.append(Reward(x, pkt, int(y), info))
             out.append(lst)
         result = out[0] if R == 1 else out
@@ -609,7 +611,7 @@ class Network:
         rp = self._run_params(agent, lr)
         rp.inject_mode, rp.inj_events, rp.inj_cap = nat.INJECT_TRACE, empty.data_ptr(), 2
         self._timing(rp, self.__dict__.get("_last_duration", 1), 1)
-        rp.clock0, rp.phase, rp.rewards = self.clock - rp.slot, 2, self._scratch("rewards", (R, N, 12), torch.int32).data_ptr()
+        rp.clock0, rp.phase, rp.rewards = self.clock - rp.slot, 2, self._scratch("rewards", (R, N, 16), torch.int32).data_ptr()
         nat.check(nat.lib().rlr_run_steps(h, 1, C.byref(rp), self._stream_ptr()))
         self.launch_count += 1
         self._last_rewards = None

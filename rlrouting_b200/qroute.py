@@ -88,9 +88,6 @@ class CQ(Qroute):
     def clean(self):
         pass        # Network.reset re-initialises the confidence table on the device (rlr_reset), qroute.py:66-71
 
-    def learn(self, rewards, lr={}):
-        raise NotImplementedError("CQ / CDRQ learn inside Network.train on the device; the split Network.step / "
-                                  "agent.learn path is not implemented for them")
 
 
 class CDRQ(CQ):

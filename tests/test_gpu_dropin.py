@@ -93,7 +93,9 @@ def test_unsupported_policies_and_calls_raise(compat_path):
 
 
 @pytest.mark.parametrize("policy,rng,R", [("Qroute", "trace", 1), ("Shortest", "trace", 1), ("HybridQ", "philox", 3),
-                                          ("MaHybridQ", "philox", 2), ("Qroute", "philox", 4)])
+                                          ("MaHybridQ", "philox", 2), ("Qroute", "philox", 4), ("CQ", "trace", 1),
+                                          ("CQ", "philox", 3), ("CDRQ", "trace", 1), ("CDRQ", "philox", 3),
+                                          ("GlobalRoute", "philox", 2)])
 def test_manual_loop_equals_fused_train(policy, rng, R):
     """The reference's own loop body (env.py:400-408) spelled out by the caller — inject(new_packet(l)); r = step(1);
     agent.learn(r) — must leave exactly the state Network.train leaves, and the rewards must be the send list."""
@@ -117,13 +119,16 @@ def test_manual_loop_equals_fused_train(policy, rng, R):
         for rr, lst in enumerate([r] if R == 1 else r):
             sends[rr] += [(manual.clock, w.source, w.action, w.dest) for w in lst]
             for w in lst:
-                assert w.agent_info["t_y"] == 1 and w.agent_info["q_y"] >= 0 and w.packet.dest == w.dest
+                assert w.agent_info["t_y"] == (0 if policy == "CDRQ" else 1) and w.agent_info["q_y"] >= 0 and w.packet.dest == w.dest
+                if policy == "CDRQ":                   # Node._build_info_dual (env.py:154-160) + CDRQ.get_info (qroute.py:107-115)
+                    assert w.agent_info["q_y"] >= 1 and w.agent_info["q_x"] >= 1 and w.agent_info["t_x"] == 0
+                    assert set(w.agent_info) >= {"max_Q_b", "max_Q_f", "C_b", "C_f"}
         ma.learn(r, lr=lr) if lr else ma.learn(r)
     cf, cm = fused.counters(), manual.counters()
     for k in cf:
         assert np.array_equal(cf[k], cm[k]), k
     for name in fa._dev:
-        if name in ("Qtable", "Theta", "Trace"):
+        if name in ("Qtable", "Theta", "Trace", "confidence"):
             assert np.array_equal(fa.table_array(name).view(np.int64), ma.table_array(name).view(np.int64)), name
     for rr in range(R):
         assert np.array_equal(np.array(sends[rr], dtype=np.int32).reshape(-1, 4), fused.sendlog_rows(rr))
