@@ -382,23 +382,32 @@ def _random_net(rng, n, extra, max_deg):
     return "".join(f"1000 {i} 0 0 0\n" for i in range(n)) + "".join(f"2000 {a} {b} 0\n" for a, b in edges)
 
 
-@pytest.mark.parametrize("policy,n,extra,max_deg,R,T,lam", [
-    ("Qroute", 255, 700, 16, 3, 150, 6.0),          # maximum node count and degree: MAXD = 16, MAXW = 9 code paths
-    ("Shortest", 255, 300, 12, 2, 200, 8.0),
-    ("CDRQ", 97, 200, 9, 2, 150, 4.0),
-    ("HybridQ", 70, 120, 7, 3, 120, 3.0),
-    ("MaHybridQ", 127, 200, 10, 2, 60, 3.0),        # MaHybridQ's limit (NumPy single pairwise block: n < 128 senders)
-    ("Qroute", 2, 0, 1, 5, 300, 0.8),               # smallest graph
-    ("CQ", 33, 40, 6, 4, 200, 2.0),
-    ("GlobalRoute", 150, 250, 11, 2, 60, 6.0),
+@pytest.mark.parametrize("policy,n,extra,max_deg,R,T,lam,nkw", [
+    ("Qroute", 255, 700, 16, 3, 150, 6.0, {}),      # maximum node count and degree: MAXD = 16, MAXW = 9 code paths
+    ("Shortest", 255, 300, 12, 2, 200, 8.0, {}),
+    ("CDRQ", 97, 200, 9, 2, 150, 4.0, {}),
+    ("HybridQ", 70, 120, 7, 3, 120, 3.0, {}),
+    ("MaHybridQ", 127, 200, 10, 2, 60, 3.0, {}),    # MaHybridQ's limit (NumPy single pairwise block: n < 128 senders)
+    ("Qroute", 2, 0, 1, 5, 300, 0.8, {}),           # smallest graph
+    ("CQ", 33, 40, 6, 4, 200, 2.0, {}),
+    ("GlobalRoute", 150, 250, 11, 2, 60, 6.0, {}),
+    # the general timing model (events in flight, busy links, queue scan) on the same kinds of graph
+    ("Qroute", 255, 700, 16, 2, 100, 6.0, dict(transtime=2)),
+    ("Shortest", 200, 300, 12, 2, 150, 8.0, dict(transtime=3, bandwidth=2)),
+    ("HybridQ", 70, 120, 7, 3, 100, 3.0, dict(transtime=2, is_drop=True)),
+    ("CDRQ", 97, 200, 9, 2, 120, 4.0, dict(transtime=4, bandwidth=3)),
+    ("MaHybridQ", 40, 60, 6, 2, 80, 2.0, dict(transtime=2)),
+    ("GlobalRoute", 60, 90, 8, 2, 60, 4.0, dict(transtime=2)),
+    ("Qroute", 2, 0, 1, 4, 200, 0.8, dict(transtime=5)),
+    ("CQ", 33, 40, 6, 3, 150, 2.0, dict(transtime=2, bandwidth=0)),     # bandwidth 0: nothing can ever be sent
 ])
-def test_random_topologies_match_oracle(policy, n, extra, max_deg, R, T, lam, tmp_path):
+def test_random_topologies_match_oracle(policy, n, extra, max_deg, R, T, lam, nkw, tmp_path):
     """Random graphs written as .net text (degree-1 leaves, hubs, up to the supported maxima): device == oracle."""
     import rlrouting_b200 as rb
     rng = np.random.default_rng(n * 1000 + extra)
     path = tmp_path / "g.net"
     path.write_text(_random_net(rng, n, extra, max_deg))
-    nw = rb.Network(str(path), replicas=R, rng="philox", seed=17, replica_base=5, queue_capacity=1024)
+    nw = rb.Network(str(path), replicas=R, rng="philox", seed=17, replica_base=5, queue_capacity=1024, **nkw)
     agent = _classes()[policy](nw)
     nw.agent = agent
     topo = nw.topology
@@ -407,12 +416,13 @@ def test_random_topologies_match_oracle(policy, n, extra, max_deg, R, T, lam, tm
     res = nw.train(T, lam, lr=lr)
     envs = []
     for r in range(R):
-        e = O.OracleEnv(topo.links, policy, seed=17, replica=5 + r)
+        e = O.OracleEnv(topo.links, policy, seed=17, replica=5 + r, is_drop=nkw.get("is_drop", False),
+                        bandwidth=nkw.get("bandwidth", 1), transtime=nkw.get("transtime", 1))
         if q0 is not None:
             e.set_qtable(q0[r])
         envs.append(e)
     sends, rt, en = O.run_many(envs, T, lam, lr_q=lr["q"], lr_p=lr["p"], lr_e=lr["e"], metrics=True)
-    assert sends > 0 or lam == 0
+    assert sends > 0 or lam == 0 or nkw.get("bandwidth") == 0
     _compare_batch(nw, agent, envs, rt, en, res)
 
 

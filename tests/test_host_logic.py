@@ -154,3 +154,17 @@ def test_integration_doc_ctypes_stub_matches_the_library():
     nat.lib().rlr_struct_sizes(sizes)
     assert list(sizes) == [C.sizeof(ns[k]) for k in ("Topology", "Config", "Buffers", "RunParams")]
     assert [f[0] for f in ns["RunParams"]._fields_] == [f[0] for f in nat.RunParams._fields_]
+
+
+def test_integer_timing_arguments():
+    """slot / freq / transtime / bandwidth are integers on the device (integer-valued floats are accepted)."""
+    from rlrouting_b200.env import _as_int, trace_schedule
+    assert _as_int(2, "slot") == 2 and _as_int(3.0, "transtime") == 3 and _as_int(np.int64(4), "freq") == 4
+    for bad in (0.5, 2.25, True):
+        with pytest.raises(NotImplementedError):
+            _as_int(bad, "slot")
+    # freq > 1: iteration i of train's loop injects at Network.step call i * freq (env.py:400-403)
+    cnt = np.array([1, 0, 2], dtype=np.int32)
+    pairs = np.array([[0, 1], [2, 0], [2, 1]], dtype=np.int32)
+    ev, node = trace_schedule(cnt, pairs, 3, 0, 3, freq=3)
+    assert list(node) == [0, 2, 2] and list(ev >> 8) == [0, 6, 6] and list(ev & 0xFF) == [1, 0, 1]
