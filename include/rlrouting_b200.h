@@ -100,7 +100,7 @@ typedef struct {
     int32_t *topo_col;        /* [sum_deg]                                                   */
     uint8_t *heap_pos;        /* [(N+1)*N] heap_pos[k*N + rank]: pop position among k ties   */
     /* GlobalRoute only (per replica, persist across calls) */
-    uint8_t *gr_next_hop;     /* [R][N*N] action index chosen at x for dest d (the single True of `choice`) */
+    uint16_t *gr_choice_mask; /* [R][N*N] GlobalRoute.choice[x][d] as bits (bit j = links[x][j]); one bit unless multiway */
     int32_t *gr_distance;     /* [R][N*N] GlobalRoute.distance as integers, 0x3FFFFFFF = inf   */
     uint16_t *choice_mask;    /* [N][N] Shortest: bit j = choice[x][d][j] (all optimal neighbours with multiway=True);
                                  needed when shortest_random is set */
@@ -138,8 +138,8 @@ typedef struct {
     double discount_trace;    /* multi_agent.py:10                                           */
     double conf_decay;        /* CQ(decay=...) qroute.py:59                                  */
     int32_t clock0;           /* Network.clock before the first step                         */
-    int32_t shortest_random;  /* Shortest(random=True): next hop drawn uniformly from the choice mask (shortest.py:40-41) */
-    int32_t reserved1;
+    int32_t shortest_random;  /* Shortest / GlobalRoute(random=True): next hop drawn uniformly from the choice mask (shortest.py:40-41) */
+    int32_t multiway;         /* GlobalRoute(multiway=True): the per-step recomputation keeps every optimal neighbour */
     int32_t phase;            /* 0 or 3: fused inject+step+learn (Network.train); 1: Network.step only (env.py:333-365,
                                  rewards saved, nothing learned); 2: agent.learn of the rewards saved by phase 1.
                                  Phases 1 and 2 need n_steps == 1 and `rewards`. */
@@ -204,7 +204,9 @@ int rlr_reset(rlr_handle_t *h, void *stream);
 int rlr_init_tables(rlr_handle_t *h, double initP, void *stream);
 
 /* ---- Shortest.__init__ + _calc_distance (shortest.py:20-58): fills distance, choice, next_hop (first True of the
- *      mask) and, if bound, choice_mask; multiway != 0 keeps every optimal neighbour (shortest.py:57-58) ---- */
+ *      mask) and, if bound, choice_mask; multiway != 0 keeps every optimal neighbour (shortest.py:57-58).
+ *      For a GlobalRoute handle: GlobalRoute.__init__ (shortest.py:84-91), every replica's gr_choice_mask / gr_distance
+ *      with node weights 1 + queue_size ---- */
 int rlr_build_shortest_tables(rlr_handle_t *h, int32_t multiway, void *stream);
 
 /* ---- host helper (no device work): replays NumPy's legacy RandomState stream for n_steps calls of

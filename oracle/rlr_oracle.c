@@ -337,6 +337,8 @@ void orc_globalroute_calc(orc_t *o)
                         c[j] = 1;
                         changing = 1;
                     }
+                    if (o->multiway && isfinite(nd) && o->distance[x * N + z] == nd)     /* shortest.py:57-58 */
+                        o->choice[o->toff[x] + (int64_t)z * deg + j] = 1;
                 }
             }
         }

@@ -52,7 +52,7 @@ class Config(C.Structure):
 class Buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "q_table", "theta", "trace", "ring", "q_head", "q_tail", "counters", "status", "next_hop",
-        "distance", "choice", "topo_row_ptr", "topo_col", "heap_pos", "gr_next_hop", "gr_distance", "choice_mask", "gr_qs_off",
+        "distance", "choice", "topo_row_ptr", "topo_col", "heap_pos", "gr_choice_mask", "gr_distance", "choice_mask", "gr_qs_off",
         "link_sent", "event_heap", "event_count", "event_rec", "q_dead")]
 
 
@@ -62,7 +62,7 @@ class RunParams(C.Structure):
                 ("enlam", C.c_void_p), ("inj_thr", C.c_void_p), ("seed", C.c_uint64),
                 ("lr_q", C.c_double), ("lr_p", C.c_double), ("lr_e", C.c_double),
                 ("discount", C.c_double), ("discount_trace", C.c_double), ("conf_decay", C.c_double),
-                ("clock0", C.c_int32), ("shortest_random", C.c_int32), ("reserved1", C.c_int32), ("phase", C.c_int32),
+                ("clock0", C.c_int32), ("shortest_random", C.c_int32), ("multiway", C.c_int32), ("phase", C.c_int32),
                 ("rewards", C.c_void_p),
                 ("metrics", C.c_void_p), ("route_time_out", C.c_void_p), ("hop_out", C.c_void_p),
                 ("metrics2", C.c_void_p), ("droprate_out", C.c_void_p),

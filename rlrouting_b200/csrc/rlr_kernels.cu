@@ -71,7 +71,8 @@ struct StepParams {
     const unsigned char *next_hop;
     const unsigned short *choice_mask;    // Shortest(random=True): [N*N] bit j = choice[x][d][j]
     int shortest_random;
-    unsigned char *gr_next_hop;   // GlobalRoute: [R][N*N] per-replica next-hop tables (persist across launches)
+    unsigned short *gr_choice_mask;   // GlobalRoute: [R][N*N] per-replica choice masks, bit j = choice[x][d][j] (persist across launches)
+    int gr_multiway;              // GlobalRoute(multiway=True): keep every optimal neighbour (shortest.py:57-58)
     int *gr_distance;             // GlobalRoute: [R][N*N] distances (0x3FFFFFFF = inf)
     const int *gr_qs_off;         // GlobalRoute: [R][N] queue_size - len(queue) (non-zero only after Network.reset)
     double *Q, *Theta, *Trace;
@@ -317,7 +318,7 @@ struct SmemLayout {
         tp = o; o += align16((size_t)GN * 2);
         heappos = o; o += align16((size_t)(N + 1) * N);
         nexthop = o; o += (policy == RLR_POLICY_SHORTEST) ? align16((size_t)N * N * 2)      // u8 next hops or u16 choice masks
-                           : (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * N * N) : 0;
+                           : (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * N * N * 2) : 0;
         samp = o; o += align16((size_t)G * (ecap > N ? ecap : N) * 8);   // sample_route_time staging: (heap position, routing time) per delivery
         gr = o; o += (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * (N * N + N) * 4) : 0;   // distances + weights
         // general timing model: the event heap, this step's popped events, Node.sent per link, heap length + pop count
@@ -354,22 +355,26 @@ constexpr int kGrInf = 0x3FFFFFFF;
 // GlobalRoute._calc_distance (shortest.py:43-58 with mask = all off-diagonal, unit(y) = 1 + queue_size[y]) for ONE
 // destination column z: the columns of the distance matrix are independent, so thread z replays the reference's
 // sequential Gauss-Seidel (x, y in links[x]) sweeps on its own column.  dist/nh are [N][N] in shared memory, w[y] the
-// node weights.  A next hop is (re)written only on a strict improvement, like `choice` in the reference.
+// node weights.  mask[x][z] holds `choice[x][z]` as bits: reset to the improving neighbour on a strict improvement, and with
+// multiway every neighbour that ties the current distance is added, like the reference.
 __device__ __forceinline__ void gr_column(int z, int N, const int *rowptr, const unsigned short *col, const int *w,
-                                          int *dist, unsigned char *nh)
+                                          int *dist, unsigned short *mask, bool multiway)
 {
-    for (int x = 0; x < N; ++x) dist[x * N + z] = (x == z) ? 0 : kGrInf;
+    for (int x = 0; x < N; ++x) { dist[x * N + z] = (x == z) ? 0 : kGrInf; mask[x * N + z] = 0; }
     bool changing = true;
     while (changing) {
         changing = false;
         for (int x = 0; x < N; ++x) {
             const int rp = rowptr[x], deg = rowptr[x + 1] - rp;
             int cur = dist[x * N + z];
+            unsigned m = mask[x * N + z];
             for (int j = 0; j < deg; ++j) {
                 const int y = col[rp + j];
                 const int nd = dist[y * N + z] + w[y];
-                if (cur > nd) { cur = nd; dist[x * N + z] = nd; nh[x * N + z] = (unsigned char)j; changing = true; }
+                if (cur > nd) { cur = nd; dist[x * N + z] = nd; m = 1u << j; changing = true; }
+                if (multiway && nd < kGrInf && cur == nd) m |= 1u << j;          // shortest.py:57-58
             }
+            mask[x * N + z] = (unsigned short)m;
         }
     }
 }
@@ -454,7 +459,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     if (POLICY == RLR_POLICY_GLOBALROUTE)
         for (int i = t; i < G * N * N; i += blockDim.x) {
             const long long rr = rblock + i / (N * N);
-            s_nexthop[i] = rr < p.R ? p.gr_next_hop[rr * N * N + i % (N * N)] : 0;
+            reinterpret_cast<unsigned short *>(s_nexthop)[i] = rr < p.R ? p.gr_choice_mask[rr * N * N + i % (N * N)] : (unsigned short)0;
         }
     for (int i = t; i < G; i += blockDim.x) {
         s_rt32[i] = 0; s_sends[i] = 0; s_inj[i] = 0; s_end[i] = 0; s_hops[i] = 0; s_drop[i] = 0; s_injs[i] = 0;
@@ -647,7 +652,10 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                         const int dd = (int)(cand.x & 0xFFFFu);
                         int kk = 0;
                         if (POLICY == RLR_POLICY_GLOBALROUTE) {
-                            kk = s_nexthop[(g * N + x) * N + dd];
+                            const unsigned cm = reinterpret_cast<const unsigned short *>(s_nexthop)[(g * N + x) * N + dd];
+                            const int cnt = __popc(cm);
+                            const int idx = (p.shortest_random && cnt > 1) ? (int)__umulhi(ps.next(), (unsigned)cnt) : 0;
+                            kk = cm ? __fns(cm, 0, idx + 1) : 0;
                         } else if (POLICY == RLR_POLICY_SHORTEST) {
                             if (!p.shortest_random) {
                                 kk = s_nexthop[x * N + dd];
@@ -719,7 +727,15 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                         max_qxd = best;
                     }
                 } else if (POLICY == RLR_POLICY_GLOBALROUTE) {
-                    k = s_nexthop[(g * N + x) * N + d];                         // shortest.py:38-41 on this replica's table
+                    // shortest.py:38-41 on this replica's table: choices[0], or np.random.choice(choices) with random=True
+                    const unsigned cm = reinterpret_cast<const unsigned short *>(s_nexthop)[(g * N + x) * N + d];
+                    const int cnt = __popc(cm);
+                    int idx = 0;
+                    if (p.shortest_random && cnt > 1) {
+                        PhiloxStream ps(p.seed, stream_id, clock, x, 1);
+                        idx = (int)__umulhi(ps.next(), (unsigned)cnt);
+                    }
+                    k = cm ? __fns(cm, 0, idx + 1) : 0;
                 } else if (POLICY == RLR_POLICY_SHORTEST) {
                     if (!p.shortest_random) {
                         k = s_nexthop[x * N + d];                               // shortest.py:38-41, choices[0]
@@ -1067,7 +1083,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             // GlobalRoute.learn (shortest.py:99-104): recompute every distance with node weights 1 + queue_size[y]
             if (live) s_grw[gbase + x] = 1 + (int)(tail - head - ndead) + gr_off;
             __syncthreads();
-            if (live) gr_column(x, N, s_rowptr, s_col, s_grw + gbase, s_grdist + g * N * N, s_nexthop + g * N * N);
+            if (live) gr_column(x, N, s_rowptr, s_col, s_grw + gbase, s_grdist + g * N * N,
+                                reinterpret_cast<unsigned short *>(s_nexthop) + g * N * N, p.gr_multiway != 0);
         } else if (IS_CQ) {
             // CQ._update_qtable (qroute.py:80-93): eta = max(C, 1 - old_conf); Q += eta * (r + discount * max_Q - Q);
             // conf += eta * (C - conf); conf /= decay.  CDRQ (qroute.py:117-122) adds the backward update of
@@ -1267,7 +1284,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         for (int i = t; i < G * N * N; i += blockDim.x) {
             const long long rr = rblock + i / (N * N);
             if (rr < p.R) {
-                p.gr_next_hop[rr * N * N + i % (N * N)] = s_nexthop[i];
+                p.gr_choice_mask[rr * N * N + i % (N * N)] = reinterpret_cast<const unsigned short *>(s_nexthop)[i];
                 p.gr_distance[rr * N * N + i % (N * N)] = s_grdist[i];
             }
         }
@@ -1378,28 +1395,28 @@ __global__ void rlr_apsp_kernel(double *distance, unsigned char *choice, unsigne
 // GlobalRoute.__init__ (shortest.py:85-91): after Shortest.__init__ the mask is widened to everything off the diagonal
 // and the distances are recomputed from inf with queue_size = 0; every reachable (x, z) is strictly improved at least
 // once in that pass, so its `choice` entry is the one this kernel computes.  One CTA per replica, thread z = column z.
-__global__ void rlr_globalroute_init_kernel(unsigned char *gr_next_hop, int *gr_distance, const int *qs_off,
-                                            const int *row_ptr, const int *col, int N, int sdeg)
+__global__ void rlr_globalroute_init_kernel(unsigned short *gr_choice_mask, int *gr_distance, const int *qs_off,
+                                            const int *row_ptr, const int *col, int N, int sdeg, int multiway)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     int *dist = reinterpret_cast<int *>(smem);
     int *w = dist + N * N;
     int *rowptr = w + N;
     unsigned short *scol = reinterpret_cast<unsigned short *>(rowptr + N + 1);
-    unsigned char *nh = reinterpret_cast<unsigned char *>(scol + sdeg);
+    unsigned short *mask = scol + sdeg;
     const long long r = blockIdx.x;
     for (int i = threadIdx.x; i <= N; i += blockDim.x) rowptr[i] = row_ptr[i];
     for (int i = threadIdx.x; i < sdeg; i += blockDim.x) scol[i] = (unsigned short)col[i];
     for (int i = threadIdx.x; i < N; i += blockDim.x) w[i] = 1 + qs_off[r * N + i];
-    for (int i = threadIdx.x; i < N * N; i += blockDim.x) nh[i] = 0;
     __syncthreads();
-    for (int z = threadIdx.x; z < N; z += blockDim.x) gr_column(z, N, rowptr, scol, w, dist, nh);
+    for (int z = threadIdx.x; z < N; z += blockDim.x) gr_column(z, N, rowptr, scol, w, dist, mask, multiway != 0);
     __syncthreads();
     for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
-        gr_next_hop[r * N * N + i] = nh[i];
+        gr_choice_mask[r * N * N + i] = mask[i];
         gr_distance[r * N * N + i] = dist[i];
     }
 }
+
 
 __global__ void rlr_reduce_stats_kernel(const long long *counters, long long R, long long *out)
 {
@@ -1780,8 +1797,8 @@ int rlr_bind_buffers(rlr_handle_t *h, const rlr_buffers_t *b)
     if (h->policy == RLR_POLICY_SHORTEST && (!b->next_hop || !b->distance || !b->choice))
         return fail(RLR_E_INVALID, "rlr_bind_buffers: Shortest needs next_hop, distance and choice");
     const bool gr = h->policy == RLR_POLICY_GLOBALROUTE;
-    if (gr && (!b->gr_next_hop || !b->gr_distance || !b->gr_qs_off))
-        return fail(RLR_E_INVALID, "rlr_bind_buffers: GlobalRoute needs gr_next_hop, gr_distance and gr_qs_off");
+    if (gr && (!b->gr_choice_mask || !b->gr_distance || !b->gr_qs_off))
+        return fail(RLR_E_INVALID, "rlr_bind_buffers: GlobalRoute needs gr_choice_mask, gr_distance and gr_qs_off");
     if (!gr && h->policy >= RLR_POLICY_QROUTE && !b->q_table) return fail(RLR_E_INVALID, "rlr_bind_buffers: q_table required");
     if (!gr && h->policy >= RLR_POLICY_HYBRIDQ && !b->theta) return fail(RLR_E_INVALID, "rlr_bind_buffers: theta required");
     if (h->policy == RLR_POLICY_MAHYBRIDQ && !b->trace) return fail(RLR_E_INVALID, "rlr_bind_buffers: trace required");
@@ -1833,20 +1850,23 @@ int rlr_reset(rlr_handle_t *h, void *stream)
     return RLR_OK;
 }
 
+static int globalroute_init(rlr_handle_t *h, int multiway, void *stream)
+{
+    const size_t sm = (size_t)(h->N * h->N + h->N + h->N + 1) * 4 + (size_t)h->sdeg * 2 + (size_t)h->N * h->N * 2;
+    RLR_CUDA(cudaFuncSetAttribute((const void *)rlr_globalroute_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    rlr_globalroute_init_kernel<<<(unsigned)h->R, 128, sm, (cudaStream_t)stream>>>(h->bufs.gr_choice_mask, h->bufs.gr_distance,
+                                                                                    h->bufs.gr_qs_off, h->bufs.topo_row_ptr,
+                                                                                    h->bufs.topo_col, h->N, h->sdeg, multiway);
+    RLR_CUDA(cudaGetLastError());
+    return RLR_OK;
+}
+
 int rlr_init_tables(rlr_handle_t *h, double initP, void *stream)
 {
     if (!h || !h->bound) return fail(RLR_E_STATE, "rlr_init_tables: buffers not bound");
     if (h->policy == RLR_POLICY_SHORTEST) return RLR_OK;
     RLR_CUDA(cudaSetDevice(h->device));
-    if (h->policy == RLR_POLICY_GLOBALROUTE) {
-        const size_t sm = (size_t)(h->N * h->N + h->N + h->N + 1) * 4 + (size_t)h->sdeg * 2 + (size_t)h->N * h->N;
-        RLR_CUDA(cudaFuncSetAttribute((const void *)rlr_globalroute_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        rlr_globalroute_init_kernel<<<(unsigned)h->R, 128, sm, (cudaStream_t)stream>>>(h->bufs.gr_next_hop, h->bufs.gr_distance,
-                                                                                        h->bufs.gr_qs_off, h->bufs.topo_row_ptr,
-                                                                                        h->bufs.topo_col, h->N, h->sdeg);
-        RLR_CUDA(cudaGetLastError());
-        return RLR_OK;
-    }
+    if (h->policy == RLR_POLICY_GLOBALROUTE) return globalroute_init(h, 0, stream);       // GlobalRoute.__init__, shortest.py:85-91
     const long long total = h->R * h->tsize;
     int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     rlr_init_tables_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->bufs.q_table, h->bufs.theta, h->bufs.trace,
@@ -1859,6 +1879,10 @@ int rlr_init_tables(rlr_handle_t *h, double initP, void *stream)
 int rlr_build_shortest_tables(rlr_handle_t *h, int32_t multiway, void *stream)
 {
     if (!h || !h->bound) return fail(RLR_E_STATE, "rlr_build_shortest_tables: buffers not bound");
+    if (h->policy == RLR_POLICY_GLOBALROUTE) {           // per-replica tables with weights 1 + queue_size (shortest.py:84-104)
+        RLR_CUDA(cudaSetDevice(h->device));
+        return globalroute_init(h, multiway ? 1 : 0, stream);
+    }
     if (!h->bufs.next_hop || !h->bufs.distance || !h->bufs.choice)
         return fail(RLR_E_INVALID, "rlr_build_shortest_tables: next_hop, distance and choice are required");
     RLR_CUDA(cudaSetDevice(h->device));
@@ -1928,9 +1952,9 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     p.tsize = h->tsize;
     p.row_ptr = h->bufs.topo_row_ptr; p.col = h->bufs.topo_col; p.heap_pos = h->bufs.heap_pos; p.next_hop = h->bufs.next_hop;
     p.choice_mask = h->bufs.choice_mask; p.shortest_random = rp->shortest_random;
-    if (p.shortest_random && (h->policy != RLR_POLICY_SHORTEST || !p.choice_mask))
-        return fail(RLR_E_INVALID, "rlr_run_steps: shortest_random needs the Shortest policy and the choice_mask buffer");
-    p.gr_next_hop = h->bufs.gr_next_hop; p.gr_distance = h->bufs.gr_distance; p.gr_qs_off = h->bufs.gr_qs_off;
+    if (p.shortest_random && h->policy != RLR_POLICY_GLOBALROUTE && (h->policy != RLR_POLICY_SHORTEST || !p.choice_mask))
+        return fail(RLR_E_INVALID, "rlr_run_steps: shortest_random needs Shortest with the choice_mask buffer, or GlobalRoute");
+    p.gr_choice_mask = h->bufs.gr_choice_mask; p.gr_multiway = rp->multiway; p.gr_distance = h->bufs.gr_distance; p.gr_qs_off = h->bufs.gr_qs_off;
     p.Q = h->bufs.q_table; p.Theta = h->bufs.theta; p.Trace = h->bufs.trace;
     p.ring = (uint4 *)h->bufs.ring; p.qhead = h->bufs.q_head; p.qtail = h->bufs.q_tail;
     p.counters = (long long *)h->bufs.counters; p.status = h->bufs.status;

@@ -196,7 +196,7 @@ class Network:
         b = nat.Buffers(ptr("Qtable"), ptr("Theta"), ptr("Trace"), self._ring.data_ptr(), self._q_head.data_ptr(),
                         self._q_tail.data_ptr(), self._counters.data_ptr(), self._status.data_ptr(), ptr("next_hop"),
                         ptr("distance"), ptr("choice"), self._row_ptr.data_ptr(), self._col.data_ptr(),
-                        self._heap_pos.data_ptr(), ptr("gr_next_hop"), ptr("gr_distance"), ptr("choice_mask"),
+                        self._heap_pos.data_ptr(), ptr("gr_choice_mask"), ptr("gr_distance"), ptr("choice_mask"),
                         ptr("gr_qs_off"), *([t.data_ptr() for t in (self._link_sent, self._event_heap, self._event_count,
                                                                      self._event_rec, self._q_dead)]
                                              if self._general else [None] * 5))
@@ -531,7 +531,8 @@ class Network:
         rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
         rp.conf_decay = float(getattr(agent, "decay", 0.9))
         rp.is_drop = int(bool(self.is_drop))
-        rp.shortest_random = int(agent._kernel_policy == nat.POLICY_SHORTEST and bool(getattr(agent, "random", False)))
+        rp.shortest_random = int(agent._kernel_policy in (nat.POLICY_SHORTEST, nat.POLICY_GLOBALROUTE) and bool(getattr(agent, "random", False)))
+        rp.multiway = int(agent._kernel_policy == nat.POLICY_GLOBALROUTE and bool(getattr(agent, "multiway", False)))
         rp.seed = self.seed
         self._timing(rp)
         return rp
@@ -723,7 +724,8 @@ class Network:
         rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
         rp.conf_decay = float(getattr(agent, "decay", 0.9))
         rp.is_drop = int(bool(self.is_drop))
-        rp.shortest_random = int(agent._kernel_policy == nat.POLICY_SHORTEST and bool(getattr(agent, "random", False)))
+        rp.shortest_random = int(agent._kernel_policy in (nat.POLICY_SHORTEST, nat.POLICY_GLOBALROUTE) and bool(getattr(agent, "random", False)))
+        rp.multiway = int(agent._kernel_policy == nat.POLICY_GLOBALROUTE and bool(getattr(agent, "multiway", False)))
         rp.seed = self.seed
         slot, freq = self._timing(rp, slot, freq)
         keep = []
@@ -890,7 +892,8 @@ class Network:
         rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
         rp.conf_decay = float(getattr(agent, "decay", 0.9))
         rp.is_drop = int(bool(self.is_drop))
-        rp.shortest_random = int(agent._kernel_policy == nat.POLICY_SHORTEST and bool(getattr(agent, "random", False)))
+        rp.shortest_random = int(agent._kernel_policy in (nat.POLICY_SHORTEST, nat.POLICY_GLOBALROUTE) and bool(getattr(agent, "random", False)))
+        rp.multiway = int(agent._kernel_policy == nat.POLICY_GLOBALROUTE and bool(getattr(agent, "multiway", False)))
         rp.seed = self.seed
         rp.enlam = d_en.data_ptr()
         rp.inj_thr = d_thr.data_ptr()

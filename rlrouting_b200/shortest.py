@@ -44,18 +44,16 @@ class GlobalRoute(Shortest):
     _kernel_policy = nat.POLICY_GLOBALROUTE
 
     def __init__(self, network, multiway=False, random=False):
-        if multiway or random:
-            raise NotImplementedError("GlobalRoute(multiway=True / random=True) is not implemented on the device")
         Policy.__init__(self, network)
         self.multiway, self.random = multiway, random
         import torch
         topo, dev, R = network.topology, network.device, network.replicas
         n = topo.N
-        self._dev = {"gr_next_hop": torch.zeros((R, n * n), dtype=torch.uint8, device=dev),
+        self._dev = {"gr_choice_mask": torch.zeros((R, n * n), dtype=torch.int16, device=dev),     # bit j = choice[x][d][j]
                      "gr_distance": torch.zeros((R, n * n), dtype=torch.int32, device=dev),
                      "gr_qs_off": torch.zeros((R, n), dtype=torch.int32, device=dev)}
         self._handle = network._make_handle(self)
-        nat.check(nat.lib().rlr_init_tables(self._handle, 0.0, network._stream_ptr()))      # shortest.py:85-91
+        nat.check(nat.lib().rlr_build_shortest_tables(self._handle, int(bool(multiway)), network._stream_ptr()))   # shortest.py:85-91
         self.mask = ~np.eye(n, dtype=bool)                                                    # shortest.py:87-88
 
     INF = 0x3FFFFFFF
@@ -74,14 +72,11 @@ class GlobalRoute(Shortest):
     def choice(self):
         topo = self._network.topology
         n, R = topo.N, self._network.replicas
-        nh = self._dev["gr_next_hop"].cpu().numpy().reshape(R, n, n)
-        dist = self._dev["gr_distance"].cpu().numpy().reshape(R, n, n)
+        cm = self._dev["gr_choice_mask"].cpu().numpy().view(np.uint16).reshape(R, n, n)
         out = {}
         for x in range(n):
-            c = np.zeros((R, n, int(topo.deg[x])), dtype=bool)
-            rr, zz = np.nonzero((dist[:, x, :] < self.INF) & (np.arange(n)[None, :] != x))
-            c[rr, zz, nh[rr, x, zz]] = True
-            out[x] = self._one(c)
+            bits = (cm[:, x, :, None] >> np.arange(int(topo.deg[x]), dtype=np.uint16)[None, None, :]) & 1
+            out[x] = self._one(bits.astype(bool))
         return out
 
     @property

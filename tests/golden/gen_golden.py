@@ -114,12 +114,28 @@ CASES = [
     dict(net="lata.net", policy="Qroute", T=300, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3,
          net_kwargs={"transtime": 2, "bandwidth": 2}),
     dict(net="6x6.net", policy="Qroute", T=400, lambd=2.0, seed=1, net_kwargs={"bandwidth": 0}),
+    # GlobalRoute(multiway=True, random=True): every optimal neighbour kept by the per-step recomputation (shortest.py:57-58)
+    dict(net="6x6.net", policy="GlobalRoute", T=150, lambd=3.0, seed=1, agent_kwargs={"multiway": True}),
+    dict(net="6x6.net", policy="GlobalRoute", T=150, lambd=3.0, seed=1, rng="philox", philox_seed=7, replica=3,
+         agent_kwargs={"multiway": True, "random": True}),
+    dict(net="lata.net", policy="GlobalRoute", T=30, lambd=3.0, seed=1, rng="philox", philox_seed=7, replica=3,
+         agent_kwargs={"multiway": True, "random": True}),
+    dict(net="6x6.net", policy="GlobalRoute", T=100, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3,
+         agent_kwargs={"multiway": True, "random": True}, net_kwargs={"transtime": 2}),
 ]
 
 
 def main():
     out, arrays = [], {}
+    start = int(sys.argv[sys.argv.index("--from") + 1]) if "--from" in sys.argv else 0     # keep records [0, start) as they are
+    if start:
+        with open(os.path.join(HERE, "kat.json")) as f:
+            out = json.load(f)[:start]
+        arrays = dict(np.load(os.path.join(HERE, "np_tables.npz")))
     for i, c in enumerate(CASES):
+        if i < start:
+            assert {k: v for k, v in out[i].items() if k not in ("id", "expect")} == c, f"case {i} changed"
+            continue
         kw = dict(c)
         keep = kw.pop("keep_tables", False)
         r = H.run(kw.pop("net"), kw.pop("policy"), kw.pop("T"), kw.pop("lambd"), **kw)
