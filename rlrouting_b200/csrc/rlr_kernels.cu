@@ -298,9 +298,49 @@ __device__ __forceinline__ void set_status(int *status, long long r, int code, i
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) for staging the per-replica tables: one thread moves a whole
+// table between HBM and shared memory; sizes and addresses are multiples of 16 bytes ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Shared-memory carve-up, identical on host (sizing) and device (pointers).
 struct SmemLayout {
-    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, gr, samp, evheap, evorder, evsent, evlen, evfrom, total;
+    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, gr, samp, evheap, evorder, evsent, evlen, evfrom, mbar, total;
     __host__ __device__ SmemLayout(int N, int sdeg, int G, int threads, int policy, bool smem_tables, long long tsize, int ntab,
                                    int ecap = 0)
     {
@@ -327,6 +367,7 @@ struct SmemLayout {
         evsent = o; o += ecap ? align16((size_t)G * sdeg * 4) : 0;
         evlen = o; o += ecap ? align16((size_t)G * 2 * 4) : 0;
         evfrom = o; o += ecap ? align16((size_t)sdeg) : 0;
+        mbar = o; o += smem_tables ? 16 : 0;               // mbarrier of the bulk table load
         total = o;
     }
 };
@@ -447,6 +488,20 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     const long long tstride = (long long)p.ntab * p.tsize;         // smem doubles per replica
 
     // ---- stage topology (+ tables) into shared memory ----
+    // the tables come by TMA bulk copy: thread 0 arms an mbarrier with the byte count and issues one copy per table, the
+    // other threads stage the small topology arrays meanwhile and everybody waits on the mbarrier after the CTA barrier
+    unsigned long long *s_mbar = reinterpret_cast<unsigned long long *>(smem + L.mbar);
+    if (SMEM_TABLES && t == 0) {
+        mbar_init(s_mbar, 1);
+        int nrep = 0;
+        for (int gg = 0; gg < G; ++gg) nrep += (rblock + gg < p.R) ? 1 : 0;
+        const unsigned tbytes = (unsigned)(p.tsize * 8);
+        mbar_expect_tx(s_mbar, (unsigned)(nrep * p.ntab) * tbytes);
+        for (int gg = 0; gg < nrep; ++gg)
+            for (int tb = 0; tb < p.ntab; ++tb)
+                bulk_g2s(s_tables + gg * ((long long)p.ntab * p.tsize) + tb * p.tsize,
+                         (tb == 0 ? p.Q : tb == 1 ? p.Theta : p.Trace) + (rblock + gg) * p.tsize, tbytes, s_mbar);
+    }
     for (int i = t; i <= N; i += blockDim.x) s_rowptr[i] = p.row_ptr[i];
     for (int i = t; i < p.sdeg; i += blockDim.x) s_col[i] = (unsigned short)p.col[i];
     for (int i = t; i < (N + 1) * N; i += blockDim.x) s_heappos[i] = p.heap_pos[i];
@@ -485,19 +540,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             s_evlen[2 * i + 1] = 0;
         }
     }
-    if (SMEM_TABLES) {
-        const long long per = p.tsize / 2;                          // double2 per table
-        for (int gg = 0; gg < G; ++gg) {
-            if (rblock + gg >= p.R) break;
-            for (int tb = 0; tb < p.ntab; ++tb) {
-                const double *src = (tb == 0 ? p.Q : tb == 1 ? p.Theta : p.Trace) + (rblock + gg) * p.tsize;
-                double2 *dst = reinterpret_cast<double2 *>(s_tables + gg * tstride + tb * p.tsize);
-                const double2 *s2 = reinterpret_cast<const double2 *>(src);
-                for (long long i = t; i < per; i += blockDim.x) dst[i] = s2[i];
-            }
-        }
-    }
     __syncthreads();
+    if (SMEM_TABLES) mbar_wait(s_mbar, 0);
 
     // ---- per-thread state, constant over the launch ----
     double *Qr = nullptr, *Thr = nullptr, *Trr = nullptr;          // this replica's tables
@@ -1290,15 +1334,19 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         }
     }
     if (SMEM_TABLES) {
-        const long long per = p.tsize / 2;
-        for (int gg = 0; gg < G; ++gg) {
-            if (rblock + gg >= p.R) break;
-            for (int tb = 0; tb < p.ntab; ++tb) {
-                double *dstp = (tb == 0 ? p.Q : tb == 1 ? p.Theta : p.Trace) + (rblock + gg) * p.tsize;
-                const double2 *src = reinterpret_cast<const double2 *>(s_tables + gg * tstride + tb * p.tsize);
-                double2 *d2 = reinterpret_cast<double2 *>(dstp);
-                for (long long i = t; i < per; i += blockDim.x) d2[i] = src[i];
+        // tables go back by TMA bulk store: every thread publishes its shared-memory writes to the async proxy, then one
+        // thread issues a copy per table and waits for the group before the CTA (and its shared memory) goes away
+        fence_proxy_async();
+        __syncthreads();
+        if (t == 0) {
+            const unsigned tbytes = (unsigned)(p.tsize * 8);
+            for (int gg = 0; gg < G; ++gg) {
+                if (rblock + gg >= p.R) break;
+                for (int tb = 0; tb < p.ntab; ++tb)
+                    bulk_s2g((tb == 0 ? p.Q : tb == 1 ? p.Theta : p.Trace) + (rblock + gg) * p.tsize,
+                             s_tables + gg * tstride + tb * p.tsize, tbytes);
             }
+            bulk_commit_wait();
         }
     }
 }
