@@ -783,7 +783,10 @@ class Network:
                 keep.append(d_sched)
                 rp.clock0 = self.clock + s0 * freq * slot
             else:                                       # device Philox schedule, prefetched one chunk ahead
-                nxt = (self.clock + (s0 + K) * freq * slot, plan[ci + 1] * freq) if ci + 1 < len(plan) else None
+                # the schedule of the next launch is built on the side stream while this one runs; after the last launch
+                # of the call, speculate that the next train() call repeats this one (same duration and loads)
+                nxt = ((self.clock + (s0 + K) * freq * slot, plan[ci + 1] * freq) if ci + 1 < len(plan)
+                       else (self.clock + T * freq * slot, plan[0] * freq))
                 self._schedule(h, rp, self.clock + s0 * freq * slot, K * freq, lam_key, lam.max(), nxt)
             KS = K * freq                               # Network.step calls of this launch (K iterations of the loop)
             # per-chunk device buffers are kept across calls (a fresh 32 MB torch.empty costs ~0.2 ms each); the call
