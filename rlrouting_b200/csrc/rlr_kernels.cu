@@ -104,6 +104,7 @@ struct StepParams {
     int *event_count;             // [R]
     uint4 *event_rec;             // [R][ecap]
     int *q_dead;                  // [R][N]
+    int max_deg;                  // largest node degree (uniform loop bound of the MAXD > 4 instantiations)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1035,16 +1036,12 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             unsigned key[MAXD];
 #pragma unroll
             for (int j = 0; j < MAXD; ++j) {
+                if (MAXD > 4 && j >= p.max_deg) { key[j] = kNoKey; continue; }  // uniform: no node has a j-th neighbour
                 const unsigned tp = s_tp[nb_slot[j]];
                 const bool match = (tp & 0xFFu) == (unsigned)x;                 // kNoSend's low byte is 255 > any node id
                 unsigned base = 0;
-                if (MAXW <= 3) {
-                    base = __byte_perm(cumpack, 0u, nb_word[j]) & 0xFFu;
-                } else {
-#pragma unroll
-                    for (int i = 1; i < MAXW; ++i)
-                        if (nb_word[j] == (unsigned)i) base = cum[i];
-                }
+                if (MAXW <= 3) base = __byte_perm(cumpack, 0u, nb_word[j]) & 0xFFu;
+                else base = cum[nb_word[j]];                                    // (an indexed local array: one load, not MAXW selects)
                 const unsigned pos = s_heappos[hp_row + (match ? (tp >> 8) + base : 0u)];
                 key[j] = match ? ((pos << 16) | nb_slot[j]) : kNoKey;
             }
@@ -1060,10 +1057,11 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                     key[0] = key[1]; key[1] = key[2]; key[2] = key[3]; key[3] = kNoKey;
                 } else {
 #pragma unroll
-                    for (int j = 1; j < MAXD; ++j) best = min(best, key[j]);
+                    for (int j = 1; j < MAXD; ++j)
+                        if (j < p.max_deg) best = min(best, key[j]);
 #pragma unroll
                     for (int j = 0; j < MAXD; ++j)
-                        if (key[j] == best) key[j] = kNoKey;
+                        if (j < p.max_deg && key[j] == best) key[j] = kNoKey;
                 }
                 if (best == kNoKey) break;
                 uint4 rec = s_rec[best & 0xFFFFu];
@@ -1995,7 +1993,7 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     RLR_CUDA(cudaSetDevice(h->device));
     StepParams p;
     memset(&p, 0, sizeof(p));
-    p.N = h->N; p.sdeg = h->sdeg; p.G = h->G; p.R = (int)h->R;
+    p.N = h->N; p.sdeg = h->sdeg; p.G = h->G; p.R = (int)h->R; p.max_deg = h->max_deg;
     p.cap = h->cap; p.K = (int)n_steps; p.clock0 = rp->clock0; p.ntab = h->ntab;
     p.tsize = h->tsize;
     p.row_ptr = h->bufs.topo_row_ptr; p.col = h->bufs.topo_col; p.heap_pos = h->bufs.heap_pos; p.next_hop = h->bufs.next_hop;
