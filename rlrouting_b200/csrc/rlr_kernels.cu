@@ -1033,17 +1033,21 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             unsigned cumpack = 0;                                               // cum[0..3] as bytes (N <= 255)
             if (MAXW <= 3) cumpack = cum[0] | (cum[1] << 8) | (cum[2] << 16);
             // sort key per neighbour slot: heap pop position << 16 | send slot, or kNoKey
+            // MAXD == 4: the four keys stay in registers (sorting network below); wider nodes compact their arrivals
+            // into a short list (indexed, so it lives in local memory) and pick the minimum of what is left each time
             unsigned key[MAXD];
+            int nkey = 0;
 #pragma unroll
             for (int j = 0; j < MAXD; ++j) {
-                if (MAXD > 4 && j >= p.max_deg) { key[j] = kNoKey; continue; }  // uniform: no node has a j-th neighbour
+                if (MAXD > 4 && j >= p.max_deg) continue;                       // uniform: no node has a j-th neighbour
                 const unsigned tp = s_tp[nb_slot[j]];
                 const bool match = (tp & 0xFFu) == (unsigned)x;                 // kNoSend's low byte is 255 > any node id
                 unsigned base = 0;
                 if (MAXW <= 3) base = __byte_perm(cumpack, 0u, nb_word[j]) & 0xFFu;
                 else base = cum[nb_word[j]];                                    // (an indexed local array: one load, not MAXW selects)
                 const unsigned pos = s_heappos[hp_row + (match ? (tp >> 8) + base : 0u)];
-                key[j] = match ? ((pos << 16) | nb_slot[j]) : kNoKey;
+                if (MAXD == 4) key[j] = match ? ((pos << 16) | nb_slot[j]) : kNoKey;
+                else if (match) key[nkey++] = (pos << 16) | nb_slot[j];
             }
             if (MAXD == 4) {                                                    // 5-comparator sorting network
 #define RLR_CE(a, b) { const unsigned lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; }
@@ -1051,19 +1055,22 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
 #undef RLR_CE
             }
             RLR_T(5);                               // C: window + keys + sort
-            for (;;) {
-                unsigned best = key[0];
+            for (int taken = 0;; ++taken) {
+                unsigned best;
                 if (MAXD == 4) {
+                    best = key[0];
                     key[0] = key[1]; key[1] = key[2]; key[2] = key[3]; key[3] = kNoKey;
+                    if (best == kNoKey) break;
                 } else {
-#pragma unroll
-                    for (int j = 1; j < MAXD; ++j)
-                        if (j < p.max_deg) best = min(best, key[j]);
-#pragma unroll
-                    for (int j = 0; j < MAXD; ++j)
-                        if (j < p.max_deg && key[j] == best) key[j] = kNoKey;
+                    if (taken >= nkey) break;
+                    best = key[taken];
+                    int bi = taken;
+                    for (int b = taken + 1; b < nkey; ++b) {
+                        const unsigned v = key[b];
+                        if (v < best) { best = v; bi = b; }
+                    }
+                    key[bi] = key[taken];
                 }
-                if (best == kNoKey) break;
                 uint4 rec = s_rec[best & 0xFFFFu];
                 if (SPLIT && p.is_drop && rec.y >= (unsigned)N) {                        // env.py:355-360: too many hops, dropped
                     atomicAdd(&s_drop[g], 1u);
