@@ -172,6 +172,7 @@ class Network:
 
     # ------------------------------------------------------------------ topology (env.py:282-296)
     def read_network(self, file):
+        self.file = file
         self.topology = Topology.from_text(nets.resolve(file))
         self.links = OrderedDict((k, list(v)) for k, v in self.topology.links.items())
         self.proj = self.topology.proj
