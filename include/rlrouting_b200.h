@@ -223,6 +223,14 @@ int rlr_trace_replay_many(uint32_t *mt_keys, int32_t *mt_pos, int64_t n_streams,
                           const double *lam, int32_t *cnt_out, uint32_t *pairs_out, int64_t pairs_cap,
                           int64_t *n_pairs_out, int32_t nthreads);
 
+/* ---- host helper (no device work): turns the traces of rlr_trace_replay_many (cnt[n_streams][n_steps], packed pairs
+ *      [n_streams][pairs_cap]) into the per-node event lists rlr_run_params_t.inj_events takes, for the iterations
+ *      [it0, it1) of Network.train's loop: events[n_streams][n_nodes][cap], entry ((it - it0) * freq) << 8 | dest,
+ *      0xFFFFFFFF-terminated.  With events == NULL only *cap_out (longest list + 2) is computed. ---- */
+int rlr_trace_schedule(const int32_t *cnt, const uint32_t *pairs, int64_t pairs_cap, int64_t n_streams, int32_t n_nodes,
+                       int64_t n_steps, int64_t it0, int64_t it1, int32_t freq, uint32_t *events, int32_t cap,
+                       int32_t *cap_out, int32_t nthreads);
+
 /* ---- Network.new_packet (env.py:298-312) for n_steps steps ahead of time, Philox mode: fills params->inj_events
  *      from enlam / inj_thr / seed / clock0.  rlr_run_steps does this itself for RLR_INJECT_PHILOX; calling it
  *      separately (on another stream, then running with RLR_INJECT_TRACE) overlaps it with the previous chunk. ---- */

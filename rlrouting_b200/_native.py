@@ -74,7 +74,8 @@ class RunParams(C.Structure):
 
 EXPORTS = ("rlr_abi_version", "rlr_last_error_string", "rlr_struct_sizes", "rlr_create", "rlr_destroy", "rlr_bind_buffers",
            "rlr_launch_info", "rlr_reset", "rlr_init_tables", "rlr_build_shortest_tables",
-           "rlr_build_inject_schedule", "rlr_run_steps", "rlr_reduce_stats", "rlr_trace_replay", "rlr_trace_replay_many")
+           "rlr_build_inject_schedule", "rlr_run_steps", "rlr_reduce_stats", "rlr_trace_replay", "rlr_trace_replay_many",
+           "rlr_trace_schedule")
 
 _lib = None
 
@@ -106,6 +107,8 @@ def lib():
     L.rlr_reduce_stats.argtypes = [p, p, p]
     L.rlr_trace_replay.argtypes = [p, p, C.c_int32, C.c_int64, C.c_double, p, p, C.c_int64, p]
     L.rlr_trace_replay_many.argtypes = [p, p, C.c_int64, C.c_int32, C.c_int64, p, p, p, C.c_int64, p, C.c_int32]
+    L.rlr_trace_schedule.argtypes = [p, p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, p, C.c_int32, p,
+                                     C.c_int32]
     if L.rlr_abi_version() != ABI_VERSION:
         raise ImportError(f"ABI mismatch: library {L.rlr_abi_version()} != binding {ABI_VERSION}")
     sizes = (C.c_int32 * 4)()

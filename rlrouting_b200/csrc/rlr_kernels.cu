@@ -28,6 +28,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -1726,6 +1727,60 @@ extern "C" int rlr_trace_replay_many(uint32_t *mt_keys, int32_t *mt_pos, int64_t
 // ------------------------------------------------------------------------------------------------
 // Host side of the C ABI
 // ------------------------------------------------------------------------------------------------
+// Per-node injection event lists (the layout rlr_run_params_t.inj_events takes) from replayed traces, for the iterations
+// [it0, it1) of every stream: an event is ((it - it0) * freq) << 8 | dest, in (node, iteration, draw) order, 0xFFFFFFFF ends
+// a list.  With events == NULL only *cap_out = largest list length + 2 is computed.
+extern "C" int rlr_trace_schedule(const int32_t *cnt, const uint32_t *pairs, int64_t pairs_cap, int64_t n_streams, int32_t n_nodes,
+                                  int64_t n_steps, int64_t it0, int64_t it1, int32_t freq, uint32_t *events, int32_t cap,
+                                  int32_t *cap_out, int32_t nthreads)
+{
+    if (!cnt || !pairs || n_streams < 0 || n_nodes < 1 || n_nodes > 255 || it0 < 0 || it1 > n_steps || it0 > it1 || freq < 1)
+        return fail(RLR_E_INVALID, "rlr_trace_schedule: invalid argument");
+    if (events && cap < 2) return fail(RLR_E_INVALID, "rlr_trace_schedule: cap must be >= 2");
+    if ((it1 - it0) * freq >= (1 << 24)) return fail(RLR_E_INVALID, "rlr_trace_schedule: too many steps for the 24-bit step field");
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int64_t> next(0);
+    std::atomic<int> worst(0), bad(0);
+    auto work = [&]() {
+        std::vector<int32_t> fill((size_t)n_nodes);
+        int local_max = 0;
+        for (;;) {
+            const int64_t r = next.fetch_add(1);
+            if (r >= n_streams) break;
+            const int32_t *c = cnt + r * n_steps;
+            const uint32_t *pk = pairs + r * pairs_cap;
+            int64_t off = 0;
+            for (int64_t i = 0; i < it0; ++i) off += c[i];
+            std::fill(fill.begin(), fill.end(), 0);
+            uint32_t *ev = events ? events + (size_t)r * n_nodes * cap : nullptr;
+            for (int64_t i = it0; i < it1; ++i) {
+                for (int32_t j = 0; j < c[i]; ++j, ++off) {
+                    if (off >= pairs_cap) { bad.store(1); break; }
+                    const uint32_t src = pk[off] & 0xFFFFu, dst = pk[off] >> 16;
+                    if (src >= (uint32_t)n_nodes) { bad.store(1); continue; }
+                    int32_t &f = fill[src];
+                    if (ev) { if (f < cap - 1) ev[(size_t)src * cap + f] = ((uint32_t)((i - it0) * freq) << 8) | dst; else bad.store(2); }
+                    ++f;
+                }
+            }
+            for (int32_t x = 0; x < n_nodes; ++x) {
+                if (fill[x] > local_max) local_max = fill[x];
+                if (ev) for (int32_t f = fill[x] < cap ? fill[x] : cap - 1; f < cap; ++f) ev[(size_t)x * cap + f] = 0xFFFFFFFFu;
+            }
+        }
+        int cur = worst.load();
+        while (local_max > cur && !worst.compare_exchange_weak(cur, local_max)) {}
+    };
+    std::vector<std::thread> pool;
+    for (int i = 1; i < nthreads; ++i) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    if (bad.load() == 1) return fail(RLR_E_INVALID, "rlr_trace_schedule: trace arrays are inconsistent (pairs_cap / node ids)");
+    if (bad.load() == 2) return fail(RLR_E_INVALID, "rlr_trace_schedule: cap is smaller than the longest list + 2");
+    if (cap_out) *cap_out = worst.load() + 2;
+    return RLR_OK;
+}
+
 struct rlr_handle {
     int N, sdeg, max_deg, policy, ntab;
     long long R, replica_base, tsize;

@@ -734,7 +734,7 @@ class Network:
         traces = None
         if self.rng == "trace":
             rp.inject_mode = nat.INJECT_TRACE
-            traces = trace.draw_injections_many(self._rs, N, T, lam)
+            traces = trace.draw_batch(self._rs, N, T, lam)
         else:
             rp.inject_mode = nat.INJECT_PHILOX
             lam_key, enlam, thr, sent = self._lam_tensors(lam)
@@ -771,13 +771,8 @@ class Network:
         for ci, K in enumerate(plan):
             s0 = int(starts[ci])
             if traces is not None:                      # host replay of env.py:307-310 -> per-node event lists
-                evs = [trace_schedule(c, pr, N, s0, s0 + K, freq) for c, pr in traces]
-                per_node = [np.bincount(node, minlength=N) for _, node in evs]
-                cap = int(max(pn.max() for pn in per_node)) + 2
-                sched = np.full((R, N, cap), 0xFFFFFFFF, dtype=np.uint32)
-                for r, ((e, node), pn) in enumerate(zip(evs, per_node)):
-                    start = np.concatenate([[0], np.cumsum(pn)[:-1]])
-                    sched[r, node, np.arange(len(e)) - start[node]] = e
+                sched = traces.schedule(s0, s0 + K, freq)
+                cap = sched.shape[2]
                 d_sched = torch.from_numpy(sched.view(np.int32)).to(dev)
                 h2d += sched.nbytes
                 rp.inj_events, rp.inj_cap = d_sched.data_ptr(), cap

@@ -93,6 +93,72 @@ def _draw_native_many(streams, n_nodes, n_steps, lambdas, workers):
     return out
 
 
+class TraceBatch:
+    """The replayed injections of many replicas.  `schedule(it0, it1, freq)` gives the per-node event lists of the
+    iterations [it0, it1) as a uint32 array [R, N, cap] (the layout of rlr_run_params_t.inj_events)."""
+
+    def __init__(self, n_nodes, lists=None, cnt=None, packed=None, workers=1):
+        self.n_nodes, self.lists, self.cnt, self.packed, self.workers = n_nodes, lists, cnt, packed, workers
+
+    def schedule(self, it0, it1, freq=1):
+        N = self.n_nodes
+        if self.lists is None:                       # packed arrays of rlr_trace_replay_many: built in C, all host threads
+            import ctypes as C
+            from . import _native as nat
+            R, T = self.cnt.shape
+            cap = C.c_int32(0)
+            args = (self.cnt.ctypes.data, self.packed.ctypes.data, self.packed.shape[1], R, N, T, int(it0), int(it1), int(freq))
+            nat.check(nat.lib().rlr_trace_schedule(*args, None, 0, C.byref(cap), self.workers))
+            sched = np.empty((R, N, cap.value), dtype=np.uint32)
+            nat.check(nat.lib().rlr_trace_schedule(*args, sched.ctypes.data, cap.value, None, self.workers))
+            return sched
+        from .env import trace_schedule
+        evs = [trace_schedule(c, pr, N, it0, it1, freq) for c, pr in self.lists]
+        per_node = [np.bincount(node, minlength=N) for _, node in evs]
+        cap = int(max(pn.max() for pn in per_node)) + 2
+        sched = np.full((len(evs), N, cap), 0xFFFFFFFF, dtype=np.uint32)
+        for r, ((e, node), pn) in enumerate(zip(evs, per_node)):
+            start = np.concatenate([[0], np.cumsum(pn)[:-1]])
+            sched[r, node, np.arange(len(e)) - start[node]] = e
+        return sched
+
+
+def draw_batch(streams, n_nodes, n_steps, lambdas, workers=None):
+    """draw_injections_many as a TraceBatch; large batches stay in the packed form of the C replay."""
+    import os
+    R = len(streams)
+    if workers is None:
+        workers = min(os.cpu_count() or 1, 32)
+    lam = np.asarray(np.broadcast_to(lambdas, (R,)), dtype=np.float64)
+    native = (R >= 64 and workers >= 2 and float(lam.max()) < 10.0 and n_nodes <= 255
+              and not any(rs is np.random.mtrand._rand for rs in streams))
+    if not native:
+        return TraceBatch(n_nodes, lists=draw_injections_many(streams, n_nodes, n_steps, lam, workers))
+    cnt, packed = _replay_packed(streams, n_nodes, n_steps, lam, workers)
+    return TraceBatch(n_nodes, cnt=cnt, packed=packed, workers=workers)
+
+
+def _replay_packed(streams, n_nodes, n_steps, lam, workers):
+    """rlr_trace_replay_many on every stream (their states advance); returns (cnt[R, n_steps], packed[R, cap])."""
+    import ctypes as C
+    from . import _native as nat
+    R = len(streams)
+    states = [rs.get_state() for rs in streams]
+    keys = np.ascontiguousarray(np.stack([st[1] for st in states]), dtype=np.uint32)
+    pos = np.array([st[2] for st in states], dtype=np.int32)
+    lam = np.ascontiguousarray(lam, dtype=np.float64)
+    m = float(lam.max()) * n_steps
+    cap = int(m + 12.0 * np.sqrt(m + 1.0) + 64)
+    cnt = np.zeros((R, n_steps), dtype=np.int32)
+    packed = np.zeros((R, cap), dtype=np.uint32)
+    n_out = np.zeros(R, dtype=np.int64)
+    nat.check(nat.lib().rlr_trace_replay_many(keys.ctypes.data, pos.ctypes.data, R, n_nodes, n_steps, lam.ctypes.data,
+                                               cnt.ctypes.data, packed.ctypes.data, cap, n_out.ctypes.data, workers))
+    for r, (rs, st) in enumerate(zip(streams, states)):
+        rs.set_state((st[0], keys[r], int(pos[r]), st[3], st[4]))
+    return cnt, packed
+
+
 def draw_injections_many(streams, n_nodes, n_steps, lambdas, workers=None):
     """draw_injections for every replica's RandomState.  Replicas are independent streams: the C replay releases the
     GIL, so they are replayed on a thread pool; loads NumPy has to draw itself (lambda >= 10) go to worker processes."""

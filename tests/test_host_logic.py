@@ -168,3 +168,22 @@ def test_integer_timing_arguments():
     pairs = np.array([[0, 1], [2, 0], [2, 1]], dtype=np.int32)
     ev, node = trace_schedule(cnt, pairs, 3, 0, 3, freq=3)
     assert list(node) == [0, 2, 2] and list(ev >> 8) == [0, 6, 6] and list(ev & 0xFF) == [1, 0, 1]
+
+
+def test_trace_batch_schedule_native_equals_python():
+    """rlr_trace_schedule (C, all host threads) builds the same per-node event lists as the NumPy path."""
+    from rlrouting_b200 import trace
+    R, N, T = 96, 36, 300
+    lam = np.linspace(0.5, 3.0, R)
+    a = [np.random.RandomState(7 + r) for r in range(R)]
+    b = [np.random.RandomState(7 + r) for r in range(R)]
+    nat_batch = trace.draw_batch(a, N, T, lam, workers=4)
+    assert nat_batch.lists is None                      # the packed C form
+    py_batch = trace.TraceBatch(N, lists=[trace.draw_injections(rs, N, T, lam[r]) for r, rs in enumerate(b)])
+    for it0, it1, freq in ((0, T, 1), (37, 211, 3), (T - 1, T, 1), (5, 5, 1)):
+        s1, s2 = nat_batch.schedule(it0, it1, freq), py_batch.schedule(it0, it1, freq) if it1 > it0 else None
+        if s2 is None:
+            assert s1.shape[2] == 2 and np.all(s1 == 0xFFFFFFFF)
+            continue
+        assert s1.shape == s2.shape and np.array_equal(s1, s2)
+    assert all(np.array_equal(x.get_state()[1], y.get_state()[1]) for x, y in zip(a, b))
