@@ -312,7 +312,7 @@ def run_b200(a):
     except Exception:
         pass
     abytes, per_hop = algorithmic_bytes(a, nw.topology, hops, inj, world * R * sim * a.steps)
-    per_launch = abytes / max(launches * world, 1)
+    per_launch = abytes / max(a.steps * world, 1)                     # one step-kernel launch per GPU per bench step
     achieved = per_launch / (ms_total / a.steps * 1e-3) / 1e9        # GB/s per GPU (one launch per GPU per step)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

@@ -163,7 +163,8 @@ class Network:
             self._event_rec = torch.zeros((R, self._ecap, 4), dtype=torch.int32, device=dev)
             self._q_dead = torch.zeros((R, N), dtype=torch.int32, device=dev)
         self._handles = []
-        self.launch_count = 0          # rlr_run_steps launches issued (bench.py reports it as gpu_launches)
+        self.launch_count = 0          # kernels of this library launched: step, injection-schedule and ratio kernels
+                                       # (bench.py reports the count of its timed region as gpu_launches)
         self.last_h2d_bytes = self.last_d2h_bytes = 0
         self._resident = {}
         self.clock = 0
@@ -237,6 +238,7 @@ class Network:
             self._sched_buf(st, slot, shape)
             rp.inj_events, rp.inj_cap, rp.clock0 = st["bufs"][slot].data_ptr(), cap, clock0
             nat.check(nat.lib().rlr_build_inject_schedule(h, K, C.byref(rp), self._stream_ptr()))
+            self.launch_count += 1
         st["ready"][slot] = None
         rp.inj_events, rp.inj_cap, rp.clock0 = st["bufs"][slot].data_ptr(), cap, clock0
         rp.inject_mode = nat.INJECT_TRACE                            # "events provided"
@@ -276,6 +278,7 @@ class Network:
         C.memmove(C.byref(rp2), C.byref(rp), C.sizeof(nat.RunParams))
         rp2.inj_events, rp2.inj_cap, rp2.clock0 = st["bufs"][other].data_ptr(), cap, clock0
         nat.check(nat.lib().rlr_build_inject_schedule(h, K, C.byref(rp2), C.c_void_p(side.cuda_stream)))
+        self.launch_count += 1
         done = torch.cuda.Event()
         done.record(side)
         st["ready"][other] = ((clock0, K, lam_key, cap), done)
@@ -810,7 +813,7 @@ class Network:
                 d_rt = d_rt[freq - 1::freq].contiguous()
                 d_hop = d_hop[freq - 1::freq].contiguous() if d_hop is not None else None
                 d_drop = d_drop[freq - 1::freq].contiguous() if d_drop is not None else None
-            self.launch_count += 1
+            self.launch_count += 2 if per_step else 1           # the step kernel and, with per-step vectors, the ratio kernel
             if traces is None:
                 self._schedule_done(h, rp)
             if per_step:
