@@ -1851,7 +1851,11 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     // General timing model: one thread per replica replays the event heap serially and bounds the step, so what pays is
     // more resident replicas, not faster table reads: tables stay in HBM/L2 and a CTA carries ~256 threads (measured).
     if (smem_tables < 0 && h->ecap > 0) smem_tables = 0;
-    if (smem_tables < 0) smem_tables = (table_bytes > 0 && smem_for(1, 256, true) <= (size_t)kSmemLimit) ? 1 : 0;
+    if (smem_tables < 0) {                               // automatic: in shared memory if they fit (for the requested G, if any)
+        const int g_try = G > 0 ? G : 1;
+        const int thr_try = cfg->threads_per_block > 0 ? cfg->threads_per_block : (g_try * N + 31) / 32 * 32 + 128;
+        smem_tables = (table_bytes > 0 && smem_for(g_try, thr_try, true) <= (size_t)kSmemLimit) ? 1 : 0;
+    }
     if (G <= 0 && h->ecap > 0 && !smem_tables) G = 256 / N > 0 ? 256 / N : 1;
     if (G <= 0) G = smem_tables ? 1 : (N >= 96 ? 1 : (128 / N > 0 ? 128 / N : 1));
     if ((long long)G > h->R) G = (int)h->R;

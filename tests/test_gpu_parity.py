@@ -567,3 +567,77 @@ def test_general_timing_manual_step_loop_equals_train():
     assert np.array_equal(out[0][1].view(np.int64), out[1][1].view(np.int64))
     assert np.array_equal(out[0][2].view(np.int64), out[1][2].view(np.int64))
     assert all(np.array_equal(a, b) for a, b in zip(out[0][3], out[1][3]))
+
+
+def test_random_option_combinations_match_oracle(tmp_path):
+    """A seeded sweep over combinations the targeted tests do not pair up: policy x timing model x is_drop x launch
+    geometry x load, on small random graphs; every replica must match the oracle bit for bit."""
+    import rlrouting_b200 as rb
+    import os
+    rng = np.random.default_rng(int(os.environ.get("RLR_SWEEP_SEED", "20240")))
+    policies = ["Shortest", "Qroute", "HybridQ", "MaHybridQ", "CQ", "CDRQ", "GlobalRoute"]
+    for trial in range(int(os.environ.get("RLR_SWEEP_TRIALS", "36"))):
+        policy = policies[trial % len(policies)]
+        n = int(rng.integers(3, 41))
+        max_deg = int(rng.integers(2, 7))
+        path = tmp_path / f"g{trial}.net"
+        path.write_text(_random_net(rng, n, int(rng.integers(0, 2 * n)), max_deg))
+        nkw = {}
+        if rng.random() < 0.6:
+            nkw["transtime"] = int(rng.integers(0, 5))
+        if rng.random() < 0.4:
+            nkw["bandwidth"] = int(rng.integers(1, 4))
+        if rng.random() < 0.3:
+            nkw["is_drop"] = True
+        slot, freq = int(rng.integers(1, 4)), int(rng.integers(1, 3))
+        cfg = {}
+        if rng.random() < 0.5:
+            g = int(rng.integers(1, 4))
+            cfg = dict(replicas_per_block=g)
+            if policy in ("MaHybridQ", "CQ", "CDRQ"):
+                cfg["threads_per_block"] = min(512, ((g * n + 31) // 32) * 32 + 128)
+        if rng.random() < 0.3 and policy not in ("Shortest", "GlobalRoute"):
+            cfg["tables_in_smem"] = int(rng.integers(0, 2))
+        akw = {}
+        if policy in ("Shortest", "GlobalRoute") and rng.random() < 0.5:
+            akw = dict(multiway=True, random=bool(rng.random() < 0.5))
+        R, T, lam = int(rng.integers(1, 7)), int(rng.integers(20, 90)), float(rng.uniform(0.3, 0.15 * n + 1.0))
+        what = (trial, policy, n, nkw, slot, freq, cfg, akw, R, T, lam)
+        nw = rb.Network(str(path), replicas=R, rng="philox", seed=trial, replica_base=3 * trial, queue_capacity=1024,
+                        **nkw, **cfg)
+        try:
+            agent = _classes()[policy](nw, **akw)
+        except Exception as exc:                       # a forced geometry that cannot hold the tables in shared memory
+            assert "shared-memory footprint" in str(exc) and cfg.get("tables_in_smem") == 1, (what, str(exc))
+            continue
+        nw.agent = agent
+        lr = {"q": 0.1, "p": 0.001 if policy == "MaHybridQ" else 0.1, "e": 0.1}
+        q0 = agent.table_array("Qtable") if policy not in ("Shortest", "GlobalRoute") else None
+        try:
+            res = nw.train(T * slot, lam, slot=slot, freq=freq, lr=lr)
+        except ValueError as exc:                      # NaN probabilities (SURVEY F7): the oracle must stop at the same clock
+            assert "NaN" in str(exc), what
+            res = None
+        envs = []
+        for r in range(R):
+            e = O.OracleEnv(nw.topology.links, policy, seed=trial, replica=3 * trial + r, is_drop=nkw.get("is_drop", False),
+                            bandwidth=nkw.get("bandwidth", 1), transtime=nkw.get("transtime", 1),
+                            multiway=akw.get("multiway", False), random=akw.get("random", False))
+            if q0 is not None:
+                e.set_qtable(q0[r])
+            envs.append(e)
+        sends, rt, en = O.run_many(envs, T, lam, lr_q=lr["q"], lr_p=lr["p"], lr_e=lr["e"], metrics=True, slot=slot, freq=freq)
+        if res is None:
+            st = nw._status.cpu().numpy()
+            for r, e in enumerate(envs):
+                assert (int(st[r, 0]) == 1) == (e.status()[0] == 1), what
+                if e.status()[0] == 1:
+                    assert int(st[r, 1]) == e.status()[1], what
+            continue
+        try:
+            _compare_batch(nw, agent, envs, rt, en, res)
+            c = nw.counters()
+            for r, e in enumerate(envs):
+                assert int(c["drop_packets"][r]) == e.counters()["drop_packets"]
+        except AssertionError as exc:
+            raise AssertionError(f"{what}: {exc}") from exc
