@@ -910,6 +910,14 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         __syncthreads();                                                        // ---- barrier 1 ----
         RLR_T(1);
 
+        // Qroute's learn step only needs what this thread computed before the barrier, and every read of the tables by the
+        // other threads' get_info is behind us now: do it first, so its fp64 chain overlaps the shared-memory loads of C
+        if (POLICY == RLR_POLICY_QROUTE && do_learn && sending) {               // qroute.py:40-44
+            const double tq = __dmul_rn(p.discount, max_qy);
+            const double u1 = __dadd_rn(rwd, tq);
+            const double u2 = __dsub_rn(u1, oldq);
+            Qx[d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, u2));
+        }
         if (general) {
             // ---- C (general timing). Network.event_queue restated literally (heapq on arrive_time only, env.py:48-49):
             // one thread per replica pushes this step's events in node order and pops everything due by clock + slot;
@@ -1101,12 +1109,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 p.rewards[((size_t)r * N + x) * 4 + 1].y = max(1u, ly - ((y < x && tpy != kNoSend) ? 1u : 0u));
             }
         } else if (POLICY == RLR_POLICY_QROUTE) {
-            if (sending) {                                                      // qroute.py:40-44
-                const double tq = __dmul_rn(p.discount, max_qy);
-                const double u1 = __dadd_rn(rwd, tq);
-                const double u2 = __dsub_rn(u1, oldq);
-                Qx[d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, u2));
-            }
+            // (done right after barrier 1)
         } else if (POLICY == RLR_POLICY_HYBRIDQ) {
             if (sending) {                                                      // hybrid.py:55-62
                 double rr = rwd;
