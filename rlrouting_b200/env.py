@@ -747,7 +747,7 @@ class Network:
 
         # Launch in chunks and stream each chunk's per-step vectors to pinned host memory on a side stream
         # while the next chunk computes, so the device->host copy of [R, T] doubles hides behind the kernel.
-        # Every launch re-stages the tables in shared memory, so the default is two launches, 3/4 + 1/4 of the run:
+        # Every launch re-stages the tables in shared memory, so the default is two launches, 7/8 + 1/8 of the run:
         # only the copy of the short last chunk is exposed.
         cap = max(1, (1 << 25) // (R * freq))                   # per-launch device buffers stay under ~1 GB
         if steps_per_launch is not None:
@@ -759,7 +759,8 @@ class Network:
         plan = [cap] * (T // cap) + ([T % cap] if T % cap else [])
         if steps_per_launch is None and per_step and plan[-1] >= 64:
             last = plan.pop()
-            plan += [last - last // 4, last // 4]
+            short = max(last // 8, 32)                          # long enough to cover the copy of the long part
+            plan += [last - short, short]
         starts = np.concatenate([[0], np.cumsum(plan)]).astype(np.int64)
         _t.append(time.perf_counter())
         compute = torch.cuda.current_stream(dev)
