@@ -135,7 +135,10 @@ class Network:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         topo, R, N = self.topology, self.replicas, self.topology.N
         if queue_capacity is None:
-            queue_capacity = min(max(_floor_pow2(max((1 << 30) // (R * N), 1)), 64), 32768)
+            # the reference's queues are unbounded; by default the rings get a fifth of the device memory (16-byte
+            # records), at most 32,768 entries per queue
+            budget = int(torch.cuda.get_device_properties(self.device).total_memory * 0.2) // 16
+            queue_capacity = min(max(_floor_pow2(max(budget // (R * N), 1)), 64), 32768)
         if queue_capacity & (queue_capacity - 1):
             raise ValueError("queue_capacity must be a power of two")
         self.queue_capacity = int(queue_capacity)
