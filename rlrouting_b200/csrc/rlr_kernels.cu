@@ -213,6 +213,70 @@ __device__ double det_log2(double x)
     return __dadd_rn((double)e, __dmul_rn(lnm, 1.4426950408889634));
 }
 
+// Four independent evaluations of det_exp / det_log2 run side by side: the same operations per element (so the same
+// bits), but the four Horner chains interleave instead of running one after the other behind a call.
+__device__ __forceinline__ void det_exp4(const double (&x)[4], double (&y)[4])
+{
+    double kf[4], r[4], p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        kf[j] = rint(__dmul_rn(x[j], 1.4426950408889634));
+        r[j] = __dsub_rn(x[j], __dmul_rn(kf[j], 0.6931471803691238));
+        r[j] = __dsub_rn(r[j], __dmul_rn(kf[j], 1.9082149292705877e-10));
+        p[j] = 1.0 / 6227020800.0;
+    }
+    const double c[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
+                          1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+#pragma unroll
+    for (int i = 0; i < 13; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[j] = hstep(p[j], r[j], c[i]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = (int)kf[j], k1 = k / 2, k2 = k - k1;
+        double v = __dmul_rn(__dmul_rn(p[j], pow2i(k1)), pow2i(k2));
+        if (x[j] < -745.2) v = 0.0;                      // the special cases of det_exp, applied last
+        if (x[j] > 709.782712893384) v = CUDART_INF;
+        if (x[j] != x[j]) v = x[j];
+        y[j] = v;
+    }
+}
+
+__device__ __forceinline__ void det_log2_4(const double (&xin)[4], double (&y)[4])
+{
+    double s[4], z[4], q[4];
+    int e[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        double x = xin[j];
+        e[j] = 0;
+        if (x < 2.2250738585072014e-308) { x = __dmul_rn(x, 18014398509481984.0); e[j] = -54; }
+        const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+        e[j] += (int)(b >> 52) - 1023;
+        double m = __longlong_as_double((long long)((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
+        if (m > 1.4142135623730951) { m = __dmul_rn(m, 0.5); e[j] += 1; }
+        s[j] = __ddiv_rn(__dsub_rn(m, 1.0), __dadd_rn(m, 1.0));
+        z[j] = __dmul_rn(s[j], s[j]);
+        q[j] = 1.0 / 25.0;
+    }
+    const double c[12] = {1.0 / 23.0, 1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0,
+                          1.0 / 5.0, 1.0 / 3.0, 1.0};
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[j] = hstep(q[j], z[j], c[i]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double lnm = __dmul_rn(__dmul_rn(2.0, s[j]), q[j]);
+        double v = __dadd_rn((double)e[j], __dmul_rn(lnm, 1.4426950408889634));
+        const double x = xin[j];
+        if (x == CUDART_INF) v = x;                      // the special cases of det_log2, applied last
+        if (x == 0.0) v = -CUDART_INF;
+        if (x != x || x < 0.0) v = CUDART_NAN;
+        y[j] = v;
+    }
+}
+
 // ndarray.sum() order for a short row (NumPy pairwise sum, n < 128): sequential below 8 elements,
 // else 8 running accumulators combined as ((0+1)+(2+3))+((4+5)+(6+7)) plus a sequential tail.
 template <int MAXD>
@@ -379,8 +443,22 @@ template <int MAXD>
 __device__ __forceinline__ void softmax_row(const double *th, int deg, double (&sm)[MAXD])
 {
     double e[MAXD];
+    static_assert(MAXD % 4 == 0, "softmax_row works on groups of four");
 #pragma unroll
-    for (int j = 0; j < MAXD; ++j) e[j] = (j < deg) ? det_exp(th[j]) : 0.0;
+    for (int g4 = 0; g4 < MAXD; g4 += 4) {
+        double xin[4], yo[4];
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { xin[j] = (g4 + j < deg) ? th[g4 + j] : 0.0; any |= g4 + j < deg; }
+        if (MAXD > 4 && !__any_sync(__activemask(), any)) {          // nobody in the warp has neighbours this far out
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e[g4 + j] = 0.0;
+            continue;
+        }
+        det_exp4(xin, yo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e[g4 + j] = (g4 + j < deg) ? yo[j] : 0.0;
+    }
     const double ssum = np_sum_row<MAXD>(e, deg);
 #pragma unroll
     for (int j = 0; j < MAXD; ++j) sm[j] = (j < deg) ? __ddiv_rn(e[j], ssum) : 0.0;
@@ -1116,7 +1194,20 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                 if (p.add_entropy) {                                            // hybrid.py:38-39
                     double tmp[MAXD];
 #pragma unroll
-                    for (int j = 0; j < MAXD; ++j) tmp[j] = (j < deg) ? __dmul_rn(sm[j], det_log2(sm[j])) : 0.0;
+                    for (int g4 = 0; g4 < MAXD; g4 += 4) {
+                        double xin[4], yo[4];
+                        bool any = false;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { xin[j] = (g4 + j < deg) ? sm[g4 + j] : 1.0; any |= g4 + j < deg; }
+                        if (MAXD > 4 && !__any_sync(__activemask(), any)) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) tmp[g4 + j] = 0.0;
+                            continue;
+                        }
+                        det_log2_4(xin, yo);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) tmp[g4 + j] = (g4 + j < deg) ? __dmul_rn(sm[g4 + j], yo[j]) : 0.0;
+                    }
                     rr = __dsub_rn(rr, __dmul_rn(p.lr_e, np_sum_row<MAXD>(tmp, deg)));
                 }
                 const double tq = __dmul_rn(p.discount, max_qy);
