@@ -810,7 +810,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                                 break;
                             }
                             const unsigned a = ps.next() >> 5, b = ps.next() >> 6;
-                            const double u = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+                            const double u = __dmul_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 1.0 / 9007199254740992.0);
 #pragma unroll
                             for (int j = 0; j < MAXD - 1; ++j)
                                 if (j < deg - 1 && kk == j && __ddiv_rn(cdf[j], c) <= u) kk = j + 1;
@@ -897,7 +897,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                     }
                     PhiloxStream ps(p.seed, stream_id, clock, x, 1);
                     const unsigned a = ps.next() >> 5, b = ps.next() >> 6;
-                    const double u = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+                    const double u = __dmul_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 1.0 / 9007199254740992.0);
 #pragma unroll
                     for (int j = 0; j < MAXD - 1; ++j)
                         if (j < deg - 1 && k == j && __ddiv_rn(cdf[j], c) <= u) k = j + 1;
