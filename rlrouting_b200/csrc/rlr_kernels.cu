@@ -1951,6 +1951,9 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
         smem_tables = (table_bytes > 0 && smem_for(g_try, thr_try, true) <= (size_t)kSmemLimit) ? 1 : 0;
     }
     if (G <= 0 && h->ecap > 0 && !smem_tables) G = 256 / N > 0 ? 256 / N : 1;
+    // GlobalRoute's per-step all-pairs recomputation is one serial thread per destination column: a 256-thread CTA of
+    // several replicas keeps more columns going per SM (measured on 6x6: 1.9e8 -> 2.3e8 hops/s)
+    if (G <= 0 && h->policy == RLR_POLICY_GLOBALROUTE) G = 256 / N > 0 ? 256 / N : 1;
     if (G <= 0) G = smem_tables ? 1 : (N >= 96 ? 1 : (128 / N > 0 ? 128 / N : 1));
     if ((long long)G > h->R) G = (int)h->R;
     int threads = cfg->threads_per_block;
