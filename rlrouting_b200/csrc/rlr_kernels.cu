@@ -1945,6 +1945,12 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     // General timing model: one thread per replica replays the event heap serially and bounds the step, so what pays is
     // more resident replicas, not faster table reads: tables stay in HBM/L2 and a CTA carries ~256 threads (measured).
     if (smem_tables < 0 && h->ecap > 0) smem_tables = 0;
+    // HybridQ's step is dominated by the softmax arithmetic, not by table reads, and its two fp64 tables would leave room
+    // for only 3 replicas per SM: tables in HBM/L2 and 256-thread CTAs of several replicas run 14 per SM (measured on
+    // 6x6, 4,096 replicas: 3.6e9 -> 8.0e9 hops/s).  MaHybridQ and CQ / CDRQ keep theirs on chip: they sweep whole tables
+    // every step.
+    const bool hybrid_hbm = smem_tables < 0 && h->policy == RLR_POLICY_HYBRIDQ;
+    if (hybrid_hbm) smem_tables = 0;
     if (smem_tables < 0) {                               // automatic: in shared memory if they fit (for the requested G, if any)
         const int g_try = G > 0 ? G : 1;
         const int thr_try = cfg->threads_per_block > 0 ? cfg->threads_per_block : (g_try * N + 31) / 32 * 32 + 128;
@@ -1953,7 +1959,7 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     if (G <= 0 && h->ecap > 0 && !smem_tables) G = 256 / N > 0 ? 256 / N : 1;
     // GlobalRoute's per-step all-pairs recomputation is one serial thread per destination column: a 256-thread CTA of
     // several replicas keeps more columns going per SM (measured on 6x6: 1.9e8 -> 2.3e8 hops/s)
-    if (G <= 0 && h->policy == RLR_POLICY_GLOBALROUTE) G = 256 / N > 0 ? 256 / N : 1;
+    if (G <= 0 && ((h->policy == RLR_POLICY_GLOBALROUTE && N < 96) || hybrid_hbm)) G = 256 / N > 0 ? 256 / N : 1;
     if (G <= 0) G = smem_tables ? 1 : (N >= 96 ? 1 : (128 / N > 0 ? 128 / N : 1));
     if ((long long)G > h->R) G = (int)h->R;
     int threads = cfg->threads_per_block;
