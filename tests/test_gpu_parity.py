@@ -156,6 +156,8 @@ BATCH = [
     ("6x6.net", "Shortest", 33, 600, "sweep", dict(replicas_per_block=4)),
     ("lata.net", "Shortest", 5, 300, 3.0, {}),
     ("6x6.net", "HybridQ", 24, 300, 2.0, {}),
+    ("6x6.net", "HybridQ", 10, 300, 2.0, dict(tables_in_smem=1)),          # the default keeps HybridQ's tables in HBM/L2
+    ("6x6.net", "HybridQ", 10, 200, 1.0, dict(tables_in_smem=1, replicas_per_block=3, threads_per_block=128)),
     ("6x6-modified.net", "HybridQ", 9, 300, 1.5, dict(replicas_per_block=3)),
     ("lata.net", "HybridQ", 3, 200, 2.0, {}),
     ("6x6.net", "MaHybridQ", 10, 300, 2.0, {}),
