@@ -53,7 +53,10 @@ int fail(int code, const std::string &msg)
             return fail(RLR_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));            \
     } while (0)
 
-constexpr int kMaxThreads = 512;
+#ifndef RLR_MAXT
+#define RLR_MAXT 512
+#endif
+constexpr int kMaxThreads = RLR_MAXT;
 #ifndef RLR_MIN_BLOCKS
 #define RLR_MIN_BLOCKS 1
 #endif
@@ -404,11 +407,64 @@ __device__ __forceinline__ void bulk_commit_wait()
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- predicated memory operations.  The step is a latency-bound dependent chain: a short `if` around a
+// load or store becomes a divergent branch region that ptxas will not schedule across, so the loop-free arrival phase
+// issues its accesses as predicated instructions instead (lanes whose predicate is off do not touch memory). ----
+// (outputs are write-only: a lane whose predicate is off gets an undefined value, which every caller masks)
+__device__ __forceinline__ uint4 lds128_if(const uint4 *ptr, bool pred)
+{
+    uint4 v;
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n}"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(ptr)), "r"((int)pred) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stg128_if(uint4 *ptr, const uint4 &v, bool pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p st.global.v4.u32 [%0], {%1, %2, %3, %4};\n}"
+                 :: "l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void sts128_if(uint4 *ptr, const uint4 &v, bool pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n}"
+                 :: "r"(smem_u32(ptr)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((int)pred) : "memory");
+}
+// ---- asynchronous global -> shared copies (cp.async, SASS LDGSTS): they complete in commit groups, not on a register
+// scoreboard, so a load issued now can be consumed D steps later without any instruction in between waiting for it ----
+__device__ __forceinline__ void cp_async16_if(void *dst_smem, const void *src_gmem, bool pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p cp.async.cg.shared.global [%0], [%1], 16;\n}"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void cp_async8_if(void *dst_smem, const void *src_gmem, bool pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p cp.async.ca.shared.global [%0], [%1], 8;\n}"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }   // committed or not
+__device__ __forceinline__ void sts64_if(double *ptr, double v, bool pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.shared.f64 [%0], %1;\n}"
+                 :: "r"(smem_u32(ptr)), "d"(v), "r"((int)pred) : "memory");
+}
+
 // Shared-memory carve-up, identical on host (sizing) and device (pointers).
+// Depth of the head-record staging of the fused path: the record a node will pop D steps from now is already on its way
+// into shared memory (one cp.async per pop), so DRAM latency (~1 us on B200, more in the tail of 32 lanes) is off the step's
+// dependent chain.  Power of two.
+constexpr int kStageDepth = 2;
+
 struct SmemLayout {
-    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, gr, samp, evheap, evorder, evsent, evlen, evfrom, mbar, total;
+    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, gr, samp, evheap, evorder, evsent, evlen, evfrom, mbar,
+        stage, swin, total;
+    bool heap_in_smem;
+    // fused = the Network.train instantiation (SPLIT = false): it stages queue heads and the injection schedule in shared
+    // memory, has no sample_route_time staging, and when the tables fill shared memory it reads heap_pos through L1 instead
+    // (the table is read-only and shared by every CTA of the SM; nothing else of the fused loop allocates in L1)
     __host__ __device__ SmemLayout(int N, int sdeg, int G, int threads, int policy, bool smem_tables, long long tsize, int ntab,
-                                   int ecap = 0)
+                                   int ecap, bool fused)
     {
         const int GN = G * N;
         size_t o = 0;
@@ -422,10 +478,11 @@ struct SmemLayout {
         rowptr = o; o += align16((size_t)(N + 1) * 4);
         col = o; o += align16((size_t)sdeg * 2);
         tp = o; o += align16((size_t)GN * 2);
-        heappos = o; o += align16((size_t)(N + 1) * N);
+        heap_in_smem = !(fused && smem_tables);
+        heappos = o; o += heap_in_smem ? align16((size_t)(N + 1) * N) : 0;
         nexthop = o; o += (policy == RLR_POLICY_SHORTEST) ? align16((size_t)N * N * 2)      // u8 next hops or u16 choice masks
                            : (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * N * N * 2) : 0;
-        samp = o; o += align16((size_t)G * (ecap > N ? ecap : N) * 8);   // sample_route_time staging: (heap position, routing time) per delivery
+        samp = o; o += fused ? 0 : align16((size_t)G * (ecap > N ? ecap : N) * 8);   // sample_route_time staging: (heap position, routing time) per delivery
         gr = o; o += (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * (N * N + N) * 4) : 0;   // distances + weights
         // general timing model: the event heap, this step's popped events, Node.sent per link, heap length + pop count
         evheap = o; o += ecap ? align16((size_t)G * ((ecap + 3) & ~1) * 4) : 0;
@@ -434,6 +491,8 @@ struct SmemLayout {
         evlen = o; o += ecap ? align16((size_t)G * 2 * 4) : 0;
         evfrom = o; o += ecap ? align16((size_t)sdeg) : 0;
         mbar = o; o += smem_tables ? 16 : 0;               // mbarrier of the bulk table load
+        stage = o; o += fused ? align16((size_t)kStageDepth * GN * 16) : 0;   // [D][G*N] records at / after the queue heads
+        swin = o; o += fused ? align16((size_t)GN * 16) : 0;                   // [2][G*N][2] injection events ahead
         total = o;
     }
 };
@@ -515,7 +574,11 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     extern __shared__ __align__(16) unsigned char smem[];
     const int N = p.N, G = p.G, GN = G * N;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const SmemLayout L(N, p.sdeg, G, blockDim.x, POLICY, SMEM_TABLES, p.tsize, p.ntab, SPLIT ? p.ecap : 0);
+    constexpr bool FUSED = !SPLIT;            // the Network.train instantiation: staged queue heads, injections at step end
+    constexpr int D = kStageDepth;
+    const SmemLayout L(N, p.sdeg, G, blockDim.x, POLICY, SMEM_TABLES, p.tsize, p.ntab, SPLIT ? p.ecap : 0, FUSED);
+    constexpr bool kHeapInSmem = !(FUSED && SMEM_TABLES);
+
     double *s_tables = reinterpret_cast<double *>(smem + L.tables);
     uint4 *s_rec = reinterpret_cast<uint4 *>(smem + L.rec);
     double *s_f64 = reinterpret_cast<double *>(smem + L.f64);
@@ -527,6 +590,9 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     unsigned short *s_tp = reinterpret_cast<unsigned short *>(smem + L.tp);   // target | warp-local rank << 8
     unsigned char *s_heappos = smem + L.heappos;
     unsigned char *s_nexthop = smem + L.nexthop;
+    uint4 *s_stage = reinterpret_cast<uint4 *>(smem + L.stage);     // [D][G*N]: record i of thread t's queue at [(i & (D-1)) * GN + t]
+    unsigned *s_win = reinterpret_cast<unsigned *>(smem + L.swin);  // [2][G*N][2]: event e of thread t at [((e >> 1) & 1) * 2 * GN + 2 * t + (e & 1)]
+    auto heap_pos_at = [&](unsigned i) -> unsigned { return kHeapInSmem ? (unsigned)s_heappos[i] : (unsigned)__ldg(p.heap_pos + i); };
     // timing model (compile-time defaults in the fused instantiation)
     const bool general = SPLIT && p.general != 0;
     const int slotw = SPLIT ? p.slot : 1, ttime = SPLIT ? p.transtime : 1, freq = SPLIT ? p.freq : 1;
@@ -584,7 +650,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     }
     for (int i = t; i <= N; i += blockDim.x) s_rowptr[i] = p.row_ptr[i];
     for (int i = t; i < p.sdeg; i += blockDim.x) s_col[i] = (unsigned short)p.col[i];
-    for (int i = t; i < (N + 1) * N; i += blockDim.x) s_heappos[i] = p.heap_pos[i];
+    if (kHeapInSmem)
+        for (int i = t; i < (N + 1) * N; i += blockDim.x) s_heappos[i] = p.heap_pos[i];
     if (POLICY == RLR_POLICY_SHORTEST) {
         if (p.shortest_random)
             for (int i = t; i < N * N; i += blockDim.x) reinterpret_cast<unsigned short *>(s_nexthop)[i] = p.choice_mask[i];
@@ -650,7 +717,13 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         head = p.qhead[r * N + x];
         tail = p.qtail[r * N + x];
         myring = p.ring + ((size_t)r * N + x) * (size_t)p.cap;
-        if (head != tail) pref = myring[head & capmask];
+        if (FUSED) {                            // stage the first D records of the queue
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                cp_async16_if(s_stage + ((head + i) & (D - 1)) * GN + t, myring + ((head + i) & capmask), tail - head > (unsigned)i);
+        } else if (head != tail) {
+            pref = myring[head & capmask];
+        }
         if (general) ndead = (unsigned)p.q_dead[r * N + x];
         rp = s_rowptr[x];
         deg = s_rowptr[x + 1] - rp;
@@ -684,7 +757,20 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     // injection schedule of this node: events (local step << 8 | dest), ascending, 0xFFFFFFFF-terminated
     const unsigned *evp = p.inj_events + ((size_t)(is_node ? r : 0) * N + (is_node ? x : 0)) * (size_t)p.inj_cap;
     unsigned ev = is_node ? evp[0] : 0xFFFFFFFFu;                   // current event and the one after it: the list is
-    unsigned ev_next = (is_node && ev != 0xFFFFFFFFu) ? evp[1] : 0xFFFFFFFFu;    // read two entries ahead of its use
+    unsigned ev_next = (!FUSED && is_node && ev != 0xFFFFFFFFu) ? evp[1] : 0xFFFFFFFFu;   // read two entries ahead of its use
+    // Fused path: the list is read through a window of two 8-byte chunks (events 2c, 2c + 1 in half c & 1) that cp.async
+    // refills a chunk ahead, so no load of the schedule ever sits on a register scoreboard inside the step loop.
+    const unsigned *ev_base = evp;
+    unsigned eidx = 2u;                                             // next event of the list to take from the window
+    int win_t_old = -(1 << 20), win_t_new = -(1 << 20);             // steps at which the two resident chunks were requested
+    if (FUSED) {
+        cp_async8_if(s_win + 2 * t, ev_base, is_node);
+        cp_async8_if(s_win + 2 * GN + 2 * t, ev_base + 2, is_node && p.inj_cap > 2);
+        cp_async_wait_all();
+        ev_next = is_node ? s_win[2 * t + 1] : 0xFFFFFFFFu;         // (ev, ev_next) in registers, the rest behind them in the window
+        cp_async8_if(s_win + 2 * t, ev_base + 4, is_node && p.inj_cap > 4);     // chunk 0 is used up: chunk 2 takes its half
+        win_t_new = -1;
+    }
     evp += 1;
     bool dead = is_node ? (s_dead[g] != 0u) : true;                 // only sampled policies can die mid-launch
     const int gr_off = (POLICY == RLR_POLICY_GLOBALROUTE && is_node) ? p.gr_qs_off[r * N + x] : 0;
@@ -695,12 +781,47 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
     // status word; the masked index keeps a wrapped write inside this node's own ring.
     auto append = [&](const uint4 &rec) {
         myring[tail & capmask] = rec;
-        if (head == tail) { fresh = rec; use_fresh = true; }
+        if (FUSED) {                    // a record that lands within D of the head is staged directly (nothing will fetch it)
+            if (tail - head < (unsigned)D) s_stage[(tail & (D - 1)) * GN + t] = rec;
+        } else if (head == tail) {
+            fresh = rec;
+            use_fresh = true;
+        }
         ++tail;
     };
 
     // SPLIT = false is the fused Network.train path (both phases, no flag tests in the loop)
     const bool do_env = !SPLIT || (p.phase & 1) != 0, do_learn = !SPLIT || (p.phase & 2) != 0;
+    // Fused path: the packets of step s + 1 (new_packet + inject, env.py:298-319) are appended at the END of step s, right
+    // after the arrivals of step s — the same queue order as injecting at the start of step s + 1, but off the head of the
+    // dependent chain, and with the schedule read from the shared-memory window.
+    constexpr bool kInjectAtStart = SPLIT;
+#ifdef RLR_NOFLAT
+    constexpr bool kFlatArrivals = false;
+#else
+    constexpr bool kFlatArrivals = FUSED && MAXD == 4;
+#endif
+    constexpr bool kLearnInArrivals = kFlatArrivals && POLICY == RLR_POLICY_QROUTE && SMEM_TABLES;
+    auto inject_step = [&](int s_now, unsigned step, int clk) {
+        while ((ev >> 8) == step) {
+            append(make_uint4((ev & 0xFFu) | ((unsigned)x << 16), 0u, (unsigned)clk, (unsigned)clk));
+            ++my_inj;
+            ev = ev_next;
+            // the look-ahead register is refilled from the window (nothing waits for this read before the node's next
+            // packet); the first event of a chunk requested fewer than D + 2 steps ago (a burst of packets at one node)
+            // may still be in flight
+            if ((eidx & 1u) == 0u && s_now - win_t_old < D + 2) cp_async_wait_all();
+            ev_next = s_win[((eidx >> 1) & 1u) * 2u * GN + 2u * t + (eidx & 1u)];
+            ++eidx;
+            if ((eidx & 1u) == 0u) {    // chunk eidx/2 - 1 is used up: request chunk eidx/2 + 1 into its half
+                const unsigned c = (eidx >> 1) + 1u;
+                cp_async8_if(s_win + (c & 1u) * 2u * GN + 2u * t, ev_base + 2u * c, 2u * c < (unsigned)p.inj_cap);
+                win_t_old = win_t_new;
+                win_t_new = s_now;
+            }
+        }
+    };
+    if (!kInjectAtStart && !dead) inject_step(-1, 0u, p.clock0);
     const bool sampling = SPLIT && p.sample != nullptr;      // sample_route_time also runs on the SPLIT instantiation
 #ifdef RLR_EXP_TIMING
     long long tacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -708,6 +829,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
 #endif
     for (int s = 0; s < p.K; ++s) {
         const int clock = p.clock0 + s * slotw;
+        if (FUSED) cp_async_wait<D - 1>();      // every copy of the groups before the latest has landed (see the commit below)
         if ((IS_PG || sampling) && is_node) dead = (s_dead[g] != 0u);
         const bool live = !dead;
         bool sending = false;
@@ -740,7 +862,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
         }
         if (live && do_env) {
             // ---- A. new_packet + inject (env.py:298-319): consume this step's events of the schedule ----
-            while ((ev >> 8) == (unsigned)s) {
+            // (the fused instantiation has done this at the end of the previous step, see inject_step below)
+            while (kInjectAtStart && (ev >> 8) == (unsigned)s) {
                 append(make_uint4((ev & 0xFFu) | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock));
                 ++my_inj;
                 if (SPLIT && p.metrics2) atomicAdd(&s_injs[g], 1u);
@@ -751,7 +874,18 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             if (DUAL) s_len[t] = tail - head - ndead;                           // len(queue) before this node's own send
             bool have = false;
             uint4 rec = make_uint4(0u, 0u, 0u, 0u);
-            if (!general) {
+            if (FUSED) {
+                // the head record was staged in shared memory at least D steps ago (or by the append that created it); the
+                // pop requests the record that is now D - 1 behind the new head — the loads never touch a register
+                const bool nonempty = head != tail;
+                if (nonempty) {
+                    have = true;
+                    rec = s_stage[(head & (D - 1)) * GN + t];
+                    ++head;
+                }
+                cp_async16_if(s_stage + ((head + (D - 1)) & (D - 1)) * GN + t, myring + ((head + (D - 1)) & capmask),
+                              nonempty && tail - head > (unsigned)(D - 1));
+            } else if (!general) {
                 if (head != tail) {
                     have = true;
                     rec = use_fresh ? fresh : pref;
@@ -910,18 +1044,19 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                     max_qxd = best;
                 }
                 y = s_col[rp + k];
+                const int qoff_y = N * s_rowptr[y], deg_y = s_rowptr[y + 1] - s_rowptr[y];   // Q[y] offset and degree of the next hop
                 rec.y += 1u;                                                    // p.hops += 1, env.py:141
                 rwd = (double)(-(clock - (int)rec.w) - 1);                      // r = -q_y - t_y, qroute.py:37
                 if (IS_CQ) {                        // CQ.get_info (qroute.py:72-78): z = argmax Q[y][d], max_Q_f, C_f
-                    const int rpy = s_rowptr[y], degy = s_rowptr[y + 1] - rpy;
-                    const double *ry = Qr + N * rpy + d * degy;
+                    const int degy = deg_y;
+                    const double *ry = Qr + qoff_y + d * degy;
                     double m = ry[0];
                     int z = 0;
 #pragma unroll
                     for (int j = 1; j < MAXD; ++j)
                         if (j < degy) { const double v = ry[j]; if (v > m) { m = v; z = j; } }
                     max_qy = m;
-                    c_f = Thr[N * rpy + d * degy + z];
+                    c_f = Thr[qoff_y + d * degy + z];
                     if (DUAL) {                     // CDRQ.get_info (qroute.py:107-115) + _build_info_dual (env.py:154-160)
                         const int src = (int)(rec.x >> 16);
                         const double *rb = Qx + src * deg;
@@ -936,15 +1071,16 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                         s_src[t] = (unsigned short)src;
                     }
                 } else if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) {   // max_Q_y, qroute.py:29-30
-                    const int rpy = s_rowptr[y], degy = s_rowptr[y + 1] - rpy;
-                    const double *ry = Qr + N * rpy + d * degy;
+                    const int degy = deg_y;
+                    const double *ry = Qr + qoff_y + d * degy;
                     double m = ry[0];
 #pragma unroll
                     for (int j = 1; j < MAXD; ++j)
                         if (j < degy) { const double v = ry[j]; if (v > m) m = v; }
                     max_qy = m;
                 }
-                s_rec[t] = rec;
+                // published with the arrival time already in start_queue (env.py:129), so that the receiver appends it as is
+                s_rec[t] = make_uint4(rec.x, rec.y, rec.z, general ? rec.w : (unsigned)(clock + ttime));
                 if (general) {                      // Node._send_packet (env.py:135-145): the event outlives the step
                     p.event_rec[(size_t)r * ecap + ((unsigned)(clock + ttime) % (unsigned)(ttime + 1)) * N + x] = rec;
                     s_evsent[g * p.sdeg + rp + k] += 1;
@@ -990,7 +1126,7 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
 
         // Qroute's learn step only needs what this thread computed before the barrier, and every read of the tables by the
         // other threads' get_info is behind us now: do it first, so its fp64 chain overlaps the shared-memory loads of C
-        if (POLICY == RLR_POLICY_QROUTE && do_learn && sending) {               // qroute.py:40-44
+        if (POLICY == RLR_POLICY_QROUTE && do_learn && sending && !kLearnInArrivals) {  // qroute.py:40-44
             const double tq = __dmul_rn(p.discount, max_qy);
             const double u1 = __dadd_rn(rwd, tq);
             const double u2 = __dsub_rn(u1, oldq);
@@ -1126,16 +1262,80 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
             int nkey = 0;
 #pragma unroll
             for (int j = 0; j < MAXD; ++j) {
+                if (kFlatArrivals) break;
                 if (MAXD > 4 && j >= p.max_deg) continue;                       // uniform: no node has a j-th neighbour
                 const unsigned tp = s_tp[nb_slot[j]];
                 const bool match = (tp & 0xFFu) == (unsigned)x;                 // kNoSend's low byte is 255 > any node id
                 unsigned base = 0;
                 if (MAXW <= 3) base = __byte_perm(cumpack, 0u, nb_word[j]) & 0xFFu;
                 else base = cum[nb_word[j]];                                    // (an indexed local array: one load, not MAXW selects)
-                const unsigned pos = s_heappos[hp_row + (match ? (tp >> 8) + base : 0u)];
+                const unsigned pos = heap_pos_at(hp_row + (match ? (tp >> 8) + base : 0u));
                 if (MAXD == 4) key[j] = match ? ((pos << 16) | nb_slot[j]) : kNoKey;
                 else if (match) key[nkey++] = (pos << 16) | nb_slot[j];
             }
+            if (kLearnInArrivals) {
+                // Qroute.learn (qroute.py:40-44) in the same straight-line block as the arrival loads, so that the fp64
+                // chain fills their latency; only the store is predicated on `sending`
+                const double tq = __dmul_rn(p.discount, max_qy);
+                const double u1 = __dadd_rn(rwd, tq);
+                const double u2 = __dsub_rn(u1, oldq);
+                sts64_if(Qx + (d * deg + k), __dadd_rn(oldq, __dmul_rn(p.lr_q, u2)), sending);
+            }
+            if (kFlatArrivals) {
+                // Loop-free arrivals (degree <= 4): every matching neighbour's record and heap position are fetched side
+                // by side, a record's place in the queue is its rank among the appended ones (pairwise compares of the
+                // positions), and the <= 4 ring writes are independent of each other.
+                uint4 rc[4];
+                unsigned posv[4];
+                bool mt[4], ap[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned tp = s_tp[nb_slot[j]];
+                    mt[j] = (tp & 0xFFu) == (unsigned)x;
+                    const unsigned base = __byte_perm(cumpack, 0u, nb_word[j]) & 0xFFu;
+                    posv[j] = heap_pos_at(hp_row + (mt[j] ? (tp >> 8) + base : 0u));
+                    rc[j] = lds128_if(s_rec + nb_slot[j], mt[j]);
+                }
+                unsigned ndel = 0u, rtsum = 0u, hopsum = 0u, ndrop = 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool dropped = SPLIT && p.is_drop && rc[j].y >= (unsigned)N;      // env.py:355-360
+                    const bool del = mt[j] && !dropped && (int)(rc[j].x & 0xFFFFu) == x;    // Network.end_packet, env.py:321-331
+                    ap[j] = mt[j] && !dropped && !del;                                      // Node.receive, env.py:127-130
+                    if (SPLIT && mt[j] && dropped) ++ndrop;
+                    ndel += del ? 1u : 0u;
+                    rtsum += del ? (unsigned)(clock + ttime - (int)rc[j].z) : 0u;
+                    hopsum += del ? rc[j].y : 0u;
+                    if (sampling && del) {                                                  // env.py:325-328, ordered later
+                        const unsigned slot = atomicAdd(&s_nsamp[g], 1u);
+                        s_samp_pos[g * sstride + slot] = posv[j];
+                        s_samp_lat[g * sstride + slot] = clock + ttime - (int)rc[j].z;
+                    }
+                }
+                if (SPLIT && ndrop) atomicAdd(&s_drop[g], ndrop);
+                if (ndel) {
+                    atomicAdd(&s_end[g], ndel);
+                    atomicAdd(&s_rt32[g], rtsum);
+                    atomicAdd(&s_hops[g], hopsum);
+                }
+                const unsigned tail0 = tail;
+                unsigned keyv[4], rkv[4] = {0u, 0u, 0u, 0u};        // rank among the appended ones by heap position
+#pragma unroll
+                for (int j = 0; j < 4; ++j) keyv[j] = ap[j] ? posv[j] : 0x100u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i != j) rkv[j] += (keyv[i] < keyv[j]) ? 1u : 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned rk = rkv[j];
+                    const unsigned at = tail0 + rk;
+                    stg128_if(myring + (at & capmask), rc[j], ap[j]);
+                    sts128_if(s_stage + (at & (D - 1)) * GN + t, rc[j], ap[j] && at - head < (unsigned)D);
+                    tail += ap[j] ? 1u : 0u;
+                }
+            } else {
             if (MAXD == 4) {                                                    // 5-comparator sorting network
 #define RLR_CE(a, b) { const unsigned lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; }
                 RLR_CE(0, 1) RLR_CE(2, 3) RLR_CE(0, 2) RLR_CE(1, 3) RLR_CE(1, 2)
@@ -1177,7 +1377,8 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                     append(rec);
                 }
             }
-            if (tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
+            }
+            if (kInjectAtStart && tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
         }
         RLR_T(2);                                   // C
         // ---- D. agent.learn ----
@@ -1342,6 +1543,13 @@ __global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(c
                     th[i] = a2;
                 }
             }
+        }
+        // One commit group per step, closed here: group s holds the schedule chunks requested at the end of step s - 1 and the
+        // record requested by the pop of step s, so when the top of step s + 2 waits for it every copy in it is two steps old.
+        if (FUSED) cp_async_commit();
+        if (!kInjectAtStart && is_node && live) {   // next step's new_packet + inject (env.py:298-319); slot = 1 on this path
+            inject_step(s, (unsigned)(s + 1), clock + 1);
+            if (tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
         }
         RLR_T(3);                                   // D
         __syncthreads();                                                        // ---- barrier 2 ----
@@ -1878,7 +2086,7 @@ extern "C" int rlr_trace_schedule(const int32_t *cnt, const uint32_t *pairs, int
 struct rlr_handle {
     int N, sdeg, max_deg, policy, ntab;
     long long R, replica_base, tsize;
-    int cap, G, threads, smem_bytes, device, ecap;
+    int cap, G, threads, smem_bytes, smem_bytes_split, device, ecap;   // dynamic shared memory of the fused / split kernel
     bool smem_tables, bound;
     std::vector<int> row_ptr, col;
     rlr_buffers_t bufs;
@@ -1939,8 +2147,11 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     int G = cfg->replicas_per_block;
     int smem_tables = cfg->tables_in_smem;
     if (h->policy == RLR_POLICY_SHORTEST || h->policy == RLR_POLICY_GLOBALROUTE) smem_tables = 0;
+    // footprint of a launch: the larger of the two instantiations (fused Network.train / split phases and options)
     auto smem_for = [&](int g, int thr, bool st) {
-        return SmemLayout(N, h->sdeg, g, thr, h->policy, st, h->tsize, h->ntab, h->ecap).total;
+        const size_t a = SmemLayout(N, h->sdeg, g, thr, h->policy, st, h->tsize, h->ntab, 0, true).total;
+        const size_t b = SmemLayout(N, h->sdeg, g, thr, h->policy, st, h->tsize, h->ntab, h->ecap, false).total;
+        return a > b ? a : b;
     };
     // General timing model: one thread per replica replays the event heap serially and bounds the step, so what pays is
     // more resident replicas, not faster table reads: tables stay in HBM/L2 and a CTA carries ~256 threads (measured).
@@ -1990,16 +2201,12 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
         delete h;
         return fail(RLR_E_UNSUPPORTED, "rlr_create: shared-memory footprint exceeds 227 KB (lower replicas_per_block or set tables_in_smem=0)");
     }
-    h->G = G; h->threads = threads; h->smem_bytes = (int)smem; h->smem_tables = smem_tables != 0;
+    h->G = G; h->threads = threads; h->smem_tables = smem_tables != 0;
+    h->smem_bytes = (int)SmemLayout(N, h->sdeg, G, threads, h->policy, h->smem_tables, h->tsize, h->ntab, 0, true).total;
+    h->smem_bytes_split = (int)SmemLayout(N, h->sdeg, G, threads, h->policy, h->smem_tables, h->tsize, h->ntab, h->ecap, false).total;
     h->kernel = pick_kernel<false>(h->policy, h->N, h->max_deg, h->smem_tables);
     h->kernel_split = pick_kernel<true>(h->policy, h->N, h->max_deg, h->smem_tables);
-    cudaError_t e = cudaFuncSetAttribute((const void *)h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute((const void *)h->kernel_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        delete h;
-        return fail(RLR_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    }
+    (void)smem;                 // (the per-function shared-memory limit is set right before every launch, rlr_run_steps)
     *out = h;
     return RLR_OK;
 }
@@ -2196,9 +2403,14 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     }
     const long long blocks = (h->R + h->G - 1) / h->G;
     if (blocks > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_run_steps: too many blocks");
+    // the fused instantiation reads the schedule in 8-byte chunks (cp.async): it needs an even, 8-byte aligned list layout
     const bool plain = p.phase == 3 && !p.sample && !p.sendlog && !p.is_drop && !p.metrics2 && !p.general && slot == 1 &&
-                       freq == 1 && transtime == 1;
-    (plain ? h->kernel : h->kernel_split)<<<(unsigned)blocks, h->threads, h->smem_bytes, (cudaStream_t)stream>>>(p);
+                       freq == 1 && transtime == 1 && p.inj_cap % 2 == 0 && ((uintptr_t)p.inj_events & 7) == 0;
+    const StepKernel kern = plain ? h->kernel : h->kernel_split;
+    const int smem = plain ? h->smem_bytes : h->smem_bytes_split;
+    // the attribute belongs to the function, not to the handle: another handle of the same instantiation may have set less
+    RLR_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<(unsigned)blocks, h->threads, smem, (cudaStream_t)stream>>>(p);
     RLR_CUDA(cudaGetLastError());
     if (rp->route_time_out || rp->hop_out || rp->droprate_out) {
         const long long n = n_steps * h->R;

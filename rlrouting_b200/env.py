@@ -77,7 +77,8 @@ def schedule_capacity(lam_max, n_nodes, n_steps):
     """Entries per (replica, node) of a Philox-mode injection schedule: the Poisson(lambda/N * steps) count of
     one node, its mean plus 12 standard deviations plus slack (overflow probability < 1e-30), + terminator."""
     m = float(lam_max) / n_nodes * n_steps
-    return int(m + 12.0 * np.sqrt(m) + 24) + 1
+    cap = int(m + 12.0 * np.sqrt(m) + 24) + 1
+    return cap + (cap & 1)              # even: the fused step kernel reads the lists in 8-byte chunks (cp.async)
 
 
 def trace_schedule(cnt, pairs, n_nodes, s0, s1, freq=1):

@@ -109,6 +109,7 @@ class TraceBatch:
             cap = C.c_int32(0)
             args = (self.cnt.ctypes.data, self.packed.ctypes.data, self.packed.shape[1], R, N, T, int(it0), int(it1), int(freq))
             nat.check(nat.lib().rlr_trace_schedule(*args, None, 0, C.byref(cap), self.workers))
+            cap.value += cap.value & 1                      # even: the fused step kernel reads the lists in 8-byte chunks
             sched = np.empty((R, N, cap.value), dtype=np.uint32)
             nat.check(nat.lib().rlr_trace_schedule(*args, sched.ctypes.data, cap.value, None, self.workers))
             return sched
@@ -116,6 +117,7 @@ class TraceBatch:
         evs = [trace_schedule(c, pr, N, it0, it1, freq) for c, pr in self.lists]
         per_node = [np.bincount(node, minlength=N) for _, node in evs]
         cap = int(max(pn.max() for pn in per_node)) + 2
+        cap += cap & 1                                      # even (8-byte chunks, see above)
         sched = np.full((len(evs), N, cap), 0xFFFFFFFF, dtype=np.uint32)
         for r, ((e, node), pn) in enumerate(zip(evs, per_node)):
             start = np.concatenate([[0], np.cumsum(pn)[:-1]])

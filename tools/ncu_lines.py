@@ -54,7 +54,10 @@ def main():
         inst[line] += int(r[idx["Instructions Executed"]] or 0)
         samp[line] += int(r[idx["# Samples"]] or 0)
     ti, ts = sum(inst.values()), sum(samp.values())
-    srcfile = [l.rstrip("\n") for l in open(os.path.join(os.path.dirname(os.path.abspath(so)), "rlr_kernels.cu"))]
+    srcpath = os.path.join(os.path.dirname(os.path.abspath(so)), "rlr_kernels.cu")
+    if not os.path.exists(srcpath):
+        srcpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rlrouting_b200", "csrc", "rlr_kernels.cu")
+    srcfile = [l.rstrip("\n") for l in open(srcpath)]
     print(f"total warp-instructions {ti}, samples {ts}")
     print(f"{'line':>5} {'inst%':>6} {'samp%':>6}  source")
     for line, n in inst.most_common(top):
