@@ -51,7 +51,7 @@ class Policy:
 
     # ---- checkpoint interchange (base_policy.py:57-66): same pickle layout as the reference ----
     def _attr_value(self, k):
-        if k in self._table_names:
+        if k in self._table_names or k not in self.__dict__:        # device tables and property-backed attributes
             return getattr(self, k)
         return self.__dict__[k]
 
@@ -62,10 +62,14 @@ class Policy:
     def load(self, filename):
         with open(filename, 'rb') as f:
             for k, v in pickle.load(f).items():
-                if k in self._table_names:
-                    setattr(self, k, v)
+                if k in self._table_names or isinstance(getattr(type(self), k, None), property):
+                    setattr(self, k, v)                 # re-uploads to the device (a read-only property raises)
                 else:
                     self.__dict__[k] = v
+        self._after_load()
+
+    def _after_load(self):
+        """Hook: agents whose device tables are derived from loaded host attributes re-upload them here."""
 
     # ---- device tables <-> the reference's Dict[x -> (N, deg_x) ndarray] ----
     def table_array(self, name):

@@ -1882,9 +1882,13 @@ StepKernel pick_deg(int n_nodes, int max_deg, bool smem_tables)
 template <bool SPLIT>
 StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables)
 {
-#ifdef RLR_FAST_BUILD       // kernel-tuning builds: only the 6x6 Qroute instantiations (seconds instead of a minute)
+#ifdef RLR_FAST_BUILD       // kernel-tuning builds: only the degree-4 instantiations of one policy (seconds instead of minutes);
+                            // -DRLR_FAST_POLICY=<policy id>, Qroute (1) by default
     (void)policy; (void)n_nodes; (void)max_deg;
-    return pick_smem<RLR_POLICY_QROUTE, 4, 3, SPLIT>(smem_tables);
+#ifndef RLR_FAST_POLICY
+#define RLR_FAST_POLICY RLR_POLICY_QROUTE
+#endif
+    return pick_smem<RLR_FAST_POLICY, 4, 3, SPLIT>(smem_tables);
 #else
     switch (policy) {
     case RLR_POLICY_SHORTEST: return pick_deg<RLR_POLICY_SHORTEST, SPLIT>(n_nodes, max_deg, false);

@@ -5,9 +5,10 @@ With no new keywords a `Network(file)` is ONE environment driven by NumPy's glob
 the reference's numbers bit for bit.  The additive keywords (`replicas`, `rng`, `seed`, ...) batch R
 independent environments; every counter property then returns an array of length R.
 
-Unsupported reference options raise NotImplementedError when they are requested, never mid-run,
-and there is no CPU fallback: `bandwidth != 1`, `transtime != 1`,
-`slot != 1`, `freq != 1`, mode 'dual'/'bp', and agents that are not one of the built-in policies.
+Integer `bandwidth`, `transtime`, `slot` and `freq`, `is_drop`, `sample_route_time` and the 'dual' node mode
+(CDRQ) all run on the device.  What the device cannot do raises NotImplementedError when it is requested, never
+mid-run, and there is no CPU fallback: float-valued clocks (`slot`, `transtime` ...), mode 'bp',
+'dual' for anything but CDRQ, and agents that are not one of the built-in policies.
 """
 import ctypes as C
 from collections import OrderedDict
@@ -59,7 +60,14 @@ class Node:
 
     @property
     def sent(self):
-        return dict.fromkeys(self.links, 0)      # every event lands inside its step (env.py:349-353)
+        """Packets in flight per link (env.py:115-116): all zero between steps unless events outlive a step
+        (transtime > slot), in which case the device keeps the counts (general timing model)."""
+        nw = self.network
+        if not nw._general:
+            return dict.fromkeys(self.links, 0)  # every event lands inside its step (env.py:349-353)
+        rp = int(nw.topology.row_ptr[self.ID])
+        cnt = nw._link_sent[0, rp:rp + len(self.links)].cpu().numpy()
+        return {y: int(c) for y, c in zip(self.links, cnt)}
 
     def __repr__(self):
         return f"Node<{self.ID}, queue: {self.queue}, sent: {self.sent}>"
@@ -134,6 +142,8 @@ class Network:
             raise RuntimeError("rlrouting_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         nat.lib()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:           # 'cuda' without an index means the CURRENT device, not device 0
+            self.device = torch.device("cuda", torch.cuda.current_device())
         topo, R, N = self.topology, self.replicas, self.topology.N
         if queue_capacity is None:
             # the reference's queues are unbounded; by default the rings get a fifth of the device memory (16-byte
@@ -193,7 +203,7 @@ class Network:
         t = nat.Topology(topo.N, topo.sum_deg, topo.max_deg, topo.row_ptr.ctypes.data, topo.col.ctypes.data)
         rpb, tpb, tis = self._launch_cfg
         cfg = nat.Config(self.replicas, self.replica_base, agent._kernel_policy, self.queue_capacity, rpb, tpb, tis,
-                         self.device.index or 0, self._ecap, 0)
+                         self.device.index, self._ecap, 0)
         h = C.c_void_p()
         nat.check(nat.lib().rlr_create(C.byref(t), C.byref(cfg), C.byref(h)))
         d = agent._dev
@@ -230,7 +240,7 @@ class Network:
                                 "stream": torch.cuda.Stream(device=self.device)}
         cap = schedule_capacity(lam_max, self.topology.N, K)
         shape = (self.replicas, self.topology.N, cap)
-        key = (clock0, K, lam_key, cap)
+        key = (clock0, K, lam_key, cap, int(rp.freq), int(rp.slot), int(rp.seed))     # everything the schedule kernel reads
         compute = torch.cuda.current_stream(self.device)
         slot = next((i for i in (0, 1) if st["ready"][i] is not None and st["ready"][i][0] == key), None)
         if slot is not None:
@@ -285,7 +295,7 @@ class Network:
         self.launch_count += 1
         done = torch.cuda.Event()
         done.record(side)
-        st["ready"][other] = ((clock0, K, lam_key, cap), done)
+        st["ready"][other] = ((clock0, K, lam_key, cap, int(rp.freq), int(rp.slot), int(rp.seed)), done)
 
     def _lam_tensors(self, lam, upload=True):
         """exp(-lambda_r / N) and the exact integer injection thresholds as device tensors.  The host values are cached
@@ -424,9 +434,9 @@ class Network:
         import torch
         R, N, cap, dev = self.replicas, self.topology.N, self.queue_capacity, self.device
         want = (N, self.topology.sum_deg, R, self.replica_base, self.rng, self.bandwidth, self.transtime,
-                type(self._agent).__name__)
+                bool(self.is_drop), type(self._agent).__name__)
         got = (snap["n_nodes"], snap["sum_deg"], snap["replicas"], snap["replica_base"], snap["rng"], snap["bandwidth"],
-               snap["transtime"], snap["agent_class"])
+               snap["transtime"], bool(snap.get("is_drop", False)), snap["agent_class"])
         if snap.get("version") != 1 or want != got:
             raise ValueError(f"snapshot does not fit this network: {got} vs {want}")
         lens = torch.from_numpy(np.ascontiguousarray(snap["queue_len"], dtype=np.int64)).reshape(-1).to(dev)
@@ -685,6 +695,10 @@ class Network:
     def _check_sync(self):
         if self.__dict__.get("_desync"):
             raise RuntimeError("the replicas stopped at different clocks in sample_route_time; call reset() first")
+        if any(self.__dict__.get("_pending") or []):
+            raise NotImplementedError("packets passed to inject() are still waiting for the next step(): train(), "
+                                      "sample_route_time() and run_device() draw their own traffic and would leave them "
+                                      "behind; call step() first (the reference enqueues them immediately, env.py:314-319)")
 
     # ------------------------------------------------------------------ the hot path (env.py:367-414)
     def train(self, duration, lambd, slot=1, freq=1, lr={}, droprate=False, hop=False, *, lrq=None, lrp=None,
@@ -879,6 +893,7 @@ class Network:
         import torch
         if self.rng != "philox":
             raise NotImplementedError("run_device needs rng='philox' (trace mode uploads host-generated injections)")
+        self._check_sync()
         agent = self._agent
         h = getattr(agent, "_handle", None)
         if h is None:

@@ -36,6 +36,25 @@ class Shortest(Policy):
         choices = self.links[source][self.choice[source][dest]]                    # shortest.py:38-41
         return np.random.choice(choices) if self.random else choices[0]
 
+    def _after_load(self):
+        """`load` (base_policy.py:62-66) replaced `distance` / `choice` / `mask` on the host: the device routes by its own
+        copies (next hop = first True of a choice row, choice masks as bits), so upload them again."""
+        import torch
+        topo = self._network.topology
+        n = topo.N
+        flat = np.concatenate([np.asarray(self.choice[x], dtype=bool).reshape(n * int(topo.deg[x])) for x in range(n)])
+        nh = np.zeros((n, n), dtype=np.uint8)
+        cm = np.zeros((n, n), dtype=np.uint16)
+        for x in range(n):
+            c = np.asarray(self.choice[x], dtype=bool).reshape(n, int(topo.deg[x]))
+            any_true = c.any(axis=1)
+            nh[x] = np.where(any_true, c.argmax(axis=1), max(int(topo.deg[x]) - 1, 0))   # the APSP kernel's "no choice" value
+            cm[x] = (c.astype(np.uint16) << np.arange(c.shape[1], dtype=np.uint16)[None, :]).sum(axis=1)
+        self._dev["choice"].copy_(torch.from_numpy(flat.astype(np.uint8)))
+        self._dev["next_hop"].copy_(torch.from_numpy(nh.reshape(-1)))
+        self._dev["choice_mask"].copy_(torch.from_numpy(cm.reshape(-1).view(np.int16)))
+        self._dev["distance"].copy_(torch.from_numpy(np.ascontiguousarray(self.distance, dtype=np.float64).reshape(-1)))
+
 
 class GlobalRoute(Shortest):
     """Queue-aware global routing (reference shortest.py:84-104): after every step all distances are recomputed with
@@ -68,6 +87,14 @@ class GlobalRoute(Shortest):
         d[d >= self.INF] = np.inf
         return self._one(d)
 
+    @distance.setter
+    def distance(self, value):                              # Policy.load: back onto the device (every replica or one for all)
+        import torch
+        n, R = self._network.topology.N, self._network.replicas
+        d = np.asarray(value, dtype=np.float64).reshape(-1, n * n)
+        d = np.where(np.isfinite(d), d, float(self.INF)).astype(np.int32)
+        self._dev["gr_distance"].copy_(torch.from_numpy(np.ascontiguousarray(np.broadcast_to(d, (R, n * n)))))
+
     @property
     def choice(self):
         topo = self._network.topology
@@ -78,6 +105,20 @@ class GlobalRoute(Shortest):
             bits = (cm[:, x, :, None] >> np.arange(int(topo.deg[x]), dtype=np.uint16)[None, None, :]) & 1
             out[x] = self._one(bits.astype(bool))
         return out
+
+    @choice.setter
+    def choice(self, value):
+        import torch
+        topo = self._network.topology
+        n, R = topo.N, self._network.replicas
+        cm = np.zeros((R, n, n), dtype=np.uint16)
+        for x in range(n):
+            c = np.asarray(value[x], dtype=bool).reshape(-1, n, int(topo.deg[x]))
+            cm[:, x, :] = (c.astype(np.uint16) << np.arange(c.shape[2], dtype=np.uint16)[None, None, :]).sum(axis=2)
+        self._dev["gr_choice_mask"].copy_(torch.from_numpy(cm.reshape(R, n * n).view(np.int16)))
+
+    def _after_load(self):
+        pass                                                # distance / choice went through the setters above
 
     @property
     def queue_size(self):

@@ -186,3 +186,85 @@ def test_snapshot_restore_continues_bit_for_bit(policy, rng, nkw, akw, tmp_path)
         other = rb.Network("6x6.net", replicas=R + 1, rng=rng, seed=7, **nkw)
         other.agent = cls(other, **akw)
         other.load_state(tmp_path / "state.pkl")
+
+
+@pytest.mark.parametrize("policy,keys,akw", [
+    ("Shortest", {"links", "distance", "choice", "mask"}, {}),
+    ("Shortest", {"links", "distance", "choice", "mask"}, {"multiway": True, "random": True}),
+    ("GlobalRoute", {"links", "distance", "choice", "mask"}, {}),
+    ("CQ", {"links", "Qtable", "discount", "threshold", "confidence", "decay"}, {}),
+    ("CDRQ", {"links", "Qtable", "discount", "threshold", "confidence", "decay"}, {}),
+    ("HybridQ", {"links", "Qtable", "discount", "threshold", "Theta"}, {}),
+    ("MaHybridQ", {"links", "Qtable", "discount", "threshold", "Theta", "discount_trace", "Trace"}, {}),
+])
+def test_store_load_round_trip_every_agent(policy, keys, akw, tmp_path):
+    """Policy.store / load (base_policy.py:57-66) for every device agent: the pickle has the reference's keys and
+    per-node (N, deg_x) shapes, and an agent that loads it routes exactly like the one that stored it — including the
+    agents whose tables are properties (GlobalRoute) or are derived on the device from host attributes (Shortest)."""
+    import rlrouting_b200 as rb
+    cls = getattr(rb, policy)
+    lr = {"q": 0.1, "p": 0.001 if policy == "MaHybridQ" else 0.1}
+
+    def make(seed):
+        nw = rb.Network("6x6.net", replicas=1, rng="philox", seed=seed)
+        ag = cls(nw, **akw)
+        nw.agent = ag
+        return nw, ag
+
+    a, ag_a = make(11)
+    a.train(300, 2.5, lr=lr)                               # learned tables / congested GlobalRoute tables
+    path = tmp_path / "agent.pkl"
+    ag_a.store(str(path))
+    blob = pickle.load(open(path, "rb"))
+    assert keys <= set(blob), (set(blob), keys)
+    for k in ("Qtable", "Theta", "Trace", "confidence", "choice"):
+        if k in blob:
+            assert all(np.asarray(blob[k][x]).shape == (36, len(a.links[x])) for x in range(36)), k
+    # a fresh agent on a fresh network of the same seed, given the stored tables, continues like the original would
+    # from the same environment state
+    snap = a.snapshot()
+    b, ag_b = make(11)
+    b.restore(snap)
+    if policy == "Shortest":                               # derived device tables: wipe them so that only load() can fill them
+        for name in ("next_hop", "choice", "choice_mask"):
+            ag_b._dev[name].zero_()
+    elif policy == "GlobalRoute":
+        ag_b._dev["gr_choice_mask"].zero_()
+        ag_b._dev["gr_distance"].zero_()
+    else:
+        for name in ag_b._dev:
+            ag_b._dev[name].zero_()
+    ag_b.load(str(path))
+    for name in ag_a._dev:
+        if policy == "GlobalRoute" and name == "gr_qs_off":
+            continue
+        assert np.array_equal(ag_a._dev[name].cpu().numpy(), ag_b._dev[name].cpu().numpy()), name
+    ra, rb_ = a.train(120, 2.5, lr=lr), b.train(120, 2.5, lr=lr)
+    assert np.array_equal(ra["route_time"], rb_["route_time"])
+    ca, cb = a.counters(), b.counters()
+    assert all(np.array_equal(ca[k], cb[k]) for k in ca)
+
+
+def test_prefetched_schedule_is_keyed_by_timing_and_seed():
+    """train() prefetches the injection schedule of the call it expects next; a following call with another `freq`
+    (same clock, step count and loads) must not consume it (the cache key lacked freq / slot / seed)."""
+    import rlrouting_b200 as rb
+    from oracle import oracle as O
+    R, seed = 6, 9
+    nw = rb.Network("6x6.net", replicas=R, rng="philox", seed=seed)
+    agent = rb.Qroute(nw)
+    nw.agent = agent
+    q0 = agent.table_array("Qtable").copy()
+    nw.train(100, 2.0)
+    nw.train(34, 2.0, freq=2)                   # clock 100, 68 device steps: the same key as a repeat of ... (68, freq=1)
+    c = nw.counters()
+    for r in range(R):
+        e = O.OracleEnv(nw.topology.links, "Qroute", seed=seed, replica=r)
+        e.set_qtable(q0[r])
+        e.run(100, lambd=2.0)
+        e.run(34, lambd=2.0, freq=2)
+        oc = e.counters()
+        assert all(int(c[k][r]) == oc[k] for k in ("all_packets", "end_packets", "hops", "route_time", "sends")), r
+    with pytest.raises(NotImplementedError, match="inject"):
+        nw.inject([[rb.Packet(0, 5, nw.clock)] for _ in range(R)])
+        nw.train(10, 2.0)
