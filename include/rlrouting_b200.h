@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RLR_ABI_VERSION 2
+#define RLR_ABI_VERSION 3
 
 enum { RLR_OK = 0, RLR_E_INVALID = -1, RLR_E_UNSUPPORTED = -2, RLR_E_CUDA = -3, RLR_E_STATE = -4 };
 
@@ -243,6 +243,21 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *para
 /* ---- sums the per-replica counters into out[RLR_NUM_COUNTERS] (device pointer, int64) so a
  *      load level's statistics can be all-reduced across GPUs ---- */
 int rlr_reduce_stats(rlr_handle_t *h, int64_t *out, void *stream);
+
+/* ---- per-load-level curves: pools the per-(step, replica) records `metrics` ([n_steps][R] 16-byte records written by
+ *      rlr_run_steps: cumulative route_time u64, end_packets u32, hops u32) over the replicas of each level
+ *      (level_idx[r] in [0, n_levels)) and writes, per step and level, Network.ave_route_time / ave_hops of the pooled
+ *      level (env.py:440-446) and/or the three integer sums ([n_steps][n_levels][3] int64).  This is what leaves the
+ *      device in a load sweep instead of the [n_steps][R] vectors of env.py:394-414.  All pointers are device pointers. ---- */
+int rlr_reduce_levels(rlr_handle_t *h, const void *metrics, int64_t n_steps, const int32_t *level_idx, int32_t n_levels,
+                      double *route_time_out, double *hop_out, int64_t *sums_out, void *stream);
+
+/* ---- Q-convergence statistics of a table (0 = Qtable, 1 = Theta / confidence, 2 = Trace): per replica
+ *      {sum of entries, sum of |entry - prev entry|} into per_replica[R][2] (prev: an earlier copy of the table, or NULL
+ *      for zeros in the second slot) and, if level_out is given, the same pooled per load level into level_out[n_levels][2]
+ *      (level_idx == NULL: one level).  Fixed summation order: reproducible fp64 (what qroute.py:40-44 moved). ---- */
+int rlr_table_stats(rlr_handle_t *h, int32_t table_id, const double *prev, double *per_replica, const int32_t *level_idx,
+                    int32_t n_levels, double *level_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -10,11 +10,15 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = os.path.join(HERE, "csrc", "rlr_kernels.cu")
+CSRC = os.path.join(HERE, "csrc")
 HDR = os.path.join(ROOT, "include", "rlrouting_b200.h")
-SO = os.environ.get("RLR_LIB") or os.path.join(HERE, "csrc", "librlrouting_b200.so")   # RLR_LIB: experiment builds
+STEP_HDR = os.path.join(CSRC, "rlr_step.cuh")
+# translation units: the host side of the C ABI + one per policy family (each instantiates the step kernel for its policy)
+UNITS = ["rlr_kernels"] + ["step_" + n for n in ("shortest", "qroute", "hybridq", "mahybridq", "cq", "cdrq", "globalroute")]
+SRC = os.path.join(CSRC, "rlr_kernels.cu")
+SO = os.environ.get("RLR_LIB") or os.path.join(CSRC, "librlrouting_b200.so")   # RLR_LIB: experiment builds
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 NUM_COUNTERS = 8
 CTR = {"all_packets": 0, "end_packets": 1, "drop_packets": 2, "hops": 3, "route_time": 4, "sends": 5}
 POLICY_SHORTEST, POLICY_QROUTE, POLICY_HYBRIDQ, POLICY_MAHYBRIDQ, POLICY_CQ, POLICY_CDRQ, POLICY_GLOBALROUTE = 0, 1, 2, 3, 4, 5, 6
@@ -22,18 +26,28 @@ INJECT_TRACE, INJECT_PHILOX = 0, 1
 STATUS_OK, STATUS_NAN_PROB, STATUS_QUEUE_OVERFLOW, STATUS_INJECT_OVERFLOW = 0, 1, 2, 3
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-fmad=false", "-Xcompiler", "-fPIC", "-shared"]
+              "-fmad=false", "-Xcompiler", "-fPIC"]
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/rlr_kernels.cu -> csrc/librlrouting_b200.so for sm_100a."""
-    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
-        return SO
+    """Compile csrc/*.cu -> csrc/librlrouting_b200.so for sm_100a: every translation unit that is older than its sources is
+    rebuilt (all of them in parallel), then the objects are linked into the shared library."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", SO, SRC]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    subprocess.check_call(cmd)
+    objdir = os.path.join(CSRC, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_time = max(os.path.getmtime(HDR), os.path.getmtime(STEP_HDR))
+    jobs, objs = [], []
+    for u in UNITS:
+        src, obj = os.path.join(CSRC, u + ".cu"), os.path.join(objdir, u + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
+            cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, src] + (["-Xptxas", "-v"] if verbose else [])
+            jobs.append((u, subprocess.Popen(cmd)))
+    failed = [u for u, p in jobs if p.wait() != 0]
+    if failed:
+        raise RuntimeError(f"nvcc failed for {failed}")
+    if jobs or not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(o) for o in objs):
+        subprocess.check_call([nvcc, "-shared", "-o", SO] + objs)
     return SO
 
 
@@ -75,7 +89,7 @@ class RunParams(C.Structure):
 EXPORTS = ("rlr_abi_version", "rlr_last_error_string", "rlr_struct_sizes", "rlr_create", "rlr_destroy", "rlr_bind_buffers",
            "rlr_launch_info", "rlr_reset", "rlr_init_tables", "rlr_build_shortest_tables",
            "rlr_build_inject_schedule", "rlr_run_steps", "rlr_reduce_stats", "rlr_trace_replay", "rlr_trace_replay_many",
-           "rlr_trace_schedule")
+           "rlr_trace_schedule", "rlr_reduce_levels", "rlr_table_stats")
 
 _lib = None
 
@@ -105,6 +119,8 @@ def lib():
     L.rlr_run_steps.argtypes = [p, C.c_int64, C.POINTER(RunParams), p]
     L.rlr_build_inject_schedule.argtypes = [p, C.c_int64, C.POINTER(RunParams), p]
     L.rlr_reduce_stats.argtypes = [p, p, p]
+    L.rlr_reduce_levels.argtypes = [p, p, C.c_int64, p, C.c_int32, p, p, p, p]
+    L.rlr_table_stats.argtypes = [p, C.c_int32, p, p, p, C.c_int32, p, p]
     L.rlr_trace_replay.argtypes = [p, p, C.c_int32, C.c_int64, C.c_double, p, p, C.c_int64, p]
     L.rlr_trace_replay_many.argtypes = [p, p, C.c_int64, C.c_int32, C.c_int64, p, p, p, C.c_int64, p, C.c_int32]
     L.rlr_trace_schedule.argtypes = [p, p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, p, C.c_int32, p,

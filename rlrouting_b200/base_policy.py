@@ -76,6 +76,10 @@ class Policy:
         """The whole table as a NumPy array [R, N*sum_deg] (packed layout of Topology.pack)."""
         return self._dev[name].cpu().numpy()
 
+    def table_device(self, name):
+        """The device tensor [R, N*sum_deg] behind a table (no copy); `.clone()` it to keep a copy for Network.table_stats."""
+        return self._dev[name]
+
     def _get_table(self, name):
         topo = self._network.topology
         flat = self.table_array(name)

@@ -22,19 +22,7 @@
 //
 // All fp64 arithmetic on tables uses the explicitly rounded intrinsics (__dmul_rn/__dadd_rn/...),
 // never FMA, because the reference evaluates every NumPy scalar operation separately.
-#include <cuda_runtime.h>
-#include <math_constants.h>
-#include <stdint.h>
-#include <stdio.h>
-#include <string.h>
-
-#include <algorithm>
-#include <atomic>
-#include <string>
-#include <thread>
-#include <vector>
-
-#include "../../include/rlrouting_b200.h"
+#include "rlr_step.cuh"
 
 namespace {
 
@@ -52,1612 +40,6 @@ int fail(int code, const std::string &msg)
         if (e_ != cudaSuccess)                                                                      \
             return fail(RLR_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));            \
     } while (0)
-
-#ifndef RLR_MAXT
-#define RLR_MAXT 512
-#endif
-constexpr int kMaxThreads = RLR_MAXT;
-#ifndef RLR_MIN_BLOCKS
-#define RLR_MIN_BLOCKS 1
-#endif
-constexpr int kSmemLimit = 227 * 1024;
-
-// ------------------------------------------------------------------------------------------------
-// Device parameter block of the step kernel
-// ------------------------------------------------------------------------------------------------
-struct StepParams {
-    int N, sdeg, G, R;
-    int cap, K, clock0, ntab;
-    long long tsize;
-    const int *row_ptr;
-    const int *col;
-    const unsigned char *heap_pos;
-    const unsigned char *next_hop;
-    const unsigned short *choice_mask;    // Shortest(random=True): [N*N] bit j = choice[x][d][j]
-    int shortest_random;
-    unsigned short *gr_choice_mask;   // GlobalRoute: [R][N*N] per-replica choice masks, bit j = choice[x][d][j] (persist across launches)
-    int gr_multiway;              // GlobalRoute(multiway=True): keep every optimal neighbour (shortest.py:57-58)
-    int *gr_distance;             // GlobalRoute: [R][N*N] distances (0x3FFFFFFF = inf)
-    const int *gr_qs_off;         // GlobalRoute: [R][N] queue_size - len(queue) (non-zero only after Network.reset)
-    double *Q, *Theta, *Trace;
-    uint4 *ring;
-    unsigned *qhead, *qtail;
-    long long *counters;
-    int *status;
-    int inj_cap, add_entropy;
-    int is_drop;                  // Network(is_drop=True), env.py:355-360
-    int phase;                    // bit 0: inject + send + arrive (Network.step); bit 1: agent.learn
-    uint4 *rewards;               // [R][N][4] saved Reward records (phase 1 writes, phase 2 reads)
-    const unsigned *inj_events;
-    unsigned long long seed;
-    long long replica_base;
-    double lr_q, lr_p, lr_e, discount, discount_trace, conf_decay;
-    uint4 *metrics;
-    int *sample;                  // Network.sample_route_time: [R][sample_size] routing times in delivery order
-    int *sample_idx;              // [R] Network._sample_idx (persists across calls)
-    int *sample_clock;            // [R] clock at which the replica reached sample_size deliveries
-    int sample_size;
-    uint2 *metrics2;              // [K][R] {all_packets, drop_packets} after each step (for the droprate vector)
-    unsigned *sendlog;
-    // timing model (SPLIT instantiation only): clock advances `slot` per step, arrivals at clock + transtime
-    int slot, freq, transtime, bandwidth;
-    int general;                  // events outlive a step: persistent heap, busy links, queue scan (env.py:171-190)
-    int ecap;                     // event capacity per replica = N * (transtime + 1)
-    int *link_sent;               // [R][sdeg]
-    unsigned long long *event_heap;   // [R][ecap]
-    int *event_count;             // [R]
-    uint4 *event_rec;             // [R][ecap]
-    int *q_dead;                  // [R][N]
-    int max_deg;                  // largest node degree (uniform loop bound of the MAXD > 4 instantiations)
-};
-
-// ------------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al. SC'11).  Stream law shared with oracle/rlr_oracle.c:
-//   counter = (clock, node | purpose<<16 | block<<24, replica_lo, replica_hi), key = seed.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
-{
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u;
-        k.y += 0xBB67AE85u;
-    }
-    return c;
-}
-
-struct PhiloxStream {
-    uint4 w;
-    unsigned c0, c1, c2, c3;
-    uint2 key;
-    int have, block;
-    __device__ __forceinline__ PhiloxStream(unsigned long long seed, unsigned long long replica, int clock,
-                                            int node, int purpose)
-        : c0((unsigned)clock), c1((unsigned)node | ((unsigned)purpose << 16)), c2((unsigned)replica),
-          c3((unsigned)(replica >> 32)), key(make_uint2((unsigned)seed, (unsigned)(seed >> 32))), have(0), block(0)
-    {
-    }
-    __device__ __forceinline__ unsigned next()
-    {
-        if (have == 0) {
-            w = philox4x32_10(make_uint4(c0, c1 | ((unsigned)block << 24), c2, c3), key);
-            have = 4;
-            ++block;
-        }
-        const unsigned r = w.x;
-        w.x = w.y; w.y = w.z; w.z = w.w;
-        --have;
-        return r;
-    }
-};
-
-// ------------------------------------------------------------------------------------------------
-// Deterministic exp / log2: the algorithm documented in DESIGN.md §5 and restated independently in
-// oracle/rlr_oracle.c — IEEE +,-,*,/ and rint only, so CPU and GPU agree bit for bit.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double pow2i(int k) { return __longlong_as_double((long long)(k + 1023) << 52); }
-
-__device__ __forceinline__ double hstep(double p, double r, double c) { return __dadd_rn(__dmul_rn(p, r), c); }
-
-__device__ double det_exp(double x)
-{
-    if (x != x) return x;
-    if (x > 709.782712893384) return CUDART_INF;
-    if (x < -745.2) return 0.0;
-    const double kf = rint(__dmul_rn(x, 1.4426950408889634));
-    double r = __dsub_rn(x, __dmul_rn(kf, 0.6931471803691238));
-    r = __dsub_rn(r, __dmul_rn(kf, 1.9082149292705877e-10));
-    double p = 1.0 / 6227020800.0;
-    p = hstep(p, r, 1.0 / 479001600.0);
-    p = hstep(p, r, 1.0 / 39916800.0);
-    p = hstep(p, r, 1.0 / 3628800.0);
-    p = hstep(p, r, 1.0 / 362880.0);
-    p = hstep(p, r, 1.0 / 40320.0);
-    p = hstep(p, r, 1.0 / 5040.0);
-    p = hstep(p, r, 1.0 / 720.0);
-    p = hstep(p, r, 1.0 / 120.0);
-    p = hstep(p, r, 1.0 / 24.0);
-    p = hstep(p, r, 1.0 / 6.0);
-    p = hstep(p, r, 0.5);
-    p = hstep(p, r, 1.0);
-    p = hstep(p, r, 1.0);
-    const int k = (int)kf, k1 = k / 2, k2 = k - k1;
-    return __dmul_rn(__dmul_rn(p, pow2i(k1)), pow2i(k2));
-}
-
-__device__ double det_log2(double x)
-{
-    if (x != x || x < 0.0) return CUDART_NAN;
-    if (x == 0.0) return -CUDART_INF;
-    if (x == CUDART_INF) return x;
-    int e = 0;
-    if (x < 2.2250738585072014e-308) { x = __dmul_rn(x, 18014398509481984.0); e = -54; }
-    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
-    e += (int)(b >> 52) - 1023;
-    double m = __longlong_as_double((long long)((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
-    if (m > 1.4142135623730951) { m = __dmul_rn(m, 0.5); e += 1; }
-    const double s = __ddiv_rn(__dsub_rn(m, 1.0), __dadd_rn(m, 1.0)), z = __dmul_rn(s, s);
-    double q = 1.0 / 25.0;
-    q = hstep(q, z, 1.0 / 23.0);
-    q = hstep(q, z, 1.0 / 21.0);
-    q = hstep(q, z, 1.0 / 19.0);
-    q = hstep(q, z, 1.0 / 17.0);
-    q = hstep(q, z, 1.0 / 15.0);
-    q = hstep(q, z, 1.0 / 13.0);
-    q = hstep(q, z, 1.0 / 11.0);
-    q = hstep(q, z, 1.0 / 9.0);
-    q = hstep(q, z, 1.0 / 7.0);
-    q = hstep(q, z, 1.0 / 5.0);
-    q = hstep(q, z, 1.0 / 3.0);
-    q = hstep(q, z, 1.0);
-    const double lnm = __dmul_rn(__dmul_rn(2.0, s), q);
-    return __dadd_rn((double)e, __dmul_rn(lnm, 1.4426950408889634));
-}
-
-// Four independent evaluations of det_exp / det_log2 run side by side: the same operations per element (so the same
-// bits), but the four Horner chains interleave instead of running one after the other behind a call.
-__device__ __forceinline__ void det_exp4(const double (&x)[4], double (&y)[4])
-{
-    double kf[4], r[4], p[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        kf[j] = rint(__dmul_rn(x[j], 1.4426950408889634));
-        r[j] = __dsub_rn(x[j], __dmul_rn(kf[j], 0.6931471803691238));
-        r[j] = __dsub_rn(r[j], __dmul_rn(kf[j], 1.9082149292705877e-10));
-        p[j] = 1.0 / 6227020800.0;
-    }
-    const double c[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
-                          1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
-#pragma unroll
-    for (int i = 0; i < 13; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) p[j] = hstep(p[j], r[j], c[i]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int k = (int)kf[j], k1 = k / 2, k2 = k - k1;
-        double v = __dmul_rn(__dmul_rn(p[j], pow2i(k1)), pow2i(k2));
-        if (x[j] < -745.2) v = 0.0;                      // the special cases of det_exp, applied last
-        if (x[j] > 709.782712893384) v = CUDART_INF;
-        if (x[j] != x[j]) v = x[j];
-        y[j] = v;
-    }
-}
-
-__device__ __forceinline__ void det_log2_4(const double (&xin)[4], double (&y)[4])
-{
-    double s[4], z[4], q[4];
-    int e[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        double x = xin[j];
-        e[j] = 0;
-        if (x < 2.2250738585072014e-308) { x = __dmul_rn(x, 18014398509481984.0); e[j] = -54; }
-        const unsigned long long b = (unsigned long long)__double_as_longlong(x);
-        e[j] += (int)(b >> 52) - 1023;
-        double m = __longlong_as_double((long long)((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
-        if (m > 1.4142135623730951) { m = __dmul_rn(m, 0.5); e[j] += 1; }
-        s[j] = __ddiv_rn(__dsub_rn(m, 1.0), __dadd_rn(m, 1.0));
-        z[j] = __dmul_rn(s[j], s[j]);
-        q[j] = 1.0 / 25.0;
-    }
-    const double c[12] = {1.0 / 23.0, 1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0,
-                          1.0 / 5.0, 1.0 / 3.0, 1.0};
-#pragma unroll
-    for (int i = 0; i < 12; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) q[j] = hstep(q[j], z[j], c[i]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const double lnm = __dmul_rn(__dmul_rn(2.0, s[j]), q[j]);
-        double v = __dadd_rn((double)e[j], __dmul_rn(lnm, 1.4426950408889634));
-        const double x = xin[j];
-        if (x == CUDART_INF) v = x;                      // the special cases of det_log2, applied last
-        if (x == 0.0) v = -CUDART_INF;
-        if (x != x || x < 0.0) v = CUDART_NAN;
-        y[j] = v;
-    }
-}
-
-// ndarray.sum() order for a short row (NumPy pairwise sum, n < 128): sequential below 8 elements,
-// else 8 running accumulators combined as ((0+1)+(2+3))+((4+5)+(6+7)) plus a sequential tail.
-template <int MAXD>
-__device__ __forceinline__ double np_sum_row(const double (&a)[MAXD], int n)
-{
-    if (MAXD < 8 || n < 8) {
-        double r = 0.0;
-#pragma unroll
-        for (int j = 0; j < MAXD; ++j)
-            if (j < n) r = __dadd_rn(r, a[j]);
-        return r;
-    }
-    double acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = a[j < MAXD ? j : 0];
-    const int nb = n - (n % 8);
-#pragma unroll
-    for (int j = 8; j < MAXD; ++j)
-        if (j < nb) acc[j & 7] = __dadd_rn(acc[j & 7], a[j]);
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(acc[0], acc[1]), __dadd_rn(acc[2], acc[3])),
-                           __dadd_rn(__dadd_rn(acc[4], acc[5]), __dadd_rn(acc[6], acc[7])));
-#pragma unroll
-    for (int j = 8; j < MAXD; ++j)
-        if (j >= nb && j < n) res = __dadd_rn(res, a[j]);
-    return res;
-}
-
-// ndarray.sum() in NumPy's order over the values of one replica's senders (MaHybridQ.learn's r.sum(), max_Q_y.sum(),
-// max_Q_x_d.sum(), multi_agent.py:28-29), computed by one whole warp: the three reductions run on helper warps while
-// the node warps process arrivals.  v is indexed by thread slot; the replica's senders are the set bits of its window of the
-// CTA-wide "sent" bit array (words wm[wlo .. wlo+nw), first/last word masked).  n < 128 (NumPy's single pairwise block).
-template <int MAXW>
-__device__ double np_sum_warp(const double *v, const unsigned *wm, int wlo, int nw, unsigned mfirst, unsigned mlast, int lane)
-{
-    unsigned m[MAXW], cum[MAXW + 1];
-    cum[0] = 0;
-#pragma unroll
-    for (int i = 0; i < MAXW; ++i) {
-        m[i] = (i < nw) ? wm[wlo + i] : 0u;
-        if (i == 0) m[i] &= mfirst;
-        if (i == nw - 1) m[i] &= mlast;
-        cum[i + 1] = cum[i] + __popc(m[i]);
-    }
-    const int n = (int)cum[MAXW];
-    double a[4];                                    // element e = lane + 32 q of the compacted sender list
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int e = lane + 32 * q;
-        a[q] = 0.0;
-        if (e < n) {
-#pragma unroll
-            for (int i = 0; i < MAXW; ++i)
-                if ((unsigned)e >= cum[i] && (unsigned)e < cum[i + 1])
-                    a[q] = v[(wlo + i) * 32 + __fns(m[i], 0, e - (int)cum[i] + 1)];
-        }
-    }
-    const unsigned full = 0xFFFFFFFFu;
-    double res = 0.0;
-    if (n < 8) {
-        for (int i = 0; i < n; ++i) res = __dadd_rn(res, __shfl_sync(full, a[0], i));
-        return res;
-    }
-    const int nb = n - (n % 8);
-    double acc = a[0];                              // lanes 0..7 hold the eight running accumulators
-    for (int mm = 1; 8 * mm < nb; ++mm) {
-        const int q = mm >> 2, src = (lane + 8 * (mm & 3)) & 31;
-        const double val = __shfl_sync(full, q == 0 ? a[0] : q == 1 ? a[1] : q == 2 ? a[2] : a[3], src);
-        if (lane < 8 && lane + 8 * mm < nb) acc = __dadd_rn(acc, val);
-    }
-    const double t1 = __dadd_rn(acc, __shfl_down_sync(full, acc, 1));          // (r0+r1) at lane 0, (r2+r3) at lane 2, ...
-    const double t2 = __dadd_rn(t1, __shfl_down_sync(full, t1, 2));            // ((r0+r1)+(r2+r3)) at lane 0, ... at lane 4
-    res = __dadd_rn(t2, __shfl_down_sync(full, t2, 4));
-    res = __shfl_sync(full, res, 0);
-    for (int i = nb; i < n; ++i) {
-        const int q = i >> 5;
-        res = __dadd_rn(res, __shfl_sync(full, q == 0 ? a[0] : q == 1 ? a[1] : q == 2 ? a[2] : a[3], i & 31));
-    }
-    return res;
-}
-
-__device__ __forceinline__ void set_status(int *status, long long r, int code, int clock)
-{
-    if (atomicCAS(&status[2 * r], 0, code) == 0) status[2 * r + 1] = clock;
-}
-
-__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
-
-// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) for staging the per-replica tables: one thread moves a whole
-// table between HBM and shared memory; sizes and addresses are multiples of 16 bytes ----
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, void *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, unsigned bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit_wait()
-{
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// ---- predicated memory operations.  The step is a latency-bound dependent chain: a short `if` around a
-// load or store becomes a divergent branch region that ptxas will not schedule across, so the loop-free arrival phase
-// issues its accesses as predicated instructions instead (lanes whose predicate is off do not touch memory). ----
-// (outputs are write-only: a lane whose predicate is off gets an undefined value, which every caller masks)
-__device__ __forceinline__ uint4 lds128_if(const uint4 *ptr, bool pred)
-{
-    uint4 v;
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n}"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(ptr)), "r"((int)pred) : "memory");
-    return v;
-}
-__device__ __forceinline__ void stg128_if(uint4 *ptr, const uint4 &v, bool pred)
-{
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p st.global.v4.u32 [%0], {%1, %2, %3, %4};\n}"
-                 :: "l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((int)pred) : "memory");
-}
-__device__ __forceinline__ void sts128_if(uint4 *ptr, const uint4 &v, bool pred)
-{
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n}"
-                 :: "r"(smem_u32(ptr)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((int)pred) : "memory");
-}
-// ---- asynchronous global -> shared copies (cp.async, SASS LDGSTS): they complete in commit groups, not on a register
-// scoreboard, so a load issued now can be consumed D steps later without any instruction in between waiting for it ----
-__device__ __forceinline__ void cp_async16_if(void *dst_smem, const void *src_gmem, bool pred)
-{
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p cp.async.cg.shared.global [%0], [%1], 16;\n}"
-                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"((int)pred) : "memory");
-}
-__device__ __forceinline__ void cp_async8_if(void *dst_smem, const void *src_gmem, bool pred)
-{
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p cp.async.ca.shared.global [%0], [%1], 8;\n}"
-                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"((int)pred) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N_PENDING>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }   // committed or not
-__device__ __forceinline__ void sts64_if(double *ptr, double v, bool pred)
-{
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.shared.f64 [%0], %1;\n}"
-                 :: "r"(smem_u32(ptr)), "d"(v), "r"((int)pred) : "memory");
-}
-
-// Shared-memory carve-up, identical on host (sizing) and device (pointers).
-// Depth of the head-record staging of the fused path: the record a node will pop D steps from now is already on its way
-// into shared memory (one cp.async per pop), so DRAM latency (~1 us on B200, more in the tail of 32 lanes) is off the step's
-// dependent chain.  Power of two.
-constexpr int kStageDepth = 2;
-
-struct SmemLayout {
-    size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, gr, samp, evheap, evorder, evsent, evlen, evfrom, mbar,
-        stage, swin, total;
-    bool heap_in_smem;
-    // fused = the Network.train instantiation (SPLIT = false): it stages queue heads and the injection schedule in shared
-    // memory, has no sample_route_time staging, and when the tables fill shared memory it reads heap_pos through L1 instead
-    // (the table is read-only and shared by every CTA of the SM; nothing else of the fused loop allocates in L1)
-    __host__ __device__ SmemLayout(int N, int sdeg, int G, int threads, int policy, bool smem_tables, long long tsize, int ntab,
-                                   int ecap, bool fused)
-    {
-        const int GN = G * N;
-        size_t o = 0;
-        tables = o; o += smem_tables ? align16((size_t)G * ntab * tsize * 8) : 0;
-        rec = o; o += align16((size_t)GN * 16);
-        f64 = o; o += (policy == RLR_POLICY_MAHYBRIDQ) ? align16((size_t)(3 * GN + 4 * G) * 8)
-                       : (policy == RLR_POLICY_CDRQ) ? align16((size_t)GN * 32) : 0;   // CDRQ: {C_b, max_Q_b}, len, q_x, d|k, src
-        ull = o; o += align16((size_t)G * 3 * 8);            // route_time, sends, injected
-        u32 = o; o += align16((size_t)G * 8 * 4);            // end, hops, dead, drop, injected-so-far
-        wmask = o; o += align16((size_t)(threads / 32 + 1) * 4);
-        rowptr = o; o += align16((size_t)(N + 1) * 4);
-        col = o; o += align16((size_t)sdeg * 2);
-        tp = o; o += align16((size_t)GN * 2);
-        heap_in_smem = !(fused && smem_tables);
-        heappos = o; o += heap_in_smem ? align16((size_t)(N + 1) * N) : 0;
-        nexthop = o; o += (policy == RLR_POLICY_SHORTEST) ? align16((size_t)N * N * 2)      // u8 next hops or u16 choice masks
-                           : (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * N * N * 2) : 0;
-        samp = o; o += fused ? 0 : align16((size_t)G * (ecap > N ? ecap : N) * 8);   // sample_route_time staging: (heap position, routing time) per delivery
-        gr = o; o += (policy == RLR_POLICY_GLOBALROUTE) ? align16((size_t)G * (N * N + N) * 4) : 0;   // distances + weights
-        // general timing model: the event heap, this step's popped events, Node.sent per link, heap length + pop count
-        evheap = o; o += ecap ? align16((size_t)G * ((ecap + 3) & ~1) * 4) : 0;
-        evorder = o; o += align16((size_t)G * ecap * 4);
-        evsent = o; o += ecap ? align16((size_t)G * sdeg * 4) : 0;
-        evlen = o; o += ecap ? align16((size_t)G * 2 * 4) : 0;
-        evfrom = o; o += ecap ? align16((size_t)sdeg) : 0;
-        mbar = o; o += smem_tables ? 16 : 0;               // mbarrier of the bulk table load
-        stage = o; o += fused ? align16((size_t)kStageDepth * GN * 16) : 0;   // [D][G*N] records at / after the queue heads
-        swin = o; o += fused ? align16((size_t)GN * 16) : 0;                   // [2][G*N][2] injection events ahead
-        total = o;
-    }
-};
-
-// PolicyGradient._softmax (hybrid.py:16-18): exp(theta) / exp(theta).sum(), no max-subtraction; NumPy sum order.
-template <int MAXD>
-__device__ __forceinline__ void softmax_row(const double *th, int deg, double (&sm)[MAXD])
-{
-    double e[MAXD];
-    static_assert(MAXD % 4 == 0, "softmax_row works on groups of four");
-#pragma unroll
-    for (int g4 = 0; g4 < MAXD; g4 += 4) {
-        double xin[4], yo[4];
-        bool any = false;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { xin[j] = (g4 + j < deg) ? th[g4 + j] : 0.0; any |= g4 + j < deg; }
-        if (MAXD > 4 && !__any_sync(__activemask(), any)) {          // nobody in the warp has neighbours this far out
-#pragma unroll
-            for (int j = 0; j < 4; ++j) e[g4 + j] = 0.0;
-            continue;
-        }
-        det_exp4(xin, yo);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) e[g4 + j] = (g4 + j < deg) ? yo[j] : 0.0;
-    }
-    const double ssum = np_sum_row<MAXD>(e, deg);
-#pragma unroll
-    for (int j = 0; j < MAXD; ++j) sm[j] = (j < deg) ? __ddiv_rn(e[j], ssum) : 0.0;
-}
-
-#ifdef RLR_EXP_TIMING
-__device__ unsigned long long g_phase_cycles[8];
-#define RLR_T(i) do { const long long now_ = clock64(); tacc_[i] += now_ - tmark_; tmark_ = now_; } while (0)
-#else
-#define RLR_T(i) do { } while (0)
-#endif
-
-constexpr int kGrInf = 0x3FFFFFFF;
-
-// GlobalRoute._calc_distance (shortest.py:43-58 with mask = all off-diagonal, unit(y) = 1 + queue_size[y]) for ONE
-// destination column z: the columns of the distance matrix are independent, so thread z replays the reference's
-// sequential Gauss-Seidel (x, y in links[x]) sweeps on its own column.  dist/nh are [N][N] in shared memory, w[y] the
-// node weights.  mask[x][z] holds `choice[x][z]` as bits: reset to the improving neighbour on a strict improvement, and with
-// multiway every neighbour that ties the current distance is added, like the reference.
-__device__ __forceinline__ void gr_column(int z, int N, const int *rowptr, const unsigned short *col, const int *w,
-                                          int *dist, unsigned short *mask, bool multiway)
-{
-    for (int x = 0; x < N; ++x) { dist[x * N + z] = (x == z) ? 0 : kGrInf; mask[x * N + z] = 0; }
-    bool changing = true;
-    while (changing) {
-        changing = false;
-        for (int x = 0; x < N; ++x) {
-            const int rp = rowptr[x], deg = rowptr[x + 1] - rp;
-            int cur = dist[x * N + z];
-            unsigned m = mask[x * N + z];
-            for (int j = 0; j < deg; ++j) {
-                const int y = col[rp + j];
-                const int nd = dist[y * N + z] + w[y];
-                if (cur > nd) { cur = nd; dist[x * N + z] = nd; m = 1u << j; changing = true; }
-                if (multiway && nd < kGrInf && cur == nd) m |= 1u << j;          // shortest.py:57-58
-            }
-            mask[x * N + z] = (unsigned short)m;
-        }
-    }
-}
-
-constexpr unsigned kNoKey = 0xFFFFFFFFu;   // "no arrival" sort key (real keys are heap position << 16 | send slot)
-constexpr unsigned kNoSend = 0xFFFFu;      // s_tp entry of a node that did not send this step
-constexpr unsigned kDeadRec = 0xFFFFFFFFu; // word 0 of a ring entry that was sent from the middle of the queue (general timing)
-
-// ------------------------------------------------------------------------------------------------
-// The step kernel: n_steps iterations of Network.train's loop body (env.py:400-413, slot=freq=1).
-//   MAXD  >= max degree (row loops are fully unrolled and predicated)
-//   MAXW  >= 32-bit words a replica's N consecutive thread slots can span (3 for N <= 64, else 9)
-// ------------------------------------------------------------------------------------------------
-template <int POLICY, int MAXD, int MAXW, bool SMEM_TABLES, bool SPLIT>
-__global__ void __launch_bounds__(kMaxThreads, RLR_MIN_BLOCKS) rlr_step_kernel(const __grid_constant__ StepParams p)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int N = p.N, G = p.G, GN = G * N;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    constexpr bool FUSED = !SPLIT;            // the Network.train instantiation: staged queue heads, injections at step end
-    constexpr int D = kStageDepth;
-    const SmemLayout L(N, p.sdeg, G, blockDim.x, POLICY, SMEM_TABLES, p.tsize, p.ntab, SPLIT ? p.ecap : 0, FUSED);
-    constexpr bool kHeapInSmem = !(FUSED && SMEM_TABLES);
-
-    double *s_tables = reinterpret_cast<double *>(smem + L.tables);
-    uint4 *s_rec = reinterpret_cast<uint4 *>(smem + L.rec);
-    double *s_f64 = reinterpret_cast<double *>(smem + L.f64);
-    unsigned long long *s_ull = reinterpret_cast<unsigned long long *>(smem + L.ull);
-    unsigned *s_u32 = reinterpret_cast<unsigned *>(smem + L.u32);
-    unsigned *s_wmask = reinterpret_cast<unsigned *>(smem + L.wmask);
-    int *s_rowptr = reinterpret_cast<int *>(smem + L.rowptr);
-    unsigned short *s_col = reinterpret_cast<unsigned short *>(smem + L.col);
-    unsigned short *s_tp = reinterpret_cast<unsigned short *>(smem + L.tp);   // target | warp-local rank << 8
-    unsigned char *s_heappos = smem + L.heappos;
-    unsigned char *s_nexthop = smem + L.nexthop;
-    uint4 *s_stage = reinterpret_cast<uint4 *>(smem + L.stage);     // [D][G*N]: record i of thread t's queue at [(i & (D-1)) * GN + t]
-    unsigned *s_win = reinterpret_cast<unsigned *>(smem + L.swin);  // [2][G*N][2]: event e of thread t at [((e >> 1) & 1) * 2 * GN + 2 * t + (e & 1)]
-    auto heap_pos_at = [&](unsigned i) -> unsigned { return kHeapInSmem ? (unsigned)s_heappos[i] : (unsigned)__ldg(p.heap_pos + i); };
-    // timing model (compile-time defaults in the fused instantiation)
-    const bool general = SPLIT && p.general != 0;
-    const int slotw = SPLIT ? p.slot : 1, ttime = SPLIT ? p.transtime : 1, freq = SPLIT ? p.freq : 1;
-    const int ecap = SPLIT ? p.ecap : 0, ecap1 = ecap > 0 ? ecap : 1;
-    const int sstride = ecap > N ? ecap : N;                        // deliveries one step can stage per replica
-    int *s_samp_lat = reinterpret_cast<int *>(smem + L.samp);        // [G][sstride] routing times of this step's deliveries
-    unsigned *s_samp_pos = reinterpret_cast<unsigned *>(smem + L.samp) + G * sstride;   // their heap pop positions
-    // general timing: Network.event_queue as the heapq array of 32-bit items (arrive_time - clock0) << 16 | link, item i
-    // of replica g at s_evheap[g * hstride + 1 + i] so that the children 2i+1, 2i+2 form one aligned 8-byte pair
-    unsigned *s_evheap = reinterpret_cast<unsigned *>(smem + L.evheap);
-    const int hstride = (ecap + 3) & ~1;
-    unsigned *s_evorder = reinterpret_cast<unsigned *>(smem + L.evorder);   // [G][ecap] items popped this step, in pop order
-    unsigned char *s_evfrom = smem + L.evfrom;                       // [sdeg] sender of each directed link
-    int *s_evsent = reinterpret_cast<int *>(smem + L.evsent);        // [G][sdeg] Node.sent per directed link
-    int *s_evlen = reinterpret_cast<int *>(smem + L.evlen);          // [G] {len(event_queue), pops of this step}
-    int *s_grdist = reinterpret_cast<int *>(smem + L.gr);          // GlobalRoute: [G][N*N] distances, then [G][N] weights
-    int *s_grw = s_grdist + G * N * N;
-    // per-replica accumulators of this launch
-    unsigned long long *s_sends = s_ull + G, *s_inj = s_ull + 2 * G;
-    unsigned *s_end = s_u32, *s_hops = s_u32 + G, *s_dead = s_u32 + 2 * G, *s_drop = s_u32 + 3 * G, *s_injs = s_u32 + 4 * G,
-             *s_rt32 = s_u32 + 5 * G, *s_nsamp = s_u32 + 6 * G, *s_sidx = s_u32 + 7 * G;        // delivery latencies of the current step (drained every step by the metric thread)
-    // MaHybridQ scratch: r, max_Q_y, max_Q_x_d per node; three sums + spare per replica
-    double *s_r = s_f64, *s_qy = s_f64 + GN, *s_qx = s_f64 + 2 * GN, *s_sum = s_f64 + 3 * GN;
-    // CDRQ scratch (same region): backward-update inputs of each sender and the queue lengths of 'dual' mode
-    double2 *s_bk = reinterpret_cast<double2 *>(s_f64);                          // {C_b, max_Q_b}
-    unsigned *s_len = reinterpret_cast<unsigned *>(s_f64 + 2 * GN);              // queue length after injection
-    int *s_qxi = reinterpret_cast<int *>(s_f64 + 2 * GN) + GN;                   // q_x = max(1, own length after the pop)
-    unsigned short *s_dk = reinterpret_cast<unsigned short *>(s_f64 + 3 * GN);   // dest | action index << 8
-    unsigned short *s_src = s_dk + GN;                                           // packet.source
-    constexpr bool IS_PG = POLICY == RLR_POLICY_HYBRIDQ || POLICY == RLR_POLICY_MAHYBRIDQ;   // softmax-sampled
-    constexpr bool IS_CQ = POLICY == RLR_POLICY_CQ || POLICY == RLR_POLICY_CDRQ;             // confidence tables
-    constexpr bool DUAL = POLICY == RLR_POLICY_CDRQ;                                         // Node mode 'dual'
-
-    const long long rblock = (long long)blockIdx.x * G;            // first replica of this CTA
-    const int g = t / N, x = t - g * N;
-    const long long r = rblock + g;
-    const bool is_node = (t < GN) && (r < p.R);
-    const int gbase = g * N;
-    const long long tstride = (long long)p.ntab * p.tsize;         // smem doubles per replica
-
-    // ---- stage topology (+ tables) into shared memory ----
-    // the tables come by TMA bulk copy: thread 0 arms an mbarrier with the byte count and issues one copy per table, the
-    // other threads stage the small topology arrays meanwhile and everybody waits on the mbarrier after the CTA barrier
-    unsigned long long *s_mbar = reinterpret_cast<unsigned long long *>(smem + L.mbar);
-    if (SMEM_TABLES && t == 0) {
-        mbar_init(s_mbar, 1);
-        int nrep = 0;
-        for (int gg = 0; gg < G; ++gg) nrep += (rblock + gg < p.R) ? 1 : 0;
-        const unsigned tbytes = (unsigned)(p.tsize * 8);
-        mbar_expect_tx(s_mbar, (unsigned)(nrep * p.ntab) * tbytes);
-        for (int gg = 0; gg < nrep; ++gg)
-            for (int tb = 0; tb < p.ntab; ++tb)
-                bulk_g2s(s_tables + gg * ((long long)p.ntab * p.tsize) + tb * p.tsize,
-                         (tb == 0 ? p.Q : tb == 1 ? p.Theta : p.Trace) + (rblock + gg) * p.tsize, tbytes, s_mbar);
-    }
-    for (int i = t; i <= N; i += blockDim.x) s_rowptr[i] = p.row_ptr[i];
-    for (int i = t; i < p.sdeg; i += blockDim.x) s_col[i] = (unsigned short)p.col[i];
-    if (kHeapInSmem)
-        for (int i = t; i < (N + 1) * N; i += blockDim.x) s_heappos[i] = p.heap_pos[i];
-    if (POLICY == RLR_POLICY_SHORTEST) {
-        if (p.shortest_random)
-            for (int i = t; i < N * N; i += blockDim.x) reinterpret_cast<unsigned short *>(s_nexthop)[i] = p.choice_mask[i];
-        else
-            for (int i = t; i < N * N; i += blockDim.x) s_nexthop[i] = p.next_hop[i];
-    }
-    if (POLICY == RLR_POLICY_GLOBALROUTE)
-        for (int i = t; i < G * N * N; i += blockDim.x) {
-            const long long rr = rblock + i / (N * N);
-            reinterpret_cast<unsigned short *>(s_nexthop)[i] = rr < p.R ? p.gr_choice_mask[rr * N * N + i % (N * N)] : (unsigned short)0;
-        }
-    for (int i = t; i < G; i += blockDim.x) {
-        s_rt32[i] = 0; s_sends[i] = 0; s_inj[i] = 0; s_end[i] = 0; s_hops[i] = 0; s_drop[i] = 0; s_injs[i] = 0;
-        s_dead[i] = (rblock + i < p.R) ? (unsigned)(p.status[2 * (rblock + i)] != 0) : 1u;
-        s_nsamp[i] = 0;
-        s_sidx[i] = (p.sample && rblock + i < p.R) ? (unsigned)p.sample_idx[rblock + i] : 0u;
-        if (p.sample && s_sidx[i] >= (unsigned)p.sample_size) s_dead[i] = 2u;     // already has its samples: frozen
-    }
-    if (general) {
-        for (int i = t; i < G * ecap; i += blockDim.x) {
-            const int gg = i / ecap1, j = i - gg * ecap1;
-            const unsigned long long e = rblock + gg < p.R ? p.event_heap[(rblock + gg) * ecap + j] : 0ull;
-            s_evheap[gg * hstride + 1 + j] = (((unsigned)(e >> 32) - (unsigned)p.clock0) << 16) | ((unsigned)(e >> 16) & 0xFFFFu);
-        }
-        for (int i = t; i < N; i += blockDim.x)
-            for (int j = p.row_ptr[i]; j < p.row_ptr[i + 1]; ++j) s_evfrom[j] = (unsigned char)i;
-        for (int i = t; i < G * p.sdeg; i += blockDim.x) {
-            const long long rr = rblock + i / p.sdeg;
-            s_evsent[i] = rr < p.R ? p.link_sent[rr * p.sdeg + i % p.sdeg] : 0;
-        }
-        for (int i = t; i < G; i += blockDim.x) {
-            s_evlen[2 * i] = rblock + i < p.R ? p.event_count[rblock + i] : 0;
-            s_evlen[2 * i + 1] = 0;
-        }
-    }
-    __syncthreads();
-    if (SMEM_TABLES) mbar_wait(s_mbar, 0);
-
-    // ---- per-thread state, constant over the launch ----
-    double *Qr = nullptr, *Thr = nullptr, *Trr = nullptr;          // this replica's tables
-    if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE && t < GN && r < p.R) {
-        if (SMEM_TABLES) {
-            Qr = s_tables + g * tstride;
-            Thr = Qr + p.tsize;
-            Trr = Qr + 2 * p.tsize;
-        } else {
-            Qr = p.Q + r * p.tsize;
-            Thr = p.Theta ? p.Theta + r * p.tsize : nullptr;
-            Trr = p.Trace ? p.Trace + r * p.tsize : nullptr;
-        }
-    }
-    const unsigned capmask = (unsigned)p.cap - 1u;
-    unsigned head = 0, tail = 0;
-    uint4 pref = make_uint4(0, 0, 0, 0), fresh = pref;            // head record: prefetched from the ring / just appended
-    bool use_fresh = false;
-    uint4 *myring = nullptr;
-    int rp = 0, deg = 0;
-    unsigned my_sends = 0, my_inj = 0;
-    unsigned ndead = 0;                 // general timing: ring entries in [head, tail) already sent out of order
-    long long base_rt = 0, base_end = 0, base_hops = 0, base_all = 0, base_drop = 0, run_rt = 0;
-    double *Qx = nullptr, *Thx = nullptr, *Trx = nullptr;          // table[x] of this node
-    if (is_node) {
-        head = p.qhead[r * N + x];
-        tail = p.qtail[r * N + x];
-        myring = p.ring + ((size_t)r * N + x) * (size_t)p.cap;
-        if (FUSED) {                            // stage the first D records of the queue
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-                cp_async16_if(s_stage + ((head + i) & (D - 1)) * GN + t, myring + ((head + i) & capmask), tail - head > (unsigned)i);
-        } else if (head != tail) {
-            pref = myring[head & capmask];
-        }
-        if (general) ndead = (unsigned)p.q_dead[r * N + x];
-        rp = s_rowptr[x];
-        deg = s_rowptr[x + 1] - rp;
-        if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) {
-            Qx = Qr + (long long)N * rp;
-            Thx = Thr ? Thr + (long long)N * rp : nullptr;
-            Trx = Trr ? Trr + (long long)N * rp : nullptr;
-        }
-        if (x == N - 1) {                      // the last node's thread keeps the per-step metric record
-            base_rt = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_ROUTE_TIME];
-            base_end = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_END_PACKETS];
-            base_hops = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_HOPS];
-            base_all = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_ALL_PACKETS];
-            base_drop = p.counters[r * RLR_NUM_COUNTERS + RLR_CTR_DROP_PACKETS];
-        }
-    }
-    const unsigned long long stream_id = (unsigned long long)(p.replica_base + r);
-    // the replica's N thread slots as a window of the CTA-wide "sent this step" bit array (one word per warp)
-    const int wlo = gbase >> 5, nw = ((gbase + N - 1) >> 5) - wlo + 1;
-    const unsigned mfirst = 0xFFFFFFFFu << (gbase & 31), mlast = 0xFFFFFFFFu >> (31 - ((gbase + N - 1) & 31));
-    const unsigned prank_mask = ((1u << lane) - 1u) & ((gbase > (warp << 5)) ? (0xFFFFFFFFu << (gbase - (warp << 5))) : 0xFFFFFFFFu);
-    // neighbour send slots (own slot for j >= deg: a node never sends to itself, so it never matches) and the
-    // window word each one falls in
-    unsigned nb_slot[MAXD], nb_word[MAXD];
-#pragma unroll
-    for (int j = 0; j < MAXD; ++j) {
-        const int z = (is_node && j < deg) ? s_col[rp + j] : x;
-        nb_slot[j] = (unsigned)(gbase + z);
-        nb_word[j] = (unsigned)(((gbase + z) >> 5) - wlo);
-    }
-    // injection schedule of this node: events (local step << 8 | dest), ascending, 0xFFFFFFFF-terminated
-    const unsigned *evp = p.inj_events + ((size_t)(is_node ? r : 0) * N + (is_node ? x : 0)) * (size_t)p.inj_cap;
-    unsigned ev = is_node ? evp[0] : 0xFFFFFFFFu;                   // current event and the one after it: the list is
-    unsigned ev_next = (!FUSED && is_node && ev != 0xFFFFFFFFu) ? evp[1] : 0xFFFFFFFFu;   // read two entries ahead of its use
-    // Fused path: the list is read through a window of two 8-byte chunks (events 2c, 2c + 1 in half c & 1) that cp.async
-    // refills a chunk ahead, so no load of the schedule ever sits on a register scoreboard inside the step loop.
-    const unsigned *ev_base = evp;
-    unsigned eidx = 2u;                                             // next event of the list to take from the window
-    int win_t_old = -(1 << 20), win_t_new = -(1 << 20);             // steps at which the two resident chunks were requested
-    if (FUSED) {
-        cp_async8_if(s_win + 2 * t, ev_base, is_node);
-        cp_async8_if(s_win + 2 * GN + 2 * t, ev_base + 2, is_node && p.inj_cap > 2);
-        cp_async_wait_all();
-        ev_next = is_node ? s_win[2 * t + 1] : 0xFFFFFFFFu;         // (ev, ev_next) in registers, the rest behind them in the window
-        cp_async8_if(s_win + 2 * t, ev_base + 4, is_node && p.inj_cap > 4);     // chunk 0 is used up: chunk 2 takes its half
-        win_t_new = -1;
-    }
-    evp += 1;
-    bool dead = is_node ? (s_dead[g] != 0u) : true;                 // only sampled policies can die mid-launch
-    const int gr_off = (POLICY == RLR_POLICY_GLOBALROUTE && is_node) ? p.gr_qs_off[r * N + x] : 0;
-    // rarely used options (send log, is_drop, droprate records, sampling, split phases) live in the SPLIT instantiation only
-    unsigned *sendlog = (SPLIT && p.sendlog && is_node) ? p.sendlog + r * (long long)p.K * N + x : nullptr;
-
-    // Ring append.  Overflow is detected once per step (tail - head > cap) and reported through the sticky
-    // status word; the masked index keeps a wrapped write inside this node's own ring.
-    auto append = [&](const uint4 &rec) {
-        myring[tail & capmask] = rec;
-        if (FUSED) {                    // a record that lands within D of the head is staged directly (nothing will fetch it)
-            if (tail - head < (unsigned)D) s_stage[(tail & (D - 1)) * GN + t] = rec;
-        } else if (head == tail) {
-            fresh = rec;
-            use_fresh = true;
-        }
-        ++tail;
-    };
-
-    // SPLIT = false is the fused Network.train path (both phases, no flag tests in the loop)
-    const bool do_env = !SPLIT || (p.phase & 1) != 0, do_learn = !SPLIT || (p.phase & 2) != 0;
-    // Fused path: the packets of step s + 1 (new_packet + inject, env.py:298-319) are appended at the END of step s, right
-    // after the arrivals of step s — the same queue order as injecting at the start of step s + 1, but off the head of the
-    // dependent chain, and with the schedule read from the shared-memory window.
-    constexpr bool kInjectAtStart = SPLIT;
-#ifdef RLR_NOFLAT
-    constexpr bool kFlatArrivals = false;
-#else
-    constexpr bool kFlatArrivals = FUSED && MAXD == 4;
-#endif
-    constexpr bool kLearnInArrivals = kFlatArrivals && POLICY == RLR_POLICY_QROUTE && SMEM_TABLES;
-    auto inject_step = [&](int s_now, unsigned step, int clk) {
-        while ((ev >> 8) == step) {
-            append(make_uint4((ev & 0xFFu) | ((unsigned)x << 16), 0u, (unsigned)clk, (unsigned)clk));
-            ++my_inj;
-            ev = ev_next;
-            // the look-ahead register is refilled from the window (nothing waits for this read before the node's next
-            // packet); the first event of a chunk requested fewer than D + 2 steps ago (a burst of packets at one node)
-            // may still be in flight
-            if ((eidx & 1u) == 0u && s_now - win_t_old < D + 2) cp_async_wait_all();
-            ev_next = s_win[((eidx >> 1) & 1u) * 2u * GN + 2u * t + (eidx & 1u)];
-            ++eidx;
-            if ((eidx & 1u) == 0u) {    // chunk eidx/2 - 1 is used up: request chunk eidx/2 + 1 into its half
-                const unsigned c = (eidx >> 1) + 1u;
-                cp_async8_if(s_win + (c & 1u) * 2u * GN + 2u * t, ev_base + 2u * c, 2u * c < (unsigned)p.inj_cap);
-                win_t_old = win_t_new;
-                win_t_new = s_now;
-            }
-        }
-    };
-    if (!kInjectAtStart && !dead) inject_step(-1, 0u, p.clock0);
-    const bool sampling = SPLIT && p.sample != nullptr;      // sample_route_time also runs on the SPLIT instantiation
-#ifdef RLR_EXP_TIMING
-    long long tacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tmark_ = clock64();
-#endif
-    for (int s = 0; s < p.K; ++s) {
-        const int clock = p.clock0 + s * slotw;
-        if (FUSED) cp_async_wait<D - 1>();      // every copy of the groups before the latest has landed (see the commit below)
-        if ((IS_PG || sampling) && is_node) dead = (s_dead[g] != 0u);
-        const bool live = !dead;
-        bool sending = false;
-        int d = 0, k = 0, y = 0;
-        double oldq = 0.0, max_qy = 0.0, max_qxd = 0.0, rwd = 0.0, c_f = 0.0;
-        int qy_dual = 1;                            // 'dual' mode q_y = max(1, len(nodes[y].queue)), env.py:156
-        double sm[MAXD];
-        if (live && !do_env) {
-            // learn-only call (agent.learn after Network.step): restore this node's Reward of that step
-            const uint4 *rw = p.rewards + ((size_t)r * N + x) * 4;
-            const uint4 meta = rw[1];
-            sending = (meta.x & 1u) != 0u;
-            if (sending) {
-                k = (int)((meta.x >> 1) & 0xFFu); y = (int)((meta.x >> 9) & 0xFFu); d = (int)(meta.x >> 17);
-                rwd = (double)(-(int)meta.y - 1);
-                const double2 mq = *reinterpret_cast<const double2 *>(rw + 2);
-                max_qy = mq.x; max_qxd = mq.y;
-                if (IS_CQ) c_f = mq.y;
-                if (DUAL) {                         // what CDRQ.learn reads from the other senders' rewards
-                    qy_dual = (int)meta.y;
-                    s_bk[t] = *reinterpret_cast<const double2 *>(rw + 3);
-                    s_qxi[t] = (int)meta.z;
-                    s_dk[t] = (unsigned short)(d | (k << 8));
-                    s_src[t] = (unsigned short)(rw[0].x >> 16);
-                }
-                if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) oldq = Qx[d * deg + k];
-                if (IS_PG) softmax_row<MAXD>(Thx + d * deg, deg, sm);
-                if (POLICY == RLR_POLICY_MAHYBRIDQ) { s_r[t] = rwd; s_qy[t] = max_qy; s_qx[t] = max_qxd; }
-            }
-        }
-        if (live && do_env) {
-            // ---- A. new_packet + inject (env.py:298-319): consume this step's events of the schedule ----
-            // (the fused instantiation has done this at the end of the previous step, see inject_step below)
-            while (kInjectAtStart && (ev >> 8) == (unsigned)s) {
-                append(make_uint4((ev & 0xFFu) | ((unsigned)x << 16), 0u, (unsigned)clock, (unsigned)clock));
-                ++my_inj;
-                if (SPLIT && p.metrics2) atomicAdd(&s_injs[g], 1u);
-                ev = ev_next;
-                if (ev != 0xFFFFFFFFu) ev_next = *++evp;
-            }
-            // ---- B. Node._send_default (env.py:162-191): pop the head, choose, get_info ----
-            if (DUAL) s_len[t] = tail - head - ndead;                           // len(queue) before this node's own send
-            bool have = false;
-            uint4 rec = make_uint4(0u, 0u, 0u, 0u);
-            if (FUSED) {
-                // the head record was staged in shared memory at least D steps ago (or by the append that created it); the
-                // pop requests the record that is now D - 1 behind the new head — the loads never touch a register
-                const bool nonempty = head != tail;
-                if (nonempty) {
-                    have = true;
-                    rec = s_stage[(head & (D - 1)) * GN + t];
-                    ++head;
-                }
-                cp_async16_if(s_stage + ((head + (D - 1)) & (D - 1)) * GN + t, myring + ((head + (D - 1)) & capmask),
-                              nonempty && tail - head > (unsigned)(D - 1));
-            } else if (!general) {
-                if (head != tail) {
-                    have = true;
-                    rec = use_fresh ? fresh : pref;
-                    use_fresh = false;
-                    ++head;
-                    if (head != tail) pref = myring[head & capmask];           // prefetch the next head
-                }
-            } else if (head != tail) {
-                // env.py:171-190 with busy links: avaliable_path is evaluated once, then the queue is scanned in order
-                // for the first packet whose chosen link is free; agent.choose runs (and, for the sampled policies,
-                // draws from this node's stream of the step) once per packet looked at.
-                unsigned am = 0u;
-#pragma unroll
-                for (int j = 0; j < MAXD; ++j)
-                    if (j < deg && s_evsent[g * p.sdeg + rp + j] < p.bandwidth) am |= 1u << j;
-                PhiloxStream ps(p.seed, stream_id, clock, x, 1);
-                unsigned pos = head;
-                while (am != 0u && pos != tail) {
-                    // the head record is kept in registers (prefetched when the head last moved, or just appended)
-                    const uint4 cand = (pos == head) ? (use_fresh ? fresh : pref) : myring[pos & capmask];
-                    if (cand.x != kDeadRec) {
-                        const int dd = (int)(cand.x & 0xFFFFu);
-                        int kk = 0;
-                        if (POLICY == RLR_POLICY_GLOBALROUTE) {
-                            const unsigned cm = reinterpret_cast<const unsigned short *>(s_nexthop)[(g * N + x) * N + dd];
-                            const int cnt = __popc(cm);
-                            const int idx = (p.shortest_random && cnt > 1) ? (int)__umulhi(ps.next(), (unsigned)cnt) : 0;
-                            kk = cm ? __fns(cm, 0, idx + 1) : 0;
-                        } else if (POLICY == RLR_POLICY_SHORTEST) {
-                            if (!p.shortest_random) {
-                                kk = s_nexthop[x * N + dd];
-                            } else {
-                                const unsigned cm = reinterpret_cast<const unsigned short *>(s_nexthop)[x * N + dd];
-                                const int cnt = __popc(cm);
-                                const int idx = cnt > 1 ? (int)__umulhi(ps.next(), (unsigned)cnt) : 0;
-                                kk = __fns(cm, 0, idx + 1);
-                            }
-                        } else if (POLICY == RLR_POLICY_QROUTE || IS_CQ) {
-                            const double *row = Qx + dd * deg;
-                            double best = row[0];
-#pragma unroll
-                            for (int j = 1; j < MAXD; ++j)
-                                if (j < deg) { const double v = row[j]; if (v > best) { best = v; kk = j; } }
-                        } else {
-                            softmax_row<MAXD>(Thx + dd * deg, deg, sm);
-                            bool bad = false;
-                            double c = 0.0, cdf[MAXD];
-#pragma unroll
-                            for (int j = 0; j < MAXD; ++j) {
-                                if (j < deg) { bad |= (sm[j] != sm[j]); c = __dadd_rn(c, sm[j]); }
-                                cdf[j] = c;
-                            }
-                            if (bad) {
-                                set_status(p.status, r, RLR_STATUS_NAN_PROB, clock);
-                                s_dead[g] = 1u;
-                                break;
-                            }
-                            const unsigned a = ps.next() >> 5, b = ps.next() >> 6;
-                            const double u = __dmul_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 1.0 / 9007199254740992.0);
-#pragma unroll
-                            for (int j = 0; j < MAXD - 1; ++j)
-                                if (j < deg - 1 && kk == j && __ddiv_rn(cdf[j], c) <= u) kk = j + 1;
-                        }
-                        if ((am >> kk) & 1u) { have = true; rec = cand; k = kk; break; }
-                    }
-                    ++pos;
-                }
-                if (have) {                                                     // queue.pop(i), env.py:177
-                    if (pos == head) {
-                        ++head;
-                        use_fresh = false;
-                        while (head != tail) {                                  // next live entry becomes the head
-                            pref = myring[head & capmask];
-                            if (pref.x != kDeadRec) break;
-                            ++head;
-                            --ndead;
-                        }
-                    } else {
-                        reinterpret_cast<unsigned *>(myring + (pos & capmask))[0] = kDeadRec;
-                        ++ndead;
-                    }
-                }
-            }
-            if (have) {
-                sending = true;
-                d = (int)(rec.x & 0xFFFFu);
-                RLR_T(6);                           // A + pop
-                if (general) {
-                    // k was chosen by the scan; pick up the values Qroute/HybridQ.get_info and learn need
-                    if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) {
-                        const double *row = Qx + d * deg;
-                        double best = row[0];
-                        oldq = row[0];
-#pragma unroll
-                        for (int j = 1; j < MAXD; ++j)
-                            if (j < deg) { const double v = row[j]; if (v > best) best = v; if (j == k) oldq = v; }
-                        max_qxd = best;
-                    }
-                } else if (POLICY == RLR_POLICY_GLOBALROUTE) {
-                    // shortest.py:38-41 on this replica's table: choices[0], or np.random.choice(choices) with random=True
-                    const unsigned cm = reinterpret_cast<const unsigned short *>(s_nexthop)[(g * N + x) * N + d];
-                    const int cnt = __popc(cm);
-                    int idx = 0;
-                    if (p.shortest_random && cnt > 1) {
-                        PhiloxStream ps(p.seed, stream_id, clock, x, 1);
-                        idx = (int)__umulhi(ps.next(), (unsigned)cnt);
-                    }
-                    k = cm ? __fns(cm, 0, idx + 1) : 0;
-                } else if (POLICY == RLR_POLICY_SHORTEST) {
-                    if (!p.shortest_random) {
-                        k = s_nexthop[x * N + d];                               // shortest.py:38-41, choices[0]
-                    } else {                                                    // np.random.choice(choices), shortest.py:40-41
-                        const unsigned cm = reinterpret_cast<const unsigned short *>(s_nexthop)[x * N + d];
-                        const int cnt = __popc(cm);
-                        int idx = 0;
-                        if (cnt > 1) {
-                            PhiloxStream ps(p.seed, stream_id, clock, x, 1);
-                            idx = (int)__umulhi(ps.next(), (unsigned)cnt);
-                        }
-                        k = __fns(cm, 0, idx + 1);
-                    }
-                } else if (POLICY == RLR_POLICY_QROUTE || IS_CQ) {
-                    const double *row = Qx + d * deg;                           // qroute.py:22-27
-                    double best = row[0];
-#pragma unroll
-                    for (int j = 1; j < MAXD; ++j)
-                        if (j < deg) { const double v = row[j]; if (v > best) { best = v; k = j; } }
-                    max_qxd = best;
-                    oldq = best;
-                } else {
-                    // PolicyGradient.choose (hybrid.py:16-23): softmax(theta) sampled by inverse CDF
-                    softmax_row<MAXD>(Thx + d * deg, deg, sm);
-                    bool bad = false;
-                    double c = 0.0, cdf[MAXD];
-#pragma unroll
-                    for (int j = 0; j < MAXD; ++j) {
-                        if (j < deg) { bad |= (sm[j] != sm[j]); c = __dadd_rn(c, sm[j]); }
-                        cdf[j] = c;
-                    }
-                    if (bad) {
-                        set_status(p.status, r, RLR_STATUS_NAN_PROB, clock);
-                        s_dead[g] = 1u;        // takes effect next step; this step's state is void
-                    }
-                    PhiloxStream ps(p.seed, stream_id, clock, x, 1);
-                    const unsigned a = ps.next() >> 5, b = ps.next() >> 6;
-                    const double u = __dmul_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 1.0 / 9007199254740992.0);
-#pragma unroll
-                    for (int j = 0; j < MAXD - 1; ++j)
-                        if (j < deg - 1 && k == j && __ddiv_rn(cdf[j], c) <= u) k = j + 1;
-                    const double *row = Qx + d * deg;                           // hybrid.py:49-53
-                    double best = row[0];
-                    oldq = row[0];
-#pragma unroll
-                    for (int j = 1; j < MAXD; ++j)
-                        if (j < deg) { const double v = row[j]; if (v > best) best = v; if (j == k) oldq = v; }
-                    max_qxd = best;
-                }
-                y = s_col[rp + k];
-                const int qoff_y = N * s_rowptr[y], deg_y = s_rowptr[y + 1] - s_rowptr[y];   // Q[y] offset and degree of the next hop
-                rec.y += 1u;                                                    // p.hops += 1, env.py:141
-                rwd = (double)(-(clock - (int)rec.w) - 1);                      // r = -q_y - t_y, qroute.py:37
-                if (IS_CQ) {                        // CQ.get_info (qroute.py:72-78): z = argmax Q[y][d], max_Q_f, C_f
-                    const int degy = deg_y;
-                    const double *ry = Qr + qoff_y + d * degy;
-                    double m = ry[0];
-                    int z = 0;
-#pragma unroll
-                    for (int j = 1; j < MAXD; ++j)
-                        if (j < degy) { const double v = ry[j]; if (v > m) { m = v; z = j; } }
-                    max_qy = m;
-                    c_f = Thr[qoff_y + d * degy + z];
-                    if (DUAL) {                     // CDRQ.get_info (qroute.py:107-115) + _build_info_dual (env.py:154-160)
-                        const int src = (int)(rec.x >> 16);
-                        const double *rb = Qx + src * deg;
-                        double mb = rb[0];
-                        int w = 0;
-#pragma unroll
-                        for (int j = 1; j < MAXD; ++j)
-                            if (j < deg) { const double v = rb[j]; if (v > mb) { mb = v; w = j; } }
-                        s_bk[t] = make_double2(Thx[src * deg + w], mb);
-                        s_qxi[t] = (int)max(1u, tail - head - ndead);
-                        s_dk[t] = (unsigned short)(d | (k << 8));
-                        s_src[t] = (unsigned short)src;
-                    }
-                } else if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) {   // max_Q_y, qroute.py:29-30
-                    const int degy = deg_y;
-                    const double *ry = Qr + qoff_y + d * degy;
-                    double m = ry[0];
-#pragma unroll
-                    for (int j = 1; j < MAXD; ++j)
-                        if (j < degy) { const double v = ry[j]; if (v > m) m = v; }
-                    max_qy = m;
-                }
-                // published with the arrival time already in start_queue (env.py:129), so that the receiver appends it as is
-                s_rec[t] = make_uint4(rec.x, rec.y, rec.z, general ? rec.w : (unsigned)(clock + ttime));
-                if (general) {                      // Node._send_packet (env.py:135-145): the event outlives the step
-                    p.event_rec[(size_t)r * ecap + ((unsigned)(clock + ttime) % (unsigned)(ttime + 1)) * N + x] = rec;
-                    s_evsent[g * p.sdeg + rp + k] += 1;
-                }
-                if (POLICY == RLR_POLICY_MAHYBRIDQ) { s_r[t] = rwd; s_qy[t] = max_qy; s_qx[t] = max_qxd; }
-                ++my_sends;
-                if (!do_learn && p.rewards) {                                   // Network.step(): hand the Reward to the host
-                    uint4 *rw = p.rewards + ((size_t)r * N + x) * 4;
-                    rw[0] = rec;
-                    rw[1] = make_uint4(1u | ((unsigned)k << 1) | ((unsigned)y << 9) | ((unsigned)d << 17),
-                                       (unsigned)(clock - (int)rec.w), DUAL ? (unsigned)s_qxi[t] : 0u, 0u);
-                    *reinterpret_cast<double2 *>(rw + 2) = make_double2(max_qy, IS_CQ ? c_f : max_qxd);
-                    if (DUAL) *reinterpret_cast<double2 *>(rw + 3) = s_bk[t];
-                }
-            } else if (!do_learn && p.rewards) {
-                p.rewards[((size_t)r * N + x) * 4 + 1] = make_uint4(0u, 0u, 0u, 0u);
-            }
-        }
-        if (POLICY == RLR_POLICY_MAHYBRIDQ && t >= GN && do_learn) {
-            // MaHybridQ.learn, multi_agent.py:32-33: Trace *= discount_trace.  Nothing reads Trace during the send
-            // phase, so the helper threads (t >= G*N) do this dense pass while the node threads send.
-            const int h = t - GN, nh = blockDim.x - GN;
-            for (int gg = 0; gg < G; ++gg) {
-                if (rblock + gg >= p.R || s_dead[gg]) continue;
-                double2 *tr = reinterpret_cast<double2 *>(SMEM_TABLES ? s_tables + gg * tstride + 2 * p.tsize
-                                                                      : p.Trace + (rblock + gg) * p.tsize);
-                const int n2 = (int)(p.tsize >> 1);
-                for (int i = h; i < n2; i += nh) {
-                    double2 v = tr[i];
-                    v.x = __dmul_rn(v.x, p.discount_trace);
-                    v.y = __dmul_rn(v.y, p.discount_trace);
-                    tr[i] = v;
-                }
-            }
-        }
-        RLR_T(0);                                   // A + B
-        if (sendlog) sendlog[(long long)s * N] = sending ? ((unsigned)y | ((unsigned)d << 16)) : 0xFFFFFFFFu;
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, sending);
-        if (lane == 0) s_wmask[warp] = bal;
-        if (t < GN) s_tp[t] = sending ? (unsigned short)(y | ((general ? k : __popc(bal & prank_mask)) << 8)) : (unsigned short)kNoSend;
-        __syncthreads();                                                        // ---- barrier 1 ----
-        RLR_T(1);
-
-        // Qroute's learn step only needs what this thread computed before the barrier, and every read of the tables by the
-        // other threads' get_info is behind us now: do it first, so its fp64 chain overlaps the shared-memory loads of C
-        if (POLICY == RLR_POLICY_QROUTE && do_learn && sending && !kLearnInArrivals) {  // qroute.py:40-44
-            const double tq = __dmul_rn(p.discount, max_qy);
-            const double u1 = __dadd_rn(rwd, tq);
-            const double u2 = __dsub_rn(u1, oldq);
-            Qx[d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, u2));
-        }
-        if (general) {
-            // ---- C (general timing). Network.event_queue restated literally (heapq on arrive_time only, env.py:48-49):
-            // one thread per replica pushes this step's events in node order and pops everything due by clock + slot;
-            // the receivers then take their arrivals from the popped list in pop order.
-            // heappush (env.py:144) never sifts here: a new event's arrive_time is >= every one in the heap and `<` is strict,
-            // so this step's events are appended in node order — each sender writes its own item at its rank
-            unsigned *hp1 = s_evheap + g * hstride;                             // item i at hp1[i + 1]
-            unsigned nsend = 0;
-            if (live && do_env) {
-                unsigned rank = 0;
-#pragma unroll
-                for (int i = 0; i < MAXW; ++i) {
-                    unsigned m = (i < nw) ? s_wmask[wlo + i] : 0u;
-                    if (i == 0) m &= mfirst;
-                    if (i == nw - 1) m &= mlast;
-                    nsend += __popc(m);
-                    if (wlo + i < warp) rank += __popc(m);
-                    else if (wlo + i == warp) rank += __popc(m & ((1u << lane) - 1u));
-                }
-                if (sending) hp1[1 + s_evlen[2 * g] + rank] = ((unsigned)(clock + ttime - p.clock0) << 16) | (unsigned)(rp + k);
-            }
-            __syncthreads();
-            RLR_T(7);                               // general: parallel append + barrier
-            if (live && do_env && x == 0) {
-                unsigned *ord = s_evorder + g * ecap;
-                int len = s_evlen[2 * g] + (int)nsend, npop = 0;
-                const unsigned end_rel = (unsigned)(clock + slotw - p.clock0);
-                while (len > 0 && (hp1[1] >> 16) <= end_rel) {                  // heappop, env.py:350-353 (heapq restated)
-                    const unsigned last = hp1[len];
-                    --len;
-                    unsigned ret = last;
-                    if (len > 0) {
-                        ret = hp1[1];
-                        int pos = 0, child = 1;                                 // _siftup: bubble the smaller child up to a leaf
-                        while (child < len) {
-                            const uint2 pr = *reinterpret_cast<const uint2 *>(hp1 + child + 1);    // items child, child + 1
-                            const bool right = (child + 1 < len) && !(pr.x < (pr.y & 0xFFFF0000u));   // not (left < right)
-                            hp1[pos + 1] = right ? pr.y : pr.x;
-                            pos = child + (right ? 1 : 0);
-                            child = 2 * pos + 1;
-                        }
-                        while (pos > 0) {                                       // _siftdown(heap, 0, pos) of the former last item
-                            const int parent = (pos - 1) >> 1;
-                            const unsigned pv = hp1[parent + 1];
-                            if (last < (pv & 0xFFFF0000u)) { hp1[pos + 1] = pv; pos = parent; continue; }
-                            break;
-                        }
-                        hp1[pos + 1] = last;
-                    }
-                    ord[npop++] = ret;
-                }
-                s_evlen[2 * g] = len;
-                s_evlen[2 * g + 1] = npop;
-            }
-            __syncthreads();
-            RLR_T(5);                               // general: heap pops + barrier
-            if (live && do_env) {
-                // arrivals in pop order: first find this node's events in the popped list (shared-memory reads only), fetch
-                // their records together, then process them in order; a node with more than MAXD events (several arrival
-                // times due in one drain) repeats the pass from where it stopped
-                const int npop = s_evlen[2 * g + 1];
-                for (int skip = 0;; skip += MAXD) {
-                    unsigned mine[MAXD];
-                    int nm = 0, seen = 0;
-#pragma unroll 4
-                    for (int i = 0; i < npop; ++i) {                            // branch-free: the list is the same for every lane
-                        const unsigned e = s_evorder[g * ecap + i];
-                        const bool m = (int)s_col[e & 0xFFFFu] == x;
-                        const bool take = m && seen >= skip && nm < MAXD;
-#pragma unroll
-                        for (int j = 0; j < MAXD; ++j)
-                            if (take && j == nm) mine[j] = (e & 0xFFFF0000u) | (unsigned)i;      // arrive offset | pop index
-                        nm += take ? 1 : 0;
-                        seen += m ? 1 : 0;
-                    }
-                    uint4 recs[MAXD];
-#pragma unroll
-                    for (int j = 0; j < MAXD; ++j)
-                        if (j < nm) {
-                            const unsigned e = s_evorder[g * ecap + (mine[j] & 0xFFFFu)];
-                            const int at = p.clock0 + (int)(e >> 16);
-                            s_evsent[g * p.sdeg + (e & 0xFFFFu)] -= 1;         // env.py:352
-                            recs[j] = p.event_rec[(size_t)r * ecap + ((unsigned)at % (unsigned)(ttime + 1)) * N + s_evfrom[e & 0xFFFFu]];
-                        }
-#pragma unroll
-                    for (int j = 0; j < MAXD; ++j)
-                        if (j < nm) {
-                            uint4 rec = recs[j];
-                            const int at = p.clock0 + (int)(mine[j] >> 16);
-                            if (p.is_drop && rec.y >= (unsigned)N) {            // env.py:355-360
-                                atomicAdd(&s_drop[g], 1u);
-                            } else if ((int)(rec.x & 0xFFFFu) == x) {           // Network.end_packet, env.py:321-331
-                                if (sampling) {
-                                    const unsigned slot = atomicAdd(&s_nsamp[g], 1u);
-                                    s_samp_pos[g * sstride + slot] = mine[j] & 0xFFFFu;
-                                    s_samp_lat[g * sstride + slot] = at - (int)rec.z;
-                                }
-                                atomicAdd(&s_end[g], 1u);
-                                atomicAdd(&s_rt32[g], (unsigned)(at - (int)rec.z));
-                                atomicAdd(&s_hops[g], rec.y);
-                            } else {                                            // Node.receive, env.py:127-130
-                                rec.w = (unsigned)at;
-                                append(rec);
-                            }
-                        }
-                    if (seen <= skip + MAXD) break;
-                }
-                if (tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
-            }
-        } else if (live && do_env) {
-            // ---- C. event drain (env.py:349-364): gather arrivals from neighbours in heap-tie order ----
-            unsigned cum[MAXW + 1];         // senders of this replica in the window words before word i
-            cum[0] = 0;
-#pragma unroll
-            for (int i = 0; i < MAXW; ++i) {
-                unsigned m = (i < nw) ? s_wmask[wlo + i] : 0u;
-                if (i == 0) m &= mfirst;
-                if (i == nw - 1) m &= mlast;
-                cum[i + 1] = cum[i] + __popc(m);
-            }
-            const unsigned hp_row = cum[MAXW] * (unsigned)N;                    // heap_pos row k = number of senders
-            unsigned cumpack = 0;                                               // cum[0..3] as bytes (N <= 255)
-            if (MAXW <= 3) cumpack = cum[0] | (cum[1] << 8) | (cum[2] << 16);
-            // sort key per neighbour slot: heap pop position << 16 | send slot, or kNoKey
-            // MAXD == 4: the four keys stay in registers (sorting network below); wider nodes compact their arrivals
-            // into a short list (indexed, so it lives in local memory) and pick the minimum of what is left each time
-            unsigned key[MAXD];
-            int nkey = 0;
-#pragma unroll
-            for (int j = 0; j < MAXD; ++j) {
-                if (kFlatArrivals) break;
-                if (MAXD > 4 && j >= p.max_deg) continue;                       // uniform: no node has a j-th neighbour
-                const unsigned tp = s_tp[nb_slot[j]];
-                const bool match = (tp & 0xFFu) == (unsigned)x;                 // kNoSend's low byte is 255 > any node id
-                unsigned base = 0;
-                if (MAXW <= 3) base = __byte_perm(cumpack, 0u, nb_word[j]) & 0xFFu;
-                else base = cum[nb_word[j]];                                    // (an indexed local array: one load, not MAXW selects)
-                const unsigned pos = heap_pos_at(hp_row + (match ? (tp >> 8) + base : 0u));
-                if (MAXD == 4) key[j] = match ? ((pos << 16) | nb_slot[j]) : kNoKey;
-                else if (match) key[nkey++] = (pos << 16) | nb_slot[j];
-            }
-            if (kLearnInArrivals) {
-                // Qroute.learn (qroute.py:40-44) in the same straight-line block as the arrival loads, so that the fp64
-                // chain fills their latency; only the store is predicated on `sending`
-                const double tq = __dmul_rn(p.discount, max_qy);
-                const double u1 = __dadd_rn(rwd, tq);
-                const double u2 = __dsub_rn(u1, oldq);
-                sts64_if(Qx + (d * deg + k), __dadd_rn(oldq, __dmul_rn(p.lr_q, u2)), sending);
-            }
-            if (kFlatArrivals) {
-                // Loop-free arrivals (degree <= 4): every matching neighbour's record and heap position are fetched side
-                // by side, a record's place in the queue is its rank among the appended ones (pairwise compares of the
-                // positions), and the <= 4 ring writes are independent of each other.
-                uint4 rc[4];
-                unsigned posv[4];
-                bool mt[4], ap[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const unsigned tp = s_tp[nb_slot[j]];
-                    mt[j] = (tp & 0xFFu) == (unsigned)x;
-                    const unsigned base = __byte_perm(cumpack, 0u, nb_word[j]) & 0xFFu;
-                    posv[j] = heap_pos_at(hp_row + (mt[j] ? (tp >> 8) + base : 0u));
-                    rc[j] = lds128_if(s_rec + nb_slot[j], mt[j]);
-                }
-                unsigned ndel = 0u, rtsum = 0u, hopsum = 0u, ndrop = 0u;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool dropped = SPLIT && p.is_drop && rc[j].y >= (unsigned)N;      // env.py:355-360
-                    const bool del = mt[j] && !dropped && (int)(rc[j].x & 0xFFFFu) == x;    // Network.end_packet, env.py:321-331
-                    ap[j] = mt[j] && !dropped && !del;                                      // Node.receive, env.py:127-130
-                    if (SPLIT && mt[j] && dropped) ++ndrop;
-                    ndel += del ? 1u : 0u;
-                    rtsum += del ? (unsigned)(clock + ttime - (int)rc[j].z) : 0u;
-                    hopsum += del ? rc[j].y : 0u;
-                    if (sampling && del) {                                                  // env.py:325-328, ordered later
-                        const unsigned slot = atomicAdd(&s_nsamp[g], 1u);
-                        s_samp_pos[g * sstride + slot] = posv[j];
-                        s_samp_lat[g * sstride + slot] = clock + ttime - (int)rc[j].z;
-                    }
-                }
-                if (SPLIT && ndrop) atomicAdd(&s_drop[g], ndrop);
-                if (ndel) {
-                    atomicAdd(&s_end[g], ndel);
-                    atomicAdd(&s_rt32[g], rtsum);
-                    atomicAdd(&s_hops[g], hopsum);
-                }
-                const unsigned tail0 = tail;
-                unsigned keyv[4], rkv[4] = {0u, 0u, 0u, 0u};        // rank among the appended ones by heap position
-#pragma unroll
-                for (int j = 0; j < 4; ++j) keyv[j] = ap[j] ? posv[j] : 0x100u;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (i != j) rkv[j] += (keyv[i] < keyv[j]) ? 1u : 0u;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const unsigned rk = rkv[j];
-                    const unsigned at = tail0 + rk;
-                    stg128_if(myring + (at & capmask), rc[j], ap[j]);
-                    sts128_if(s_stage + (at & (D - 1)) * GN + t, rc[j], ap[j] && at - head < (unsigned)D);
-                    tail += ap[j] ? 1u : 0u;
-                }
-            } else {
-            if (MAXD == 4) {                                                    // 5-comparator sorting network
-#define RLR_CE(a, b) { const unsigned lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; }
-                RLR_CE(0, 1) RLR_CE(2, 3) RLR_CE(0, 2) RLR_CE(1, 3) RLR_CE(1, 2)
-#undef RLR_CE
-            }
-            RLR_T(5);                               // C: window + keys + sort
-            for (int taken = 0;; ++taken) {
-                unsigned best;
-                if (MAXD == 4) {
-                    best = key[0];
-                    key[0] = key[1]; key[1] = key[2]; key[2] = key[3]; key[3] = kNoKey;
-                    if (best == kNoKey) break;
-                } else {
-                    if (taken >= nkey) break;
-                    best = key[taken];
-                    int bi = taken;
-                    for (int b = taken + 1; b < nkey; ++b) {
-                        const unsigned v = key[b];
-                        if (v < best) { best = v; bi = b; }
-                    }
-                    key[bi] = key[taken];
-                }
-                uint4 rec = s_rec[best & 0xFFFFu];
-                if (SPLIT && p.is_drop && rec.y >= (unsigned)N) {                        // env.py:355-360: too many hops, dropped
-                    atomicAdd(&s_drop[g], 1u);
-                    continue;
-                }
-                if ((int)(rec.x & 0xFFFFu) == x) {                              // Network.end_packet, env.py:321-331
-                    if (sampling) {                                             // env.py:325-328, ordered later by pop position
-                        const unsigned slot = atomicAdd(&s_nsamp[g], 1u);
-                        s_samp_pos[g * sstride + slot] = best >> 16;
-                        s_samp_lat[g * sstride + slot] = clock + ttime - (int)rec.z;
-                    }
-                    atomicAdd(&s_end[g], 1u);
-                    atomicAdd(&s_rt32[g], (unsigned)(clock + ttime - (int)rec.z));
-                    atomicAdd(&s_hops[g], rec.y);
-                } else {                                                        // Node.receive, env.py:127-130
-                    rec.w = (unsigned)(clock + ttime);
-                    append(rec);
-                }
-            }
-            }
-            if (kInjectAtStart && tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
-        }
-        RLR_T(2);                                   // C
-        // ---- D. agent.learn ----
-        if (!do_learn) {
-            if (DUAL && live && sending && p.rewards) {     // Network.step() in 'dual' mode: q_y needs every node's send (env.py:156)
-                const unsigned ly = s_len[gbase + y], tpy = s_tp[gbase + y];
-                p.rewards[((size_t)r * N + x) * 4 + 1].y = max(1u, ly - ((y < x && tpy != kNoSend) ? 1u : 0u));
-            }
-        } else if (POLICY == RLR_POLICY_QROUTE) {
-            // (done right after barrier 1)
-        } else if (POLICY == RLR_POLICY_HYBRIDQ) {
-            if (sending) {                                                      // hybrid.py:55-62
-                double rr = rwd;
-                if (p.add_entropy) {                                            // hybrid.py:38-39
-                    double tmp[MAXD];
-#pragma unroll
-                    for (int g4 = 0; g4 < MAXD; g4 += 4) {
-                        double xin[4], yo[4];
-                        bool any = false;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { xin[j] = (g4 + j < deg) ? sm[g4 + j] : 1.0; any |= g4 + j < deg; }
-                        if (MAXD > 4 && !__any_sync(__activemask(), any)) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) tmp[g4 + j] = 0.0;
-                            continue;
-                        }
-                        det_log2_4(xin, yo);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) tmp[g4 + j] = (g4 + j < deg) ? __dmul_rn(sm[g4 + j], yo[j]) : 0.0;
-                    }
-                    rr = __dsub_rn(rr, __dmul_rn(p.lr_e, np_sum_row<MAXD>(tmp, deg)));
-                }
-                const double tq = __dmul_rn(p.discount, max_qy);
-                const double u1 = __dadd_rn(rr, tq);
-                Qx[d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, __dsub_rn(u1, oldq)));
-                const double adv = __dsub_rn(u1, max_qxd);                      // hybrid.py:32-36
-                double *th = Thx + d * deg;
-#pragma unroll
-                for (int j = 0; j < MAXD; ++j)
-                    if (j < deg) {
-                        double gj = -sm[j];
-                        if (j == k) gj = __dadd_rn(gj, 1.0);
-                        th[j] = __dadd_rn(th[j], __dmul_rn(__dmul_rn(p.lr_p, gj), adv));
-                    }
-            }
-        } else if (POLICY == RLR_POLICY_GLOBALROUTE) {
-            // GlobalRoute.learn (shortest.py:99-104): recompute every distance with node weights 1 + queue_size[y]
-            if (live) s_grw[gbase + x] = 1 + (int)(tail - head - ndead) + gr_off;
-            __syncthreads();
-            if (live) gr_column(x, N, s_rowptr, s_col, s_grw + gbase, s_grdist + g * N * N,
-                                reinterpret_cast<unsigned short *>(s_nexthop) + g * N * N, p.gr_multiway != 0);
-        } else if (IS_CQ) {
-            // CQ._update_qtable (qroute.py:80-93): eta = max(C, 1 - old_conf); Q += eta * (r + discount * max_Q - Q);
-            // conf += eta * (C - conf); conf /= decay.  CDRQ (qroute.py:117-122) adds the backward update of
-            // Q[y][packet.source][idx(x)] with r_b = -q_x; rewards are applied in sender order, forward then backward.
-            auto cq_update = [&](double &q, double &c, double rr, double C, double maxQ) {
-                const double one_minus = __dsub_rn(1.0, c);
-                const double eta = (one_minus > C) ? one_minus : C;
-                q = __dadd_rn(q, __dmul_rn(eta, __dsub_rn(__dadd_rn(rr, __dmul_rn(p.discount, maxQ)), q)));
-                c = __ddiv_rn(__dadd_rn(c, __dmul_rn(eta, __dsub_rn(C, c))), p.conf_decay);
-            };
-            if (sending) {
-                const int cell = d * deg + k;
-                double q = oldq, c = Thx[cell];
-                if (!DUAL) {
-                    cq_update(q, c, rwd, c_f, max_qy);
-                } else {
-                    const int yt = gbase + y;                                   // my next hop's thread slot
-                    const unsigned ly = s_len[yt];
-                    const unsigned tpy = s_tp[yt];
-                    // len(nodes[y].queue) as the sequential node loop sees it: y already popped its packet if y < x and y sent
-                    // (with busy links a non-empty queue does not imply a send); a learn-only call gets it from the saved reward
-                    if (do_env) qy_dual = (int)max(1u, ly - ((y < x && tpy != kNoSend) ? 1u : 0u));
-                    const double r_f = -(double)qy_dual;
-                    // does y's backward update land on this very cell?  (y sends to me a packet whose source is my dest)
-                    const bool hit = tpy != kNoSend && (tpy & 0xFFu) == (unsigned)x && s_src[yt] == (unsigned short)d;
-                    const double2 bk = s_bk[yt];
-                    const double r_by = -(double)s_qxi[yt];
-                    if (hit && y < x) cq_update(q, c, r_by, bk.x, bk.y);        // reward y precedes reward x
-                    cq_update(q, c, r_f, c_f, max_qy);
-                    if (hit && y > x) cq_update(q, c, r_by, bk.x, bk.y);
-                }
-                Qx[cell] = q;
-                Thx[cell] = c;
-                if (DUAL) {                                                     // my backward update on y's table
-                    const int src = (int)s_src[t];
-                    const int rpy = s_rowptr[y], degy = s_rowptr[y + 1] - rpy;
-                    int idx = 0;
-                    for (int j = 1; j < degy; ++j)
-                        if (s_col[rpy + j] == (unsigned short)x) idx = j;
-                    const unsigned tpy = s_tp[gbase + y];
-                    const bool owned_by_y = tpy != kNoSend && s_dk[gbase + y] == (unsigned short)(src | (idx << 8));
-                    if (!owned_by_y) {                                          // else y applies it with its own forward update
-                        const int cb = N * rpy + src * degy + idx;
-                        double qb = Qr[cb], cbv = Thr[cb];
-                        const double2 bk = s_bk[t];
-                        cq_update(qb, cbv, -(double)s_qxi[t], bk.x, bk.y);
-                        Qr[cb] = qb;
-                        Thr[cb] = cbv;
-                    }
-                }
-            }
-            __syncthreads();
-            // CQ.confidence_decay (qroute.py:99-101): every confidence entry *= decay, every step
-            for (int gg = 0; gg < G; ++gg) {
-                if (rblock + gg >= p.R || s_dead[gg]) continue;
-                double2 *cf = reinterpret_cast<double2 *>(SMEM_TABLES ? s_tables + gg * tstride + p.tsize
-                                                                      : p.Theta + (rblock + gg) * p.tsize);
-                const int n2 = (int)(p.tsize >> 1);
-                for (int i = t; i < n2; i += blockDim.x) {
-                    double2 v = cf[i];
-                    v.x = __dmul_rn(v.x, p.conf_decay);
-                    v.y = __dmul_rn(v.y, p.conf_decay);
-                    cf[i] = v;
-                }
-            }
-        } else if (POLICY == RLR_POLICY_MAHYBRIDQ) {
-            // MaHybridQ.learn (multi_agent.py:17-43).  Trace was decayed by the helper threads before barrier 1.
-            if (sending) {                                                      // multi_agent.py:35-40
-                double *trow = Trx + d * deg;
-#pragma unroll
-                for (int j = 0; j < MAXD; ++j)
-                    if (j < deg) {
-                        double gj = -sm[j];
-                        if (j == k) gj = __dadd_rn(gj, 1.0);
-                        trow[j] = __dadd_rn(trow[j], gj);
-                    }
-                const double u1 = __dadd_rn(rwd, __dmul_rn(p.discount, max_qy));
-                Qx[d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, __dsub_rn(u1, oldq)));
-            }
-            {   // r.sum(), max_Q_y.sum(), max_Q_x_d.sum() (multi_agent.py:28-29), one helper warp per (replica, sum)
-                const int hw0 = (GN + 31) >> 5, nhw = (int)(blockDim.x >> 5) - hw0;
-                if (warp >= hw0) {
-                    for (int pair = warp - hw0; pair < 3 * G; pair += nhw) {
-                        const int gg = pair / 3, q = pair - 3 * gg;
-                        if (rblock + gg >= p.R || s_dead[gg]) continue;
-                        const int gb = gg * N, wl = gb >> 5, nwg = ((gb + N - 1) >> 5) - wl + 1;
-                        const double *v = (q == 0) ? s_r : (q == 1) ? s_qy : s_qx;
-                        const double sum = np_sum_warp<MAXW>(v, s_wmask, wl, nwg, 0xFFFFFFFFu << (gb & 31),
-                                                             0xFFFFFFFFu >> (31 - ((gb + N - 1) & 31)), lane);
-                        if (lane == 0) s_sum[gg * 4 + q] = sum;
-                    }
-                }
-            }
-            __syncthreads();
-            // dense pass: Theta += (lr_p * delta) * Trace                          (multi_agent.py:28-30,42-43)
-            for (int gg = 0; gg < G; ++gg) {
-                if (rblock + gg >= p.R || s_dead[gg]) continue;
-                const double d1 = __dadd_rn(s_sum[gg * 4 + 0], 0.0);            // + reward_shape (always 0)
-                const double d3 = __dadd_rn(d1, __dmul_rn(p.discount, s_sum[gg * 4 + 1]));
-                const double ld = __dmul_rn(p.lr_p, __dsub_rn(d3, s_sum[gg * 4 + 2]));
-                double2 *th = reinterpret_cast<double2 *>(SMEM_TABLES ? s_tables + gg * tstride + p.tsize
-                                                                      : p.Theta + (rblock + gg) * p.tsize);
-                const double2 *tr = reinterpret_cast<const double2 *>(SMEM_TABLES ? s_tables + gg * tstride + 2 * p.tsize
-                                                                                  : p.Trace + (rblock + gg) * p.tsize);
-                const int n2 = (int)(p.tsize >> 1);
-                for (int i = t; i < n2; i += blockDim.x) {
-                    double2 a2 = th[i];
-                    const double2 b2 = tr[i];
-                    a2.x = __dadd_rn(a2.x, __dmul_rn(ld, b2.x));
-                    a2.y = __dadd_rn(a2.y, __dmul_rn(ld, b2.y));
-                    th[i] = a2;
-                }
-            }
-        }
-        // One commit group per step, closed here: group s holds the schedule chunks requested at the end of step s - 1 and the
-        // record requested by the pop of step s, so when the top of step s + 2 waits for it every copy in it is two steps old.
-        if (FUSED) cp_async_commit();
-        if (!kInjectAtStart && is_node && live) {   // next step's new_packet + inject (env.py:298-319); slot = 1 on this path
-            inject_step(s, (unsigned)(s + 1), clock + 1);
-            if (tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
-        }
-        RLR_T(3);                                   // D
-        __syncthreads();                                                        // ---- barrier 2 ----
-        RLR_T(4);
-        if (is_node && x == N - 1) {                // the metric thread: 64-bit running route_time, per-step record
-            run_rt += (long long)s_rt32[g];
-            s_rt32[g] = 0u;                         // next deliveries come after the next barrier 1
-        }
-        if (sampling) {                             // Network.sample_route_time (env.py:416-438): file this step's deliveries
-            if (is_node && x == N - 1 && !dead) {
-                const int n = (int)s_nsamp[g];
-                for (int i = 1; i < n; ++i) {       // insertion sort by heap pop position = the reference's delivery order
-                    const unsigned kp = s_samp_pos[g * sstride + i];
-                    const int kl = s_samp_lat[g * sstride + i];
-                    int j = i - 1;
-                    while (j >= 0 && s_samp_pos[g * sstride + j] > kp) {
-                        s_samp_pos[g * sstride + j + 1] = s_samp_pos[g * sstride + j];
-                        s_samp_lat[g * sstride + j + 1] = s_samp_lat[g * sstride + j];
-                        --j;
-                    }
-                    s_samp_pos[g * sstride + j + 1] = kp;
-                    s_samp_lat[g * sstride + j + 1] = kl;
-                }
-                int idx = (int)s_sidx[g];
-                for (int i = 0; i < n; ++i, ++idx)
-                    p.sample[r * (long long)p.sample_size + (idx < p.sample_size - 1 ? idx : p.sample_size - 1)] = s_samp_lat[g * sstride + i];
-                s_sidx[g] = (unsigned)idx;
-                s_nsamp[g] = 0u;
-                // the reference finishes the iteration (all `freq` steps) in which the sample filled up, env.py:426-428
-                if (idx >= p.sample_size && (s + 1) % freq == 0) { s_dead[g] = 2u; p.sample_clock[r] = clock + slotw; }
-            }
-            __syncthreads();
-        }
-        if (is_node && x == N - 1 && p.metrics) {                               // env.py:409-413 (cumulative counters)
-            const long long rt = base_rt + run_rt;
-            const unsigned en = (unsigned)(base_end + s_end[g]), hps = (unsigned)(base_hops + s_hops[g]);
-            p.metrics[(long long)s * p.R + r] = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hps);
-            if (SPLIT && p.metrics2)
-                p.metrics2[(long long)s * p.R + r] = make_uint2((unsigned)(base_all + s_injs[g]), (unsigned)(base_drop + s_drop[g]));
-        }
-    }
-
-#ifdef RLR_EXP_TIMING
-    if (t == 0)
-        for (int i = 0; i < 8; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)tacc_[i]);
-#endif
-    // ---- write back ----
-    if (is_node) {
-        p.qhead[r * N + x] = head;
-        p.qtail[r * N + x] = tail;
-        if (general) p.q_dead[r * N + x] = (int)ndead;
-        if (my_sends) atomicAdd(&s_sends[g], (unsigned long long)my_sends);
-        if (my_inj) atomicAdd(&s_inj[g], (unsigned long long)my_inj);
-    }
-    __syncthreads();
-    if (is_node && x == N - 1) {
-        long long *c = p.counters + r * RLR_NUM_COUNTERS;
-        c[RLR_CTR_ALL_PACKETS] += (long long)s_inj[g];
-        c[RLR_CTR_END_PACKETS] += (long long)s_end[g];
-        c[RLR_CTR_DROP_PACKETS] += (long long)s_drop[g];
-        c[RLR_CTR_HOPS] += (long long)s_hops[g];
-        c[RLR_CTR_ROUTE_TIME] += run_rt;
-        if (sampling) p.sample_idx[r] = (int)s_sidx[g];
-        c[RLR_CTR_SENDS] += (long long)s_sends[g];
-    }
-    if (general) {
-        for (int i = t; i < G * ecap; i += blockDim.x) {
-            const int gg = i / ecap1, j = i - gg * ecap1;
-            if (rblock + gg < p.R && j < s_evlen[2 * gg]) {
-                const unsigned e = s_evheap[gg * hstride + 1 + j], link = e & 0xFFFFu;
-                const unsigned at = (unsigned)p.clock0 + (e >> 16);
-                p.event_heap[(rblock + gg) * ecap + j] = ((unsigned long long)at << 32) | (link << 16) |
-                                                         ((at % (unsigned)(ttime + 1)) * N + s_evfrom[link]);
-            }
-        }
-        for (int i = t; i < G * p.sdeg; i += blockDim.x) {
-            const long long rr = rblock + i / p.sdeg;
-            if (rr < p.R) p.link_sent[rr * p.sdeg + i % p.sdeg] = s_evsent[i];
-        }
-        for (int i = t; i < G; i += blockDim.x)
-            if (rblock + i < p.R) p.event_count[rblock + i] = s_evlen[2 * i];
-    }
-    if (POLICY == RLR_POLICY_GLOBALROUTE && do_learn) {
-        for (int i = t; i < G * N * N; i += blockDim.x) {
-            const long long rr = rblock + i / (N * N);
-            if (rr < p.R) {
-                p.gr_choice_mask[rr * N * N + i % (N * N)] = reinterpret_cast<const unsigned short *>(s_nexthop)[i];
-                p.gr_distance[rr * N * N + i % (N * N)] = s_grdist[i];
-            }
-        }
-    }
-    if (SMEM_TABLES) {
-        // tables go back by TMA bulk store: every thread publishes its shared-memory writes to the async proxy, then one
-        // thread issues a copy per table and waits for the group before the CTA (and its shared memory) goes away
-        fence_proxy_async();
-        __syncthreads();
-        if (t == 0) {
-            const unsigned tbytes = (unsigned)(p.tsize * 8);
-            for (int gg = 0; gg < G; ++gg) {
-                if (rblock + gg >= p.R) break;
-                for (int tb = 0; tb < p.ntab; ++tb)
-                    bulk_s2g((tb == 0 ? p.Q : tb == 1 ? p.Theta : p.Trace) + (rblock + gg) * p.tsize,
-                             s_tables + gg * tstride + tb * p.tsize, tbytes);
-            }
-            bulk_commit_wait();
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Qroute.__init__ structure overrides (qroute.py:16-20), Theta = initP, Trace = 0.
@@ -1856,52 +238,130 @@ __global__ void rlr_ratio_kernel(const uint4 *metrics, const uint2 *metrics2, lo
     }
 }
 
-using StepKernel = void (*)(const StepParams);
-
-template <int POLICY, int MAXD, int MAXW, bool SPLIT>
-StepKernel pick_smem(bool smem_tables)
+// Per-load-level curves (north star: only reduced statistics leave the device).  The step kernel leaves one cumulative
+// record (route_time, end_packets, hops) per (step, replica); this kernel pools them over the replicas of each load level
+// — integer sums, so the result does not depend on the order — and forms the level's ave_route_time / ave_hops
+// (env.py:440-446) per step.  One CTA per step; replicas of a level are contiguous, so a warp normally adds one value.
+__global__ void rlr_reduce_levels_kernel(const uint4 *metrics, long long R, const int *level_idx, int n_levels,
+                                         double *route_time_out, double *hop_out, long long *sums_out)
 {
-    if (POLICY == RLR_POLICY_SHORTEST || POLICY == RLR_POLICY_GLOBALROUTE)
-        return (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT>;
-    return smem_tables ? (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, true, SPLIT>
-                       : (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT>;
-}
-
-template <int POLICY, bool SPLIT>
-StepKernel pick_deg(int n_nodes, int max_deg, bool smem_tables)
-{
-    if (n_nodes <= 64) {
-        if (max_deg <= 4) return pick_smem<POLICY, 4, 3, SPLIT>(smem_tables);
-        if (max_deg <= 8) return pick_smem<POLICY, 8, 3, SPLIT>(smem_tables);
-        return pick_smem<POLICY, 16, 3, SPLIT>(smem_tables);
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(smem);       // [n_levels][3]
+    const long long s = blockIdx.x;
+    for (int i = threadIdx.x; i < 3 * n_levels; i += blockDim.x) acc[i] = 0ull;
+    __syncthreads();
+    const uint4 *row = metrics + s * R;
+    for (long long r0 = 0; r0 < R; r0 += blockDim.x) {
+        const long long r = r0 + threadIdx.x;
+        const bool ok = r < R;
+        const int lv = ok ? level_idx[r] : -1;
+        uint4 m = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) m = row[r];
+        unsigned long long rt = ((unsigned long long)m.y << 32) | m.x, en = m.z, hp = m.w;
+        const int lv0 = __shfl_sync(0xFFFFFFFFu, lv, 0);
+        if (__all_sync(0xFFFFFFFFu, lv == lv0)) {                                  // the whole warp is one level
+            for (int o = 16; o > 0; o >>= 1) {
+                rt += __shfl_down_sync(0xFFFFFFFFu, rt, o);
+                en += __shfl_down_sync(0xFFFFFFFFu, en, o);
+                hp += __shfl_down_sync(0xFFFFFFFFu, hp, o);
+            }
+            if ((threadIdx.x & 31) == 0 && lv0 >= 0 && lv0 < n_levels) {
+                atomicAdd(&acc[3 * lv0], rt); atomicAdd(&acc[3 * lv0 + 1], en); atomicAdd(&acc[3 * lv0 + 2], hp);
+            }
+        } else if (ok && lv >= 0 && lv < n_levels) {
+            atomicAdd(&acc[3 * lv], rt); atomicAdd(&acc[3 * lv + 1], en); atomicAdd(&acc[3 * lv + 2], hp);
+        }
     }
-    if (max_deg <= 8) return pick_smem<POLICY, 8, 9, SPLIT>(smem_tables);
-    return pick_smem<POLICY, 16, 9, SPLIT>(smem_tables);
+    __syncthreads();
+    for (int l = threadIdx.x; l < n_levels; l += blockDim.x) {
+        const long long rt = (long long)acc[3 * l], en = (long long)acc[3 * l + 1], hp = (long long)acc[3 * l + 2];
+        if (route_time_out) route_time_out[s * n_levels + l] = en ? __ddiv_rn((double)rt, (double)en) : 0.0;
+        if (hop_out) hop_out[s * n_levels + l] = en ? __ddiv_rn((double)hp, (double)en) : 0.0;
+        if (sums_out) { sums_out[(s * n_levels + l) * 3] = rt; sums_out[(s * n_levels + l) * 3 + 1] = en; sums_out[(s * n_levels + l) * 3 + 2] = hp; }
+    }
 }
 
-template <bool SPLIT>
-StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables)
+// Q-convergence statistics (north star: "final allreduce of delivery-time and Q-convergence statistics"): per replica the
+// sum of a table's entries and, against a previous copy of it, the sum of |table - prev| — what the TD updates of
+// qroute.py:40-44 moved since the copy was taken.  One warp per replica, lane-strided partial sums combined by a fixed
+// shuffle tree, so the fp64 result is reproducible; a second pass pools the replicas of a load level in index order.
+__global__ void rlr_table_stats_kernel(const double *table, const double *prev, long long R, long long tsize, double *per_replica)
 {
-#ifdef RLR_FAST_BUILD       // kernel-tuning builds: only the degree-4 instantiations of one policy (seconds instead of minutes);
-                            // -DRLR_FAST_POLICY=<policy id>, Qroute (1) by default
-    (void)policy; (void)n_nodes; (void)max_deg;
+    const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const double *t = table + r * tsize, *q = prev ? prev + r * tsize : nullptr;
+    double s = 0.0, d = 0.0;
+    for (long long i = lane; i < tsize; i += 32) {
+        const double v = t[i];
+        s = __dadd_rn(s, v);
+        if (q) d = __dadd_rn(d, fabs(__dsub_rn(v, q[i])));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s = __dadd_rn(s, __shfl_down_sync(0xFFFFFFFFu, s, o));
+        d = __dadd_rn(d, __shfl_down_sync(0xFFFFFFFFu, d, o));
+    }
+    if (lane == 0) { per_replica[2 * r] = s; per_replica[2 * r + 1] = d; }
+}
+
+__global__ void rlr_level_sums_kernel(const double *per_replica, long long R, const int *level_idx, int n_levels, double *out)
+{
+    const int l = blockIdx.x, lane = threadIdx.x;            // one warp per level, replicas in index order
+    if (l >= n_levels) return;
+    double s = 0.0, d = 0.0;
+    for (long long r0 = 0; r0 < R; r0 += 32) {
+        const long long r = r0 + lane;
+        const bool mine = r < R && (level_idx ? level_idx[r] == l : true);
+        if (mine) { s = __dadd_rn(s, per_replica[2 * r]); d = __dadd_rn(d, per_replica[2 * r + 1]); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s = __dadd_rn(s, __shfl_down_sync(0xFFFFFFFFu, s, o));
+        d = __dadd_rn(d, __shfl_down_sync(0xFFFFFFFFu, d, o));
+    }
+    if (lane == 0) { out[2 * l] = s; out[2 * l + 1] = d; }
+}
+
+}  // namespace
+
+// the per-policy instantiations live in step_<policy>.cu (RLR_DEFINE_STEP_PICK); a -DRLR_FAST_BUILD tuning build is one
+// translation unit holding only the degree-4 instantiations of one policy (-DRLR_FAST_POLICY=<id>, Qroute by default)
+#ifdef RLR_FAST_BUILD
 #ifndef RLR_FAST_POLICY
 #define RLR_FAST_POLICY RLR_POLICY_QROUTE
 #endif
-    return pick_smem<RLR_FAST_POLICY, 4, 3, SPLIT>(smem_tables);
+static void *rlr_pick_fast(bool split, bool smem_tables)
+{
+    return split ? (void *)pick_smem<RLR_FAST_POLICY, 4, 3, true>(smem_tables) : (void *)pick_smem<RLR_FAST_POLICY, 4, 3, false>(smem_tables);
+}
+#else
+void *rlr_pick_step_shortest(bool, int, int, bool, int);
+void *rlr_pick_step_qroute(bool, int, int, bool, int);
+void *rlr_pick_step_hybridq(bool, int, int, bool, int);
+void *rlr_pick_step_mahybridq(bool, int, int, bool, int);
+void *rlr_pick_step_cq(bool, int, int, bool, int);
+void *rlr_pick_step_cdrq(bool, int, int, bool, int);
+void *rlr_pick_step_globalroute(bool, int, int, bool, int);
+#endif
+
+namespace {
+template <bool SPLIT>
+StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables, int threads)
+{
+#ifdef RLR_FAST_BUILD
+    (void)policy; (void)n_nodes; (void)max_deg; (void)threads;
+    return (StepKernel)rlr_pick_fast(SPLIT, smem_tables);
 #else
     switch (policy) {
-    case RLR_POLICY_SHORTEST: return pick_deg<RLR_POLICY_SHORTEST, SPLIT>(n_nodes, max_deg, false);
-    case RLR_POLICY_QROUTE: return pick_deg<RLR_POLICY_QROUTE, SPLIT>(n_nodes, max_deg, smem_tables);
-    case RLR_POLICY_HYBRIDQ: return pick_deg<RLR_POLICY_HYBRIDQ, SPLIT>(n_nodes, max_deg, smem_tables);
-    case RLR_POLICY_MAHYBRIDQ: return pick_deg<RLR_POLICY_MAHYBRIDQ, SPLIT>(n_nodes, max_deg, smem_tables);
-    case RLR_POLICY_CQ: return pick_deg<RLR_POLICY_CQ, SPLIT>(n_nodes, max_deg, smem_tables);
-    case RLR_POLICY_GLOBALROUTE: return pick_deg<RLR_POLICY_GLOBALROUTE, SPLIT>(n_nodes, max_deg, false);
-    default: return pick_deg<RLR_POLICY_CDRQ, SPLIT>(n_nodes, max_deg, smem_tables);
+    case RLR_POLICY_SHORTEST: return (StepKernel)rlr_pick_step_shortest(SPLIT, n_nodes, max_deg, false, threads);
+    case RLR_POLICY_QROUTE: return (StepKernel)rlr_pick_step_qroute(SPLIT, n_nodes, max_deg, smem_tables, threads);
+    case RLR_POLICY_HYBRIDQ: return (StepKernel)rlr_pick_step_hybridq(SPLIT, n_nodes, max_deg, smem_tables, threads);
+    case RLR_POLICY_MAHYBRIDQ: return (StepKernel)rlr_pick_step_mahybridq(SPLIT, n_nodes, max_deg, smem_tables, threads);
+    case RLR_POLICY_CQ: return (StepKernel)rlr_pick_step_cq(SPLIT, n_nodes, max_deg, smem_tables, threads);
+    case RLR_POLICY_GLOBALROUTE: return (StepKernel)rlr_pick_step_globalroute(SPLIT, n_nodes, max_deg, false, threads);
+    default: return (StepKernel)rlr_pick_step_cdrq(SPLIT, n_nodes, max_deg, smem_tables, threads);
     }
 #endif
 }
-
 }  // namespace
 
 
@@ -2208,8 +668,8 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     h->G = G; h->threads = threads; h->smem_tables = smem_tables != 0;
     h->smem_bytes = (int)SmemLayout(N, h->sdeg, G, threads, h->policy, h->smem_tables, h->tsize, h->ntab, 0, true).total;
     h->smem_bytes_split = (int)SmemLayout(N, h->sdeg, G, threads, h->policy, h->smem_tables, h->tsize, h->ntab, h->ecap, false).total;
-    h->kernel = pick_kernel<false>(h->policy, h->N, h->max_deg, h->smem_tables);
-    h->kernel_split = pick_kernel<true>(h->policy, h->N, h->max_deg, h->smem_tables);
+    h->kernel = pick_kernel<false>(h->policy, h->N, h->max_deg, h->smem_tables, h->threads);
+    h->kernel_split = pick_kernel<true>(h->policy, h->N, h->max_deg, h->smem_tables, h->threads);
     (void)smem;                 // (the per-function shared-memory limit is set right before every launch, rlr_run_steps)
     *out = h;
     return RLR_OK;
@@ -2434,6 +894,40 @@ int rlr_reduce_stats(rlr_handle_t *h, int64_t *out, void *stream)
     const int blocks = (int)((h->R + 255) / 256 < 148 * 4 ? (h->R + 255) / 256 : 148 * 4);
     rlr_reduce_stats_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const long long *)h->bufs.counters, h->R, (long long *)out);
     RLR_CUDA(cudaGetLastError());
+    return RLR_OK;
+}
+
+int rlr_reduce_levels(rlr_handle_t *h, const void *metrics, int64_t n_steps, const int32_t *level_idx, int32_t n_levels,
+                      double *route_time_out, double *hop_out, int64_t *sums_out, void *stream)
+{
+    if (!h || !h->bound) return fail(RLR_E_STATE, "rlr_reduce_levels: buffers not bound");
+    if (!metrics || !level_idx || n_steps < 1 || n_levels < 1 || n_levels > 2048)
+        return fail(RLR_E_INVALID, "rlr_reduce_levels: metrics, level_idx, n_steps >= 1 and 1 <= n_levels <= 2048 are required");
+    if (!route_time_out && !hop_out && !sums_out) return fail(RLR_E_INVALID, "rlr_reduce_levels: no output requested");
+    if (n_steps > 0x7FFFFFFFll) return fail(RLR_E_INVALID, "rlr_reduce_levels: too many steps");
+    RLR_CUDA(cudaSetDevice(h->device));
+    rlr_reduce_levels_kernel<<<(unsigned)n_steps, 256, (size_t)n_levels * 24, (cudaStream_t)stream>>>(
+        (const uint4 *)metrics, h->R, level_idx, n_levels, route_time_out, hop_out, (long long *)sums_out);
+    RLR_CUDA(cudaGetLastError());
+    return RLR_OK;
+}
+
+int rlr_table_stats(rlr_handle_t *h, int32_t table_id, const double *prev, double *per_replica, const int32_t *level_idx,
+                    int32_t n_levels, double *level_out, void *stream)
+{
+    if (!h || !h->bound) return fail(RLR_E_STATE, "rlr_table_stats: buffers not bound");
+    const double *tab = table_id == 0 ? h->bufs.q_table : table_id == 1 ? h->bufs.theta : table_id == 2 ? h->bufs.trace : nullptr;
+    if (!tab || h->ntab <= table_id) return fail(RLR_E_INVALID, "rlr_table_stats: the policy has no such table");
+    if (!per_replica) return fail(RLR_E_INVALID, "rlr_table_stats: per_replica ([R][2] doubles) is required");
+    if (level_out && n_levels < 1) return fail(RLR_E_INVALID, "rlr_table_stats: level_out needs n_levels >= 1");
+    RLR_CUDA(cudaSetDevice(h->device));
+    const long long warps = h->R, blocks = (warps * 32 + 255) / 256;
+    rlr_table_stats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(tab, prev, h->R, h->tsize, per_replica);
+    RLR_CUDA(cudaGetLastError());
+    if (level_out) {
+        rlr_level_sums_kernel<<<(unsigned)n_levels, 32, 0, (cudaStream_t)stream>>>(per_replica, h->R, level_idx, n_levels, level_out);
+        RLR_CUDA(cudaGetLastError());
+    }
     return RLR_OK;
 }
 

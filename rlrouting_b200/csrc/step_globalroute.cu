@@ -1,0 +1,4 @@
+// step_globalroute.cu — the rlr_step_kernel instantiations of one policy family (see rlr_step.cuh).
+#include "rlr_step.cuh"
+
+RLR_DEFINE_STEP_PICK(globalroute, RLR_POLICY_GLOBALROUTE)

@@ -702,7 +702,7 @@ class Network:
 
     # ------------------------------------------------------------------ the hot path (env.py:367-414)
     def train(self, duration, lambd, slot=1, freq=1, lr={}, droprate=False, hop=False, *, lrq=None, lrp=None,
-              per_step=None, sendlog=False, steps_per_launch=None):
+              per_step=None, sendlog=False, steps_per_launch=None, level_index=None, next_clock0=None):
         """Runs int(duration/slot) steps of inject -> step -> learn on the device.
 
         Returns the reference's dict (`route_time` = cumulative mean delivery time after each step,
@@ -710,6 +710,13 @@ class Network:
         R replicas.  `lambd` may be a scalar or a length-R vector (one load per replica).
         The legacy call `train(T, lambd=l, lrq=.., lrp=..)` (reference train.py:52) returns the tuple
         (route_time, drop_rate) instead.
+
+        `level_index` (length R, values in [0, L)) groups the replicas into L load levels: the per-step vectors are then
+        pooled per level ON THE DEVICE (rlr_reduce_levels: sum of route_time / sum of end_packets over the level's
+        replicas, i.e. env.py:440-446 for the level as one population) and come back as [L, steps] — what a load sweep
+        needs, at L/R of the device->host traffic of the per-replica vectors.
+        `next_clock0`: clock at which the next train() call will start if not where this one ends (0 when every call is a
+        fresh episode after `reset()`); only steers which injection schedule is prefetched.
         """
         import time
         import torch
@@ -728,16 +735,30 @@ class Network:
             lrd["p"] = lrp
         T, R, N, dev = int(duration / _as_int(slot, "slot")), self.replicas, self.topology.N, self.device
         lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (R,)) * slot         # Poisson(lambd * slot), env.py:401
+        d_lv, L = None, 0
+        if level_index is not None:
+            lv = np.ascontiguousarray(np.broadcast_to(np.asarray(level_index), (R,)), dtype=np.int32)
+            if lv.min() < 0:
+                raise ValueError("level_index must be >= 0")
+            L = int(lv.max()) + 1
+            if droprate and self.is_drop:
+                raise NotImplementedError("per-level droprate vectors are not implemented; use the per-replica vectors")
+            cached = self._resident.get("level_index")
+            if cached is None or not np.array_equal(cached[0], lv):
+                cached = self._resident["level_index"] = (lv, torch.from_numpy(lv).to(self.device))
+            d_lv = cached[1]
+            per_step = True
         if per_step is None:
             per_step = R * T <= (1 << 26)
         result = {}
+        W = L if d_lv is not None else R                       # width of the per-step vectors that go to the host
         if T == 0:
-            result["route_time"] = np.zeros((R, 0))
+            result["route_time"] = np.zeros((W, 0))
             if droprate:
-                result["droprate"] = np.zeros((R, 0))
+                result["droprate"] = np.zeros((W, 0))
             if hop:
-                result["hop"] = np.zeros((R, 0))
-            return self._finish(result, legacy, R)
+                result["hop"] = np.zeros((W, 0))
+            return self._finish(result, legacy, R if d_lv is None else 0)
 
         rp = nat.RunParams()
         rp.add_entropy = int(bool(getattr(agent, "add_entropy", True)))
@@ -784,8 +805,8 @@ class Network:
         compute = torch.cuda.current_stream(dev)
         copier = self._copy_stream()
         # results land in pooled page-locked buffers handed out zero-copy (rlrouting_b200.pinned)
-        host_rt, out_rt = pinned.POOL.take((T, R)) if per_step else (None, None)       # step-major
-        host_hop, out_hop = pinned.POOL.take((T, R)) if (per_step and hop) else (None, None)
+        host_rt, out_rt = pinned.POOL.take((T, W)) if per_step else (None, None)       # step-major
+        host_hop, out_hop = pinned.POOL.take((T, W)) if (per_step and hop) else (None, None)
         want_drop = bool(per_step and droprate and self.is_drop)
         host_drop, out_drop = pinned.POOL.take((T, R)) if want_drop else (None, None)
         log_chunks = []
@@ -804,7 +825,7 @@ class Network:
                 # the schedule of the next launch is built on the side stream while this one runs; after the last launch
                 # of the call, speculate that the next train() call repeats this one (same duration and loads)
                 nxt = ((self.clock + (s0 + K) * freq * slot, plan[ci + 1] * freq) if ci + 1 < len(plan)
-                       else (self.clock + T * freq * slot, plan[0] * freq))
+                       else (self.clock + T * freq * slot if next_clock0 is None else int(next_clock0), plan[0] * freq))
                 self._schedule(h, rp, self.clock + s0 * freq * slot, K * freq, lam_key, lam.max(), nxt)
             KS = K * freq                               # Network.step calls of this launch (K iterations of the loop)
             # per-chunk device buffers are kept across calls (a fresh 32 MB torch.empty costs ~0.2 ms each); the call
@@ -813,14 +834,15 @@ class Network:
             d_rec = d_rt = None
             if per_step and keepbuf:
                 d_rec = self._scratch(("rec", ci), (KS, R, 2), torch.int64)
-                d_rt = self._scratch(("rt", ci), (KS, R), torch.float64)
+                d_rt = self._scratch(("rt", ci), (KS, W), torch.float64)
             elif per_step:
                 d_rec = torch.empty((KS, R, 2), dtype=torch.int64, device=dev)
-                d_rt = torch.empty((KS, R), dtype=torch.float64, device=dev)
+                d_rt = torch.empty((KS, W), dtype=torch.float64, device=dev)
             rp.metrics = d_rec.data_ptr() if d_rec is not None else None
-            d_hop = torch.empty((KS, R), dtype=torch.float64, device=dev) if host_hop is not None else None
-            rp.route_time_out = d_rt.data_ptr() if d_rt is not None else None
-            rp.hop_out = d_hop.data_ptr() if d_hop is not None else None
+            d_hop = torch.empty((KS, W), dtype=torch.float64, device=dev) if host_hop is not None else None
+            # per-replica vectors: the ratio kernel runs behind the step kernel; per-level vectors: rlr_reduce_levels below
+            rp.route_time_out = d_rt.data_ptr() if (d_rt is not None and d_lv is None) else None
+            rp.hop_out = d_hop.data_ptr() if (d_hop is not None and d_lv is None) else None
             d_rec2 = torch.empty((KS, R, 2), dtype=torch.int32, device=dev) if want_drop else None
             d_drop = torch.empty((KS, R), dtype=torch.float64, device=dev) if want_drop else None
             rp.metrics2 = d_rec2.data_ptr() if want_drop else None
@@ -828,6 +850,9 @@ class Network:
             log = torch.empty((R, KS, N), dtype=torch.int32, device=dev) if sendlog else None
             rp.sendlog = log.data_ptr() if log is not None else None
             nat.check(nat.lib().rlr_run_steps(h, KS, C.byref(rp), stream))
+            if d_lv is not None:
+                nat.check(nat.lib().rlr_reduce_levels(h, d_rec.data_ptr(), KS, d_lv.data_ptr(), L, d_rt.data_ptr(),
+                                                      d_hop.data_ptr() if d_hop is not None else None, None, stream))
             if freq > 1 and per_step:                   # the vectors hold one entry per iteration (env.py:409-413)
                 d_rt = d_rt[freq - 1::freq].contiguous()
                 d_hop = d_hop[freq - 1::freq].contiguous() if d_hop is not None else None
@@ -862,7 +887,7 @@ class Network:
                             "wait_compute_ms": 1e3 * (_t[3] - _t[2]), "wait_copy_ms": 1e3 * (_t[4] - _t[3])}
         self._raise_on_status(status)
         self.last_h2d_bytes = h2d
-        self.last_d2h_bytes = status.nbytes + (R * T * 8 * (2 if host_hop is not None else 1) if per_step
+        self.last_d2h_bytes = status.nbytes + (W * T * 8 * (2 if host_hop is not None else 1) if per_step
                                                else R * nat.NUM_COUNTERS * 8) + (R * T * N * 4 if sendlog else 0)
         if per_step:
             result["route_time"] = out_rt.T                                    # [R, T] view; env.py:409, 444-446
@@ -881,15 +906,17 @@ class Network:
                 c = self._counters.cpu().numpy()
                 result["droprate"] = np.where(c[:, 0:1] > 0, c[:, 2:3] / np.maximum(c[:, 0:1], 1), 0.0)
             else:
-                result["droprate"] = np.broadcast_to(np.zeros((R, 1)), result["route_time"].shape)
+                result["droprate"] = np.broadcast_to(np.zeros((W, 1)), result["route_time"].shape)
         if sendlog:
             self.last_sendlog = torch.cat(log_chunks, dim=1).cpu().numpy().view(np.uint32)
-        return self._finish(result, legacy, R)
+        return self._finish(result, legacy, R if d_lv is None else 0)
 
-    def run_device(self, n_steps, lambd, lr={}):
+    def run_device(self, n_steps, lambd, lr={}, next_clock0=None):
         """Device-resident variant of `train` for Philox mode: one rlr_run_steps launch, inputs (the
         exp(-lambda/N) vector) and outputs (the [R, n_steps] per-step records) stay in HBM, nothing is
-        copied and the stream is not synchronised.  The records are left in `self.metrics_device`."""
+        copied and the stream is not synchronised.  The records are left in `self.metrics_device`.
+        `next_clock0`: clock at which the NEXT call will start (default: where this one ends; 0 when every call is a
+        fresh episode after `reset()`), so that its injection schedule is prefetched on the side stream."""
         import torch
         if self.rng != "philox":
             raise NotImplementedError("run_device needs rng='philox' (trace mode uploads host-generated injections)")
@@ -921,7 +948,8 @@ class Network:
         rp.inj_thr = d_thr.data_ptr()
         rp.metrics = self._resident["metrics"].data_ptr()
         self._timing(rp)
-        self._schedule(h, rp, self.clock, K, key, lam.max(), (self.clock + K, K))    # next call's schedule is prefetched
+        nxt = self.clock + K if next_clock0 is None else int(next_clock0)
+        self._schedule(h, rp, self.clock, K, key, lam.max(), (nxt, K))                # next call's schedule is prefetched
         nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), self._stream_ptr()))
         self.launch_count += 1
         self._schedule_done(h, rp)
@@ -1012,6 +1040,32 @@ class Network:
             raise NotImplementedError("bind a device policy first")
         nat.check(nat.lib().rlr_reduce_stats(h, self._stats.data_ptr(), self._stream_ptr()))
         return self._stats
+
+    def table_stats(self, prev=None, level_index=None, table="Qtable"):
+        """Q-convergence statistics of the bound agent's table on the device (rlr_table_stats): per replica the sum of
+        the entries and the sum of |entry - prev entry| against an earlier copy `prev` (a device tensor shaped like the
+        table, e.g. `agent.table_device('Qtable').clone()`), and the same pooled per load level.  Returns device tensors
+        {"per_replica": [R, 2], "levels": [L, 2]} (L = 1 without `level_index`), fp64 in a fixed summation order."""
+        import torch
+        h = self._handle_or_raise()
+        agent = self._agent
+        names = list(getattr(agent, "_table_names", ()))
+        if table not in names:
+            raise ValueError(f"{type(agent).__name__} has no table {table!r}")
+        if prev is not None and (prev.dtype != torch.float64 or tuple(prev.shape) != (self.replicas, self.topology.tsize)
+                                 or prev.device != self.device or not prev.is_contiguous()):
+            raise ValueError("prev must be a contiguous float64 device tensor shaped like the table [R, tsize]")
+        d_lv, L = None, 1
+        if level_index is not None:
+            lv = np.ascontiguousarray(np.broadcast_to(np.asarray(level_index), (self.replicas,)), dtype=np.int32)
+            L = int(lv.max()) + 1
+            d_lv = torch.from_numpy(lv).to(self.device)
+        per = torch.empty((self.replicas, 2), dtype=torch.float64, device=self.device)
+        lev = torch.empty((L, 2), dtype=torch.float64, device=self.device)
+        nat.check(nat.lib().rlr_table_stats(h, names.index(table), prev.data_ptr() if prev is not None else None, per.data_ptr(),
+                                            d_lv.data_ptr() if d_lv is not None else None, L, lev.data_ptr(), self._stream_ptr()))
+        self.launch_count += 2
+        return {"per_replica": per, "levels": lev}
 
     def _queue_len_device(self):
         """len(Node.queue) per (replica, node) as a device tensor."""

@@ -41,8 +41,23 @@ class Qroute(Policy):
         for name in self._table_names[1:]:
             self._dev[name] = torch.empty_like(self._dev["Qtable"])
         self._handle = network._make_handle(self)
+        self._initP = float(initP)
         # qroute.py:16-20 structure overrides; Theta = initP (hybrid.py:13-14); Trace = 0 (multi_agent.py:14-15)
         nat.check(nat.lib().rlr_init_tables(self._handle, float(initP), network._stream_ptr()))
+
+    def reset_tables(self):
+        """Back to the tables the constructor produced (the same N(initQ,1) draws, structure overrides, Theta = initP,
+        Trace = 0) without leaving the device: what re-running `Policy(network)` with the same seed would give.  Together
+        with `Network.reset()` this starts a fresh episode; the first call keeps a device copy of the initial draws."""
+        q = self._dev["Qtable"]
+        if getattr(self, "_q_initial", None) is None:
+            raise RuntimeError("reset_tables() needs the initial draws: call keep_initial_tables() before the first step")
+        q.copy_(self._q_initial)
+        nat.check(nat.lib().rlr_init_tables(self._handle, self._initP, self._network._stream_ptr()))
+
+    def keep_initial_tables(self):
+        """Keeps a device copy of the current Qtable as the state `reset_tables()` returns to."""
+        self._q_initial = self._dev["Qtable"].clone()
 
     def set_initial_q(self, normals, initP=0.0):
         """Replace the constructor's draws: `normals` is [tsize] or [R, tsize] (packed layout); the

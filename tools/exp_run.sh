@@ -8,7 +8,7 @@ for lib in "$@"; do
     name=$(basename "$lib" .so)
     RLR_LIB=$PWD/$lib timeout 300 python tools/exp_check.py > gpurun_out/exp_$name.check 2>&1
     echo "check $name rc=$?: $(tail -1 gpurun_out/exp_$name.check)"
-    RLR_LIB=$PWD/$lib timeout 300 python bench.py --steps ${EXP_STEPS:-10} --warmup 3 --no-cpu-baseline ${EXP_ARGS} > gpurun_out/exp_$name.bench 2> gpurun_out/exp_$name.err
+    RLR_LIB=$PWD/$lib timeout 300 python bench.py --steps ${EXP_STEPS:-10} --warmup 3 --no-cpu-baseline --no-extra ${EXP_ARGS} > gpurun_out/exp_$name.bench 2> gpurun_out/exp_$name.err
     python - <<PY
 import json
 try:
