@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError(f"nvcc failed for {failed}")
     if jobs or not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(o) for o in objs):
-        subprocess.check_call([nvcc, "-shared", "-o", SO] + objs)
+        subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs)   # (no default-arch stub)
     return SO
 
 
