@@ -227,10 +227,10 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def algorithmic_bytes(policy, topo, hops, injections, replica_steps):
+def algorithmic_bytes(policy, topo, hops, injections, replica_steps, esize=8):
     """per node-step head+tail 16 B; per injection a 16 B record; per hop a 16 B record read,
-    the policy's rows, its writes and a 16 B record write (counted for every hop)."""
-    w, dbar = 8, 4 if topo.max_deg <= 4 else topo.max_deg          # padded-row convention of SURVEY §8(d)
+    the policy's rows, its writes and a 16 B record write (counted for every hop).  esize: bytes per table entry."""
+    w, dbar = esize, 4 if topo.max_deg <= 4 else topo.max_deg      # padded-row convention of SURVEY §8(d)
     per_hop = {"Shortest": 16 + 2 + 16, "GlobalRoute": 16 + 1 + 16,
                "Qroute": 16 + w * dbar + w * dbar + w + 16,
                "HybridQ": 16 + w * dbar + w * dbar + w + 16 + 2 * w * dbar,
@@ -246,10 +246,12 @@ def algorithmic_bytes(policy, topo, hops, injections, replica_steps):
 # one workload on this rank's GPU: device-resident episodes (`value`) and Network.train episodes (`e2e`)
 # ------------------------------------------------------------------------------------------------
 class Workload:
-    def __init__(self, key, net, policy, replicas, sim_steps, loads, note="", launch=(0, 0, -1), queue_capacity=0, agent_kw=None):
+    def __init__(self, key, net, policy, replicas, sim_steps, loads, note="", launch=(0, 0, -1), queue_capacity=0, agent_kw=None,
+                 dtype="float64"):
         self.key, self.net, self.policy, self.replicas, self.sim_steps = key, net, policy, int(replicas), int(sim_steps)
         self.loads, self.note, self.launch, self.queue_capacity = list(loads), note, launch, queue_capacity
         self.agent_kw = agent_kw or {}
+        self.dtype = dtype
 
 
 def measure(w, steps, warmup, rank, world, dev, sampler=None, vectors_steps=0):
@@ -272,7 +274,7 @@ def measure(w, steps, warmup, rank, world, dev, sampler=None, vectors_steps=0):
         torch.cuda.synchronize()
 
     nw = rb.Network(w.net, replicas=R, rng="philox", seed=1, replica_base=rank * R, queue_capacity=cap,
-                    replicas_per_block=w.launch[0], threads_per_block=w.launch[1], tables_in_smem=w.launch[2])
+                    replicas_per_block=w.launch[0], threads_per_block=w.launch[1], tables_in_smem=w.launch[2], dtype=w.dtype)
     agent = getattr(rb, w.policy)(nw, **w.agent_kw)
     nw.agent = agent
     learns = hasattr(agent, "keep_initial_tables")
@@ -378,13 +380,14 @@ def measure(w, steps, warmup, rank, world, dev, sampler=None, vectors_steps=0):
                "note": "same, with the per-replica [R, sim_steps] route_time vectors copied to the host instead of the level curves"}
     topo = nw.topology
     ring_gb = R * topo.N * cap * 16 / 1e9
-    table_mb = R * topo.tsize * 8 * len(getattr(agent, "_table_names", ())) / 1e6
+    table_mb = R * topo.tsize * (4 if w.dtype == "float32" else 8) * len(getattr(agent, "_table_names", ())) / 1e6
     del nw, agent
     torch.cuda.empty_cache()
     if rank != 0:
         return None
     peak, peak_src = measured_peak()
-    abytes, per_hop = algorithmic_bytes(w.policy, topo, hops, inj, world * R * T * steps)
+    esize = 4 if w.dtype == "float32" else 8
+    abytes, per_hop = algorithmic_bytes(w.policy, topo, hops, inj, world * R * T * steps, esize)
     per_launch = abytes / max(steps * world, 1)                       # one step-kernel launch per GPU per bench step
     achieved = per_launch / (kernel_ms * 1e-3) / 1e9                 # GB/s per GPU over the kernel's own launch duration
     achieved_step = per_launch / (ms_total / steps * 1e-3) / 1e9     # ... over the whole bench step (reset, re-init, statistics)
@@ -398,7 +401,7 @@ def measure(w, steps, warmup, rank, world, dev, sampler=None, vectors_steps=0):
         pass
     lev = final.get("levels", {})
     return {
-        "key": w.key, "workload": workload_name(w.net, w.policy, w.loads[0] if L == 1 else f"{w.loads[0]}..{w.loads[-1]} ({L} levels)", R, T),
+        "key": w.key, "table_dtype": w.dtype, "workload": workload_name(w.net, w.policy, w.loads[0] if L == 1 else f"{w.loads[0]}..{w.loads[-1]} ({L} levels)", R, T),
         "note": w.note, "value": value, "unit": UNIT, "n_gpus": world, "replicas_total": world * R, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_total / steps, "step_ms": step_ms, "hops_in_timed_region": hops, "gpu_launches": launches,
         "launch": info, "queue_capacity": cap,
@@ -428,6 +431,10 @@ def extra_workloads(world):
     import numpy as np
     sweep = [float(x) for x in np.linspace(1.0, 4.0, 16)]
     return [
+        Workload("headline_fp32_storage", "6x6.net", "Qroute", 8192, 5000, [2.0],
+                 "NOT the headline (which stays fp64): the headline workload with the Q table STORED in fp32 (Network(dtype='float32')): "
+                 "14 instead of 7 replicas per SM; bit-exact against the oracle's float-rounded-store law, statistically equal to fp64",
+                 dtype="float32"),
         Workload("config2_shortest_sweep", "6x6.net", "Shortest", 4096, 2000, sweep,
                  "BASELINE config 2: shortest-path routing, 4096 replicas, 16 load levels 1.0-4.0 (256 replicas each) per GPU"),
         Workload("config3_6x6mod_qroute", "6x6-modified.net", "Qroute", 16384, 2000, [2.0],

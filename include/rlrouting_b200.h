@@ -78,7 +78,9 @@ typedef struct {
     int32_t device;           /* CUDA device ordinal the buffers live on                    */
     int32_t event_capacity;   /* events that can be in flight per replica when they outlive a step (transtime > slot,
                                  env.py:143-145): N * (transtime + 1); 0 = the default timing model only */
-    int32_t reserved;
+    int32_t table_dtype;          /* 0: Q table stored as float64 (the reference's precision, the default); 1: float32 storage
+                                   * (Qroute only): rows are widened to fp64 when read, updates computed in fp64 and rounded
+                                   * on store — `prev` of rlr_table_stats and the q_table buffer are then float arrays */
 } rlr_config_t;
 
 /* Raw DEVICE pointers borrowed from the caller.  R = replicas, N = n_nodes,

@@ -39,6 +39,7 @@ def lib():
         L.orc_set_decay.argtypes = [p, f64]
         L.orc_set_is_drop.argtypes = [p, i32]
         L.orc_set_timing.argtypes = [p, i32, i32, i32, i32]
+        L.orc_set_q_f32.argtypes = [p, i32]
         L.orc_in_flight.restype = i32
         L.orc_in_flight.argtypes = [p]
         L.orc_set_shortest_flags.argtypes = [p, i32, i32]
@@ -126,9 +127,15 @@ class OracleEnv:
             _lib.orc_destroy(self.h)
             self.h = None
 
+    def set_q_storage_f32(self, on=True):
+        """Checker of the product's fp32 table-storage mode (Qroute): Q values are rounded to float whenever they are
+        stored; call before set_qtable."""
+        self.q_f32 = bool(on)
+        lib().orc_set_q_f32(self.h, int(on))
+
     def set_qtable(self, normals, initP=0.0):
         """normals: flat [tsize] N(initQ,1) draws in packed layout; applies qroute.py:16-20."""
-        self.Q[:] = normals
+        self.Q[:] = np.asarray(normals, dtype=np.float32) if getattr(self, "q_f32", False) else normals
         lib().orc_qtable_structure(self.h)
         self.Theta[:] = initP
         self.Trace[:] = 0.0

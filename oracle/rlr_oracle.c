@@ -70,6 +70,8 @@ typedef struct orc {
     int slot, freq;           /* Network.train(slot=1, freq=1), env.py:367-373 (integers) */
     int *sent;                /* Node.sent[y] per directed link (env.py:100,115-116,142,352) */
     int64_t probes;           /* diagnostic: agent.choose calls made by the send loops (queue entries looked at) */
+    int q_f32;                /* checker of the product's fp32 STORAGE mode (not in the reference): every value written to the
+                               * Q table is rounded to float; arithmetic stays fp64, as the device widens rows when it reads them */
     int multiway, random_choice; /* Shortest(multiway=..., random=...), shortest.py:20-23,38-41 */
     int64_t *sample; int64_t sample_size, sample_idx;   /* Network.sample / _sample_idx (env.py:242, 325-328, 424-425) */
     int64_t *queue_size;      /* GlobalRoute.queue_size (shortest.py:89): +1 per receive callback, -1 per send callback */
@@ -196,6 +198,7 @@ void orc_set_hparams(orc_t *o, double discount, double discount_trace, int add_e
 
 void orc_set_decay(orc_t *o, double decay) { o->decay = decay; }
 void orc_set_is_drop(orc_t *o, int is_drop) { o->is_drop = is_drop; }
+void orc_set_q_f32(orc_t *o, int on) { o->q_f32 = on; }
 void orc_set_timing(orc_t *o, int bandwidth, int transtime, int slot, int freq)
 {
     o->bandwidth = bandwidth; o->transtime = transtime; o->slot = slot; o->freq = freq;
@@ -715,6 +718,7 @@ static inline void q_update(orc_t *o, const reward_t *rw, double r, double lr)
     double v = u - old;
     double w = lr * v;
     *cell = old + w;
+    if (o->q_f32) *cell = (double)(float)*cell;
 }
 
 /* agent.learn(rewards, lr) for the four in-scope policies. */

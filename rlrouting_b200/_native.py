@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 HDR = os.path.join(ROOT, "include", "rlrouting_b200.h")
 STEP_HDR = os.path.join(CSRC, "rlr_step.cuh")
 # translation units: the host side of the C ABI + one per policy family (each instantiates the step kernel for its policy)
-UNITS = ["rlr_kernels"] + ["step_" + n for n in ("shortest", "qroute", "hybridq", "mahybridq", "cq", "cdrq", "globalroute")]
+UNITS = ["rlr_kernels"] + ["step_" + n for n in ("shortest", "qroute", "qroute_f32", "hybridq", "mahybridq", "cq", "cdrq", "globalroute")]
 SRC = os.path.join(CSRC, "rlr_kernels.cu")
 SO = os.environ.get("RLR_LIB") or os.path.join(CSRC, "librlrouting_b200.so")   # RLR_LIB: experiment builds
 
@@ -60,7 +60,7 @@ class Config(C.Structure):
     _fields_ = [("replicas", C.c_int64), ("replica_base", C.c_int64), ("policy", C.c_int32),
                 ("queue_capacity", C.c_int32), ("replicas_per_block", C.c_int32),
                 ("threads_per_block", C.c_int32), ("tables_in_smem", C.c_int32), ("device", C.c_int32),
-                ("event_capacity", C.c_int32), ("reserved", C.c_int32)]
+                ("event_capacity", C.c_int32), ("table_dtype", C.c_int32)]
 
 
 class Buffers(C.Structure):

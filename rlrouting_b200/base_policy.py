@@ -98,4 +98,4 @@ class Policy:
             flat = np.repeat(topo.pack(tables)[None, :], R, axis=0)
         else:
             flat = np.concatenate([np.asarray(tables[x], dtype=np.float64).reshape(R, -1) for x in range(topo.N)], axis=1)
-        dev.copy_(torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float64)))
+        dev.copy_(torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float64)))      # (rounds to the table's storage type)

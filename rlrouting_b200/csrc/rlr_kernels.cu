@@ -45,7 +45,8 @@ int fail(int code, const std::string &msg)
 // Qroute.__init__ structure overrides (qroute.py:16-20), Theta = initP, Trace = 0.
 // ------------------------------------------------------------------------------------------------
 // conf_mode: Theta is CQ.confidence and receives CQ.clean's structure (qroute.py:66-71: 0, conf[links[x]] = eye).
-__global__ void rlr_init_tables_kernel(double *Q, double *Theta, double *Trace, const int *row_ptr, const int *col,
+template <typename QT>
+__global__ void rlr_init_tables_kernel(QT *Q, double *Theta, double *Trace, const int *row_ptr, const int *col,
                                        int N, int sdeg, long long R, double initP, int conf_mode)
 {
     const long long tsize = (long long)N * sdeg;
@@ -57,10 +58,17 @@ __global__ void rlr_init_tables_kernel(double *Q, double *Theta, double *Trace, 
         while (row_ptr[x + 1] <= e) ++x;          // small N: linear search
         const int rp = row_ptr[x], deg = row_ptr[x + 1] - rp, j = e - rp, y = col[e];
         if (Q) {
-            double *tab = Q + r * tsize + (long long)N * rp;
-            for (int k = 0; k < deg; ++k) tab[(long long)y * deg + k] = (j == k) ? -1.0 : -0.0;   // -eye
+            QT *tab = Q + r * tsize + (long long)N * rp;
+            // -eye: -1 on the diagonal and NEGATIVE zero off it (NumPy's -0.0).  The float table is written as bit patterns:
+            // the compiler folds `cond ? -1.0f : -0.0f` into an integer-to-float conversion that loses the sign of zero
+            for (int k = 0; k < deg; ++k) {
+                if constexpr (sizeof(QT) == 4)
+                    reinterpret_cast<unsigned *>(tab)[(long long)y * deg + k] = (j == k) ? 0xBF800000u : 0x80000000u;
+                else
+                    tab[(long long)y * deg + k] = (QT)((j == k) ? -1.0 : -0.0);
+            }
             if (j == 0)
-                for (int k = 0; k < deg; ++k) tab[(long long)x * deg + k] = 0.0;                  // table[x] = 0
+                for (int k = 0; k < deg; ++k) tab[(long long)x * deg + k] = (QT)0.0;              // table[x] = 0
         }
     }
     const long long tot2 = R * tsize;
@@ -285,17 +293,18 @@ __global__ void rlr_reduce_levels_kernel(const uint4 *metrics, long long R, cons
 // sum of a table's entries and, against a previous copy of it, the sum of |table - prev| — what the TD updates of
 // qroute.py:40-44 moved since the copy was taken.  One warp per replica, lane-strided partial sums combined by a fixed
 // shuffle tree, so the fp64 result is reproducible; a second pass pools the replicas of a load level in index order.
-__global__ void rlr_table_stats_kernel(const double *table, const double *prev, long long R, long long tsize, double *per_replica)
+template <typename QT>
+__global__ void rlr_table_stats_kernel(const QT *table, const QT *prev, long long R, long long tsize, double *per_replica)
 {
     const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= R) return;
-    const double *t = table + r * tsize, *q = prev ? prev + r * tsize : nullptr;
+    const QT *t = table + r * tsize, *q = prev ? prev + r * tsize : nullptr;
     double s = 0.0, d = 0.0;
     for (long long i = lane; i < tsize; i += 32) {
         const double v = t[i];
         s = __dadd_rn(s, v);
-        if (q) d = __dadd_rn(d, fabs(__dsub_rn(v, q[i])));
+        if (q) d = __dadd_rn(d, fabs(__dsub_rn(v, (double)q[i])));
     }
     for (int o = 16; o > 0; o >>= 1) {
         s = __dadd_rn(s, __shfl_down_sync(0xFFFFFFFFu, s, o));
@@ -336,6 +345,7 @@ static void *rlr_pick_fast(bool split, bool smem_tables)
 #else
 void *rlr_pick_step_shortest(bool, int, int, bool, int);
 void *rlr_pick_step_qroute(bool, int, int, bool, int);
+void *rlr_pick_step_qroute_f32(bool, int, int, bool, int);
 void *rlr_pick_step_hybridq(bool, int, int, bool, int);
 void *rlr_pick_step_mahybridq(bool, int, int, bool, int);
 void *rlr_pick_step_cq(bool, int, int, bool, int);
@@ -345,15 +355,16 @@ void *rlr_pick_step_globalroute(bool, int, int, bool, int);
 
 namespace {
 template <bool SPLIT>
-StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables, int threads)
+StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables, int threads, bool f32)
 {
 #ifdef RLR_FAST_BUILD
-    (void)policy; (void)n_nodes; (void)max_deg; (void)threads;
+    (void)policy; (void)n_nodes; (void)max_deg; (void)threads; (void)f32;
     return (StepKernel)rlr_pick_fast(SPLIT, smem_tables);
 #else
     switch (policy) {
     case RLR_POLICY_SHORTEST: return (StepKernel)rlr_pick_step_shortest(SPLIT, n_nodes, max_deg, false, threads);
-    case RLR_POLICY_QROUTE: return (StepKernel)rlr_pick_step_qroute(SPLIT, n_nodes, max_deg, smem_tables, threads);
+    case RLR_POLICY_QROUTE: return f32 ? (StepKernel)rlr_pick_step_qroute_f32(SPLIT, n_nodes, max_deg, smem_tables, threads)
+                                       : (StepKernel)rlr_pick_step_qroute(SPLIT, n_nodes, max_deg, smem_tables, threads);
     case RLR_POLICY_HYBRIDQ: return (StepKernel)rlr_pick_step_hybridq(SPLIT, n_nodes, max_deg, smem_tables, threads);
     case RLR_POLICY_MAHYBRIDQ: return (StepKernel)rlr_pick_step_mahybridq(SPLIT, n_nodes, max_deg, smem_tables, threads);
     case RLR_POLICY_CQ: return (StepKernel)rlr_pick_step_cq(SPLIT, n_nodes, max_deg, smem_tables, threads);
@@ -551,6 +562,7 @@ struct rlr_handle {
     int N, sdeg, max_deg, policy, ntab;
     long long R, replica_base, tsize;
     int cap, G, threads, smem_bytes, smem_bytes_split, device, ecap;   // dynamic shared memory of the fused / split kernel
+    int esize;                           // bytes per Q-table entry: 8, or 4 for Qroute's fp32 storage mode
     bool smem_tables, bound;
     std::vector<int> row_ptr, col;
     rlr_buffers_t bufs;
@@ -602,24 +614,38 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     h->R = cfg->replicas; h->replica_base = cfg->replica_base;
     h->tsize = (long long)N * topo->sum_deg;
     h->cap = cap; h->bound = false; h->device = cfg->device; h->ecap = cfg->event_capacity;
+    h->esize = cfg->table_dtype == 1 ? 4 : 8;
+    if (cfg->table_dtype != 0 && cfg->table_dtype != 1) { delete h; return fail(RLR_E_INVALID, "rlr_create: table_dtype must be 0 (fp64) or 1 (fp32)"); }
+    if (h->esize == 4 && cfg->policy != RLR_POLICY_QROUTE) {
+        delete h;
+        return fail(RLR_E_UNSUPPORTED, "rlr_create: fp32 table storage is implemented for Qroute only");
+    }
+#ifdef RLR_FAST_BUILD
+    if (h->esize == 4) { delete h; return fail(RLR_E_UNSUPPORTED, "rlr_create: this tuning build has no fp32 instantiations"); }
+#endif
     h->row_ptr.assign(topo->row_ptr, topo->row_ptr + N + 1);
     h->col.assign(topo->col, topo->col + topo->sum_deg);
     memset(&h->bufs, 0, sizeof(h->bufs));
 
     // launch geometry
-    const size_t table_bytes = (size_t)h->ntab * h->tsize * 8;
+    const size_t table_bytes = (size_t)h->ntab * h->tsize * h->esize;
     int G = cfg->replicas_per_block;
     int smem_tables = cfg->tables_in_smem;
     if (h->policy == RLR_POLICY_SHORTEST || h->policy == RLR_POLICY_GLOBALROUTE) smem_tables = 0;
     // footprint of a launch: the larger of the two instantiations (fused Network.train / split phases and options)
     auto smem_for = [&](int g, int thr, bool st) {
-        const size_t a = SmemLayout(N, h->sdeg, g, thr, h->policy, st, h->tsize, h->ntab, 0, true).total;
-        const size_t b = SmemLayout(N, h->sdeg, g, thr, h->policy, st, h->tsize, h->ntab, h->ecap, false).total;
+        const size_t a = SmemLayout(N, h->sdeg, g, thr, h->policy, st, h->tsize, h->ntab, 0, true, h->esize).total;
+        const size_t b = SmemLayout(N, h->sdeg, g, thr, h->policy, st, h->tsize, h->ntab, h->ecap, false, h->esize).total;
         return a > b ? a : b;
     };
     // General timing model: one thread per replica replays the event heap serially and bounds the step, so what pays is
     // more resident replicas, not faster table reads: tables stay in HBM/L2 and a CTA carries ~256 threads (measured).
     if (smem_tables < 0 && h->ecap > 0) smem_tables = 0;
+    // the bulk copies that stage a table move multiples of 16 bytes
+    if (table_bytes % 16 != 0) {
+        if (smem_tables > 0) { delete h; return fail(RLR_E_UNSUPPORTED, "rlr_create: a table in shared memory must be a multiple of 16 bytes"); }
+        smem_tables = 0;
+    }
     // HybridQ's step is dominated by the softmax arithmetic, not by table reads, and its two fp64 tables would leave room
     // for only 3 replicas per SM: tables in HBM/L2 and 256-thread CTAs of several replicas run 14 per SM (measured on
     // 6x6, 4,096 replicas: 3.6e9 -> 8.0e9 hops/s).  MaHybridQ and CQ / CDRQ keep theirs on chip: they sweep whole tables
@@ -635,6 +661,9 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     // GlobalRoute's per-step all-pairs recomputation is one serial thread per destination column: a 256-thread CTA of
     // several replicas keeps more columns going per SM (measured on 6x6: 1.9e8 -> 2.3e8 hops/s)
     if (G <= 0 && ((h->policy == RLR_POLICY_GLOBALROUTE && N < 96) || hybrid_hbm)) G = 256 / N > 0 ? 256 / N : 1;
+    // fp32 storage: the tables are no longer what limits residency, so whole replicas are packed into 128-thread CTAs and
+    // fewer, fuller warps issue the same work (measured on 6x6: 2.9e10 with one replica per CTA -> 3.8e10 hops/s with three)
+    if (G <= 0 && h->esize == 4 && smem_tables && N <= 64) G = 128 / N > 0 ? 128 / N : 1;
     if (G <= 0) G = smem_tables ? 1 : (N >= 96 ? 1 : (128 / N > 0 ? 128 / N : 1));
     if ((long long)G > h->R) G = (int)h->R;
     int threads = cfg->threads_per_block;
@@ -666,10 +695,10 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
         return fail(RLR_E_UNSUPPORTED, "rlr_create: shared-memory footprint exceeds 227 KB (lower replicas_per_block or set tables_in_smem=0)");
     }
     h->G = G; h->threads = threads; h->smem_tables = smem_tables != 0;
-    h->smem_bytes = (int)SmemLayout(N, h->sdeg, G, threads, h->policy, h->smem_tables, h->tsize, h->ntab, 0, true).total;
-    h->smem_bytes_split = (int)SmemLayout(N, h->sdeg, G, threads, h->policy, h->smem_tables, h->tsize, h->ntab, h->ecap, false).total;
-    h->kernel = pick_kernel<false>(h->policy, h->N, h->max_deg, h->smem_tables, h->threads);
-    h->kernel_split = pick_kernel<true>(h->policy, h->N, h->max_deg, h->smem_tables, h->threads);
+    h->smem_bytes = (int)SmemLayout(N, h->sdeg, G, threads, h->policy, h->smem_tables, h->tsize, h->ntab, 0, true, h->esize).total;
+    h->smem_bytes_split = (int)SmemLayout(N, h->sdeg, G, threads, h->policy, h->smem_tables, h->tsize, h->ntab, h->ecap, false, h->esize).total;
+    h->kernel = pick_kernel<false>(h->policy, h->N, h->max_deg, h->smem_tables, h->threads, h->esize == 4);
+    h->kernel_split = pick_kernel<true>(h->policy, h->N, h->max_deg, h->smem_tables, h->threads, h->esize == 4);
     (void)smem;                 // (the per-function shared-memory limit is set right before every launch, rlr_run_steps)
     *out = h;
     return RLR_OK;
@@ -735,7 +764,7 @@ int rlr_reset(rlr_handle_t *h, void *stream)
     if (h->policy == RLR_POLICY_CQ || h->policy == RLR_POLICY_CDRQ) {              // CQ.clean (qroute.py:66-71)
         const long long total = h->R * h->tsize;
         int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-        rlr_init_tables_kernel<<<blocks, 256, 0, st>>>(nullptr, h->bufs.theta, nullptr, h->bufs.topo_row_ptr, h->bufs.topo_col,
+        rlr_init_tables_kernel<double><<<blocks, 256, 0, st>>>(nullptr, h->bufs.theta, nullptr, h->bufs.topo_row_ptr, h->bufs.topo_col,
                                                        h->N, h->sdeg, h->R, 0.0, 1);
         RLR_CUDA(cudaGetLastError());
     }
@@ -761,9 +790,15 @@ int rlr_init_tables(rlr_handle_t *h, double initP, void *stream)
     if (h->policy == RLR_POLICY_GLOBALROUTE) return globalroute_init(h, 0, stream);       // GlobalRoute.__init__, shortest.py:85-91
     const long long total = h->R * h->tsize;
     int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    rlr_init_tables_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->bufs.q_table, h->bufs.theta, h->bufs.trace,
-                                                                      h->bufs.topo_row_ptr, h->bufs.topo_col, h->N, h->sdeg,
-                                                                      h->R, initP, (h->policy == RLR_POLICY_CQ || h->policy == RLR_POLICY_CDRQ) ? 1 : 0);
+    const int conf = (h->policy == RLR_POLICY_CQ || h->policy == RLR_POLICY_CDRQ) ? 1 : 0;
+    if (h->esize == 4)
+        rlr_init_tables_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float *)h->bufs.q_table, h->bufs.theta, h->bufs.trace,
+                                                                                 h->bufs.topo_row_ptr, h->bufs.topo_col, h->N, h->sdeg,
+                                                                                 h->R, initP, conf);
+    else
+        rlr_init_tables_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(h->bufs.q_table, h->bufs.theta, h->bufs.trace,
+                                                                                  h->bufs.topo_row_ptr, h->bufs.topo_col, h->N, h->sdeg,
+                                                                                  h->R, initP, conf);
     RLR_CUDA(cudaGetLastError());
     return RLR_OK;
 }
@@ -922,7 +957,10 @@ int rlr_table_stats(rlr_handle_t *h, int32_t table_id, const double *prev, doubl
     if (level_out && n_levels < 1) return fail(RLR_E_INVALID, "rlr_table_stats: level_out needs n_levels >= 1");
     RLR_CUDA(cudaSetDevice(h->device));
     const long long warps = h->R, blocks = (warps * 32 + 255) / 256;
-    rlr_table_stats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(tab, prev, h->R, h->tsize, per_replica);
+    if (h->esize == 4 && table_id == 0)
+        rlr_table_stats_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float *)tab, (const float *)prev, h->R, h->tsize, per_replica);
+    else
+        rlr_table_stats_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(tab, prev, h->R, h->tsize, per_replica);
     RLR_CUDA(cudaGetLastError());
     if (level_out) {
         rlr_level_sums_kernel<<<(unsigned)n_levels, 32, 0, (cudaStream_t)stream>>>(per_replica, h->R, level_idx, n_levels, level_out);

@@ -415,6 +415,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N_PENDING>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }   // committed or not
+__device__ __forceinline__ void sts32f_if(float *ptr, float v, bool pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.shared.f32 [%0], %1;\n}"
+                 :: "r"(smem_u32(ptr)), "f"(v), "r"((int)pred) : "memory");
+}
 __device__ __forceinline__ void sts64_if(double *ptr, double v, bool pred)
 {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.shared.f64 [%0], %1;\n}"
@@ -439,11 +444,11 @@ struct SmemLayout {
     // memory, has no sample_route_time staging, and when the tables fill shared memory it reads heap_pos through L1 instead
     // (the table is read-only and shared by every CTA of the SM; nothing else of the fused loop allocates in L1)
     __host__ __device__ SmemLayout(int N, int sdeg, int G, int threads, int policy, bool smem_tables, long long tsize, int ntab,
-                                   int ecap, bool fused)
+                                   int ecap, bool fused, int esize = 8)
     {
         const int GN = G * N;
         size_t o = 0;
-        tables = o; o += smem_tables ? align16((size_t)G * ntab * tsize * 8) : 0;
+        tables = o; o += smem_tables ? align16((size_t)G * ntab * tsize * esize) : 0;      // esize: 8 (fp64) or 4 (fp32 Qroute)
         rec = o; o += align16((size_t)GN * 16);
         f64 = o; o += (policy == RLR_POLICY_MAHYBRIDQ) ? align16((size_t)(3 * GN + 4 * G) * 8)
                        : (policy == RLR_POLICY_CDRQ) ? align16((size_t)GN * 32) : 0;   // CDRQ: {C_b, max_Q_b}, len, q_x, d|k, src
@@ -547,7 +552,10 @@ constexpr unsigned kDeadRec = 0xFFFFFFFFu; // word 0 of a ring entry that was se
 //         (one 65..128-node replica per CTA, e.g. lata.net), compiled for RLR_LB1_BLOCKS resident CTAs per SM: the step is
 //         bound by the latency of the table rows it reads from L2 / HBM, so what pays is warps in flight (80 registers
 //         instead of 126, no spills once the row loops are sized 12 and not 16)
-template <int POLICY, int MAXD, int MAXW, bool SMEM_TABLES, bool SPLIT, int LB = 0>
+//   QT    element type of the Q table in memory: double, or float for Qroute's fp32 STORAGE mode (Network(dtype='float32')):
+//         rows are widened to fp64 when they are read, the TD update is evaluated in fp64 with the same unfused operations
+//         and rounded once when it is stored — half the bytes per table, so twice the replicas per SM
+template <int POLICY, int MAXD, int MAXW, bool SMEM_TABLES, bool SPLIT, int LB = 0, typename QT = double>
 __global__ void __launch_bounds__(LB ? 128 : kMaxThreads, LB ? RLR_LB1_BLOCKS : RLR_MIN_BLOCKS)
 rlr_step_kernel(const __grid_constant__ StepParams p)
 {
@@ -557,7 +565,8 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     constexpr bool FUSED = !SPLIT;            // the Network.train instantiation: staged queue heads, injections at step end
     constexpr int D = stage_depth(SMEM_TABLES);
     constexpr int kStageWait = SMEM_TABLES ? D - 1 : D - 2;    // commit groups that may still be in flight at the top of a step
-    const SmemLayout L(N, p.sdeg, G, blockDim.x, POLICY, SMEM_TABLES, p.tsize, p.ntab, SPLIT ? p.ecap : 0, FUSED);
+    static_assert(sizeof(QT) == 8 || POLICY == RLR_POLICY_QROUTE, "fp32 table storage is implemented for Qroute");
+    const SmemLayout L(N, p.sdeg, G, blockDim.x, POLICY, SMEM_TABLES, p.tsize, p.ntab, SPLIT ? p.ecap : 0, FUSED, (int)sizeof(QT));
     constexpr bool kHeapInSmem = !(FUSED && SMEM_TABLES);
 
     double *s_tables = reinterpret_cast<double *>(smem + L.tables);
@@ -622,12 +631,13 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
         mbar_init(s_mbar, 1);
         int nrep = 0;
         for (int gg = 0; gg < G; ++gg) nrep += (rblock + gg < p.R) ? 1 : 0;
-        const unsigned tbytes = (unsigned)(p.tsize * 8);
+        const unsigned tbytes = (unsigned)(p.tsize * sizeof(QT));
         mbar_expect_tx(s_mbar, (unsigned)(nrep * p.ntab) * tbytes);
         for (int gg = 0; gg < nrep; ++gg)
             for (int tb = 0; tb < p.ntab; ++tb)
-                bulk_g2s(s_tables + gg * ((long long)p.ntab * p.tsize) + tb * p.tsize,
-                         (tb == 0 ? p.Q : tb == 1 ? p.Theta : p.Trace) + (rblock + gg) * p.tsize, tbytes, s_mbar);
+                bulk_g2s(reinterpret_cast<char *>(s_tables) + ((size_t)gg * p.ntab + tb) * tbytes,
+                         reinterpret_cast<const char *>(tb == 0 ? p.Q : tb == 1 ? p.Theta : p.Trace) + (size_t)(rblock + gg) * tbytes,
+                         tbytes, s_mbar);
     }
     for (int i = t; i <= N; i += blockDim.x) s_rowptr[i] = p.row_ptr[i];
     for (int i = t; i < p.sdeg; i += blockDim.x) s_col[i] = (unsigned short)p.col[i];
@@ -672,14 +682,15 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     if (SMEM_TABLES) mbar_wait(s_mbar, 0);
 
     // ---- per-thread state, constant over the launch ----
-    double *Qr = nullptr, *Thr = nullptr, *Trr = nullptr;          // this replica's tables
+    QT *Qr = nullptr;                                              // this replica's tables
+    double *Thr = nullptr, *Trr = nullptr;
     if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE && t < GN && r < p.R) {
         if (SMEM_TABLES) {
-            Qr = s_tables + g * tstride;
-            Thr = Qr + p.tsize;
-            Trr = Qr + 2 * p.tsize;
+            Qr = reinterpret_cast<QT *>(s_tables) + g * tstride;
+            Thr = s_tables + g * tstride + p.tsize;
+            Trr = s_tables + g * tstride + 2 * p.tsize;
         } else {
-            Qr = p.Q + r * p.tsize;
+            Qr = reinterpret_cast<QT *>(p.Q) + r * p.tsize;
             Thr = p.Theta ? p.Theta + r * p.tsize : nullptr;
             Trr = p.Trace ? p.Trace + r * p.tsize : nullptr;
         }
@@ -693,7 +704,8 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     unsigned my_sends = 0, my_inj = 0;
     unsigned ndead = 0;                 // general timing: ring entries in [head, tail) already sent out of order
     long long base_rt = 0, base_end = 0, base_hops = 0, base_all = 0, base_drop = 0, run_rt = 0;
-    double *Qx = nullptr, *Thx = nullptr, *Trx = nullptr;          // table[x] of this node
+    QT *Qx = nullptr;                                              // table[x] of this node
+    double *Thx = nullptr, *Trx = nullptr;
     if (is_node) {
         head = p.qhead[r * N + x];
         tail = p.qtail[r * N + x];
@@ -870,7 +882,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                     // tables in HBM: the record behind the one just popped is next step's head (staged at least three commit
                     // groups ago, or written by the append that created it); bring the rows `choose` will read for it into L1
                     const unsigned dn = s_stage[(head & (D - 1)) * GN + t].x & 0xFFFFu;
-                    const double *rowq = Qx + dn * deg;
+                    const QT *rowq = Qx + dn * deg;
                     prefetch_l1(rowq);
                     prefetch_l1(rowq + (deg - 1));
                     if (IS_PG) { prefetch_l1(Thx + dn * deg); prefetch_l1(Thx + dn * deg + (deg - 1)); }
@@ -914,7 +926,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                                 kk = __fns(cm, 0, idx + 1);
                             }
                         } else if (POLICY == RLR_POLICY_QROUTE || IS_CQ) {
-                            const double *row = Qx + dd * deg;
+                            const QT *row = Qx + dd * deg;
                             double best = row[0];
 #pragma unroll
                             for (int j = 1; j < MAXD; ++j)
@@ -966,7 +978,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 if (general) {
                     // k was chosen by the scan; pick up the values Qroute/HybridQ.get_info and learn need
                     if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) {
-                        const double *row = Qx + d * deg;
+                        const QT *row = Qx + d * deg;
                         double best = row[0];
                         oldq = row[0];
 #pragma unroll
@@ -998,7 +1010,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                         k = __fns(cm, 0, idx + 1);
                     }
                 } else if (POLICY == RLR_POLICY_QROUTE || IS_CQ) {
-                    const double *row = Qx + d * deg;                           // qroute.py:22-27
+                    const QT *row = Qx + d * deg;                           // qroute.py:22-27
                     double best = row[0];
 #pragma unroll
                     for (int j = 1; j < MAXD; ++j)
@@ -1025,7 +1037,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
 #pragma unroll
                     for (int j = 0; j < MAXD - 1; ++j)
                         if (j < deg - 1 && k == j && __ddiv_rn(cdf[j], c) <= u) k = j + 1;
-                    const double *row = Qx + d * deg;                           // hybrid.py:49-53
+                    const QT *row = Qx + d * deg;                           // hybrid.py:49-53
                     double best = row[0];
                     oldq = row[0];
 #pragma unroll
@@ -1039,7 +1051,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 rwd = (double)(-(clock - (int)rec.w) - 1);                      // r = -q_y - t_y, qroute.py:37
                 if (IS_CQ) {                        // CQ.get_info (qroute.py:72-78): z = argmax Q[y][d], max_Q_f, C_f
                     const int degy = deg_y;
-                    const double *ry = Qr + qoff_y + d * degy;
+                    const QT *ry = Qr + qoff_y + d * degy;
                     double m = ry[0];
                     int z = 0;
 #pragma unroll
@@ -1049,7 +1061,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                     c_f = Thr[qoff_y + d * degy + z];
                     if (DUAL) {                     // CDRQ.get_info (qroute.py:107-115) + _build_info_dual (env.py:154-160)
                         const int src = (int)(rec.x >> 16);
-                        const double *rb = Qx + src * deg;
+                        const QT *rb = Qx + src * deg;
                         double mb = rb[0];
                         int w = 0;
 #pragma unroll
@@ -1062,7 +1074,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                     }
                 } else if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) {   // max_Q_y, qroute.py:29-30
                     const int degy = deg_y;
-                    const double *ry = Qr + qoff_y + d * degy;
+                    const QT *ry = Qr + qoff_y + d * degy;
                     double m = ry[0];
 #pragma unroll
                     for (int j = 1; j < MAXD; ++j)
@@ -1120,7 +1132,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
             const double tq = __dmul_rn(p.discount, max_qy);
             const double u1 = __dadd_rn(rwd, tq);
             const double u2 = __dsub_rn(u1, oldq);
-            Qx[d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, u2));
+            Qx[d * deg + k] = (QT)__dadd_rn(oldq, __dmul_rn(p.lr_q, u2));
         }
         if (general) {
             // ---- C (general timing). Network.event_queue restated literally (heapq on arrive_time only, env.py:48-49):
@@ -1269,7 +1281,9 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 const double tq = __dmul_rn(p.discount, max_qy);
                 const double u1 = __dadd_rn(rwd, tq);
                 const double u2 = __dsub_rn(u1, oldq);
-                sts64_if(Qx + (d * deg + k), __dadd_rn(oldq, __dmul_rn(p.lr_q, u2)), sending);
+                const double newq = __dadd_rn(oldq, __dmul_rn(p.lr_q, u2));
+                if constexpr (sizeof(QT) == 8) sts64_if(reinterpret_cast<double *>(Qx) + (d * deg + k), newq, sending);
+                else sts32f_if(reinterpret_cast<float *>(Qx) + (d * deg + k), (float)newq, sending);
             }
             if (kFlatArrivals) {
                 // Loop-free arrivals (degree <= 4): every matching neighbour's record and heap position are fetched side
@@ -1403,7 +1417,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 }
                 const double tq = __dmul_rn(p.discount, max_qy);
                 const double u1 = __dadd_rn(rr, tq);
-                Qx[d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, __dsub_rn(u1, oldq)));
+                Qx[d * deg + k] = (QT)__dadd_rn(oldq, __dmul_rn(p.lr_q, __dsub_rn(u1, oldq)));
                 const double adv = __dsub_rn(u1, max_qxd);                      // hybrid.py:32-36
                 double *th = Thx + d * deg;
 #pragma unroll
@@ -1451,7 +1465,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                     cq_update(q, c, r_f, c_f, max_qy);
                     if (hit && y > x) cq_update(q, c, r_by, bk.x, bk.y);
                 }
-                Qx[cell] = q;
+                Qx[cell] = (QT)q;
                 Thx[cell] = c;
                 if (DUAL) {                                                     // my backward update on y's table
                     const int src = (int)s_src[t];
@@ -1466,7 +1480,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                         double qb = Qr[cb], cbv = Thr[cb];
                         const double2 bk = s_bk[t];
                         cq_update(qb, cbv, -(double)s_qxi[t], bk.x, bk.y);
-                        Qr[cb] = qb;
+                        Qr[cb] = (QT)qb;
                         Thr[cb] = cbv;
                     }
                 }
@@ -1497,7 +1511,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                         trow[j] = __dadd_rn(trow[j], gj);
                     }
                 const double u1 = __dadd_rn(rwd, __dmul_rn(p.discount, max_qy));
-                Qx[d * deg + k] = __dadd_rn(oldq, __dmul_rn(p.lr_q, __dsub_rn(u1, oldq)));
+                Qx[d * deg + k] = (QT)__dadd_rn(oldq, __dmul_rn(p.lr_q, __dsub_rn(u1, oldq)));
             }
             {   // r.sum(), max_Q_y.sum(), max_Q_x_d.sum() (multi_agent.py:28-29), one helper warp per (replica, sum)
                 const int hw0 = (GN + 31) >> 5, nhw = (int)(blockDim.x >> 5) - hw0;
@@ -1637,12 +1651,12 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
         fence_proxy_async();
         __syncthreads();
         if (t == 0) {
-            const unsigned tbytes = (unsigned)(p.tsize * 8);
+            const unsigned tbytes = (unsigned)(p.tsize * sizeof(QT));
             for (int gg = 0; gg < G; ++gg) {
                 if (rblock + gg >= p.R) break;
                 for (int tb = 0; tb < p.ntab; ++tb)
-                    bulk_s2g((tb == 0 ? p.Q : tb == 1 ? p.Theta : p.Trace) + (rblock + gg) * p.tsize,
-                             s_tables + gg * tstride + tb * p.tsize, tbytes);
+                    bulk_s2g(reinterpret_cast<char *>(tb == 0 ? p.Q : tb == 1 ? p.Theta : p.Trace) + (size_t)(rblock + gg) * tbytes,
+                             reinterpret_cast<const char *>(s_tables) + ((size_t)gg * p.ntab + tb) * tbytes, tbytes);
             }
             bulk_commit_wait();
         }
@@ -1651,30 +1665,30 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
 
 using StepKernel = void (*)(const StepParams);
 
-template <int POLICY, int MAXD, int MAXW, bool SPLIT, int LB = 0>
+template <int POLICY, int MAXD, int MAXW, bool SPLIT, int LB = 0, typename QT = double>
 StepKernel pick_smem(bool smem_tables)
 {
     if (POLICY == RLR_POLICY_SHORTEST || POLICY == RLR_POLICY_GLOBALROUTE || LB != 0)
-        return (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT, LB>;
-    return smem_tables ? (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, true, SPLIT, 0>
-                       : (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT, 0>;
+        return (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT, LB, QT>;
+    return smem_tables ? (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, true, SPLIT, 0, QT>
+                       : (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT, 0, QT>;
 }
 
-template <int POLICY, bool SPLIT>
+template <int POLICY, bool SPLIT, typename QT = double>
 StepKernel pick_deg(int n_nodes, int max_deg, bool smem_tables, int threads)
 {
     if (n_nodes <= 64) {
-        if (max_deg <= 4) return pick_smem<POLICY, 4, 3, SPLIT>(smem_tables);
-        if (max_deg <= 8) return pick_smem<POLICY, 8, 3, SPLIT>(smem_tables);
-        return pick_smem<POLICY, 16, 3, SPLIT>(smem_tables);
+        if (max_deg <= 4) return pick_smem<POLICY, 4, 3, SPLIT, 0, QT>(smem_tables);
+        if (max_deg <= 8) return pick_smem<POLICY, 8, 3, SPLIT, 0, QT>(smem_tables);
+        return pick_smem<POLICY, 16, 3, SPLIT, 0, QT>(smem_tables);
     }
     // small CTAs reading their tables from HBM (lata.net: 116 nodes, 128 threads): the high-occupancy build
     constexpr bool kHasLb1 = POLICY == RLR_POLICY_QROUTE || POLICY == RLR_POLICY_HYBRIDQ || POLICY == RLR_POLICY_SHORTEST;
     if (kHasLb1 && !SPLIT && !smem_tables && threads <= 128 && max_deg > 8 && max_deg <= 12)
-        return pick_smem<POLICY, 12, 9, SPLIT, kHasLb1 && !SPLIT ? 1 : 0>(false);
-    if (max_deg <= 8) return pick_smem<POLICY, 8, 9, SPLIT>(smem_tables);
-    if (max_deg <= 12) return pick_smem<POLICY, 12, 9, SPLIT>(smem_tables);      // lata.net: degree 9 (row loops sized 12, not 16)
-    return pick_smem<POLICY, 16, 9, SPLIT>(smem_tables);
+        return pick_smem<POLICY, 12, 9, SPLIT, kHasLb1 && !SPLIT ? 1 : 0, QT>(false);
+    if (max_deg <= 8) return pick_smem<POLICY, 8, 9, SPLIT, 0, QT>(smem_tables);
+    if (max_deg <= 12) return pick_smem<POLICY, 12, 9, SPLIT, 0, QT>(smem_tables);      // lata.net: degree 9 (row loops sized 12, not 16)
+    return pick_smem<POLICY, 16, 9, SPLIT, 0, QT>(smem_tables);
 }
 
 }  // namespace
@@ -1686,4 +1700,12 @@ StepKernel pick_deg(int n_nodes, int max_deg, bool smem_tables, int threads)
     {                                                                                                             \
         return split ? (void *)pick_deg<POLICY, true>(n_nodes, max_deg, smem_tables, threads)                      \
                      : (void *)pick_deg<POLICY, false>(n_nodes, max_deg, smem_tables, threads);                    \
+    }
+
+// The same for Qroute with its table stored in fp32 (step_qroute_f32.cu).
+#define RLR_DEFINE_STEP_PICK_F32(NAME, POLICY)                                                                    \
+    void *rlr_pick_step_##NAME(bool split, int n_nodes, int max_deg, bool smem_tables, int threads)                \
+    {                                                                                                             \
+        return split ? (void *)pick_deg<POLICY, true, float>(n_nodes, max_deg, smem_tables, threads)               \
+                     : (void *)pick_deg<POLICY, false, float>(n_nodes, max_deg, smem_tables, threads);             \
     }

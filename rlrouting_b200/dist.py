@@ -63,7 +63,7 @@ def level_stats(counters, level_idx, n_levels):
     """Sums per-replica counters [R, C] into per-load-level rows [n_levels, C] (torch, on device)."""
     import torch
     out = torch.zeros((n_levels, counters.shape[1]), dtype=counters.dtype, device=counters.device)
-    out.index_add_(0, torch.as_tensor(level_idx, device=counters.device, dtype=torch.long), counters)
+    out.index_add_(0, torch.as_tensor(np.array(level_idx), device=counters.device, dtype=torch.long), counters)
     return out
 
 

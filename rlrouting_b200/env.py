@@ -114,7 +114,7 @@ def _floor_pow2(v):
 class Network:
     def __init__(self, file, bandwidth=1, transtime=1, is_drop=False, *, replicas=1, device=None,
                  rng="trace", seed=None, replica_base=0, queue_capacity=None,
-                 replicas_per_block=0, threads_per_block=0, tables_in_smem=-1):
+                 replicas_per_block=0, threads_per_block=0, tables_in_smem=-1, dtype="float64"):
         bandwidth, transtime = _as_int(bandwidth, "bandwidth"), _as_int(transtime, "transtime")
         if bandwidth < 0 or transtime < 0:
             raise ValueError("bandwidth and transtime must be >= 0")
@@ -122,6 +122,12 @@ class Network:
             raise ValueError("rng must be 'trace' or 'philox'")
         if replicas < 1:
             raise ValueError("replicas must be >= 1")
+        # Q-table STORAGE type: 'float64' is the reference's precision and the parity mode; 'float32' (Qroute
+        # only) halves the table so that twice the replicas fit in an SM — rows are widened to fp64 when read and the TD
+        # update is rounded once on store, so trajectories agree with fp64 until the first near-tie forks them
+        self.dtype = np.dtype(dtype).name
+        if self.dtype not in ("float64", "float32"):
+            raise ValueError("dtype must be 'float64' or 'float32'")
         self.bandwidth, self.transtime, self.is_drop = bandwidth, transtime, is_drop
         self.replicas, self.rng, self.replica_base = int(replicas), rng, int(replica_base)
         self.read_network(file)
@@ -203,7 +209,7 @@ class Network:
         t = nat.Topology(topo.N, topo.sum_deg, topo.max_deg, topo.row_ptr.ctypes.data, topo.col.ctypes.data)
         rpb, tpb, tis = self._launch_cfg
         cfg = nat.Config(self.replicas, self.replica_base, agent._kernel_policy, self.queue_capacity, rpb, tpb, tis,
-                         self.device.index, self._ecap, 0)
+                         self.device.index, self._ecap, 1 if (self.dtype == "float32" and agent._kernel_policy == nat.POLICY_QROUTE) else 0)
         h = C.c_void_p()
         nat.check(nat.lib().rlr_create(C.byref(t), C.byref(cfg), C.byref(h)))
         d = agent._dev
@@ -745,7 +751,7 @@ class Network:
                 raise NotImplementedError("per-level droprate vectors are not implemented; use the per-replica vectors")
             cached = self._resident.get("level_index")
             if cached is None or not np.array_equal(cached[0], lv):
-                cached = self._resident["level_index"] = (lv, torch.from_numpy(lv).to(self.device))
+                cached = self._resident["level_index"] = (lv, torch.from_numpy(np.array(lv)).to(self.device))
             d_lv = cached[1]
             per_step = True
         if per_step is None:
@@ -1052,14 +1058,15 @@ class Network:
         names = list(getattr(agent, "_table_names", ()))
         if table not in names:
             raise ValueError(f"{type(agent).__name__} has no table {table!r}")
-        if prev is not None and (prev.dtype != torch.float64 or tuple(prev.shape) != (self.replicas, self.topology.tsize)
+        tdt = self._agent._dev[table].dtype
+        if prev is not None and (prev.dtype != tdt or tuple(prev.shape) != (self.replicas, self.topology.tsize)
                                  or prev.device != self.device or not prev.is_contiguous()):
-            raise ValueError("prev must be a contiguous float64 device tensor shaped like the table [R, tsize]")
+            raise ValueError("prev must be a contiguous device tensor of the table's dtype and shape [R, tsize]")
         d_lv, L = None, 1
         if level_index is not None:
             lv = np.ascontiguousarray(np.broadcast_to(np.asarray(level_index), (self.replicas,)), dtype=np.int32)
             L = int(lv.max()) + 1
-            d_lv = torch.from_numpy(lv).to(self.device)
+            d_lv = torch.from_numpy(np.array(lv)).to(self.device)
         per = torch.empty((self.replicas, 2), dtype=torch.float64, device=self.device)
         lev = torch.empty((L, 2), dtype=torch.float64, device=self.device)
         nat.check(nat.lib().rlr_table_stats(h, names.index(table), prev.data_ptr() if prev is not None else None, per.data_ptr(),

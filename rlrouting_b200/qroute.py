@@ -37,6 +37,10 @@ class Qroute(Policy):
     def _alloc_tables(self, network, initQ, initP):
         import torch
         q0 = _draw_initial_q(network, initQ, self._q_draws)
+        if network.dtype == "float32":
+            if self._kernel_policy != nat.POLICY_QROUTE:
+                raise NotImplementedError(f"dtype='float32' (fp32 table storage) is implemented for Qroute, not for {type(self).__name__}")
+            q0 = q0.astype(np.float32)          # the fp64 draws, rounded once
         self._dev = {"Qtable": torch.from_numpy(q0).to(network.device)}
         for name in self._table_names[1:]:
             self._dev[name] = torch.empty_like(self._dev["Qtable"])
@@ -65,7 +69,7 @@ class Qroute(Policy):
         import torch
         net = self._network
         a = np.array(np.broadcast_to(np.asarray(normals, dtype=np.float64), (net.replicas, net.topology.tsize)))
-        self._dev["Qtable"].copy_(torch.from_numpy(a))
+        self._dev["Qtable"].copy_(torch.from_numpy(a))                   # (rounds to the table's storage type)
         nat.check(nat.lib().rlr_init_tables(self._handle, float(initP), net._stream_ptr()))
 
     Qtable = property(lambda self: self._get_table("Qtable"), lambda self, v: self._set_table("Qtable", v))

@@ -93,7 +93,7 @@ class GlobalRoute(Shortest):
         n, R = self._network.topology.N, self._network.replicas
         d = np.asarray(value, dtype=np.float64).reshape(-1, n * n)
         d = np.where(np.isfinite(d), d, float(self.INF)).astype(np.int32)
-        self._dev["gr_distance"].copy_(torch.from_numpy(np.ascontiguousarray(np.broadcast_to(d, (R, n * n)))))
+        self._dev["gr_distance"].copy_(torch.from_numpy(np.array(np.broadcast_to(d, (R, n * n)))))
 
     @property
     def choice(self):
