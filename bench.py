@@ -381,8 +381,10 @@ def measure(w, steps, warmup, rank, world, dev, sampler=None, vectors_steps=0):
     topo = nw.topology
     ring_gb = R * topo.N * cap * 16 / 1e9
     table_mb = R * topo.tsize * (4 if w.dtype == "float32" else 8) * len(getattr(agent, "_table_names", ())) / 1e6
-    del nw, agent
-    torch.cuda.empty_cache()
+    del nw, agent, out
+    import gc
+    gc.collect()                                    # Network <-> Node reference cycles: free the rings now, not inside
+    torch.cuda.empty_cache()                        # the next workload's timed region
     if rank != 0:
         return None
     peak, peak_src = measured_peak()

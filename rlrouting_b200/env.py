@@ -545,9 +545,12 @@ class Network:
         rp.slot, rp.freq, rp.transtime, rp.bandwidth, rp.general = slot, freq, self.transtime, self.bandwidth, int(self._general)
         return slot, freq
 
-    def _run_params(self, agent, lr):
-        lrd = dict(getattr(agent, "_lr_default", {}))
-        lrd.update(lr or {})
+    def _run_params(self, agent, lr, merged=False):
+        """Run parameters every entry point shares: learning rates (the agent's defaults overridden by `lr`; `merged`: `lr`
+        already is the merged dict), the agent's hyper-parameters, Network options, seed and the default timing block."""
+        lrd = dict(lr) if merged else dict(getattr(agent, "_lr_default", {}))
+        if not merged:
+            lrd.update(lr or {})
         rp = nat.RunParams()
         rp.add_entropy = int(bool(getattr(agent, "add_entropy", True)))
         rp.lr_q, rp.lr_p, rp.lr_e = float(lrd.get("q", 0.1)), float(lrd.get("p", 0.1)), float(lrd.get("e", 0.1))
@@ -766,16 +769,7 @@ class Network:
                 result["hop"] = np.zeros((W, 0))
             return self._finish(result, legacy, R if d_lv is None else 0)
 
-        rp = nat.RunParams()
-        rp.add_entropy = int(bool(getattr(agent, "add_entropy", True)))
-        rp.lr_q, rp.lr_p, rp.lr_e = float(lrd.get("q", 0.1)), float(lrd.get("p", 0.1)), float(lrd.get("e", 0.1))
-        rp.discount = float(getattr(agent, "discount", 0.99))
-        rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
-        rp.conf_decay = float(getattr(agent, "decay", 0.9))
-        rp.is_drop = int(bool(self.is_drop))
-        rp.shortest_random = int(agent._kernel_policy in (nat.POLICY_SHORTEST, nat.POLICY_GLOBALROUTE) and bool(getattr(agent, "random", False)))
-        rp.multiway = int(agent._kernel_policy == nat.POLICY_GLOBALROUTE and bool(getattr(agent, "multiway", False)))
-        rp.seed = self.seed
+        rp = self._run_params(agent, lrd, merged=True)
         slot, freq = self._timing(rp, slot, freq)
         keep = []
         h2d = 0
@@ -937,23 +931,11 @@ class Network:
         if self._resident.get("metrics_shape") != (R, K):
             self._resident["metrics"] = torch.empty((K, R, 2), dtype=torch.int64, device=self.device)
             self._resident["metrics_shape"] = (R, K)
-        lrd = dict(getattr(agent, "_lr_default", {}))
-        lrd.update(lr or {})
-        rp = nat.RunParams()
+        rp = self._run_params(agent, lr)
         rp.inject_mode = nat.INJECT_PHILOX
-        rp.add_entropy = int(bool(getattr(agent, "add_entropy", True)))
-        rp.lr_q, rp.lr_p, rp.lr_e = float(lrd.get("q", 0.1)), float(lrd.get("p", 0.1)), float(lrd.get("e", 0.1))
-        rp.discount = float(getattr(agent, "discount", 0.99))
-        rp.discount_trace = float(getattr(agent, "discount_trace", 0.6))
-        rp.conf_decay = float(getattr(agent, "decay", 0.9))
-        rp.is_drop = int(bool(self.is_drop))
-        rp.shortest_random = int(agent._kernel_policy in (nat.POLICY_SHORTEST, nat.POLICY_GLOBALROUTE) and bool(getattr(agent, "random", False)))
-        rp.multiway = int(agent._kernel_policy == nat.POLICY_GLOBALROUTE and bool(getattr(agent, "multiway", False)))
-        rp.seed = self.seed
         rp.enlam = d_en.data_ptr()
         rp.inj_thr = d_thr.data_ptr()
         rp.metrics = self._resident["metrics"].data_ptr()
-        self._timing(rp)
         nxt = self.clock + K if next_clock0 is None else int(next_clock0)
         self._schedule(h, rp, self.clock, K, key, lam.max(), (nxt, K))                # next call's schedule is prefetched
         nat.check(nat.lib().rlr_run_steps(h, K, C.byref(rp), self._stream_ptr()))

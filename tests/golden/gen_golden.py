@@ -122,6 +122,9 @@ CASES = [
          agent_kwargs={"multiway": True, "random": True}),
     dict(net="6x6.net", policy="GlobalRoute", T=100, lambd=2.0, seed=1, rng="philox", philox_seed=7, replica=3,
          agent_kwargs={"multiway": True, "random": True}, net_kwargs={"transtime": 2}),
+    # SURVEY §8(c) starter rows 2 and 3 at their full horizon (trajectory hashes d99579f950a89093 / 1553ae894a6cd64f)
+    dict(net="6x6-modified.net", policy="Qroute", T=10000, lambd=2.0, seed=1),     # BASELINE config 3's network, T = 10,000
+    dict(net="lata.net", policy="Qroute", T=10000, lambd=2.0, seed=1),             # BASELINE config 4's network, T = 10,000
 ]
 
 
