@@ -1255,25 +1255,66 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 cum[i + 1] = cum[i] + __popc(m);
             }
             const unsigned hp_row = cum[MAXW] * (unsigned)N;                    // heap_pos row k = number of senders
-            unsigned cumpack = 0;                                               // cum[0..3] as bytes (N <= 255)
-            if (MAXW <= 3) cumpack = cum[0] | (cum[1] << 8) | (cum[2] << 16);
-            // sort key per neighbour slot: heap pop position << 16 | send slot, or kNoKey
-            // MAXD == 4: the four keys stay in registers (sorting network below); wider nodes compact their arrivals
-            // into a short list (indexed, so it lives in local memory) and pick the minimum of what is left each time
+            // cum[] as bytes (N <= 255) of up to three registers, looked up with byte_perm: no indexed local array
+            unsigned cumpack = 0, cumpack1 = 0, cumpack2 = 0;
+            cumpack = cum[0] | (cum[1] << 8) | (cum[2] << 16) | ((MAXW > 3 ? cum[MAXW > 3 ? 3 : 0] : 0u) << 24);
+            if (MAXW > 4) cumpack1 = cum[MAXW > 4 ? 4 : 0] | (cum[MAXW > 5 ? 5 : 0] << 8) | (cum[MAXW > 6 ? 6 : 0] << 16) | (cum[MAXW > 7 ? 7 : 0] << 24);
+            if (MAXW > 8) cumpack2 = cum[MAXW > 8 ? 8 : 0];
+            auto cum_at = [&](unsigned w) -> unsigned {
+                if (MAXW <= 4) return __byte_perm(cumpack, 0u, w) & 0xFFu;
+                const unsigned reg = w < 4u ? cumpack : (w < 8u ? cumpack1 : cumpack2);
+                return __byte_perm(reg, 0u, w & 3u) & 0xFFu;
+            };
+            // sort key per arrival: heap pop position << 16 | send slot, or kNoKey.
+            // MAXD == 4: one key per neighbour slot, sorted by a 5-comparator network.  Wider nodes: a first pass only marks
+            // the slots that hold a packet for this node (a node receives about one packet a step whatever its degree);
+            // the marked slots' keys are then inserted, sorted, into four registers.  Only a node with more than four
+            // arrivals in one step falls back to a list in local memory.
             unsigned key[MAXD];
+            unsigned q4[4] = {kNoKey, kNoKey, kNoKey, kNoKey};
             int nkey = 0;
+            bool use_list = false;
+            if (MAXD == 4 && !kFlatArrivals) {
 #pragma unroll
-            for (int j = 0; j < MAXD; ++j) {
-                if (kFlatArrivals) break;
-                if (MAXD > 4 && j >= p.max_deg) continue;                       // uniform: no node has a j-th neighbour
-                const unsigned tp = s_tp[nb_slot[j]];
-                const bool match = (tp & 0xFFu) == (unsigned)x;                 // kNoSend's low byte is 255 > any node id
-                unsigned base = 0;
-                if (MAXW <= 3) base = __byte_perm(cumpack, 0u, nb_word[j]) & 0xFFu;
-                else base = cum[nb_word[j]];                                    // (an indexed local array: one load, not MAXW selects)
-                const unsigned pos = heap_pos_at(hp_row + (match ? (tp >> 8) + base : 0u));
-                if (MAXD == 4) key[j] = match ? ((pos << 16) | nb_slot[j]) : kNoKey;
-                else if (match) key[nkey++] = (pos << 16) | nb_slot[j];
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned tp = s_tp[nb_slot[j]];
+                    const bool match = (tp & 0xFFu) == (unsigned)x;             // kNoSend's low byte is 255 > any node id
+                    const unsigned pos = heap_pos_at(hp_row + (match ? (tp >> 8) + cum_at(nb_word[j]) : 0u));
+                    q4[j] = match ? ((pos << 16) | nb_slot[j]) : kNoKey;
+                }
+#define RLR_CE(a, b) { const unsigned lo_ = min(q4[a], q4[b]), hi_ = max(q4[a], q4[b]); q4[a] = lo_; q4[b] = hi_; }
+                RLR_CE(0, 1) RLR_CE(2, 3) RLR_CE(0, 2) RLR_CE(1, 3) RLR_CE(1, 2)
+#undef RLR_CE
+            } else if (MAXD > 4) {
+                unsigned marks = 0u;
+#pragma unroll
+                for (int j = 0; j < MAXD; ++j) {
+                    if (j >= p.max_deg) continue;                               // uniform: no node has a j-th neighbour
+                    marks |= ((s_tp[nb_slot[j]] & 0xFFu) == (unsigned)x ? 1u : 0u) << j;
+                }
+                use_list = __popc(marks) > 4;
+                if (!use_list) {
+                    while (marks) {
+                        const int j = __ffs((int)marks) - 1;
+                        marks &= marks - 1u;
+                        const unsigned slot = (unsigned)gbase + s_col[rp + j];
+                        const unsigned tp = s_tp[slot];
+                        const unsigned pos = heap_pos_at(hp_row + (tp >> 8) + cum_at((slot >> 5) - (unsigned)wlo));
+                        unsigned tk = (pos << 16) | slot, lo_;                  // sorted insert (ascending)
+                        lo_ = min(q4[0], tk); tk = max(q4[0], tk); q4[0] = lo_;
+                        lo_ = min(q4[1], tk); tk = max(q4[1], tk); q4[1] = lo_;
+                        lo_ = min(q4[2], tk); tk = max(q4[2], tk); q4[2] = lo_;
+                        q4[3] = min(q4[3], tk);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < MAXD; ++j) {
+                        if (j >= p.max_deg) continue;
+                        const unsigned tp = s_tp[nb_slot[j]];
+                        if ((tp & 0xFFu) == (unsigned)x)
+                            key[nkey++] = (heap_pos_at(hp_row + (tp >> 8) + cum_at(nb_word[j])) << 16) | nb_slot[j];
+                    }
+                }
             }
             if (kLearnInArrivals) {
                 // Qroute.learn (qroute.py:40-44) in the same straight-line block as the arrival loads, so that the fp64
@@ -1296,7 +1337,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 for (int j = 0; j < 4; ++j) {
                     const unsigned tp = s_tp[nb_slot[j]];
                     mt[j] = (tp & 0xFFu) == (unsigned)x;
-                    const unsigned base = __byte_perm(cumpack, 0u, nb_word[j]) & 0xFFu;
+                    const unsigned base = cum_at(nb_word[j]);
                     posv[j] = heap_pos_at(hp_row + (mt[j] ? (tp >> 8) + base : 0u));
                     rc[j] = lds128_if(s_rec + nb_slot[j], mt[j]);
                 }
@@ -1340,17 +1381,12 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                     tail += ap[j] ? 1u : 0u;
                 }
             } else {
-            if (MAXD == 4) {                                                    // 5-comparator sorting network
-#define RLR_CE(a, b) { const unsigned lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; }
-                RLR_CE(0, 1) RLR_CE(2, 3) RLR_CE(0, 2) RLR_CE(1, 3) RLR_CE(1, 2)
-#undef RLR_CE
-            }
             RLR_T(5);                               // C: window + keys + sort
             for (int taken = 0;; ++taken) {
                 unsigned best;
-                if (MAXD == 4) {
-                    best = key[0];
-                    key[0] = key[1]; key[1] = key[2]; key[2] = key[3]; key[3] = kNoKey;
+                if (!use_list) {
+                    best = q4[0];
+                    q4[0] = q4[1]; q4[1] = q4[2]; q4[2] = q4[3]; q4[3] = kNoKey;
                     if (best == kNoKey) break;
                 } else {
                     if (taken >= nkey) break;

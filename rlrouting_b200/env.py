@@ -11,6 +11,7 @@ mid-run, and there is no CPU fallback: float-valued clocks (`slot`
 'dual' for anything but CDRQ, and agents that are not one of the built-in policies.
 """
 import ctypes as C
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -183,6 +184,9 @@ class Network:
             self._event_rec = torch.zeros((R, self._ecap, 4), dtype=torch.int32, device=dev)
             self._q_dead = torch.zeros((R, N), dtype=torch.int32, device=dev)
         self._handles = []
+        # Philox injection schedules are built one launch ahead on a side stream by default; False builds each one in-stream
+        # right before the step kernel that consumes it (no kernel then runs beside the step kernel)
+        self.schedule_prefetch = os.environ.get("RLR_SCHED_INLINE", "") != "1"
         self.launch_count = 0          # kernels of this library launched: step, injection-schedule and ratio kernels
                                        # (bench.py reports the count of its timed region as gpu_launches)
         self.last_h2d_bytes = self.last_d2h_bytes = 0
@@ -282,7 +286,7 @@ class Network:
         used = torch.cuda.Event()
         used.record(torch.cuda.current_stream(self.device))
         st["used"][slot] = used
-        if next_key is None:
+        if next_key is None or not self.schedule_prefetch:
             return
         clock0, K = next_key
         other = 1 - slot
