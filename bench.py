@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--replicas-per-block", type=int, default=0)
     ap.add_argument("--threads-per-block", type=int, default=0)
     ap.add_argument("--tables-in-smem", type=int, default=-1)
+    ap.add_argument("--page-records", type=int, default=0, help="> 0: paged queues with pages of this many packets instead of rings")
+    ap.add_argument("--pages-per-replica", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip BASELINE.json's configs 2-5 after the headline")
     ap.add_argument("--only-extra", default="", help="run only these extra configs (comma-separated keys), no headline")
@@ -247,11 +249,12 @@ def algorithmic_bytes(policy, topo, hops, injections, replica_steps, esize=8):
 # ------------------------------------------------------------------------------------------------
 class Workload:
     def __init__(self, key, net, policy, replicas, sim_steps, loads, note="", launch=(0, 0, -1), queue_capacity=0, agent_kw=None,
-                 dtype="float64"):
+                 dtype="float64", page_records=0, pages_per_replica=0):
         self.key, self.net, self.policy, self.replicas, self.sim_steps = key, net, policy, int(replicas), int(sim_steps)
         self.loads, self.note, self.launch, self.queue_capacity = list(loads), note, launch, queue_capacity
         self.agent_kw = agent_kw or {}
         self.dtype = dtype
+        self.page_records, self.pages_per_replica = int(page_records), int(pages_per_replica)
 
 
 def measure(w, steps, warmup, rank, world, dev, sampler=None, vectors_steps=0):
@@ -274,7 +277,8 @@ def measure(w, steps, warmup, rank, world, dev, sampler=None, vectors_steps=0):
         torch.cuda.synchronize()
 
     nw = rb.Network(w.net, replicas=R, rng="philox", seed=1, replica_base=rank * R, queue_capacity=cap,
-                    replicas_per_block=w.launch[0], threads_per_block=w.launch[1], tables_in_smem=w.launch[2], dtype=w.dtype)
+                    replicas_per_block=w.launch[0], threads_per_block=w.launch[1], tables_in_smem=w.launch[2], dtype=w.dtype,
+                    page_records=w.page_records, pages_per_replica=w.pages_per_replica or None)
     agent = getattr(rb, w.policy)(nw, **w.agent_kw)
     nw.agent = agent
     learns = hasattr(agent, "keep_initial_tables")
@@ -379,7 +383,8 @@ def measure(w, steps, warmup, rank, world, dev, sampler=None, vectors_steps=0):
                "d2h_bytes_per_step": d2h // vectors_steps,
                "note": "same, with the per-replica [R, sim_steps] route_time vectors copied to the host instead of the level curves"}
     topo = nw.topology
-    ring_gb = R * topo.N * cap * 16 / 1e9
+    ring_gb = nw.queue_memory_bytes / 1e9
+    live_peak = int(final["active_packets"]) / max(world * R, 1)        # packets alive per replica at the end of the last episode
     table_mb = R * topo.tsize * (4 if w.dtype == "float32" else 8) * len(getattr(agent, "_table_names", ())) / 1e6
     del nw, agent, out
     import gc
@@ -407,7 +412,10 @@ def measure(w, steps, warmup, rank, world, dev, sampler=None, vectors_steps=0):
         "note": w.note, "value": value, "unit": UNIT, "n_gpus": world, "replicas_total": world * R, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_total / steps, "step_ms": step_ms, "hops_in_timed_region": hops, "gpu_launches": launches,
         "launch": info, "queue_capacity": cap,
-        "l2_policy": "state larger than L2: tables %.0f MB + queue rings %.1f GB per GPU, every episode starts cold" % (table_mb, ring_gb),
+        "queues": ({"kind": "paged", "page_records": w.page_records, "pages_per_replica": w.pages_per_replica} if w.page_records
+                   else {"kind": "rings", "slots_per_queue": cap}),
+        "queue_memory_bytes_per_replica": int(ring_gb * 1e9 / R), "live_packets_per_replica_at_end": live_peak,
+        "l2_policy": "state larger than L2: tables %.0f MB + queues %.1f GB per GPU, every episode starts cold" % (table_mb, ring_gb),
         "e2e": e2e, "e2e_per_replica_vectors": vec, "clocks": clocks,
         "loads": [float(x) for x in w.loads],
         "mean_delivery_time_per_level": [float(x) for x in lev.get("ave_route_time", [])],
@@ -470,7 +478,8 @@ def run_b200(a):
             sampler.stop()
         return
     head = Workload("headline", a.net, a.policy, a.replicas_per_gpu, a.sim_steps, [a.load],
-                    launch=(a.replicas_per_block, a.threads_per_block, a.tables_in_smem), queue_capacity=a.queue_capacity)
+                    launch=(a.replicas_per_block, a.threads_per_block, a.tables_in_smem), queue_capacity=a.queue_capacity,
+                    page_records=a.page_records, pages_per_replica=a.pages_per_replica)
     rec = measure(head, a.steps, a.warmup, rank, world, dev, sampler, vectors_steps=min(3, a.steps))
     extra_recs = []
     if not a.no_extra:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RLR_ABI_VERSION 3
+#define RLR_ABI_VERSION 4
 
 enum { RLR_OK = 0, RLR_E_INVALID = -1, RLR_E_UNSUPPORTED = -2, RLR_E_CUDA = -3, RLR_E_STATE = -4 };
 
@@ -81,6 +81,11 @@ typedef struct {
     int32_t table_dtype;          /* 0: Q table stored as float64 (the reference's precision, the default); 1: float32 storage
                                    * (Qroute only): rows are widened to fp64 when read, updates computed in fp64 and rounded
                                    * on store — `prev` of rlr_table_stats and the q_table buffer are then float arrays */
+    int32_t page_records;         /* 0: one ring of queue_capacity slots per (replica, node).  A power of two >= 4: PAGED queues —
+                                   * the reference's unbounded lists (env.py:100,130) as linked pages of this many records taken
+                                   * from a per-replica pool, so memory follows the packets alive, not the worst node of the run;
+                                   * served by the fused Network.train path (rlr_run_steps with default options) */
+    int32_t pages_per_replica;    /* pool size (<= 65535; >= 2 * N + 1); an empty pool sets RLR_STATUS_QUEUE_OVERFLOW */
 } rlr_config_t;
 
 /* Raw DEVICE pointers borrowed from the caller.  R = replicas, N = n_nodes,
@@ -117,6 +122,14 @@ typedef struct {
                                  (arrive_time mod (transtime + 1)) * N + sender                                 */
     int32_t *q_dead;          /* [R][N] ring entries between head and tail already sent out of order (queue.pop(i),
                                  env.py:177): len(queue) = tail - head - q_dead                                 */
+    /* paged queues (page_records > 0; `ring` may then be NULL).  Record i of a queue (q_head <= i < q_tail) is at offset
+     * i mod page_records of the (i / page_records - q_head / page_records)-th page of the list that starts at q_pages[..][0]
+     * and follows page_next.  rlr_reset initialises all of them. */
+    void *pool;               /* [R][pages_per_replica * page_records] 16-byte packet records                           */
+    uint16_t *page_next;      /* [R][pages_per_replica] the page that follows in its queue                              */
+    uint16_t *page_free;      /* [R][pages_per_replica] stack of free pages                                             */
+    int32_t *page_top;        /* [R] entries on that stack                                                              */
+    uint16_t *q_pages;        /* [R][N][4] {page under q_head, page under q_tail, the node's spare page, 0}            */
 } rlr_buffers_t;
 
 typedef struct {

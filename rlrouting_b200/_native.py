@@ -18,7 +18,7 @@ UNITS = ["rlr_kernels"] + ["step_" + n for n in ("shortest", "qroute", "qroute_f
 SRC = os.path.join(CSRC, "rlr_kernels.cu")
 SO = os.environ.get("RLR_LIB") or os.path.join(CSRC, "librlrouting_b200.so")   # RLR_LIB: experiment builds
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 NUM_COUNTERS = 8
 CTR = {"all_packets": 0, "end_packets": 1, "drop_packets": 2, "hops": 3, "route_time": 4, "sends": 5}
 POLICY_SHORTEST, POLICY_QROUTE, POLICY_HYBRIDQ, POLICY_MAHYBRIDQ, POLICY_CQ, POLICY_CDRQ, POLICY_GLOBALROUTE = 0, 1, 2, 3, 4, 5, 6
@@ -60,14 +60,16 @@ class Config(C.Structure):
     _fields_ = [("replicas", C.c_int64), ("replica_base", C.c_int64), ("policy", C.c_int32),
                 ("queue_capacity", C.c_int32), ("replicas_per_block", C.c_int32),
                 ("threads_per_block", C.c_int32), ("tables_in_smem", C.c_int32), ("device", C.c_int32),
-                ("event_capacity", C.c_int32), ("table_dtype", C.c_int32)]
+                ("event_capacity", C.c_int32), ("table_dtype", C.c_int32),
+                ("page_records", C.c_int32), ("pages_per_replica", C.c_int32)]
 
 
 class Buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "q_table", "theta", "trace", "ring", "q_head", "q_tail", "counters", "status", "next_hop",
         "distance", "choice", "topo_row_ptr", "topo_col", "heap_pos", "gr_choice_mask", "gr_distance", "choice_mask", "gr_qs_off",
-        "link_sent", "event_heap", "event_count", "event_rec", "q_dead")]
+        "link_sent", "event_heap", "event_count", "event_rec", "q_dead",
+        "pool", "page_next", "page_free", "page_top", "q_pages")]
 
 
 class RunParams(C.Structure):

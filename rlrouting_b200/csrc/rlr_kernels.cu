@@ -164,6 +164,22 @@ __global__ void rlr_globalroute_init_kernel(unsigned short *gr_choice_mask, int 
 }
 
 
+// Paged queues after Network.reset: node x of every replica owns page x (head = tail page) and spare N + x; pages
+// 2N .. n_pages-1 are on the replica's free stack.
+__global__ void rlr_paged_reset_kernel(unsigned short *page_free, int *page_top, unsigned short *q_pages, long long R, int N, int n_pages)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= R * n_pages) return;
+    const long long r = i / n_pages;
+    const int j = (int)(i - r * n_pages);
+    if (j < n_pages - 2 * N) page_free[i] = (unsigned short)(2 * N + j);
+    if (j == 0) page_top[r] = n_pages - 2 * N;
+    if (j < N) {
+        unsigned short *qp = q_pages + (r * N + j) * 4;
+        qp[0] = (unsigned short)j; qp[1] = (unsigned short)j; qp[2] = (unsigned short)(N + j); qp[3] = 0;
+    }
+}
+
 __global__ void rlr_reduce_stats_kernel(const long long *counters, long long R, long long *out)
 {
     __shared__ long long acc[RLR_NUM_COUNTERS];
@@ -343,33 +359,33 @@ static void *rlr_pick_fast(bool split, bool smem_tables)
     return split ? (void *)pick_smem<RLR_FAST_POLICY, 4, 3, true>(smem_tables) : (void *)pick_smem<RLR_FAST_POLICY, 4, 3, false>(smem_tables);
 }
 #else
-void *rlr_pick_step_shortest(bool, int, int, bool, int);
-void *rlr_pick_step_qroute(bool, int, int, bool, int);
-void *rlr_pick_step_qroute_f32(bool, int, int, bool, int);
-void *rlr_pick_step_hybridq(bool, int, int, bool, int);
-void *rlr_pick_step_mahybridq(bool, int, int, bool, int);
-void *rlr_pick_step_cq(bool, int, int, bool, int);
-void *rlr_pick_step_cdrq(bool, int, int, bool, int);
-void *rlr_pick_step_globalroute(bool, int, int, bool, int);
+void *rlr_pick_step_shortest(bool, int, int, bool, int, bool);
+void *rlr_pick_step_qroute(bool, int, int, bool, int, bool);
+void *rlr_pick_step_qroute_f32(bool, int, int, bool, int, bool);
+void *rlr_pick_step_hybridq(bool, int, int, bool, int, bool);
+void *rlr_pick_step_mahybridq(bool, int, int, bool, int, bool);
+void *rlr_pick_step_cq(bool, int, int, bool, int, bool);
+void *rlr_pick_step_cdrq(bool, int, int, bool, int, bool);
+void *rlr_pick_step_globalroute(bool, int, int, bool, int, bool);
 #endif
 
 namespace {
 template <bool SPLIT>
-StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables, int threads, bool f32)
+StepKernel pick_kernel(int policy, int n_nodes, int max_deg, bool smem_tables, int threads, bool f32, bool paged)
 {
 #ifdef RLR_FAST_BUILD
-    (void)policy; (void)n_nodes; (void)max_deg; (void)threads; (void)f32;
+    (void)policy; (void)n_nodes; (void)max_deg; (void)threads; (void)f32; (void)paged;
     return (StepKernel)rlr_pick_fast(SPLIT, smem_tables);
 #else
     switch (policy) {
-    case RLR_POLICY_SHORTEST: return (StepKernel)rlr_pick_step_shortest(SPLIT, n_nodes, max_deg, false, threads);
-    case RLR_POLICY_QROUTE: return f32 ? (StepKernel)rlr_pick_step_qroute_f32(SPLIT, n_nodes, max_deg, smem_tables, threads)
-                                       : (StepKernel)rlr_pick_step_qroute(SPLIT, n_nodes, max_deg, smem_tables, threads);
-    case RLR_POLICY_HYBRIDQ: return (StepKernel)rlr_pick_step_hybridq(SPLIT, n_nodes, max_deg, smem_tables, threads);
-    case RLR_POLICY_MAHYBRIDQ: return (StepKernel)rlr_pick_step_mahybridq(SPLIT, n_nodes, max_deg, smem_tables, threads);
-    case RLR_POLICY_CQ: return (StepKernel)rlr_pick_step_cq(SPLIT, n_nodes, max_deg, smem_tables, threads);
-    case RLR_POLICY_GLOBALROUTE: return (StepKernel)rlr_pick_step_globalroute(SPLIT, n_nodes, max_deg, false, threads);
-    default: return (StepKernel)rlr_pick_step_cdrq(SPLIT, n_nodes, max_deg, smem_tables, threads);
+    case RLR_POLICY_SHORTEST: return (StepKernel)rlr_pick_step_shortest(SPLIT, n_nodes, max_deg, false, threads, paged);
+    case RLR_POLICY_QROUTE: return f32 ? (StepKernel)rlr_pick_step_qroute_f32(SPLIT, n_nodes, max_deg, smem_tables, threads, paged)
+                                       : (StepKernel)rlr_pick_step_qroute(SPLIT, n_nodes, max_deg, smem_tables, threads, paged);
+    case RLR_POLICY_HYBRIDQ: return (StepKernel)rlr_pick_step_hybridq(SPLIT, n_nodes, max_deg, smem_tables, threads, paged);
+    case RLR_POLICY_MAHYBRIDQ: return (StepKernel)rlr_pick_step_mahybridq(SPLIT, n_nodes, max_deg, smem_tables, threads, paged);
+    case RLR_POLICY_CQ: return (StepKernel)rlr_pick_step_cq(SPLIT, n_nodes, max_deg, smem_tables, threads, paged);
+    case RLR_POLICY_GLOBALROUTE: return (StepKernel)rlr_pick_step_globalroute(SPLIT, n_nodes, max_deg, false, threads, paged);
+    default: return (StepKernel)rlr_pick_step_cdrq(SPLIT, n_nodes, max_deg, smem_tables, threads, paged);
     }
 #endif
 }
@@ -563,6 +579,7 @@ struct rlr_handle {
     long long R, replica_base, tsize;
     int cap, G, threads, smem_bytes, smem_bytes_split, device, ecap;   // dynamic shared memory of the fused / split kernel
     int esize;                           // bytes per Q-table entry: 8, or 4 for Qroute's fp32 storage mode
+    int page_log, n_pages;               // paged queues: log2(records per page) (0 = rings), pages per replica
     bool smem_tables, bound;
     std::vector<int> row_ptr, col;
     rlr_buffers_t bufs;
@@ -603,6 +620,15 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
         return fail(RLR_E_UNSUPPORTED, "rlr_create: unknown policy id");
     const int cap = cfg->queue_capacity;
     if (cap < 2 || (cap & (cap - 1))) return fail(RLR_E_INVALID, "rlr_create: queue_capacity must be a power of two >= 2");
+    int page_log = 0;
+    if (cfg->page_records != 0) {
+        const int pr = cfg->page_records;
+        if (pr < 4 || pr > 4096 || (pr & (pr - 1))) return fail(RLR_E_INVALID, "rlr_create: page_records must be 0 or a power of two in [4, 4096]");
+        while ((1 << page_log) < pr) ++page_log;
+        if (cfg->pages_per_replica < 2 * N + 1 || cfg->pages_per_replica > 65535)
+            return fail(RLR_E_INVALID, "rlr_create: pages_per_replica must be in [2 * n_nodes + 1, 65535]");
+        if (cfg->event_capacity > 0) return fail(RLR_E_UNSUPPORTED, "rlr_create: paged queues do not serve the general timing model");
+    }
 
     RLR_CUDA(cudaSetDevice(cfg->device));
     if (cfg->event_capacity < 0 || cfg->event_capacity > 65535 || topo->sum_deg > 65535)
@@ -615,6 +641,7 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     h->tsize = (long long)N * topo->sum_deg;
     h->cap = cap; h->bound = false; h->device = cfg->device; h->ecap = cfg->event_capacity;
     h->esize = cfg->table_dtype == 1 ? 4 : 8;
+    h->page_log = page_log; h->n_pages = page_log ? cfg->pages_per_replica : 0;
     if (cfg->table_dtype != 0 && cfg->table_dtype != 1) { delete h; return fail(RLR_E_INVALID, "rlr_create: table_dtype must be 0 (fp64) or 1 (fp32)"); }
     if (h->esize == 4 && cfg->policy != RLR_POLICY_QROUTE) {
         delete h;
@@ -697,8 +724,8 @@ int rlr_create(const rlr_topology_t *topo, const rlr_config_t *cfg, rlr_handle_t
     h->G = G; h->threads = threads; h->smem_tables = smem_tables != 0;
     h->smem_bytes = (int)SmemLayout(N, h->sdeg, G, threads, h->policy, h->smem_tables, h->tsize, h->ntab, 0, true, h->esize).total;
     h->smem_bytes_split = (int)SmemLayout(N, h->sdeg, G, threads, h->policy, h->smem_tables, h->tsize, h->ntab, h->ecap, false, h->esize).total;
-    h->kernel = pick_kernel<false>(h->policy, h->N, h->max_deg, h->smem_tables, h->threads, h->esize == 4);
-    h->kernel_split = pick_kernel<true>(h->policy, h->N, h->max_deg, h->smem_tables, h->threads, h->esize == 4);
+    h->kernel = pick_kernel<false>(h->policy, h->N, h->max_deg, h->smem_tables, h->threads, h->esize == 4, h->page_log != 0);
+    h->kernel_split = pick_kernel<true>(h->policy, h->N, h->max_deg, h->smem_tables, h->threads, h->esize == 4, false);
     (void)smem;                 // (the per-function shared-memory limit is set right before every launch, rlr_run_steps)
     *out = h;
     return RLR_OK;
@@ -713,8 +740,10 @@ int rlr_destroy(rlr_handle_t *h)
 int rlr_bind_buffers(rlr_handle_t *h, const rlr_buffers_t *b)
 {
     if (!h || !b) return fail(RLR_E_INVALID, "rlr_bind_buffers: null argument");
-    if (!b->ring || !b->q_head || !b->q_tail || !b->counters || !b->status || !b->topo_row_ptr || !b->topo_col || !b->heap_pos)
+    if ((!b->ring && !h->page_log) || !b->q_head || !b->q_tail || !b->counters || !b->status || !b->topo_row_ptr || !b->topo_col || !b->heap_pos)
         return fail(RLR_E_INVALID, "rlr_bind_buffers: ring, q_head, q_tail, counters, status, topo_* and heap_pos are required");
+    if (h->page_log && (!b->pool || !b->page_next || !b->page_free || !b->page_top || !b->q_pages || ((uintptr_t)b->pool & 15)))
+        return fail(RLR_E_INVALID, "rlr_bind_buffers: paged queues need pool (16-byte aligned), page_next, page_free, page_top and q_pages");
     if (h->policy == RLR_POLICY_SHORTEST && (!b->next_hop || !b->distance || !b->choice))
         return fail(RLR_E_INVALID, "rlr_bind_buffers: Shortest needs next_hop, distance and choice");
     const bool gr = h->policy == RLR_POLICY_GLOBALROUTE;
@@ -760,6 +789,12 @@ int rlr_reset(rlr_handle_t *h, void *stream)
         RLR_CUDA(cudaMemsetAsync(h->bufs.link_sent, 0, (size_t)h->R * h->sdeg * 4, st));
         RLR_CUDA(cudaMemsetAsync(h->bufs.event_count, 0, (size_t)h->R * 4, st));
         RLR_CUDA(cudaMemsetAsync(h->bufs.q_dead, 0, RN * 4, st));
+    }
+    if (h->page_log) {                                   // every queue gets its first page and a spare, the rest is free
+        const long long n = h->R * h->n_pages;
+        rlr_paged_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->bufs.page_free, h->bufs.page_top, h->bufs.q_pages,
+                                                                            h->R, h->N, h->n_pages);
+        RLR_CUDA(cudaGetLastError());
     }
     if (h->policy == RLR_POLICY_CQ || h->policy == RLR_POLICY_CDRQ) {              // CQ.clean (qroute.py:66-71)
         const long long total = h->R * h->tsize;
@@ -905,6 +940,11 @@ int rlr_run_steps(rlr_handle_t *h, int64_t n_steps, const rlr_run_params_t *rp, 
     // the fused instantiation reads the schedule in 8-byte chunks (cp.async): it needs an even, 8-byte aligned list layout
     const bool plain = p.phase == 3 && !p.sample && !p.sendlog && !p.is_drop && !p.metrics2 && !p.general && slot == 1 &&
                        freq == 1 && transtime == 1 && p.inj_cap % 2 == 0 && ((uintptr_t)p.inj_events & 7) == 0;
+    if (h->page_log && !plain)
+        return fail(RLR_E_UNSUPPORTED, "rlr_run_steps: paged queues are served by the fused Network.train path only (no split phases, "
+                                       "send log, is_drop, sampling or non-default timing)");
+    p.pool = (uint4 *)h->bufs.pool; p.page_next = h->bufs.page_next; p.page_free = h->bufs.page_free; p.page_top = h->bufs.page_top;
+    p.q_pages = h->bufs.q_pages; p.page_log = h->page_log; p.n_pages = h->n_pages;
     const StepKernel kern = plain ? h->kernel : h->kernel_split;
     const int smem = plain ? h->smem_bytes : h->smem_bytes_split;
     // the attribute belongs to the function, not to the handle: another handle of the same instantiation may have set less

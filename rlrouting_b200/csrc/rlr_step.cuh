@@ -80,6 +80,13 @@ struct StepParams {
     uint4 *event_rec;             // [R][ecap]
     int *q_dead;                  // [R][N]
     int max_deg;                  // largest node degree (uniform loop bound of the MAXD > 4 instantiations)
+    // paged queues (PAGED instantiations): a per-replica pool of pages of 2^page_log records, linked per queue
+    uint4 *pool;                  // [R][n_pages << page_log] records
+    unsigned short *page_next;    // [R][n_pages] page that follows in its queue
+    unsigned short *page_free;    // [R][n_pages] stack of free pages
+    int *page_top;                // [R] entries on that stack
+    unsigned short *q_pages;      // [R][N][4] {head page, tail page, spare page, -}
+    int page_log, n_pages;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -453,7 +460,7 @@ struct SmemLayout {
         f64 = o; o += (policy == RLR_POLICY_MAHYBRIDQ) ? align16((size_t)(3 * GN + 4 * G) * 8)
                        : (policy == RLR_POLICY_CDRQ) ? align16((size_t)GN * 32) : 0;   // CDRQ: {C_b, max_Q_b}, len, q_x, d|k, src
         ull = o; o += align16((size_t)G * 3 * 8);            // route_time, sends, injected
-        u32 = o; o += align16((size_t)G * 8 * 4);            // end, hops, dead, drop, injected-so-far
+        u32 = o; o += align16((size_t)G * 9 * 4);            // end, hops, dead, drop, injected-so-far, ..., free pages
         wmask = o; o += align16((size_t)(threads / 32 + 1) * 4);
         rowptr = o; o += align16((size_t)(N + 1) * 4);
         col = o; o += align16((size_t)sdeg * 2);
@@ -555,7 +562,13 @@ constexpr unsigned kDeadRec = 0xFFFFFFFFu; // word 0 of a ring entry that was se
 //   QT    element type of the Q table in memory: double, or float for Qroute's fp32 STORAGE mode (Network(dtype='float32')):
 //         rows are widened to fp64 when they are read, the TD update is evaluated in fp64 with the same unfused operations
 //         and rounded once when it is stored — half the bytes per table, so twice the replicas per SM
-template <int POLICY, int MAXD, int MAXW, bool SMEM_TABLES, bool SPLIT, int LB = 0, typename QT = double>
+//   PAGED queues live in a per-replica pool of small pages instead of one fixed ring per node (fused instantiation only): the
+//         reference's queues are unbounded (env.py:100,130) and a ring must be sized for the worst node of the whole run,
+//         which is an order of magnitude more than the packets alive at any time.  A queue is a linked list of pages; the
+//         node thread keeps the pages under its head and tail and one spare in registers, so a record's address costs a
+//         select and a shift more than in a ring, and pages are taken from / returned to the replica's free stack only when
+//         a cursor crosses a page boundary (pops return pages before barrier 1, appends take pages after it).
+template <int POLICY, int MAXD, int MAXW, bool SMEM_TABLES, bool SPLIT, int LB = 0, typename QT = double, bool PAGED = false>
 __global__ void __launch_bounds__(LB ? 128 : kMaxThreads, LB ? RLR_LB1_BLOCKS : RLR_MIN_BLOCKS)
 rlr_step_kernel(const __grid_constant__ StepParams p)
 {
@@ -566,6 +579,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     constexpr int D = stage_depth(SMEM_TABLES);
     constexpr int kStageWait = SMEM_TABLES ? D - 1 : D - 2;    // commit groups that may still be in flight at the top of a step
     static_assert(sizeof(QT) == 8 || POLICY == RLR_POLICY_QROUTE, "fp32 table storage is implemented for Qroute");
+    static_assert(!PAGED || !SPLIT, "paged queues are implemented for the fused Network.train instantiation");
     const SmemLayout L(N, p.sdeg, G, blockDim.x, POLICY, SMEM_TABLES, p.tsize, p.ntab, SPLIT ? p.ecap : 0, FUSED, (int)sizeof(QT));
     constexpr bool kHeapInSmem = !(FUSED && SMEM_TABLES);
 
@@ -603,7 +617,8 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     // per-replica accumulators of this launch
     unsigned long long *s_sends = s_ull + G, *s_inj = s_ull + 2 * G;
     unsigned *s_end = s_u32, *s_hops = s_u32 + G, *s_dead = s_u32 + 2 * G, *s_drop = s_u32 + 3 * G, *s_injs = s_u32 + 4 * G,
-             *s_rt32 = s_u32 + 5 * G, *s_nsamp = s_u32 + 6 * G, *s_sidx = s_u32 + 7 * G;        // delivery latencies of the current step (drained every step by the metric thread)
+             *s_rt32 = s_u32 + 5 * G, *s_nsamp = s_u32 + 6 * G, *s_sidx = s_u32 + 7 * G;
+    int *s_ptop = reinterpret_cast<int *>(s_u32 + 8 * G);          // paged queues: [G] free pages of each replica of the CTA        // delivery latencies of the current step (drained every step by the metric thread)
     // MaHybridQ scratch: r, max_Q_y, max_Q_x_d per node; three sums + spare per replica
     double *s_r = s_f64, *s_qy = s_f64 + GN, *s_qx = s_f64 + 2 * GN, *s_sum = s_f64 + 3 * GN;
     // CDRQ scratch (same region): backward-update inputs of each sender and the queue lengths of 'dual' mode
@@ -658,6 +673,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
         s_rt32[i] = 0; s_sends[i] = 0; s_inj[i] = 0; s_end[i] = 0; s_hops[i] = 0; s_drop[i] = 0; s_injs[i] = 0;
         s_dead[i] = (rblock + i < p.R) ? (unsigned)(p.status[2 * (rblock + i)] != 0) : 1u;
         s_nsamp[i] = 0;
+        s_ptop[i] = (PAGED && rblock + i < p.R) ? p.page_top[rblock + i] : 0;
         s_sidx[i] = (p.sample && rblock + i < p.R) ? (unsigned)p.sample_idx[rblock + i] : 0u;
         if (p.sample && s_sidx[i] >= (unsigned)p.sample_size) s_dead[i] = 2u;     // already has its samples: frozen
     }
@@ -700,6 +716,11 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     uint4 pref = make_uint4(0, 0, 0, 0), fresh = pref;            // head record: prefetched from the ring / just appended
     bool use_fresh = false;
     uint4 *myring = nullptr;
+    // paged queues: the pages under the head and the tail, the page after the head's (0xFFFF until it is linked) and a spare
+    unsigned hpage = 0, hnext = 0xFFFFu, tpage = 0, spare = 0;
+    const unsigned plog = PAGED ? (unsigned)p.page_log : 0u, pmask = (1u << plog) - 1u;
+    uint4 *pool = nullptr;
+    unsigned short *pnext = nullptr, *pfree = nullptr;
     int rp = 0, deg = 0;
     unsigned my_sends = 0, my_inj = 0;
     unsigned ndead = 0;                 // general timing: ring entries in [head, tail) already sent out of order
@@ -709,8 +730,21 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     if (is_node) {
         head = p.qhead[r * N + x];
         tail = p.qtail[r * N + x];
-        myring = p.ring + ((size_t)r * N + x) * (size_t)p.cap;
-        if (FUSED) {                            // stage the first D records of the queue
+        myring = PAGED ? nullptr : p.ring + ((size_t)r * N + x) * (size_t)p.cap;
+        if (PAGED) {
+            pool = p.pool + ((size_t)r * p.n_pages << plog);
+            pnext = p.page_next + (size_t)r * p.n_pages;
+            pfree = p.page_free + (size_t)r * p.n_pages;
+            const unsigned short *qp = p.q_pages + ((size_t)r * N + x) * 4;
+            hpage = qp[0]; tpage = qp[1]; spare = qp[2];
+            hnext = hpage == tpage ? 0xFFFFu : (unsigned)pnext[hpage];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const unsigned idx = head + i;
+                const unsigned pg = ((idx ^ head) >> plog) ? hnext : hpage;
+                cp_async16_if(s_stage + (idx & (D - 1)) * GN + t, pool + ((pg << plog) | (idx & pmask)), tail - head > (unsigned)i);
+            }
+        } else if (FUSED) {                     // stage the first D records of the queue
 #pragma unroll
             for (int i = 0; i < D; ++i)
                 cp_async16_if(s_stage + ((head + i) & (D - 1)) * GN + t, myring + ((head + i) & capmask), tail - head > (unsigned)i);
@@ -772,8 +806,33 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
 
     // Ring append.  Overflow is detected once per step (tail - head > cap) and reported through the sticky
     // status word; the masked index keeps a wrapped write inside this node's own ring.
+    // paged queues: a page from the replica's free stack (only called after barrier 1 of a step, when nobody returns pages)
+    auto take_page = [&]() -> unsigned {
+        const int i = atomicSub(&s_ptop[g], 1) - 1;
+        if (i < 0) {                    // pool exhausted: sticky status, the replica stops stepping from the next step on;
+            atomicAdd(&s_ptop[g], 1);   // page 0 keeps this step's remaining writes inside the pool
+            set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, p.clock0);
+            s_dead[g] = 1u;
+            return 0u;
+        }
+        return (unsigned)pfree[i];
+    };
+    // the tail has filled its page: link the spare behind it, write there from now on, and fetch a new spare
+    auto next_tail_page = [&]() {
+        pnext[tpage] = (unsigned short)spare;
+        if (tpage == hpage) hnext = spare;
+        tpage = spare;
+        spare = take_page();
+    };
     auto append = [&](const uint4 &rec) {
-        myring[tail & capmask] = rec;
+        if (PAGED) pool[(tpage << plog) | (tail & pmask)] = rec;
+        else myring[tail & capmask] = rec;
+        if (PAGED) {
+            if (tail - head < (unsigned)D) s_stage[(tail & (D - 1)) * GN + t] = rec;
+            ++tail;
+            if ((tail & pmask) == 0u) next_tail_page();
+            return;
+        }
         if (FUSED) {                    // a record that lands within D of the head is staged directly (nothing will fetch it)
             if (tail - head < (unsigned)D) s_stage[(tail & (D - 1)) * GN + t] = rec;
         } else if (head == tail) {
@@ -815,6 +874,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
         }
     };
     if (!kInjectAtStart && !dead) inject_step(-1, 0u, p.clock0);
+    if (PAGED) __syncthreads();                 // these appends took pages; the first pops below return pages
     const bool sampling = SPLIT && p.sample != nullptr;      // sample_route_time also runs on the SPLIT instantiation
 #ifdef RLR_EXP_TIMING
     long long tacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -823,7 +883,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     for (int s = 0; s < p.K; ++s) {
         const int clock = p.clock0 + s * slotw;
         if (FUSED) cp_async_wait<kStageWait>(); // every copy of the groups before the latest one (two) has landed (see the commit below)
-        if ((IS_PG || sampling) && is_node) dead = (s_dead[g] != 0u);
+        if ((IS_PG || sampling || PAGED) && is_node) dead = (s_dead[g] != 0u);
         const bool live = !dead;
         bool sending = false;
         int d = 0, k = 0, y = 0;
@@ -875,7 +935,18 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                     have = true;
                     rec = s_stage[(head & (D - 1)) * GN + t];
                     ++head;
+                    if (PAGED && (head & pmask) == 0u) {        // the head left its page: back onto the free stack
+                        pfree[atomicAdd(&s_ptop[g], 1)] = (unsigned short)hpage;
+                        hpage = hnext;
+                        hnext = hpage == tpage ? 0xFFFFu : (unsigned)pnext[hpage];
+                    }
                 }
+                if (PAGED) {
+                    const unsigned idx = head + (D - 1);
+                    const unsigned pg = ((idx ^ head) >> plog) ? hnext : hpage;
+                    cp_async16_if(s_stage + (idx & (D - 1)) * GN + t, pool + ((pg << plog) | (idx & pmask)),
+                                  nonempty && tail - head > (unsigned)(D - 1));
+                } else
                 cp_async16_if(s_stage + ((head + (D - 1)) & (D - 1)) * GN + t, myring + ((head + (D - 1)) & capmask),
                               nonempty && tail - head > (unsigned)(D - 1));
                 if (!SMEM_TABLES && POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE && head != tail) {
@@ -1376,10 +1447,16 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 for (int j = 0; j < 4; ++j) {
                     const unsigned rk = rkv[j];
                     const unsigned at = tail0 + rk;
-                    stg128_if(myring + (at & capmask), rc[j], ap[j]);
+                    if (PAGED) {                    // at most one page boundary inside the batch (pages hold >= 4 records)
+                        const unsigned pg = ((at ^ tail0) >> plog) ? spare : tpage;
+                        stg128_if(pool + ((pg << plog) | (at & pmask)), rc[j], ap[j]);
+                    } else {
+                        stg128_if(myring + (at & capmask), rc[j], ap[j]);
+                    }
                     sts128_if(s_stage + (at & (D - 1)) * GN + t, rc[j], ap[j] && at - head < (unsigned)D);
                     tail += ap[j] ? 1u : 0u;
                 }
+                if (PAGED && ((tail ^ tail0) >> plog)) next_tail_page();
             } else {
             RLR_T(5);                               // C: window + keys + sort
             for (int taken = 0;; ++taken) {
@@ -1589,7 +1666,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
         if (FUSED) cp_async_commit();
         if (!kInjectAtStart && is_node && live) {   // next step's new_packet + inject (env.py:298-319); slot = 1 on this path
             inject_step(s, (unsigned)(s + 1), clock + 1);
-            if (tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
+            if (!PAGED && tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
         }
         RLR_T(3);                                   // D
         __syncthreads();                                                        // ---- barrier 2 ----
@@ -1640,11 +1717,16 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     if (is_node) {
         p.qhead[r * N + x] = head;
         p.qtail[r * N + x] = tail;
+        if (PAGED) {
+            unsigned short *qp = p.q_pages + ((size_t)r * N + x) * 4;
+            qp[0] = (unsigned short)hpage; qp[1] = (unsigned short)tpage; qp[2] = (unsigned short)spare;
+        }
         if (general) p.q_dead[r * N + x] = (int)ndead;
         if (my_sends) atomicAdd(&s_sends[g], (unsigned long long)my_sends);
         if (my_inj) atomicAdd(&s_inj[g], (unsigned long long)my_inj);
     }
     __syncthreads();
+    if (PAGED && t < G && rblock + t < p.R) p.page_top[rblock + t] = s_ptop[t];
     if (is_node && x == N - 1) {
         long long *c = p.counters + r * RLR_NUM_COUNTERS;
         c[RLR_CTR_ALL_PACKETS] += (long long)s_inj[g];
@@ -1701,30 +1783,30 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
 
 using StepKernel = void (*)(const StepParams);
 
-template <int POLICY, int MAXD, int MAXW, bool SPLIT, int LB = 0, typename QT = double>
+template <int POLICY, int MAXD, int MAXW, bool SPLIT, int LB = 0, typename QT = double, bool PAGED = false>
 StepKernel pick_smem(bool smem_tables)
 {
     if (POLICY == RLR_POLICY_SHORTEST || POLICY == RLR_POLICY_GLOBALROUTE || LB != 0)
-        return (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT, LB, QT>;
-    return smem_tables ? (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, true, SPLIT, 0, QT>
-                       : (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT, 0, QT>;
+        return (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT, LB, QT, PAGED>;
+    return smem_tables ? (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, true, SPLIT, 0, QT, PAGED>
+                       : (StepKernel)rlr_step_kernel<POLICY, MAXD, MAXW, false, SPLIT, 0, QT, PAGED>;
 }
 
-template <int POLICY, bool SPLIT, typename QT = double>
+template <int POLICY, bool SPLIT, typename QT = double, bool PAGED = false>
 StepKernel pick_deg(int n_nodes, int max_deg, bool smem_tables, int threads)
 {
     if (n_nodes <= 64) {
-        if (max_deg <= 4) return pick_smem<POLICY, 4, 3, SPLIT, 0, QT>(smem_tables);
-        if (max_deg <= 8) return pick_smem<POLICY, 8, 3, SPLIT, 0, QT>(smem_tables);
-        return pick_smem<POLICY, 16, 3, SPLIT, 0, QT>(smem_tables);
+        if (max_deg <= 4) return pick_smem<POLICY, 4, 3, SPLIT, 0, QT, PAGED>(smem_tables);
+        if (max_deg <= 8) return pick_smem<POLICY, 8, 3, SPLIT, 0, QT, PAGED>(smem_tables);
+        return pick_smem<POLICY, 16, 3, SPLIT, 0, QT, PAGED>(smem_tables);
     }
     // small CTAs reading their tables from HBM (lata.net: 116 nodes, 128 threads): the high-occupancy build
     constexpr bool kHasLb1 = POLICY == RLR_POLICY_QROUTE || POLICY == RLR_POLICY_HYBRIDQ || POLICY == RLR_POLICY_SHORTEST;
     if (kHasLb1 && !SPLIT && !smem_tables && threads <= 128 && max_deg > 8 && max_deg <= 12)
-        return pick_smem<POLICY, 12, 9, SPLIT, kHasLb1 && !SPLIT ? 1 : 0, QT>(false);
-    if (max_deg <= 8) return pick_smem<POLICY, 8, 9, SPLIT, 0, QT>(smem_tables);
-    if (max_deg <= 12) return pick_smem<POLICY, 12, 9, SPLIT, 0, QT>(smem_tables);      // lata.net: degree 9 (row loops sized 12, not 16)
-    return pick_smem<POLICY, 16, 9, SPLIT, 0, QT>(smem_tables);
+        return pick_smem<POLICY, 12, 9, SPLIT, kHasLb1 && !SPLIT ? 1 : 0, QT, PAGED>(false);
+    if (max_deg <= 8) return pick_smem<POLICY, 8, 9, SPLIT, 0, QT, PAGED>(smem_tables);
+    if (max_deg <= 12) return pick_smem<POLICY, 12, 9, SPLIT, 0, QT, PAGED>(smem_tables);      // lata.net: degree 9 (row loops sized 12, not 16)
+    return pick_smem<POLICY, 16, 9, SPLIT, 0, QT, PAGED>(smem_tables);
 }
 
 }  // namespace
@@ -1732,16 +1814,18 @@ StepKernel pick_deg(int n_nodes, int max_deg, bool smem_tables, int threads)
 // One definition per policy family (step_<policy>.cu): the instantiation serving (n_nodes, max_deg, tables in shared memory),
 // fused Network.train loop (split = false) or the split-phase / options variant (split = true).
 #define RLR_DEFINE_STEP_PICK(NAME, POLICY)                                                                        \
-    void *rlr_pick_step_##NAME(bool split, int n_nodes, int max_deg, bool smem_tables, int threads)                \
+    void *rlr_pick_step_##NAME(bool split, int n_nodes, int max_deg, bool smem_tables, int threads, bool paged)    \
     {                                                                                                             \
+        if (paged && !split) return (void *)pick_deg<POLICY, false, double, true>(n_nodes, max_deg, smem_tables, threads);   \
         return split ? (void *)pick_deg<POLICY, true>(n_nodes, max_deg, smem_tables, threads)                      \
                      : (void *)pick_deg<POLICY, false>(n_nodes, max_deg, smem_tables, threads);                    \
     }
 
 // The same for Qroute with its table stored in fp32 (step_qroute_f32.cu).
 #define RLR_DEFINE_STEP_PICK_F32(NAME, POLICY)                                                                    \
-    void *rlr_pick_step_##NAME(bool split, int n_nodes, int max_deg, bool smem_tables, int threads)                \
+    void *rlr_pick_step_##NAME(bool split, int n_nodes, int max_deg, bool smem_tables, int threads, bool paged)    \
     {                                                                                                             \
+        if (paged && !split) return (void *)pick_deg<POLICY, false, float, true>(n_nodes, max_deg, smem_tables, threads);    \
         return split ? (void *)pick_deg<POLICY, true, float>(n_nodes, max_deg, smem_tables, threads)               \
                      : (void *)pick_deg<POLICY, false, float>(n_nodes, max_deg, smem_tables, threads);             \
     }

@@ -115,7 +115,8 @@ def _floor_pow2(v):
 class Network:
     def __init__(self, file, bandwidth=1, transtime=1, is_drop=False, *, replicas=1, device=None,
                  rng="trace", seed=None, replica_base=0, queue_capacity=None,
-                 replicas_per_block=0, threads_per_block=0, tables_in_smem=-1, dtype="float64"):
+                 replicas_per_block=0, threads_per_block=0, tables_in_smem=-1, dtype="float64",
+                 page_records=0, pages_per_replica=None):
         bandwidth, transtime = _as_int(bandwidth, "bandwidth"), _as_int(transtime, "transtime")
         if bandwidth < 0 or transtime < 0:
             raise ValueError("bandwidth and transtime must be >= 0")
@@ -162,7 +163,30 @@ class Network:
         self.queue_capacity = int(queue_capacity)
         self._launch_cfg = (int(replicas_per_block), int(threads_per_block), int(tables_in_smem))
         dev = self.device
-        self._ring = torch.empty((R, N, self.queue_capacity, 4), dtype=torch.int32, device=dev)
+        # Paged queues (page_records > 0): the reference's unbounded lists (env.py:100,130) as linked pages of `page_records`
+        # packets from a per-replica pool of `pages_per_replica` pages, instead of one ring of `queue_capacity` slots per
+        # node — memory follows the packets alive in a replica, not the worst node of the run.  Served by train() /
+        # run_device() with default options (the fused kernel); the call-by-call API needs rings.
+        self.page_records = int(page_records)
+        self._paged = self.page_records > 0
+        if self._paged:
+            if self.page_records < 4 or self.page_records & (self.page_records - 1):
+                raise ValueError("page_records must be a power of two >= 4")
+            if self._general_requested(bandwidth, transtime):
+                raise NotImplementedError("paged queues do not serve the general timing model (transtime > 1 or bandwidth < 1)")
+            if pages_per_replica is None:
+                budget = int(torch.cuda.get_device_properties(self.device).total_memory * 0.2) // 16
+                pages_per_replica = budget // (R * self.page_records)
+            self.pages_per_replica = int(min(max(int(pages_per_replica), 2 * N + 1), 65535))
+            NP, P = self.pages_per_replica, self.page_records
+            self._pool = torch.empty((R, NP * P, 4), dtype=torch.int32, device=dev)
+            self._page_next = torch.zeros((R, NP), dtype=torch.int16, device=dev)
+            self._page_free = torch.zeros((R, NP), dtype=torch.int16, device=dev)
+            self._page_top = torch.zeros(R, dtype=torch.int32, device=dev)
+            self._q_pages = torch.zeros((R, N, 4), dtype=torch.int16, device=dev)
+            self._paged_reset_host()
+        self._ring = (torch.empty((1, 1, 2, 4), dtype=torch.int32, device=dev) if self._paged
+                      else torch.empty((R, N, self.queue_capacity, 4), dtype=torch.int32, device=dev))
         self._q_head = torch.zeros((R, N), dtype=torch.int32, device=dev)
         self._q_tail = torch.zeros((R, N), dtype=torch.int32, device=dev)
         self._counters = torch.zeros((R, nat.NUM_COUNTERS), dtype=torch.int64, device=dev)
@@ -195,6 +219,31 @@ class Network:
         self._agent = Policy(self)
         self.last_sendlog = None
 
+    @staticmethod
+    def _general_requested(bandwidth, transtime):
+        return transtime > 1 or bandwidth < 1
+
+    def _paged_reset_host(self):
+        """Initial page lists (what rlr_reset does on the device once a handle exists): node x owns page x and spare N + x."""
+        import torch
+        N, NP, dev = self.topology.N, self.pages_per_replica, self.device
+        ids = torch.arange(NP, device=dev)
+        free = torch.where(ids < NP - 2 * N, ids + 2 * N, torch.zeros_like(ids)).to(torch.int16)
+        self._page_free.copy_(free.unsqueeze(0).expand(self.replicas, NP))
+        self._page_top.fill_(NP - 2 * N)
+        qp = torch.zeros((N, 4), dtype=torch.int64, device=dev)
+        qp[:, 0] = torch.arange(N, device=dev)
+        qp[:, 1] = qp[:, 0]
+        qp[:, 2] = qp[:, 0] + N
+        self._q_pages.copy_(qp.to(torch.int16).unsqueeze(0).expand(self.replicas, N, 4))
+
+    @property
+    def queue_memory_bytes(self):
+        """Device bytes that hold queued packets: the rings, or the page pool with its links and free stack."""
+        if self._paged:
+            return sum(t.numel() * t.element_size() for t in (self._pool, self._page_next, self._page_free, self._q_pages))
+        return self._ring.numel() * 4
+
     # ------------------------------------------------------------------ topology (env.py:282-296)
     def read_network(self, file):
         self.file = file
@@ -213,7 +262,8 @@ class Network:
         t = nat.Topology(topo.N, topo.sum_deg, topo.max_deg, topo.row_ptr.ctypes.data, topo.col.ctypes.data)
         rpb, tpb, tis = self._launch_cfg
         cfg = nat.Config(self.replicas, self.replica_base, agent._kernel_policy, self.queue_capacity, rpb, tpb, tis,
-                         self.device.index, self._ecap, 1 if (self.dtype == "float32" and agent._kernel_policy == nat.POLICY_QROUTE) else 0)
+                         self.device.index, self._ecap, 1 if (self.dtype == "float32" and agent._kernel_policy == nat.POLICY_QROUTE) else 0,
+                         self.page_records, self.pages_per_replica if self._paged else 0)
         h = C.c_void_p()
         nat.check(nat.lib().rlr_create(C.byref(t), C.byref(cfg), C.byref(h)))
         d = agent._dev
@@ -225,7 +275,9 @@ class Network:
                         self._heap_pos.data_ptr(), ptr("gr_choice_mask"), ptr("gr_distance"), ptr("choice_mask"),
                         ptr("gr_qs_off"), *([t.data_ptr() for t in (self._link_sent, self._event_heap, self._event_count,
                                                                      self._event_rec, self._q_dead)]
-                                             if self._general else [None] * 5))
+                                             if self._general else [None] * 5),
+                        *([t.data_ptr() for t in (self._pool, self._page_next, self._page_free, self._page_top, self._q_pages)]
+                          if self._paged else [None] * 5))
         nat.check(nat.lib().rlr_bind_buffers(h, C.byref(b)))
         self._handles.append(h)
         return h
@@ -399,6 +451,8 @@ class Network:
         else:
             for t in (self._q_head, self._q_tail, self._counters, self._status):
                 t.zero_()
+            if self._paged:
+                self._paged_reset_host()
             if self._general:
                 for t in (self._link_sent, self._event_count, self._q_dead):
                     t.zero_()
@@ -422,7 +476,10 @@ class Network:
         lens = (self._q_tail.reshape(-1).to(torch.int64) - head) & 0xFFFFFFFF          # ring entries, tombstones included
         qid = torch.repeat_interleave(torch.arange(R * N, device=dev), lens)
         j = torch.arange(int(lens.sum().item()), device=dev) - (torch.cumsum(lens, 0) - lens)[qid]
-        recs = self._ring.view(R * N, cap, 4)[qid, (head[qid] + j) & (cap - 1)]
+        if self._paged:
+            recs = self._pool[qid // N, self._paged_record_index(qid, j, head)]
+        else:
+            recs = self._ring.view(R * N, cap, 4)[qid, (head[qid] + j) & (cap - 1)]
         snap = {"version": 1, "n_nodes": N, "sum_deg": self.topology.sum_deg, "replicas": R,
                 "replica_base": self.replica_base, "rng": self.rng, "seed": self.seed, "clock": int(self.clock),
                 "bandwidth": self.bandwidth, "transtime": self.transtime, "is_drop": bool(self.is_drop),
@@ -450,11 +507,35 @@ class Network:
         if snap.get("version") != 1 or want != got:
             raise ValueError(f"snapshot does not fit this network: {got} vs {want}")
         lens = torch.from_numpy(np.ascontiguousarray(snap["queue_len"], dtype=np.int64)).reshape(-1).to(dev)
-        if int(lens.max().item()) > cap:
+        if not self._paged and int(lens.max().item()) > cap:
             raise OverflowError(f"snapshot holds a queue of {int(lens.max().item())} entries; queue_capacity is {cap}")
         qid = torch.repeat_interleave(torch.arange(R * N, device=dev), lens)
         j = torch.arange(int(lens.sum().item()), device=dev) - (torch.cumsum(lens, 0) - lens)[qid]
-        self._ring.view(R * N, cap, 4)[qid, j] = torch.from_numpy(np.ascontiguousarray(snap["queue_rec"], dtype=np.int32)).to(dev)
+        recs = torch.from_numpy(np.ascontiguousarray(snap["queue_rec"], dtype=np.int32)).to(dev)
+        if self._paged:
+            # every queue gets len // P + 1 consecutive pages of its replica (the page under the tail always exists), then
+            # the N spares, and what is left goes onto the free stack
+            P, NP = self.page_records, self.pages_per_replica
+            npg = (lens // P + 1).reshape(R, N)
+            start = torch.cumsum(npg, 1) - npg
+            used = npg.sum(1)
+            if int(used.max().item()) + N > NP:
+                raise OverflowError(f"snapshot needs {int(used.max().item()) + N} pages per replica; pages_per_replica is {NP}")
+            startf = start.reshape(-1)
+            self._pool[qid // N, (startf[qid] + j // P) * P + j % P] = recs
+            ids = torch.arange(NP, device=dev).unsqueeze(0).expand(R, NP)
+            self._page_next.copy_((ids + 1).to(torch.int16))             # consecutive pages: next = id + 1 inside a queue
+            qp = torch.zeros((R, N, 4), dtype=torch.int64, device=dev)
+            qp[:, :, 0] = start
+            qp[:, :, 1] = start + npg - 1
+            qp[:, :, 2] = used.unsqueeze(1) + torch.arange(N, device=dev).unsqueeze(0)
+            self._q_pages.copy_(qp.to(torch.int16))
+            nfree = NP - used - N
+            free = used.unsqueeze(1) + N + ids
+            self._page_free.copy_(torch.where(ids < nfree.unsqueeze(1), free, torch.zeros_like(free)).to(torch.int16))
+            self._page_top.copy_(nfree.to(torch.int32))
+        else:
+            self._ring.view(R * N, cap, 4)[qid, j] = recs
         self._q_head.zero_()
         self._q_tail.copy_(lens.reshape(R, N).to(torch.int32))
         self._counters.copy_(torch.from_numpy(np.ascontiguousarray(snap["counters"])))
@@ -573,6 +654,7 @@ class Network:
         or a list of R lists, to be passed to `agent.learn`."""
         import torch
         duration = _as_int(duration, "duration")
+        self._no_paged("Network.step (the split-phase kernel)")
         h = self._handle_or_raise()
         R, N = self.replicas, self.topology.N
         pend = self.__dict__.get("_pending") or [[] for _ in range(R)]
@@ -656,6 +738,7 @@ class Network:
         again."""
         import torch
         self._check_sync()
+        self._no_paged("sample_route_time")
         agent = self._agent
         h = self._handle_or_raise()
         R, N, dev = self.replicas, self.topology.N, self.device
@@ -705,6 +788,11 @@ class Network:
         out = samp.cpu().numpy().astype(np.float64)
         return out[0] if R == 1 else out
 
+    def _no_paged(self, what):
+        if self._paged:
+            raise NotImplementedError(f"{what} is not available with paged queues (page_records > 0): they are served by the "
+                                      "fused train() / run_device() kernel; build the Network with rings for this call")
+
     def _check_sync(self):
         if self.__dict__.get("_desync"):
             raise RuntimeError("the replicas stopped at different clocks in sample_route_time; call reset() first")
@@ -746,6 +834,8 @@ class Network:
             lrd["q"] = lrq
         if lrp is not None:
             lrd["p"] = lrp
+        if self._paged and (sendlog or self.is_drop or _as_int(slot, "slot") != 1 or _as_int(freq, "freq") != 1 or self.transtime != 1):
+            self._no_paged("train() with sendlog, is_drop, slot, freq or transtime other than the defaults")
         T, R, N, dev = int(duration / _as_int(slot, "slot")), self.replicas, self.topology.N, self.device
         lam = np.broadcast_to(np.asarray(lambd, dtype=np.float64), (R,)) * slot         # Poisson(lambd * slot), env.py:401
         d_lv, L = None, 0
@@ -1065,13 +1155,35 @@ class Network:
         n = self._q_tail - self._q_head
         return n - self._q_dead if self._general else n
 
+    def _paged_record_index(self, qid, j, head):
+        """Pool index (within its replica) of record j (0 = head) of every queue in `qid` (flat replica * N + node ids), all
+        device tensors: follows each queue's page list for j's page distance from the head page."""
+        import torch
+        P, N = self.page_records, self.topology.N
+        off = (head[qid] & (P - 1)) + j                                  # offset from the start of the head page
+        hop = off // P
+        page = (self._q_pages.view(-1, 4)[qid, 0].to(torch.int64)) & 0xFFFF
+        nxt = self._page_next.to(torch.int64) & 0xFFFF
+        rep_of = qid // N
+        for k in range(int(hop.max().item()) if hop.numel() else 0):
+            page = torch.where(hop > k, nxt[rep_of, page], page)
+        return page * P + off % P
+
     def queue_array(self, x, r=0):
         """Queue of node x of replica r, head first: rows (dest, source, hops, birth, start_queue)."""
         head = int(self._q_head[r, x].item()) & 0xFFFFFFFF
         tail = int(self._q_tail[r, x].item()) & 0xFFFFFFFF
         n = (tail - head) & 0xFFFFFFFF
-        idx = (head + np.arange(n, dtype=np.int64)) & (self.queue_capacity - 1)
-        rec = self._ring[r, x].cpu().numpy()[idx].view(np.uint32).reshape(n, 4)
+        if self._paged:
+            import torch
+            dev = self.device
+            qid = torch.full((n,), r * self.topology.N + x, dtype=torch.int64, device=dev)
+            hd = (self._q_head.reshape(-1).to(torch.int64)) & 0xFFFFFFFF
+            idx = self._paged_record_index(qid, torch.arange(n, device=dev), hd)
+            rec = self._pool[r][idx].cpu().numpy().view(np.uint32).reshape(n, 4)
+        else:
+            idx = (head + np.arange(n, dtype=np.int64)) & (self.queue_capacity - 1)
+            rec = self._ring[r, x].cpu().numpy()[idx].view(np.uint32).reshape(n, 4)
         out = np.empty((n, 5), dtype=np.int32)
         out[:, 0] = rec[:, 0] & 0xFFFF
         out[:, 1] = rec[:, 0] >> 16

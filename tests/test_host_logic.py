@@ -36,7 +36,7 @@ def test_struct_sizes_match_header_layout():
     sizes = (C.c_int32 * 4)()
     assert nat.lib().rlr_struct_sizes(sizes) == 0
     assert list(sizes) == [C.sizeof(nat.Topology), C.sizeof(nat.Config), C.sizeof(nat.Buffers), C.sizeof(nat.RunParams)]
-    assert C.sizeof(nat.Buffers) == 23 * 8
+    assert C.sizeof(nat.Buffers) == 28 * 8
 
 
 def test_builtin_topologies_layout():

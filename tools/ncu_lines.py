@@ -20,22 +20,25 @@ import tempfile
 def sass_lines(so, func_pat):
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
-    cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
-    out, cur, active = [], None, False
-    for l in txt.splitlines():
-        if l.startswith("//----") and ".text." in l:
-            active = re.search(func_pat, l) is not None
-            continue
-        if not active:
-            continue
-        m = re.search(r'//## File "([^"]+)", line (\d+)', l)
-        if m:
-            cur = int(m.group(2))
-            continue
-        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
-        if m:
-            out.append((int(m.group(1), 16), cur, m.group(2).strip()))
+    out = []
+    for cub in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):      # one cubin per translation unit
+        txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+        cur, active = None, False
+        for l in txt.splitlines():
+            if l.startswith("//----") and ".text." in l:
+                active = re.search(func_pat, l) is not None
+                continue
+            if not active:
+                continue
+            m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+            if m:
+                cur = int(m.group(2))
+                continue
+            m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
+            if m:
+                out.append((int(m.group(1), 16), cur, m.group(2).strip()))
+        if out:
+            break
     return out
 
 
@@ -54,9 +57,9 @@ def main():
         inst[line] += int(r[idx["Instructions Executed"]] or 0)
         samp[line] += int(r[idx["# Samples"]] or 0)
     ti, ts = sum(inst.values()), sum(samp.values())
-    srcpath = os.path.join(os.path.dirname(os.path.abspath(so)), "rlr_kernels.cu")
+    srcpath = os.path.join(os.path.dirname(os.path.abspath(so)), "rlr_step.cuh")
     if not os.path.exists(srcpath):
-        srcpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rlrouting_b200", "csrc", "rlr_kernels.cu")
+        srcpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rlrouting_b200", "csrc", "rlr_step.cuh")
     srcfile = [l.rstrip("\n") for l in open(srcpath)]
     print(f"total warp-instructions {ti}, samples {ts}")
     print(f"{'line':>5} {'inst%':>6} {'samp%':>6}  source")
