@@ -322,11 +322,21 @@ class Network:
 
     def _sched_buf(self, st, slot, shape):
         import torch
-        b = st["bufs"][slot]
-        if b is None or tuple(b.shape) != tuple(shape):
-            if b is not None:
-                torch.cuda.synchronize(self.device)                  # shape change: nothing may still use the old buffer
-            st["bufs"][slot] = torch.empty(shape, dtype=torch.int32, device=self.device)
+        # One flat allocation per slot, grown when a schedule needs more (a call alternates between the shapes of its long
+        # and its short launch: re-allocating on every shape change would synchronise the device twice per call).
+        # The storage is allocated ON THE SIDE STREAM: the caching allocator hands a block that was just freed on the
+        # compute stream (e.g. a per-launch metrics buffer whose ratio kernel is still queued) to the next compute-stream
+        # allocation, which is safe in stream order there — but the prefetch writes the schedule from the side stream,
+        # and that queued kernel would then scribble over it.
+        n = int(np.prod(shape))
+        store = st.setdefault("store", [None, None])
+        if store[slot] is None or store[slot].numel() < n:
+            if store[slot] is not None:
+                torch.cuda.synchronize(self.device)                  # nothing may still use the old buffer
+            with torch.cuda.stream(st["stream"]):
+                store[slot] = torch.empty(n, dtype=torch.int32, device=self.device)
+            store[slot].record_stream(torch.cuda.current_stream(self.device))   # ... and it is read on the compute stream
+        st["bufs"][slot] = store[slot][:n].view(shape)
         return st["bufs"][slot]
 
     def _schedule_done(self, h, rp):
@@ -353,6 +363,11 @@ class Network:
         rp2 = nat.RunParams()
         C.memmove(C.byref(rp2), C.byref(rp), C.sizeof(nat.RunParams))
         rp2.inj_events, rp2.inj_cap, rp2.clock0 = st["bufs"][other].data_ptr(), cap, clock0
+        # the side stream reads the load vectors, which were allocated on the compute stream: tell the caching allocator, so
+        # that a Network dropped while its last (speculative) prefetch is still running does not hand them out again
+        if lam_st is not None:
+            lam_st["d_en"].record_stream(side)
+            lam_st["d_thr"].record_stream(side)
         nat.check(nat.lib().rlr_build_inject_schedule(h, K, C.byref(rp2), C.c_void_p(side.cuda_stream)))
         self.launch_count += 1
         done = torch.cuda.Event()
@@ -441,7 +456,7 @@ class Network:
     def reset(self):
         self.clock = 0
         self._desync = False
-        self._pending = [[] for _ in range(self.replicas)]
+        self._pending = None                    # (per-replica lists are only created by inject())
         self._last_rewards = None
         h = getattr(self._agent, "_handle", None)
         if hasattr(self._agent, "_before_network_reset"):
@@ -550,7 +565,7 @@ class Network:
                 rs.set_state(st)
         self.seed = int(snap["seed"])                               # Philox key of the runs that follow
         self.clock = int(snap["clock"])
-        self._pending = [list(map(tuple, pk)) for pk in snap["pending"]] or [[] for _ in range(R)]
+        self._pending = [list(map(tuple, pk)) for pk in snap["pending"]] or None
         self._desync, self._last_rewards = False, None
         if self.__dict__.get("_sched") is not None:                 # injection schedules prefetched for the old state
             torch.cuda.synchronize(dev)
@@ -608,7 +623,9 @@ class Network:
         per = [packets] if self.replicas == 1 else packets
         if len(per) != self.replicas:
             raise ValueError("inject expects one packet list per replica")
-        pend = self.__dict__.setdefault("_pending", [[] for _ in range(self.replicas)])
+        pend = self.__dict__.get("_pending")
+        if pend is None:
+            pend = self._pending = [[] for _ in range(self.replicas)]
         for r, pk in enumerate(per):
             for q in pk:
                 if q.source == q.dest:
@@ -679,7 +696,7 @@ class Network:
         self.launch_count += 1
         self.clock += duration
         self._last_duration = duration
-        self._pending = [[] for _ in range(R)]
+        self._pending = None
         raw = rew.cpu().numpy()
         self._raise_on_status(self._status.cpu().numpy())
         out = []
@@ -890,7 +907,7 @@ class Network:
         if self._general:                                       # event times are 16-bit offsets from the launch's clock
             cap = max(1, min(cap, (65535 - self.transtime) // (slot * freq)))
         plan = [cap] * (T // cap) + ([T % cap] if T % cap else [])
-        if steps_per_launch is None and per_step and plan[-1] >= 64:
+        if steps_per_launch is None and per_step and plan[-1] >= 64 and d_lv is None:   # (level curves are tiny: one launch)
             last = plan.pop()
             short = max(last // 8, 32)                          # long enough to cover the copy of the long part
             plan += [last - short, short]
