@@ -46,10 +46,11 @@ class Reward:
 
 
 class Node:
-    """Read-only view of one node of replica 0 (reference env.py:73-210)."""
+    """Read-only view of one node of one replica (reference env.py:73-210).  `Network.nodes` holds the views of replica 0,
+    like the reference's single environment; `Network.nodes_of(r)` gives those of replica r."""
 
-    def __init__(self, ID, network):
-        self.ID, self.network = ID, network
+    def __init__(self, ID, network, replica=0):
+        self.ID, self.network, self.replica = ID, network, int(replica)
 
     @property
     def links(self):
@@ -57,7 +58,7 @@ class Node:
 
     @property
     def queue(self):
-        return [Packet(int(s), int(d), int(b), int(h), int(q)) for d, s, h, b, q in self.network.queue_array(self.ID)]
+        return [Packet(int(s), int(d), int(b), int(h), int(q)) for d, s, h, b, q in self.network.queue_array(self.ID, self.replica)]
 
     @property
     def sent(self):
@@ -67,11 +68,17 @@ class Node:
         if not nw._general:
             return dict.fromkeys(self.links, 0)  # every event lands inside its step (env.py:349-353)
         rp = int(nw.topology.row_ptr[self.ID])
-        cnt = nw._link_sent[0, rp:rp + len(self.links)].cpu().numpy()
+        cnt = nw._link_sent[self.replica, rp:rp + len(self.links)].cpu().numpy()
         return {y: int(c) for y, c in zip(self.links, cnt)}
 
     def __repr__(self):
         return f"Node<{self.ID}, queue: {self.queue}, sent: {self.sent}>"
+
+
+def _nodes_of(network, replica):
+    if not 0 <= int(replica) < network.replicas:
+        raise IndexError(f"replica {replica} out of range [0, {network.replicas})")
+    return OrderedDict((i, Node(i, network, replica)) for i in network.links.keys())
 
 
 def injection_threshold(enlam):
@@ -243,6 +250,10 @@ class Network:
         if self._paged:
             return sum(t.numel() * t.element_size() for t in (self._pool, self._page_next, self._page_free, self._q_pages))
         return self._ring.numel() * 4
+
+    def nodes_of(self, replica):
+        """`Network.nodes` (env.py:244-246) of replica `replica`: an ordered dict of read-only Node views."""
+        return _nodes_of(self, replica)
 
     # ------------------------------------------------------------------ topology (env.py:282-296)
     def read_network(self, file):

@@ -268,3 +268,21 @@ def test_prefetched_schedule_is_keyed_by_timing_and_seed():
     with pytest.raises(NotImplementedError, match="inject"):
         nw.inject([[rb.Packet(0, 5, nw.clock)] for _ in range(R)])
         nw.train(10, 2.0)
+
+
+def test_node_views_of_any_replica():
+    """Network.nodes (env.py:244-246) shows replica 0; nodes_of(r) the same read-only views for replica r."""
+    import rlrouting_b200 as rb
+    nw = rb.Network("6x6.net", replicas=3, rng="philox", seed=4)
+    nw.agent = rb.Shortest(nw)
+    nw.train(60, np.array([1.0, 3.0, 5.0]))
+    for r in range(3):
+        nodes = nw.nodes_of(r)
+        assert list(nodes) == list(nw.links)
+        for x in (0, 7, 35):
+            q = nodes[x].queue
+            ref = nw.queue_array(x, r)
+            assert [(p.dest, p.source, p.hops, p.birth) for p in q] == [tuple(int(v) for v in row[:4]) for row in ref]
+    assert [(p.dest, p.source) for p in nw.nodes[7].queue] == [(p.dest, p.source) for p in nw.nodes_of(0)[7].queue]
+    with pytest.raises(IndexError):
+        nw.nodes_of(3)
