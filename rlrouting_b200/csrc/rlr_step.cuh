@@ -876,6 +876,10 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     if (!kInjectAtStart && !dead) inject_step(-1, 0u, p.clock0);
     if (PAGED) __syncthreads();                 // these appends took pages; the first pops below return pages
     const bool sampling = SPLIT && p.sample != nullptr;      // sample_route_time also runs on the SPLIT instantiation
+    // Very wide nodes (MAXD > 8, e.g. lata.net): the row scans run in groups of four slots, and a group is skipped (one uniform
+    // branch per group, so the loads inside a group still issue back to back) when no node of the warp has a neighbour that
+    // far: lata Qroute +10 %.  (With MAXD = 8 the branch costs more than the second group: 6x6-modified.net -3 %.)
+    const int wdeg = MAXD > 8 ? __reduce_max_sync(0xFFFFFFFFu, is_node ? deg : 1) : MAXD;
 #ifdef RLR_EXP_TIMING
     long long tacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tmark_ = clock64();
@@ -1083,9 +1087,19 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 } else if (POLICY == RLR_POLICY_QROUTE || IS_CQ) {
                     const QT *row = Qx + d * deg;                           // qroute.py:22-27
                     double best = row[0];
+                    if constexpr (MAXD > 8) {
 #pragma unroll
-                    for (int j = 1; j < MAXD; ++j)
-                        if (j < deg) { const double v = row[j]; if (v > best) { best = v; k = j; } }
+                        for (int g4 = 0; g4 < MAXD; g4 += 4) {
+                            if (g4 > 0 && g4 >= wdeg) break;
+#pragma unroll
+                            for (int j = g4 ? g4 : 1; j < g4 + 4; ++j)
+                                if (j < deg) { const double v = row[j]; if (v > best) { best = v; k = j; } }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 1; j < MAXD; ++j)
+                            if (j < deg) { const double v = row[j]; if (v > best) { best = v; k = j; } }
+                    }
                     max_qxd = best;
                     oldq = best;
                 } else {
@@ -1111,9 +1125,19 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                     const QT *row = Qx + d * deg;                           // hybrid.py:49-53
                     double best = row[0];
                     oldq = row[0];
+                    if constexpr (MAXD > 8) {
 #pragma unroll
-                    for (int j = 1; j < MAXD; ++j)
-                        if (j < deg) { const double v = row[j]; if (v > best) best = v; if (j == k) oldq = v; }
+                        for (int g4 = 0; g4 < MAXD; g4 += 4) {
+                            if (g4 > 0 && g4 >= wdeg) break;
+#pragma unroll
+                            for (int j = g4 ? g4 : 1; j < g4 + 4; ++j)
+                                if (j < deg) { const double v = row[j]; if (v > best) best = v; if (j == k) oldq = v; }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 1; j < MAXD; ++j)
+                            if (j < deg) { const double v = row[j]; if (v > best) best = v; if (j == k) oldq = v; }
+                    }
                     max_qxd = best;
                 }
                 y = s_col[rp + k];
@@ -1145,11 +1169,22 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                     }
                 } else if (POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE) {   // max_Q_y, qroute.py:29-30
                     const int degy = deg_y;
+                    const int wdegy = MAXD > 8 ? __reduce_max_sync(__activemask(), degy) : MAXD;   // of the lanes sending now
                     const QT *ry = Qr + qoff_y + d * degy;
                     double m = ry[0];
+                    if constexpr (MAXD > 8) {
 #pragma unroll
-                    for (int j = 1; j < MAXD; ++j)
-                        if (j < degy) { const double v = ry[j]; if (v > m) m = v; }
+                        for (int g4 = 0; g4 < MAXD; g4 += 4) {
+                            if (g4 > 0 && g4 >= wdegy) break;
+#pragma unroll
+                            for (int j = g4 ? g4 : 1; j < g4 + 4; ++j)
+                                if (j < degy) { const double v = ry[j]; if (v > m) m = v; }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 1; j < MAXD; ++j)
+                            if (j < degy) { const double v = ry[j]; if (v > m) m = v; }
+                    }
                     max_qy = m;
                 }
                 // published with the arrival time already in start_queue (env.py:129), so that the receiver appends it as is
