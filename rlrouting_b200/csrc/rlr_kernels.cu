@@ -223,10 +223,34 @@ __global__ void rlr_inject_schedule_kernel(unsigned *events, int cap, long long 
     unsigned *ev = events + idx * cap;
     int n_ev = 0;
     bool overflow = false;
+    // The common case — no packet at this node and step — is one Philox block and one compare.  Its ten round keys are
+    // computed once per thread and laundered through an opaque move: left to itself the compiler keeps them on the uniform
+    // datapath and re-derives most of them inside the loop (19 of the loop's 65 issue slots).
+    const unsigned long long rep = (unsigned long long)(replica_base + r);
+    const unsigned rlo = (unsigned)rep, rhi = (unsigned)(rep >> 32);
+    unsigned kx[10], ky[10];
+    kx[0] = (unsigned)seed; ky[0] = (unsigned)(seed >> 32);
+#pragma unroll
+    for (int i = 1; i < 10; ++i) { kx[i] = kx[i - 1] + 0x9E3779B9u; ky[i] = ky[i - 1] + 0xBB67AE85u; }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        asm volatile("mov.u32 %0, %0;" : "+r"(kx[i]));
+        asm volatile("mov.u32 %0, %0;" : "+r"(ky[i]));
+    }
     for (int s = 0; s < K; s += freq) {                 // one new_packet per `freq` steps, each step `slot` long (env.py:400-403)
-        PhiloxStream ps(seed, (unsigned long long)(replica_base + r), clock0 + s * slot, x, 0);
-        const unsigned w0 = ps.next();
+        uint4 c = make_uint4((unsigned)(clock0 + s * slot), (unsigned)x, rlo, rhi);     // block 0 of purpose 0
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+            const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+            c = make_uint4(hi1 ^ c.y ^ kx[i], lo1, hi0 ^ c.w ^ ky[i], lo0);
+        }
+        const unsigned w0 = c.x;
         if ((unsigned long long)w0 < th) continue;
+        PhiloxStream ps(seed, rep, clock0 + s * slot, x, 0);
+        ps.w = make_uint4(c.y, c.z, c.w, 0u);           // the stream continues behind the word just used
+        ps.have = 3;
+        ps.block = 1;
         int n = 1;
         double prod = __dmul_rn(__dadd_rn((double)w0, 0.5), 1.0 / 4294967296.0);
         for (;;) {
