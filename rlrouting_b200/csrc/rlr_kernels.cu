@@ -237,31 +237,44 @@ __global__ void rlr_inject_schedule_kernel(unsigned *events, int cap, long long 
         asm volatile("mov.u32 %0, %0;" : "+r"(kx[i]));
         asm volatile("mov.u32 %0, %0;" : "+r"(ky[i]));
     }
-    for (int s = 0; s < K; s += freq) {                 // one new_packet per `freq` steps, each step `slot` long (env.py:400-403)
-        uint4 c = make_uint4((unsigned)(clock0 + s * slot), (unsigned)x, rlo, rhi);     // block 0 of purpose 0
+    // One new_packet per `freq` steps, each step `slot` long (env.py:400-403).  A node injects in ~lambda/N of its steps, but
+    // some lane of a warp does in most of them, so a loop that handles a hit where it finds it walks the slow path nearly
+    // every step with one or two lanes active.  Instead a thread scans kBatch steps with the common-case block only, notes
+    // its hits in a bit mask, and then takes the hits one by one: the slow path runs max-over-lanes(hits) times per batch.
+    constexpr int kBatch = 32;
+    for (int s0 = 0; s0 < K; s0 += kBatch * freq) {
+        unsigned hits = 0u;
+#pragma unroll 2
+        for (int i = 0; i < kBatch; ++i) {
+            const int s = s0 + i * freq;
+            if (s >= K) break;
+            uint4 c = make_uint4((unsigned)(clock0 + s * slot), (unsigned)x, rlo, rhi);     // block 0 of purpose 0
 #pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-            const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-            c = make_uint4(hi1 ^ c.y ^ kx[i], lo1, hi0 ^ c.w ^ ky[i], lo0);
+            for (int q = 0; q < 10; ++q) {
+                const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+                const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+                c = make_uint4(hi1 ^ c.y ^ kx[q], lo1, hi0 ^ c.w ^ ky[q], lo0);
+            }
+            if ((unsigned long long)c.x >= th) hits |= 1u << i;
         }
-        const unsigned w0 = c.x;
-        if ((unsigned long long)w0 < th) continue;
-        PhiloxStream ps(seed, rep, clock0 + s * slot, x, 0);
-        ps.w = make_uint4(c.y, c.z, c.w, 0u);           // the stream continues behind the word just used
-        ps.have = 3;
-        ps.block = 1;
-        int n = 1;
-        double prod = __dmul_rn(__dadd_rn((double)w0, 0.5), 1.0 / 4294967296.0);
-        for (;;) {
-            const double u = __dmul_rn(__dadd_rn((double)ps.next(), 0.5), 1.0 / 4294967296.0);
-            prod = __dmul_rn(prod, u);
-            if (prod > en) ++n; else break;
-        }
-        for (int i = 0; i < n; ++i) {
-            unsigned dd = __umulhi(ps.next(), (unsigned)(N - 1));
-            if (dd >= (unsigned)x) ++dd;
-            if (n_ev < cap - 1) ev[n_ev++] = ((unsigned)s << 8) | dd; else overflow = true;
+        while (hits) {
+            const int i = __ffs((int)hits) - 1;
+            hits &= hits - 1u;
+            const int s = s0 + i * freq;
+            PhiloxStream ps(seed, rep, clock0 + s * slot, x, 0);
+            const unsigned w0 = ps.next();              // the block of the scan again: only a hit pays for it twice
+            int n = 1;
+            double prod = __dmul_rn(__dadd_rn((double)w0, 0.5), 1.0 / 4294967296.0);
+            for (;;) {
+                const double u = __dmul_rn(__dadd_rn((double)ps.next(), 0.5), 1.0 / 4294967296.0);
+                prod = __dmul_rn(prod, u);
+                if (prod > en) ++n; else break;
+            }
+            for (int j = 0; j < n; ++j) {
+                unsigned dd = __umulhi(ps.next(), (unsigned)(N - 1));
+                if (dd >= (unsigned)x) ++dd;
+                if (n_ev < cap - 1) ev[n_ev++] = ((unsigned)s << 8) | dd; else overflow = true;
+            }
         }
     }
     ev[n_ev] = 0xFFFFFFFFu;

@@ -418,6 +418,85 @@ __device__ __forceinline__ void cp_async8_if(void *dst_smem, const void *src_gme
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p cp.async.ca.shared.global [%0], [%1], 8;\n}"
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"((int)pred) : "memory");
 }
+// the same on 32-bit shared-window addresses (the staged queue heads are addressed as base + (i & (D-1)) * row bytes, see
+// stage_at in the step kernel; mad_u32 keeps ptxas from turning the multiply by a 0/1 value into compare + select + add)
+__device__ __forceinline__ unsigned mad_u32(unsigned a, unsigned b, unsigned c)
+{
+    unsigned r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint4 lds128_at(unsigned addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// (volatile: the loads of one row keep their order, i.e. leave back to back instead of one before each comparison)
+__device__ __forceinline__ double lds_row(const double *ptr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_u32(ptr)) : "memory");
+    return v;
+}
+__device__ __forceinline__ double lds_row(const float *ptr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(ptr)) : "memory");
+    return (double)v;
+}
+__device__ __forceinline__ unsigned lds32_at(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128_at(unsigned addr, const uint4 &v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128_at_if(unsigned addr, const uint4 &v, bool pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n}"
+                 :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void cp_async16_at_if(unsigned dst, const void *src_gmem, bool pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p cp.async.cg.shared.global [%0], [%1], 16;\n}"
+                 :: "r"(dst), "l"(src_gmem), "r"((int)pred) : "memory");
+}
+// Loop constants of the step kernel kept in ordinary registers: xor-ing with a zero that was read from shared memory hides
+// where the value came from, so the compiler cannot go back to the parameter block and reload it (LDCU into a uniform
+// register) in every iteration.
+__device__ __forceinline__ unsigned opaque(unsigned v, unsigned zero) { return v ^ zero; }
+__device__ __forceinline__ int opaque(int v, unsigned zero) { return (int)((unsigned)v ^ zero); }
+__device__ __forceinline__ double opaque(double v, unsigned zero)
+{
+    return __hiloint2double(__double2hiint(v) ^ (int)zero, __double2loint(v) ^ (int)zero);
+}
+template <typename T>
+__device__ __forceinline__ T *opaque(T *v, unsigned zero)
+{
+    return reinterpret_cast<T *>(reinterpret_cast<unsigned long long>(v) ^ (((unsigned long long)zero << 32) | zero));
+}
+// One slot of a row scan over a row read whole from shared memory: best = max(best, v) (and k = j) if slot j exists (j < deg)
+// and v > best — the degree test is the predicate input of the fp64 compare, the selects follow: 4 (5) instructions per slot
+// (volatile, like the row loads before them: all loads of the row first, then the comparisons)
+__device__ __forceinline__ void max_slot(double &best, double v, int deg, int j)
+{
+    asm volatile("{\n.reg .pred c, p;\nsetp.gt.s32 c, %2, %3;\nsetp.gt.and.f64 p, %1, %0, c;\nselp.f64 %0, %1, %0, p;\n}"
+        : "+d"(best) : "d"(v), "r"(deg), "r"(j));
+}
+__device__ __forceinline__ void argmax_slot(double &best, int &k, double v, int deg, int j)
+{
+    asm volatile("{\n.reg .pred c, p;\nsetp.gt.s32 c, %3, %4;\nsetp.gt.and.f64 p, %2, %0, c;\nselp.f64 %0, %2, %0, p;\nselp.s32 %1, %4, %1, p;\n}"
+        : "+d"(best), "+r"(k) : "d"(v), "r"(deg), "r"(j));
+}
+// acc += v under a predicate: one predicated add, where `acc += pred ? v : 0` compiles to a select and an add
+__device__ __forceinline__ void add_if(unsigned &acc, unsigned v, bool pred)
+{
+    asm("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p add.u32 %0, %0, %1;\n}" : "+r"(acc) : "r"(v), "r"((int)pred));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_PENDING>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
@@ -445,7 +524,7 @@ __device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("pre
 
 struct SmemLayout {
     size_t tables, rec, tp, wmask, rowptr, col, nexthop, heappos, ull, u32, f64, gr, samp, evheap, evorder, evsent, evlen, evfrom, mbar,
-        stage, swin, total;
+        stage, swin, nbr, total;
     bool heap_in_smem;
     // fused = the Network.train instantiation (SPLIT = false): it stages queue heads and the injection schedule in shared
     // memory, has no sample_route_time staging, and when the tables fill shared memory it reads heap_pos through L1 instead
@@ -464,7 +543,8 @@ struct SmemLayout {
         wmask = o; o += align16((size_t)(threads / 32 + 1) * 4);
         rowptr = o; o += align16((size_t)(N + 1) * 4);
         col = o; o += align16((size_t)sdeg * 2);
-        tp = o; o += align16((size_t)GN * 2);
+        tp = o; o += align16((size_t)(threads > GN ? threads : GN) * 2);      // one entry per thread: the threads behind the last
+                                                                              // replica publish "no send" like an idle node
         heap_in_smem = !(fused && smem_tables);
         heappos = o; o += heap_in_smem ? align16((size_t)(N + 1) * N) : 0;
         nexthop = o; o += (policy == RLR_POLICY_SHORTEST) ? align16((size_t)N * N * 2)      // u8 next hops or u16 choice masks
@@ -480,6 +560,9 @@ struct SmemLayout {
         mbar = o; o += smem_tables ? 16 : 0;               // mbarrier of the bulk table load
         stage = o; o += fused ? align16((size_t)stage_depth(smem_tables) * GN * 16) : 0;   // [D][G*N] records at / after the queue heads
         swin = o; o += fused ? align16((size_t)GN * 16) : 0;                   // [2][G*N][2] injection events ahead
+        // fused loop with the tables in shared memory: per directed link (x, k) the next hop y, its degree and the offset of
+        // its table block in one word, so that get_info finds the row Q[y][d] with one lookup instead of three dependent ones
+        nbr = o; o += (fused && smem_tables) ? align16((size_t)sdeg * 4) : 0;
         total = o;
     }
 };
@@ -547,7 +630,8 @@ __device__ __forceinline__ void gr_column(int z, int N, const int *rowptr, const
 }
 
 constexpr unsigned kNoKey = 0xFFFFFFFFu;   // "no arrival" sort key (real keys are heap position << 16 | send slot)
-constexpr unsigned kNoSend = 0xFFFFu;      // s_tp entry of a node that did not send this step
+constexpr unsigned kNoSend = 0x00FFu;      // s_tp entry of a node that did not send this step: target 255 is no node (N <= 255),
+                                           // rank 0 keeps the heap_pos index formed from it inside the table
 constexpr unsigned kDeadRec = 0xFFFFFFFFu; // word 0 of a ring entry that was sent from the middle of the queue (general timing)
 
 // ------------------------------------------------------------------------------------------------
@@ -576,6 +660,18 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     const int N = p.N, G = p.G, GN = G * N;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     constexpr bool FUSED = !SPLIT;            // the Network.train instantiation: staged queue heads, injections at step end
+#ifdef RLR_NOFLAT
+    constexpr bool kFlatArrivals = false;
+#else
+    constexpr bool kFlatArrivals = FUSED && MAXD == 4;
+#endif
+    constexpr bool kLearnInArrivals = kFlatArrivals && POLICY == RLR_POLICY_QROUTE && SMEM_TABLES;
+    // Qroute's fused loop with rings: a replica cannot stop in the middle of a launch there, so "this thread is a node of a
+    // running replica" (`act`) is a constant of the launch.  Instead of branching around every phase (a warp never skips
+    // them: even the second warp of a 36-node replica holds four nodes), `act` is one more input of the three predicates
+    // that start any work — queue not empty, a neighbour's packet is for me, an injection is due — and the phases run
+    // unconditionally: an inactive lane keeps head == tail, matches nothing and has no schedule.
+    constexpr bool kStaticLive = kFlatArrivals && POLICY == RLR_POLICY_QROUTE && !PAGED;
     constexpr int D = stage_depth(SMEM_TABLES);
     constexpr int kStageWait = SMEM_TABLES ? D - 1 : D - 2;    // commit groups that may still be in flight at the top of a step
     static_assert(sizeof(QT) == 8 || POLICY == RLR_POLICY_QROUTE, "fp32 table storage is implemented for Qroute");
@@ -594,9 +690,20 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     unsigned short *s_tp = reinterpret_cast<unsigned short *>(smem + L.tp);   // target | warp-local rank << 8
     unsigned char *s_heappos = smem + L.heappos;
     unsigned char *s_nexthop = smem + L.nexthop;
-    uint4 *s_stage = reinterpret_cast<uint4 *>(smem + L.stage);     // [D][G*N]: record i of thread t's queue at [(i & (D-1)) * GN + t]
+    // [D][G*N] staged head records: record i of thread t's queue at [(i & (D-1)) * GN + t].  stage_at(i) forms its 32-bit shared
+    // address as (this thread's slot) + (i & (D-1)) * (bytes per row): a mask and a multiply-add
+    // (a thread behind the last replica is given slot 0: it only ever reads there — see kStaticLive — and slot t may not exist)
+    const unsigned stage_t_u32 = smem_u32(smem + L.stage) + (unsigned)(t < GN ? t : 0) * 16u, stage_row = (unsigned)GN * 16u;
+    auto stage_at = [&](unsigned i) -> unsigned { return mad_u32(i & (unsigned)(D - 1), stage_row, stage_t_u32); };
+    unsigned *s_nbr = reinterpret_cast<unsigned *>(smem + L.nbr);   // [sdeg]: y | deg_y << 8 | (N * row_ptr[y]) << 16 of link (x, k) at row_ptr[x] + k
+    constexpr bool kPackedNbr = FUSED && SMEM_TABLES;               // (table blocks in shared memory hold fewer than 2^16 entries)
     unsigned *s_win = reinterpret_cast<unsigned *>(smem + L.swin);  // [2][G*N][2]: event e of thread t at [((e >> 1) & 1) * 2 * GN + 2 * t + (e & 1)]
-    auto heap_pos_at = [&](unsigned i) -> unsigned { return kHeapInSmem ? (unsigned)s_heappos[i] : (unsigned)__ldg(p.heap_pos + i); };
+    // loop constants of the fused kernel (made opaque, i.e. register-resident, once the CTA's shared memory is initialised)
+    double c_discount = p.discount, c_lr_q = p.lr_q;
+    unsigned c_N = (unsigned)N, c_cap = (unsigned)p.cap, c_inj_cap = (unsigned)p.inj_cap;
+    const unsigned char *c_heap_pos = p.heap_pos;
+    int clock_run = p.clock0;
+    auto heap_pos_at = [&](unsigned i) -> unsigned { return kHeapInSmem ? (unsigned)s_heappos[i] : (unsigned)__ldg(c_heap_pos + i); };
     // timing model (compile-time defaults in the fused instantiation)
     const bool general = SPLIT && p.general != 0;
     const int slotw = SPLIT ? p.slot : 1, ttime = SPLIT ? p.transtime : 1, freq = SPLIT ? p.freq : 1;
@@ -656,6 +763,11 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     }
     for (int i = t; i <= N; i += blockDim.x) s_rowptr[i] = p.row_ptr[i];
     for (int i = t; i < p.sdeg; i += blockDim.x) s_col[i] = (unsigned short)p.col[i];
+    if (kPackedNbr)
+        for (int i = t; i < p.sdeg; i += blockDim.x) {
+            const int yy = p.col[i], ry = p.row_ptr[yy];
+            s_nbr[i] = (unsigned)yy | ((unsigned)(p.row_ptr[yy + 1] - ry) << 8) | ((unsigned)(N * ry) << 16);
+        }
     if (kHeapInSmem)
         for (int i = t; i < (N + 1) * N; i += blockDim.x) s_heappos[i] = p.heap_pos[i];
     if (POLICY == RLR_POLICY_SHORTEST) {
@@ -696,6 +808,13 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     }
     __syncthreads();
     if (SMEM_TABLES) mbar_wait(s_mbar, 0);
+    if (FUSED) {
+        const unsigned zero = s_drop[0];            // (set to 0 above)
+        c_discount = opaque(c_discount, zero); c_lr_q = opaque(c_lr_q, zero);
+        c_N = opaque(c_N, zero); c_cap = opaque(c_cap, zero); c_inj_cap = opaque(c_inj_cap, zero);
+        c_heap_pos = opaque(c_heap_pos, zero);
+        clock_run = opaque(clock_run, zero);
+    }
 
     // ---- per-thread state, constant over the launch ----
     QT *Qr = nullptr;                                              // this replica's tables
@@ -742,12 +861,12 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
             for (int i = 0; i < D; ++i) {
                 const unsigned idx = head + i;
                 const unsigned pg = ((idx ^ head) >> plog) ? hnext : hpage;
-                cp_async16_if(s_stage + (idx & (D - 1)) * GN + t, pool + ((pg << plog) | (idx & pmask)), tail - head > (unsigned)i);
+                cp_async16_at_if(stage_at(idx), pool + ((pg << plog) | (idx & pmask)), tail - head > (unsigned)i);
             }
         } else if (FUSED) {                     // stage the first D records of the queue
 #pragma unroll
             for (int i = 0; i < D; ++i)
-                cp_async16_if(s_stage + ((head + i) & (D - 1)) * GN + t, myring + ((head + i) & capmask), tail - head > (unsigned)i);
+                cp_async16_at_if(stage_at(head + i), myring + ((head + i) & capmask), tail - head > (unsigned)i);
         } else if (head != tail) {
             pref = myring[head & capmask];
         }
@@ -769,8 +888,10 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     }
     const unsigned long long stream_id = (unsigned long long)(p.replica_base + r);
     // the replica's N thread slots as a window of the CTA-wide "sent this step" bit array (one word per warp)
-    const int wlo = gbase >> 5, nw = ((gbase + N - 1) >> 5) - wlo + 1;
-    const unsigned mfirst = 0xFFFFFFFFu << (gbase & 31), mlast = 0xFFFFFFFFu >> (31 - ((gbase + N - 1) & 31));
+    // (a thread beyond the CTA's replicas sees an empty window and its own send slot, which always says "no send", as every
+    // neighbour: whatever it reads stays inside the arrays and nothing it reads can match — see kStaticLive)
+    const int wlo = is_node ? gbase >> 5 : 0, nw = is_node ? ((gbase + N - 1) >> 5) - wlo + 1 : 1;
+    const unsigned mfirst = is_node ? 0xFFFFFFFFu << (gbase & 31) : 0u, mlast = is_node ? 0xFFFFFFFFu >> (31 - ((gbase + N - 1) & 31)) : 0u;
     const unsigned prank_mask = ((1u << lane) - 1u) & ((gbase > (warp << 5)) ? (0xFFFFFFFFu << (gbase - (warp << 5))) : 0xFFFFFFFFu);
     // neighbour send slots (own slot for j >= deg: a node never sends to itself, so it never matches) and the
     // window word each one falls in
@@ -778,8 +899,8 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
 #pragma unroll
     for (int j = 0; j < MAXD; ++j) {
         const int z = (is_node && j < deg) ? s_col[rp + j] : x;
-        nb_slot[j] = (unsigned)(gbase + z);
-        nb_word[j] = (unsigned)(((gbase + z) >> 5) - wlo);
+        nb_slot[j] = is_node ? (unsigned)(gbase + z) : (unsigned)t;         // (its own slot: always "no send")
+        nb_word[j] = is_node ? (unsigned)(((gbase + z) >> 5) - wlo) : 0u;
     }
     // injection schedule of this node: events (local step << 8 | dest), ascending, 0xFFFFFFFF-terminated
     const unsigned *evp = p.inj_events + ((size_t)(is_node ? r : 0) * N + (is_node ? x : 0)) * (size_t)p.inj_cap;
@@ -800,6 +921,8 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     }
     evp += 1;
     bool dead = is_node ? (s_dead[g] != 0u) : true;                 // only sampled policies can die mid-launch
+    const bool act = !dead;                                         // (kStaticLive: constant over the launch)
+    if (kStaticLive && !act) { ev = 0xFFFFFFFFu; ev_next = 0xFFFFFFFFu; }
     const int gr_off = (POLICY == RLR_POLICY_GLOBALROUTE && is_node) ? p.gr_qs_off[r * N + x] : 0;
     // rarely used options (send log, is_drop, droprate records, sampling, split phases) live in the SPLIT instantiation only
     unsigned *sendlog = (SPLIT && p.sendlog && is_node) ? p.sendlog + r * (long long)p.K * N + x : nullptr;
@@ -828,13 +951,13 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
         if (PAGED) pool[(tpage << plog) | (tail & pmask)] = rec;
         else myring[tail & capmask] = rec;
         if (PAGED) {
-            if (tail - head < (unsigned)D) s_stage[(tail & (D - 1)) * GN + t] = rec;
+            if (tail - head < (unsigned)D) sts128_at(stage_at(tail), rec);
             ++tail;
             if ((tail & pmask) == 0u) next_tail_page();
             return;
         }
         if (FUSED) {                    // a record that lands within D of the head is staged directly (nothing will fetch it)
-            if (tail - head < (unsigned)D) s_stage[(tail & (D - 1)) * GN + t] = rec;
+            if (tail - head < (unsigned)D) sts128_at(stage_at(tail), rec);
         } else if (head == tail) {
             fresh = rec;
             use_fresh = true;
@@ -848,12 +971,6 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     // after the arrivals of step s — the same queue order as injecting at the start of step s + 1, but off the head of the
     // dependent chain, and with the schedule read from the shared-memory window.
     constexpr bool kInjectAtStart = SPLIT;
-#ifdef RLR_NOFLAT
-    constexpr bool kFlatArrivals = false;
-#else
-    constexpr bool kFlatArrivals = FUSED && MAXD == 4;
-#endif
-    constexpr bool kLearnInArrivals = kFlatArrivals && POLICY == RLR_POLICY_QROUTE && SMEM_TABLES;
     auto inject_step = [&](int s_now, unsigned step, int clk) {
         while ((ev >> 8) == step) {
             append(make_uint4((ev & 0xFFu) | ((unsigned)x << 16), 0u, (unsigned)clk, (unsigned)clk));
@@ -867,7 +984,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
             ++eidx;
             if ((eidx & 1u) == 0u) {    // chunk eidx/2 - 1 is used up: request chunk eidx/2 + 1 into its half
                 const unsigned c = (eidx >> 1) + 1u;
-                cp_async8_if(s_win + (c & 1u) * 2u * GN + 2u * t, ev_base + 2u * c, 2u * c < (unsigned)p.inj_cap);
+                cp_async8_if(s_win + (c & 1u) * 2u * GN + 2u * t, ev_base + 2u * c, 2u * c < c_inj_cap);
                 win_t_old = win_t_new;
                 win_t_new = s_now;
             }
@@ -884,14 +1001,22 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     long long tacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tmark_ = clock64();
 #endif
+    // what a sender carries from the send phase to its learn step: declared outside the step loop, so that a node which does
+    // not send keeps stale values (every use is behind `sending`) instead of zeroing eleven registers every step
+    int d = 0, k = 0, y = 0;
+    double oldq = 0.0, max_qy = 0.0, max_qxd = 0.0, rwd = 0.0, c_f = 0.0;
+    // the metric thread of a replica (its last node) and whether it writes per-step records: kept as two bits of one opaque
+    // register — left to itself the compiler re-derives both predicates from r, R, x, N and the pointer in every step
+    unsigned metric_bits = (is_node && x == N - 1) ? (p.metrics ? 3u : 1u) : 0u;
+    asm volatile("mov.u32 %0, %0;" : "+r"(metric_bits));
+    uint4 *metric_row = p.metrics ? p.metrics + r : nullptr;       // this replica's record of the current step
     for (int s = 0; s < p.K; ++s) {
-        const int clock = p.clock0 + s * slotw;
+        const int clock = clock_run;                // p.clock0 + s * slotw
+        clock_run += slotw;
         if (FUSED) cp_async_wait<kStageWait>(); // every copy of the groups before the latest one (two) has landed (see the commit below)
         if ((IS_PG || sampling || PAGED) && is_node) dead = (s_dead[g] != 0u);
         const bool live = !dead;
         bool sending = false;
-        int d = 0, k = 0, y = 0;
-        double oldq = 0.0, max_qy = 0.0, max_qxd = 0.0, rwd = 0.0, c_f = 0.0;
         int qy_dual = 1;                            // 'dual' mode q_y = max(1, len(nodes[y].queue)), env.py:156
         double sm[MAXD];
         if (live && !do_env) {
@@ -917,7 +1042,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 if (POLICY == RLR_POLICY_MAHYBRIDQ) { s_r[t] = rwd; s_qy[t] = max_qy; s_qx[t] = max_qxd; }
             }
         }
-        if (live && do_env) {
+        if ((kStaticLive || live) && do_env) {
             // ---- A. new_packet + inject (env.py:298-319): consume this step's events of the schedule ----
             // (the fused instantiation has done this at the end of the previous step, see inject_step below)
             while (kInjectAtStart && (ev >> 8) == (unsigned)s) {
@@ -930,14 +1055,18 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
             // ---- B. Node._send_default (env.py:162-191): pop the head, choose, get_info ----
             if (DUAL) s_len[t] = tail - head - ndead;                           // len(queue) before this node's own send
             bool have = false;
-            uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+            uint4 rec;
+            if (!kStaticLive) rec = make_uint4(0u, 0u, 0u, 0u);
             if (FUSED) {
                 // the head record was staged in shared memory at least D steps ago (or by the append that created it); the
                 // pop requests the record that is now D - 1 behind the new head — the loads never touch a register
-                const bool nonempty = head != tail;
+                const bool nonempty = kStaticLive ? (head != tail) & act : head != tail;
+                const unsigned head_slot = stage_at(head);              // the slot this pop vacates is the one its refill lands in:
+                                                                        // (head + 1 + (D - 1)) & (D - 1) == head & (D - 1)
+                if (kStaticLive) rec = lds128_at(head_slot);            // (read whether or not there is a head: nothing to zero)
                 if (nonempty) {
                     have = true;
-                    rec = s_stage[(head & (D - 1)) * GN + t];
+                    if (!kStaticLive) rec = lds128_at(head_slot);
                     ++head;
                     if (PAGED && (head & pmask) == 0u) {        // the head left its page: back onto the free stack
                         pfree[atomicAdd(&s_ptop[g], 1)] = (unsigned short)hpage;
@@ -948,15 +1077,15 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 if (PAGED) {
                     const unsigned idx = head + (D - 1);
                     const unsigned pg = ((idx ^ head) >> plog) ? hnext : hpage;
-                    cp_async16_if(s_stage + (idx & (D - 1)) * GN + t, pool + ((pg << plog) | (idx & pmask)),
+                    cp_async16_at_if(stage_at(idx), pool + ((pg << plog) | (idx & pmask)),
                                   nonempty && tail - head > (unsigned)(D - 1));
                 } else
-                cp_async16_if(s_stage + ((head + (D - 1)) & (D - 1)) * GN + t, myring + ((head + (D - 1)) & capmask),
+                cp_async16_at_if(head_slot, myring + ((head + (D - 1)) & capmask),       // (issued only after a pop)
                               nonempty && tail - head > (unsigned)(D - 1));
                 if (!SMEM_TABLES && POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE && head != tail) {
                     // tables in HBM: the record behind the one just popped is next step's head (staged at least three commit
                     // groups ago, or written by the append that created it); bring the rows `choose` will read for it into L1
-                    const unsigned dn = s_stage[(head & (D - 1)) * GN + t].x & 0xFFFFu;
+                    const unsigned dn = lds32_at(stage_at(head)) & 0xFFFFu;
                     const QT *rowq = Qx + dn * deg;
                     prefetch_l1(rowq);
                     prefetch_l1(rowq + (deg - 1));
@@ -1049,6 +1178,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
             if (have) {
                 sending = true;
                 d = (int)(rec.x & 0xFFFFu);
+                if (!general) k = 0;                // (the queue scan of the general timing model has chosen k already)
                 RLR_T(6);                           // A + pop
                 if (general) {
                     // k was chosen by the scan; pick up the values Qroute/HybridQ.get_info and learn need
@@ -1095,6 +1225,30 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                             for (int j = g4 ? g4 : 1; j < g4 + 4; ++j)
                                 if (j < deg) { const double v = row[j]; if (v > best) { best = v; k = j; } }
                         }
+                    } else if constexpr (SMEM_TABLES) {
+                        // the row is read whole (a slot past the node's degree is the next row's entry, or — behind the last
+                        // row — whatever follows the table in shared memory) and the degree test joins the comparison:
+                        // compare + selects instead of a predicated block per slot
+                        double rv[MAXD];
+#pragma unroll
+                        for (int j = 0; j < MAXD; ++j) rv[j] = lds_row(row + j);
+                        if constexpr (MAXD == 4) {
+                            // first-index argmax as a two-level tournament: (0 vs 1), (2 vs 3), then left vs right — a strict
+                            // comparison keeps the lower index on a tie at every level, like the sequential scan, and the two
+                            // first-level comparisons need the whole row at once, so its four loads leave together
+                            double b = rv[2];
+                            int kb = 2;
+                            best = rv[0];
+                            argmax_slot(best, k, rv[1], deg, 1);
+                            argmax_slot(b, kb, rv[3], deg, 3);
+                            const bool right = (deg > 2) & (b > best);
+                            best = right ? b : best;
+                            k = right ? kb : k;
+                        } else {
+                            best = rv[0];
+#pragma unroll
+                            for (int j = 1; j < MAXD; ++j) argmax_slot(best, k, rv[j], deg, j);
+                        }
                     } else {
 #pragma unroll
                         for (int j = 1; j < MAXD; ++j)
@@ -1140,8 +1294,14 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                     }
                     max_qxd = best;
                 }
-                y = s_col[rp + k];
-                const int qoff_y = N * s_rowptr[y], deg_y = s_rowptr[y + 1] - s_rowptr[y];   // Q[y] offset and degree of the next hop
+                int qoff_y, deg_y;                                              // Q[y] offset and degree of the next hop
+                if constexpr (kPackedNbr) {
+                    const unsigned nb = s_nbr[rp + k];
+                    y = (int)(nb & 0xFFu); deg_y = (int)((nb >> 8) & 0xFFu); qoff_y = (int)(nb >> 16);
+                } else {
+                    y = s_col[rp + k];
+                    qoff_y = N * s_rowptr[y]; deg_y = s_rowptr[y + 1] - s_rowptr[y];
+                }
                 rec.y += 1u;                                                    // p.hops += 1, env.py:141
                 rwd = (double)(-(clock - (int)rec.w) - 1);                      // r = -q_y - t_y, qroute.py:37
                 if (IS_CQ) {                        // CQ.get_info (qroute.py:72-78): z = argmax Q[y][d], max_Q_f, C_f
@@ -1179,6 +1339,21 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
 #pragma unroll
                             for (int j = g4 ? g4 : 1; j < g4 + 4; ++j)
                                 if (j < degy) { const double v = ry[j]; if (v > m) m = v; }
+                        }
+                    } else if constexpr (SMEM_TABLES) {
+                        double rv[MAXD];
+#pragma unroll
+                        for (int j = 0; j < MAXD; ++j) rv[j] = lds_row(ry + j);
+                        if constexpr (MAXD == 4) {
+                            double b = rv[2];
+                            m = rv[0];
+                            max_slot(m, rv[1], degy, 1);
+                            max_slot(b, rv[3], degy, 3);
+                            m = ((degy > 2) & (b > m)) ? b : m;
+                        } else {
+                            m = rv[0];
+#pragma unroll
+                            for (int j = 1; j < MAXD; ++j) max_slot(m, rv[j], degy, j);
                         }
                     } else {
 #pragma unroll
@@ -1228,7 +1403,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
         if (sendlog) sendlog[(long long)s * N] = sending ? ((unsigned)y | ((unsigned)d << 16)) : 0xFFFFFFFFu;
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, sending);
         if (lane == 0) s_wmask[warp] = bal;
-        if (t < GN) s_tp[t] = sending ? (unsigned short)(y | ((general ? k : __popc(bal & prank_mask)) << 8)) : (unsigned short)kNoSend;
+        s_tp[t] = sending ? (unsigned short)(y | ((general ? k : __popc(bal & prank_mask)) << 8)) : (unsigned short)kNoSend;
         __syncthreads();                                                        // ---- barrier 1 ----
         RLR_T(1);
 
@@ -1349,7 +1524,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 }
                 if (tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
             }
-        } else if (live && do_env) {
+        } else if ((kStaticLive || live) && do_env) {
             // ---- C. event drain (env.py:349-364): gather arrivals from neighbours in heap-tie order ----
             unsigned cum[MAXW + 1];         // senders of this replica in the window words before word i
             cum[0] = 0;
@@ -1360,7 +1535,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 if (i == nw - 1) m &= mlast;
                 cum[i + 1] = cum[i] + __popc(m);
             }
-            const unsigned hp_row = cum[MAXW] * (unsigned)N;                    // heap_pos row k = number of senders
+            const unsigned hp_row = cum[MAXW] * c_N;                    // heap_pos row k = number of senders
             // cum[] as bytes (N <= 255) of up to three registers, looked up with byte_perm: no indexed local array
             unsigned cumpack = 0, cumpack1 = 0, cumpack2 = 0;
             cumpack = cum[0] | (cum[1] << 8) | (cum[2] << 16) | ((MAXW > 3 ? cum[MAXW > 3 ? 3 : 0] : 0u) << 24);
@@ -1425,10 +1600,10 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
             if (kLearnInArrivals) {
                 // Qroute.learn (qroute.py:40-44) in the same straight-line block as the arrival loads, so that the fp64
                 // chain fills their latency; only the store is predicated on `sending`
-                const double tq = __dmul_rn(p.discount, max_qy);
+                const double tq = __dmul_rn(c_discount, max_qy);
                 const double u1 = __dadd_rn(rwd, tq);
                 const double u2 = __dsub_rn(u1, oldq);
-                const double newq = __dadd_rn(oldq, __dmul_rn(p.lr_q, u2));
+                const double newq = __dadd_rn(oldq, __dmul_rn(c_lr_q, u2));
                 if constexpr (sizeof(QT) == 8) sts64_if(reinterpret_cast<double *>(Qx) + (d * deg + k), newq, sending);
                 else sts32f_if(reinterpret_cast<float *>(Qx) + (d * deg + k), (float)newq, sending);
             }
@@ -1442,9 +1617,9 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const unsigned tp = s_tp[nb_slot[j]];
-                    mt[j] = (tp & 0xFFu) == (unsigned)x;
+                    mt[j] = ((tp ^ (unsigned)x) & 0xFFu) == 0u;      // (a stopped replica's nodes publish "no send" too)
                     const unsigned base = cum_at(nb_word[j]);
-                    posv[j] = heap_pos_at(hp_row + (mt[j] ? (tp >> 8) + base : 0u));
+                    posv[j] = heap_pos_at(hp_row + (tp >> 8) + base);      // (in the table for any slot: kNoSend carries rank 0)
                     rc[j] = lds128_if(s_rec + nb_slot[j], mt[j]);
                 }
                 unsigned ndel = 0u, rtsum = 0u, hopsum = 0u, ndrop = 0u;
@@ -1454,9 +1629,9 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                     const bool del = mt[j] && !dropped && (int)(rc[j].x & 0xFFFFu) == x;    // Network.end_packet, env.py:321-331
                     ap[j] = mt[j] && !dropped && !del;                                      // Node.receive, env.py:127-130
                     if (SPLIT && mt[j] && dropped) ++ndrop;
-                    ndel += del ? 1u : 0u;
-                    rtsum += del ? (unsigned)(clock + ttime - (int)rc[j].z) : 0u;
-                    hopsum += del ? rc[j].y : 0u;
+                    add_if(ndel, 1u, del);
+                    add_if(rtsum, (unsigned)(clock + ttime - (int)rc[j].z), del);
+                    add_if(hopsum, rc[j].y, del);
                     if (sampling && del) {                                                  // env.py:325-328, ordered later
                         const unsigned slot = atomicAdd(&s_nsamp[g], 1u);
                         s_samp_pos[g * sstride + slot] = posv[j];
@@ -1470,14 +1645,20 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                     atomicAdd(&s_hops[g], hopsum);
                 }
                 const unsigned tail0 = tail;
-                unsigned keyv[4], rkv[4] = {0u, 0u, 0u, 0u};        // rank among the appended ones by heap position
+                // rank among the appended ones by heap position.  Six comparisons, one per pair: the positions of two
+                // appended records are distinct, and a pair with a record that is not appended (key 0x100, above every
+                // position) only ever raises the rank of that record, which nobody uses
+                unsigned keyv[4], rkv[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) keyv[j] = ap[j] ? posv[j] : 0x100u;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (i != j) rkv[j] += (keyv[i] < keyv[j]) ? 1u : 0u;
+                {   // m_ij = -1 if key i < key j else 0 (keys are below 2^9: the sign of the difference), sums of three terms
+                    const int m01 = (int)(keyv[0] - keyv[1]) >> 31, m02 = (int)(keyv[0] - keyv[2]) >> 31, m03 = (int)(keyv[0] - keyv[3]) >> 31;
+                    const int m12 = (int)(keyv[1] - keyv[2]) >> 31, m13 = (int)(keyv[1] - keyv[3]) >> 31, m23 = (int)(keyv[2] - keyv[3]) >> 31;
+                    rkv[0] = (unsigned)(3 + m01 + m02 + m03);
+                    rkv[1] = (unsigned)(2 - m01 + m12 + m13);
+                    rkv[2] = (unsigned)(1 - m02 - m12 + m23);
+                    rkv[3] = (unsigned)(-m03 - m13 - m23);
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const unsigned rk = rkv[j];
@@ -1488,8 +1669,8 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                     } else {
                         stg128_if(myring + (at & capmask), rc[j], ap[j]);
                     }
-                    sts128_if(s_stage + (at & (D - 1)) * GN + t, rc[j], ap[j] && at - head < (unsigned)D);
-                    tail += ap[j] ? 1u : 0u;
+                    sts128_at_if(stage_at(at), rc[j], ap[j] && at - head < (unsigned)D);
+                    add_if(tail, 1u, ap[j]);
                 }
                 if (PAGED && ((tail ^ tail0) >> plog)) next_tail_page();
             } else {
@@ -1699,14 +1880,14 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
         // One commit group per step, closed here: group s holds the schedule chunks requested at the end of step s - 1 and the
         // record requested by the pop of step s, so when the top of step s + 2 waits for it every copy in it is two steps old.
         if (FUSED) cp_async_commit();
-        if (!kInjectAtStart && is_node && live) {   // next step's new_packet + inject (env.py:298-319); slot = 1 on this path
+        if (!kInjectAtStart && (kStaticLive || (is_node && live))) {   // next step's new_packet + inject (env.py:298-319); slot = 1 here
             inject_step(s, (unsigned)(s + 1), clock + 1);
-            if (!PAGED && tail - head > (unsigned)p.cap) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
+            if (!PAGED && tail - head > c_cap && (!kStaticLive || act)) set_status(p.status, r, RLR_STATUS_QUEUE_OVERFLOW, clock);
         }
         RLR_T(3);                                   // D
         __syncthreads();                                                        // ---- barrier 2 ----
         RLR_T(4);
-        if (is_node && x == N - 1) {                // the metric thread: 64-bit running route_time, per-step record
+        if (metric_bits & 1u) {                     // the metric thread: 64-bit running route_time, per-step record
             run_rt += (long long)s_rt32[g];
             s_rt32[g] = 0u;                         // next deliveries come after the next barrier 1
         }
@@ -1735,10 +1916,11 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
             }
             __syncthreads();
         }
-        if (is_node && x == N - 1 && p.metrics) {                               // env.py:409-413 (cumulative counters)
+        if (metric_bits & 2u) {                                                 // env.py:409-413 (cumulative counters)
             const long long rt = base_rt + run_rt;
             const unsigned en = (unsigned)(base_end + s_end[g]), hps = (unsigned)(base_hops + s_hops[g]);
-            p.metrics[(long long)s * p.R + r] = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hps);
+            *metric_row = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hps);
+            metric_row += p.R;
             if (SPLIT && p.metrics2)
                 p.metrics2[(long long)s * p.R + r] = make_uint2((unsigned)(base_all + s_injs[g]), (unsigned)(base_drop + s_drop[g]));
         }
