@@ -540,7 +540,7 @@ struct SmemLayout {
                        : (policy == RLR_POLICY_CDRQ) ? align16((size_t)GN * 32) : 0;   // CDRQ: {C_b, max_Q_b}, len, q_x, d|k, src
         ull = o; o += align16((size_t)G * 3 * 8);            // route_time, sends, injected
         u32 = o; o += align16((size_t)G * 9 * 4);            // end, hops, dead, drop, injected-so-far, ..., free pages
-        wmask = o; o += align16((size_t)(threads / 32 + 1) * 4);
+        wmask = o; o += align16((size_t)(threads / 32 + 3) * 4);    // (+ 2: a replica's window is read as three words, masked)
         rowptr = o; o += align16((size_t)(N + 1) * 4);
         col = o; o += align16((size_t)sdeg * 2);
         tp = o; o += align16((size_t)(threads > GN ? threads : GN) * 2);      // one entry per thread: the threads behind the last
@@ -672,6 +672,10 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     // that start any work — queue not empty, a neighbour's packet is for me, an injection is due — and the phases run
     // unconditionally: an inactive lane keeps head == tail, matches nothing and has no schedule.
     constexpr bool kStaticLive = kFlatArrivals && POLICY == RLR_POLICY_QROUTE && !PAGED;
+    // Kernels with registers to spare — the degree <= 4 fused loops of the policies without softmax rows — keep loop constants,
+    // the sender's scratch and a few addresses in registers across the steps; the others run at their register limit, where
+    // a reloaded constant is cheaper than a spill.
+    constexpr bool kRegRich = kFlatArrivals && !(POLICY == RLR_POLICY_HYBRIDQ || POLICY == RLR_POLICY_MAHYBRIDQ) && LB == 0;
     constexpr int D = stage_depth(SMEM_TABLES);
     constexpr int kStageWait = SMEM_TABLES ? D - 1 : D - 2;    // commit groups that may still be in flight at the top of a step
     static_assert(sizeof(QT) == 8 || POLICY == RLR_POLICY_QROUTE, "fp32 table storage is implemented for Qroute");
@@ -694,7 +698,11 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     // address as (this thread's slot) + (i & (D-1)) * (bytes per row): a mask and a multiply-add
     // (a thread behind the last replica is given slot 0: it only ever reads there — see kStaticLive — and slot t may not exist)
     const unsigned stage_t_u32 = smem_u32(smem + L.stage) + (unsigned)(t < GN ? t : 0) * 16u, stage_row = (unsigned)GN * 16u;
-    auto stage_at = [&](unsigned i) -> unsigned { return mad_u32(i & (unsigned)(D - 1), stage_row, stage_t_u32); };
+    auto stage_ptr = [&](unsigned i) -> uint4 * { return reinterpret_cast<uint4 *>(smem + L.stage) + (i & (unsigned)(D - 1)) * GN + t; };
+    auto stage_at = [&](unsigned i) -> unsigned {
+        if (!kRegRich) return smem_u32(stage_ptr(i));              // (uniform operands instead of two more registers)
+        return mad_u32(i & (unsigned)(D - 1), stage_row, stage_t_u32);
+    };
     unsigned *s_nbr = reinterpret_cast<unsigned *>(smem + L.nbr);   // [sdeg]: y | deg_y << 8 | (N * row_ptr[y]) << 16 of link (x, k) at row_ptr[x] + k
     constexpr bool kPackedNbr = FUSED && SMEM_TABLES;               // (table blocks in shared memory hold fewer than 2^16 entries)
     unsigned *s_win = reinterpret_cast<unsigned *>(smem + L.swin);  // [2][G*N][2]: event e of thread t at [((e >> 1) & 1) * 2 * GN + 2 * t + (e & 1)]
@@ -808,7 +816,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     }
     __syncthreads();
     if (SMEM_TABLES) mbar_wait(s_mbar, 0);
-    if (FUSED) {
+    if (kRegRich) {
         const unsigned zero = s_drop[0];            // (set to 0 above)
         c_discount = opaque(c_discount, zero); c_lr_q = opaque(c_lr_q, zero);
         c_N = opaque(c_N, zero); c_cap = opaque(c_cap, zero); c_inj_cap = opaque(c_inj_cap, zero);
@@ -890,8 +898,14 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     // the replica's N thread slots as a window of the CTA-wide "sent this step" bit array (one word per warp)
     // (a thread beyond the CTA's replicas sees an empty window and its own send slot, which always says "no send", as every
     // neighbour: whatever it reads stays inside the arrays and nothing it reads can match — see kStaticLive)
-    const int wlo = is_node ? gbase >> 5 : 0, nw = is_node ? ((gbase + N - 1) >> 5) - wlo + 1 : 1;
-    const unsigned mfirst = is_node ? 0xFFFFFFFFu << (gbase & 31) : 0u, mlast = is_node ? 0xFFFFFFFFu >> (31 - ((gbase + N - 1) & 31)) : 0u;
+    const bool in_win = is_node || !kStaticLive;
+    const int wlo = in_win ? gbase >> 5 : 0, nw = in_win ? ((gbase + N - 1) >> 5) - wlo + 1 : 1;
+    const unsigned mfirst = in_win ? 0xFFFFFFFFu << (gbase & 31) : 0u, mlast = in_win ? 0xFFFFFFFFu >> (31 - ((gbase + N - 1) & 31)) : 0u;
+    // short windows (MAXW <= 3): all three words are always read and masked — words past the replica's last one with zero
+    unsigned wmsk[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        wmsk[i] = (i < nw) ? ((i == 0 ? mfirst : 0xFFFFFFFFu) & (i == nw - 1 ? mlast : 0xFFFFFFFFu)) : 0u;
     const unsigned prank_mask = ((1u << lane) - 1u) & ((gbase > (warp << 5)) ? (0xFFFFFFFFu << (gbase - (warp << 5))) : 0xFFFFFFFFu);
     // neighbour send slots (own slot for j >= deg: a node never sends to itself, so it never matches) and the
     // window word each one falls in
@@ -899,8 +913,8 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
 #pragma unroll
     for (int j = 0; j < MAXD; ++j) {
         const int z = (is_node && j < deg) ? s_col[rp + j] : x;
-        nb_slot[j] = is_node ? (unsigned)(gbase + z) : (unsigned)t;         // (its own slot: always "no send")
-        nb_word[j] = is_node ? (unsigned)(((gbase + z) >> 5) - wlo) : 0u;
+        nb_slot[j] = in_win ? (unsigned)(gbase + z) : (unsigned)t;          // (its own slot: always "no send")
+        nb_word[j] = in_win ? (unsigned)(((gbase + z) >> 5) - wlo) : 0u;
     }
     // injection schedule of this node: events (local step << 8 | dest), ascending, 0xFFFFFFFF-terminated
     const unsigned *evp = p.inj_events + ((size_t)(is_node ? r : 0) * N + (is_node ? x : 0)) * (size_t)p.inj_cap;
@@ -951,13 +965,13 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
         if (PAGED) pool[(tpage << plog) | (tail & pmask)] = rec;
         else myring[tail & capmask] = rec;
         if (PAGED) {
-            if (tail - head < (unsigned)D) sts128_at(stage_at(tail), rec);
+            if (tail - head < (unsigned)D) { if (!kRegRich) *stage_ptr(tail) = rec; else sts128_at(stage_at(tail), rec); }
             ++tail;
             if ((tail & pmask) == 0u) next_tail_page();
             return;
         }
         if (FUSED) {                    // a record that lands within D of the head is staged directly (nothing will fetch it)
-            if (tail - head < (unsigned)D) sts128_at(stage_at(tail), rec);
+            if (tail - head < (unsigned)D) { if (!kRegRich) *stage_ptr(tail) = rec; else sts128_at(stage_at(tail), rec); }
         } else if (head == tail) {
             fresh = rec;
             use_fresh = true;
@@ -1008,11 +1022,12 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     // the metric thread of a replica (its last node) and whether it writes per-step records: kept as two bits of one opaque
     // register — left to itself the compiler re-derives both predicates from r, R, x, N and the pointer in every step
     unsigned metric_bits = (is_node && x == N - 1) ? (p.metrics ? 3u : 1u) : 0u;
-    asm volatile("mov.u32 %0, %0;" : "+r"(metric_bits));
+    if (kRegRich) asm volatile("mov.u32 %0, %0;" : "+r"(metric_bits));
     uint4 *metric_row = p.metrics ? p.metrics + r : nullptr;       // this replica's record of the current step
     for (int s = 0; s < p.K; ++s) {
-        const int clock = clock_run;                // p.clock0 + s * slotw
-        clock_run += slotw;
+        if (!kRegRich) { d = 0; k = 0; y = 0; oldq = 0.0; max_qy = 0.0; max_qxd = 0.0; rwd = 0.0; c_f = 0.0; }   // (register-poor builds: nothing lives across steps)
+        const int clock = kRegRich ? clock_run : p.clock0 + s * slotw;
+        if (kRegRich) clock_run += slotw;
         if (FUSED) cp_async_wait<kStageWait>(); // every copy of the groups before the latest one (two) has landed (see the commit below)
         if ((IS_PG || sampling || PAGED) && is_node) dead = (s_dead[g] != 0u);
         const bool live = !dead;
@@ -1064,9 +1079,10 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 const unsigned head_slot = stage_at(head);              // the slot this pop vacates is the one its refill lands in:
                                                                         // (head + 1 + (D - 1)) & (D - 1) == head & (D - 1)
                 if (kStaticLive) rec = lds128_at(head_slot);            // (read whether or not there is a head: nothing to zero)
+                const uint4 *head_ptr = stage_ptr(head);
                 if (nonempty) {
                     have = true;
-                    if (!kStaticLive) rec = lds128_at(head_slot);
+                    if (!kStaticLive) rec = !kRegRich ? *head_ptr : lds128_at(head_slot);
                     ++head;
                     if (PAGED && (head & pmask) == 0u) {        // the head left its page: back onto the free stack
                         pfree[atomicAdd(&s_ptop[g], 1)] = (unsigned short)hpage;
@@ -1085,7 +1101,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 if (!SMEM_TABLES && POLICY != RLR_POLICY_SHORTEST && POLICY != RLR_POLICY_GLOBALROUTE && head != tail) {
                     // tables in HBM: the record behind the one just popped is next step's head (staged at least three commit
                     // groups ago, or written by the append that created it); bring the rows `choose` will read for it into L1
-                    const unsigned dn = lds32_at(stage_at(head)) & 0xFFFFu;
+                    const unsigned dn = (!kRegRich ? stage_ptr(head)->x : lds32_at(stage_at(head))) & 0xFFFFu;
                     const QT *rowq = Qx + dn * deg;
                     prefetch_l1(rowq);
                     prefetch_l1(rowq + (deg - 1));
@@ -1530,9 +1546,14 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
             cum[0] = 0;
 #pragma unroll
             for (int i = 0; i < MAXW; ++i) {
-                unsigned m = (i < nw) ? s_wmask[wlo + i] : 0u;
-                if (i == 0) m &= mfirst;
-                if (i == nw - 1) m &= mlast;
+                unsigned m;
+                if (MAXW <= 3) {
+                    m = s_wmask[wlo + i] & wmsk[i < 3 ? i : 0];
+                } else {
+                    m = (i < nw) ? s_wmask[wlo + i] : 0u;
+                    if (i == 0) m &= mfirst;
+                    if (i == nw - 1) m &= mlast;
+                }
                 cum[i + 1] = cum[i] + __popc(m);
             }
             const unsigned hp_row = cum[MAXW] * c_N;                    // heap_pos row k = number of senders
@@ -1542,7 +1563,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
             if (MAXW > 4) cumpack1 = cum[MAXW > 4 ? 4 : 0] | (cum[MAXW > 5 ? 5 : 0] << 8) | (cum[MAXW > 6 ? 6 : 0] << 16) | (cum[MAXW > 7 ? 7 : 0] << 24);
             if (MAXW > 8) cumpack2 = cum[MAXW > 8 ? 8 : 0];
             auto cum_at = [&](unsigned w) -> unsigned {
-                if (MAXW <= 4) return __byte_perm(cumpack, 0u, w) & 0xFFu;
+                if (MAXW <= 4) return __byte_perm(cumpack, 0u, w);       // (selector w = bytes {w, 0, 0, 0}, and byte 0 is cum[0] = 0)
                 const unsigned reg = w < 4u ? cumpack : (w < 8u ? cumpack1 : cumpack2);
                 return __byte_perm(reg, 0u, w & 3u) & 0xFFu;
             };
@@ -1887,7 +1908,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
         RLR_T(3);                                   // D
         __syncthreads();                                                        // ---- barrier 2 ----
         RLR_T(4);
-        if (metric_bits & 1u) {                     // the metric thread: 64-bit running route_time, per-step record
+        if (kRegRich ? (metric_bits & 1u) != 0u : (is_node && x == N - 1)) {    // the metric thread: 64-bit running route_time, per-step record
             run_rt += (long long)s_rt32[g];
             s_rt32[g] = 0u;                         // next deliveries come after the next barrier 1
         }
@@ -1916,11 +1937,15 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
             }
             __syncthreads();
         }
-        if (metric_bits & 2u) {                                                 // env.py:409-413 (cumulative counters)
+        if (kRegRich ? (metric_bits & 2u) != 0u : (is_node && x == N - 1 && p.metrics)) {     // env.py:409-413 (cumulative counters)
             const long long rt = base_rt + run_rt;
             const unsigned en = (unsigned)(base_end + s_end[g]), hps = (unsigned)(base_hops + s_hops[g]);
-            *metric_row = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hps);
-            metric_row += p.R;
+            if (kRegRich) {
+                *metric_row = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hps);
+                metric_row += p.R;
+            } else {
+                p.metrics[(long long)s * p.R + r] = make_uint4((unsigned)rt, (unsigned)((unsigned long long)rt >> 32), en, hps);
+            }
             if (SPLIT && p.metrics2)
                 p.metrics2[(long long)s * p.R + r] = make_uint2((unsigned)(base_all + s_injs[g]), (unsigned)(base_drop + s_drop[g]));
         }
@@ -2019,8 +2044,12 @@ StepKernel pick_deg(int n_nodes, int max_deg, bool smem_tables, int threads)
     }
     // small CTAs reading their tables from HBM (lata.net: 116 nodes, 128 threads): the high-occupancy build
     constexpr bool kHasLb1 = POLICY == RLR_POLICY_QROUTE || POLICY == RLR_POLICY_HYBRIDQ || POLICY == RLR_POLICY_SHORTEST;
+    // (a CTA of at most 128 threads has four window words, so no replica in it spans more: MAXW = 4, one packed register of
+    // prefix counts; with MAXW = 9 the window code was 29 % of the instructions lata.net's Qroute step executed)
     if (kHasLb1 && !SPLIT && !smem_tables && threads <= 128 && max_deg > 8 && max_deg <= 12)
-        return pick_smem<POLICY, 12, 9, SPLIT, kHasLb1 && !SPLIT ? 1 : 0, QT, PAGED>(false);
+        return pick_smem<POLICY, 12, 4, SPLIT, kHasLb1 && !SPLIT ? 1 : 0, QT, PAGED>(false);
+    if (!SPLIT && n_nodes <= 128 && max_deg > 8 && max_deg <= 12)           // 65..128 nodes at any alignment: at most five words
+        return pick_smem<POLICY, 12, 5, SPLIT, 0, QT, PAGED>(smem_tables);
     if (max_deg <= 8) return pick_smem<POLICY, 8, 9, SPLIT, 0, QT, PAGED>(smem_tables);
     if (max_deg <= 12) return pick_smem<POLICY, 12, 9, SPLIT, 0, QT, PAGED>(smem_tables);      // lata.net: degree 9 (row loops sized 12, not 16)
     return pick_smem<POLICY, 16, 9, SPLIT, 0, QT, PAGED>(smem_tables);
