@@ -663,8 +663,12 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
 #ifdef RLR_NOFLAT
     constexpr bool kFlatArrivals = false;
 #else
-    constexpr bool kFlatArrivals = FUSED && MAXD == 4;
+    constexpr bool kFlatArrivals = FUSED && (MAXD == 4 || MAXD == 8);
 #endif
+    // MAXD == 8 (a graph that is mostly a grid, with a few nodes of degree 5..8: 6x6-modified.net): the first four links of every
+    // node go through the loop-free arrival code; a node that finds a packet on one of its further links in some step handles
+    // that step's arrivals — all of them — with the general sorted-list code instead.
+    constexpr bool kFlatPlus = kFlatArrivals && MAXD > 4;
     constexpr bool kLearnInArrivals = kFlatArrivals && POLICY == RLR_POLICY_QROUTE && SMEM_TABLES;
     // Qroute's fused loop with rings: a replica cannot stop in the middle of a launch there, so "this thread is a node of a
     // running replica" (`act`) is a constant of the launch.  Instead of branching around every phase (a warp never skips
@@ -1010,7 +1014,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
     // Very wide nodes (MAXD > 8, e.g. lata.net): the row scans run in groups of four slots, and a group is skipped (one uniform
     // branch per group, so the loads inside a group still issue back to back) when no node of the warp has a neighbour that
     // far: lata Qroute +10 %.  (With MAXD = 8 the branch costs more than the second group: 6x6-modified.net -3 %.)
-    const int wdeg = MAXD > 8 ? __reduce_max_sync(0xFFFFFFFFu, is_node ? deg : 1) : MAXD;
+    const int wdeg = (MAXD > 8 || kFlatPlus) ? __reduce_max_sync(0xFFFFFFFFu, is_node ? deg : 1) : MAXD;
 #ifdef RLR_EXP_TIMING
     long long tacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tmark_ = clock64();
@@ -1576,6 +1580,11 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
             unsigned q4[4] = {kNoKey, kNoKey, kNoKey, kNoKey};
             int nkey = 0;
             bool use_list = false;
+            bool far = false;               // kFlatPlus: a packet arrives on a link beyond this node's fourth
+            if (kFlatPlus && wdeg > 4) {    // (uniform: some node of the warp has such links)
+#pragma unroll
+                for (int j = 4; j < MAXD; ++j) far |= ((s_tp[nb_slot[j]] ^ (unsigned)x) & 0xFFu) == 0u;
+            }
             if (MAXD == 4 && !kFlatArrivals) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -1587,7 +1596,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
 #define RLR_CE(a, b) { const unsigned lo_ = min(q4[a], q4[b]), hi_ = max(q4[a], q4[b]); q4[a] = lo_; q4[b] = hi_; }
                 RLR_CE(0, 1) RLR_CE(2, 3) RLR_CE(0, 2) RLR_CE(1, 3) RLR_CE(1, 2)
 #undef RLR_CE
-            } else if (MAXD > 4) {
+            } else if (MAXD > 4 && (!kFlatPlus || far)) {
                 unsigned marks = 0u;
 #pragma unroll
                 for (int j = 0; j < MAXD; ++j) {
@@ -1639,6 +1648,7 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                 for (int j = 0; j < 4; ++j) {
                     const unsigned tp = s_tp[nb_slot[j]];
                     mt[j] = ((tp ^ (unsigned)x) & 0xFFu) == 0u;      // (a stopped replica's nodes publish "no send" too)
+                    if (kFlatPlus) mt[j] = mt[j] & !far;
                     const unsigned base = cum_at(nb_word[j]);
                     posv[j] = heap_pos_at(hp_row + (tp >> 8) + base);      // (in the table for any slot: kNoSend carries rank 0)
                     rc[j] = lds128_if(s_rec + nb_slot[j], mt[j]);
@@ -1694,7 +1704,8 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
                     add_if(tail, 1u, ap[j]);
                 }
                 if (PAGED && ((tail ^ tail0) >> plog)) next_tail_page();
-            } else {
+            }
+            if (!kFlatArrivals || (kFlatPlus && far)) {
             RLR_T(5);                               // C: window + keys + sort
             for (int taken = 0;; ++taken) {
                 unsigned best;
