@@ -667,15 +667,17 @@ rlr_step_kernel(const __grid_constant__ StepParams p)
 #endif
     // MAXD == 8 (a graph that is mostly a grid, with a few nodes of degree 5..8: 6x6-modified.net): the first four links of every
     // node go through the loop-free arrival code; a node that finds a packet on one of its further links in some step handles
-    // that step's arrivals — all of them — with the general sorted-list code instead.
+    // that step's arrivals — all of them — with the general sorted-list code instead.  (Not for the wide instantiations: on
+    // lata.net — average degree 2.9, hubs of up to 9 — some node of nearly every warp has such a packet, both paths run, and the
+    // four unconditional slots cost more than the mark-then-insert pass: 1.19e10 -> 0.84e10 hops/s when tried.)
     constexpr bool kFlatPlus = kFlatArrivals && MAXD > 4;
     constexpr bool kLearnInArrivals = kFlatArrivals && POLICY == RLR_POLICY_QROUTE && SMEM_TABLES;
-    // Qroute's fused loop with rings: a replica cannot stop in the middle of a launch there, so "this thread is a node of a
+    // Qroute's and Shortest's fused loops with rings: a replica cannot stop in the middle of a launch there, so "this thread is a node of a
     // running replica" (`act`) is a constant of the launch.  Instead of branching around every phase (a warp never skips
     // them: even the second warp of a 36-node replica holds four nodes), `act` is one more input of the three predicates
     // that start any work — queue not empty, a neighbour's packet is for me, an injection is due — and the phases run
     // unconditionally: an inactive lane keeps head == tail, matches nothing and has no schedule.
-    constexpr bool kStaticLive = kFlatArrivals && POLICY == RLR_POLICY_QROUTE && !PAGED;
+    constexpr bool kStaticLive = kFlatArrivals && (POLICY == RLR_POLICY_QROUTE || POLICY == RLR_POLICY_SHORTEST) && !PAGED;
     // Kernels with registers to spare — the degree <= 4 fused loops of the policies without softmax rows — keep loop constants,
     // the sender's scratch and a few addresses in registers across the steps; the others run at their register limit, where
     // a reloaded constant is cheaper than a spill.
