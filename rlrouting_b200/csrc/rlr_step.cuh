@@ -31,6 +31,9 @@ constexpr int kMaxThreads = RLR_MAXT;
 #ifndef RLR_LB1_BLOCKS
 #define RLR_LB1_BLOCKS 6
 #endif
+#ifndef RLR_LB1_BLOCKS_QROUTE
+#define RLR_LB1_BLOCKS_QROUTE 7     // 72 registers: 8 bytes of spills with the four-word window code, and the seventh resident
+#endif                              // CTA is worth 6 % on lata.net (the step waits on HBM row reads); 64 registers spill 68 bytes: -19 %
 constexpr int kSmemLimit = 227 * 1024;
 
 // ------------------------------------------------------------------------------------------------
@@ -640,7 +643,7 @@ constexpr unsigned kDeadRec = 0xFFFFFFFFu; // word 0 of a ring entry that was se
 //   MAXW  >= 32-bit words a replica's N consecutive thread slots can span (3 for N <= 64, else 9)
 // ------------------------------------------------------------------------------------------------
 //   LB    launch-bound class: 0 = any CTA up to kMaxThreads threads; 1 = CTAs of at most 128 threads with tables in HBM
-//         (one 65..128-node replica per CTA, e.g. lata.net), compiled for RLR_LB1_BLOCKS resident CTAs per SM: the step is
+//         (one 65..128-node replica per CTA, e.g. lata.net), compiled for RLR_LB1_BLOCKS (Qroute on rings: RLR_LB1_BLOCKS_QROUTE) resident CTAs per SM: the step is
 //         bound by the latency of the table rows it reads from L2 / HBM, so what pays is warps in flight (80 registers
 //         instead of 126, no spills once the row loops are sized 12 and not 16)
 //   QT    element type of the Q table in memory: double, or float for Qroute's fp32 STORAGE mode (Network(dtype='float32')):
@@ -653,7 +656,7 @@ constexpr unsigned kDeadRec = 0xFFFFFFFFu; // word 0 of a ring entry that was se
 //         select and a shift more than in a ring, and pages are taken from / returned to the replica's free stack only when
 //         a cursor crosses a page boundary (pops return pages before barrier 1, appends take pages after it).
 template <int POLICY, int MAXD, int MAXW, bool SMEM_TABLES, bool SPLIT, int LB = 0, typename QT = double, bool PAGED = false>
-__global__ void __launch_bounds__(LB ? 128 : kMaxThreads, LB ? RLR_LB1_BLOCKS : RLR_MIN_BLOCKS)
+__global__ void __launch_bounds__(LB ? 128 : kMaxThreads, LB ? (POLICY == RLR_POLICY_QROUTE && !PAGED ? RLR_LB1_BLOCKS_QROUTE : RLR_LB1_BLOCKS) : RLR_MIN_BLOCKS)
 rlr_step_kernel(const __grid_constant__ StepParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
