@@ -392,6 +392,12 @@ def _random_net(rng, n, extra, max_deg):
     ("MaHybridQ", 127, 200, 10, 2, 60, 3.0, {}),    # MaHybridQ's limit (NumPy single pairwise block: n < 128 senders)
     ("Qroute", 2, 0, 1, 5, 300, 0.8, {}),           # smallest graph
     ("CQ", 33, 40, 6, 4, 200, 2.0, {}),
+    # degree 5..8 on at most 64 nodes: four links through the loop-free arrival code, packets on further links through the list
+    ("Qroute", 40, 30, 7, 4, 300, 3.0, {}),
+    ("Shortest", 50, 40, 8, 3, 300, 4.0, {}),
+    # 65..128 nodes, degree 9..12: the 128-thread build (four window words) and, for two replicas per CTA, the five-word one
+    ("Qroute", 100, 80, 12, 3, 200, 4.0, {}),
+    ("HybridQ", 100, 60, 10, 2, 100, 3.0, {}),
     ("GlobalRoute", 150, 250, 11, 2, 60, 6.0, {}),
     # the general timing model (events in flight, busy links, queue scan) on the same kinds of graph
     ("Qroute", 255, 700, 16, 2, 100, 6.0, dict(transtime=2)),
